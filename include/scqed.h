@@ -1,0 +1,129 @@
+/*
+ * scqed.h -- C ABI of the B200 sweep engine (libscqed.so).
+ *
+ * The reference (pyscqed 0.13.0) has no FFI/plugin interface; its hot path sits behind the
+ * Python class API of pyscqed/numerical_system.py.  The entry points below are what a binding
+ * of that path needs; each one names the reference function it replaces.  Conventions:
+ *   - plain pointers and sizes only, no C++ or torch types;
+ *   - every function returns 0 on success or a negative SCQED_E* code, and never throws;
+ *     scqed_last_error() returns a thread-local message for the last failure;
+ *   - all *_dev pointers are device pointers owned by the caller (e.g. torch tensors),
+ *     complex128 data is interleaved (re, im) doubles;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - a plan is immutable after creation; one in-flight call per (plan, stream).
+ */
+#ifndef SCQED_H
+#define SCQED_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCQED_OK            0
+#define SCQED_EINVAL       -1   /* bad argument / inconsistent plan description            */
+#define SCQED_ECUDA        -2   /* CUDA runtime error (message in scqed_last_error)          */
+#define SCQED_ENOMEM       -3   /* workspace allocation failed                               */
+#define SCQED_EUNSUPPORTED -4   /* configuration outside what this build implements         */
+
+typedef struct scqed_plan scqed_plan;
+
+/*
+ * Plan description = the three tables that replace the reference's full-space QuTiP operators
+ * (numerical_system.py:185-253 getExpandedOperatorsMap) and its per-point sympy substitution
+ * (numerical_system.py:395-437 _postsub):
+ *   factor table : n_factors dense d x d complex matrices (row-major), factor f belongs to node
+ *                  factor_node[f] and starts at factor_data + 2*factor_offset[f] doubles
+ *   term table   : H(p) = sum_t c_t(p) * kron_k F[term_factors[t*n_nodes + k]]   (-1 = identity)
+ *   program      : SSA bytecode, instruction i = (op, a, b) writes register i; c_t = reg[coef_re[t]]
+ *                  + i*reg[coef_im[t]] (-1 = 0); scalar outputs reg[scalar_regs[s]].
+ *                  Opcodes: see pycqed_b200/coefprog.py.
+ */
+typedef struct {
+    int32_t n_nodes;
+    const int32_t *dims;            /* [n_nodes] first node = slowest Hilbert index          */
+    int32_t n_factors;
+    const int32_t *factor_node;     /* [n_factors]                                           */
+    const int64_t *factor_offset;   /* [n_factors] in complex elements                       */
+    const double  *factor_data;     /* interleaved complex128                                */
+    int32_t n_terms;
+    const int32_t *term_factors;    /* [n_terms * n_nodes]                                   */
+    int32_t n_swept;
+    int32_t n_instr;
+    const int32_t *instr;           /* [n_instr * 3]                                         */
+    int32_t n_consts;
+    const double  *consts;
+    const int32_t *coef_re;         /* [n_terms]                                             */
+    const int32_t *coef_im;         /* [n_terms]                                             */
+    int32_t n_scalar;
+    const int32_t *scalar_regs;     /* [n_scalar]                                            */
+} scqed_plan_desc;
+
+/* Options of one sweep (numerical_system.py:790-804 setDiagConfig + :868-875 addEvaluation). */
+typedef struct {
+    int32_t k;                /* eigvalues: number of lowest eigenpairs                      */
+    int32_t want_vectors;     /* get_vectors                                                 */
+    int32_t solver;           /* 0 auto, 1 fused small (H in shared memory), 2 dense (HBM)   */
+    int32_t tidyup;           /* 1: threshold H entries at 1e-12 like Qobj.tidyup (:594)     */
+    /* Resonator evaluable (numerical_system.py:736-784 getResonatorResponse); needs vectors */
+    int32_t resonator;        /* 0/1                                                         */
+    int32_t res_nmax;         /* nmax (strips = nmax + 1 + k)                                */
+    int32_t res_op_factor;    /* factor id of the coupled node's charge operator             */
+    int32_t res_gc;           /* scalar slot of g_C                                          */
+    int32_t res_frl;          /* scalar slot of the loaded resonator frequency               */
+    int32_t res_qb;           /* scalar slot of the node's charge bias                       */
+    int32_t reserved[6];
+} scqed_sweep_opts;
+
+/* Create / destroy.  Uploads the tables to `device`. */
+int  scqed_plan_create(const scqed_plan_desc *desc, int device, scqed_plan **plan_out);
+void scqed_plan_destroy(scqed_plan *plan);
+int  scqed_plan_hilbert_dim(const scqed_plan *plan);
+
+/* _postsub replacement (numerical_system.py:395-437): coefficients of all points.
+ * params_dev [n_pts, n_swept] row-major; coef_dev complex [n_pts, n_terms]; scalars_dev
+ * [n_pts, n_scalar] (may be NULL when n_scalar == 0). */
+int scqed_eval_coefficients(scqed_plan *plan, const double *params_dev, int64_t n_pts,
+                            double *coef_dev, double *scalars_dev, void *stream);
+
+/* getHamiltonian replacement (numerical_system.py:509-594): dense H of every point,
+ * H_dev complex [n_pts, n, n] row-major. */
+int scqed_assemble_dense(scqed_plan *plan, const double *params_dev, int64_t n_pts, int32_t tidyup,
+                         double *H_dev, void *stream);
+
+/* diagonalize / util.diagDenseH replacement (numerical_system.py:809-810, util.py:127-176):
+ * lowest k eigenpairs of `batch` Hermitian matrices (row-major, only consistent Hermitian input
+ * is supported; H_dev is overwritten).  evals_dev [batch, k] ascending; evecs_dev complex
+ * [batch, k, n] unit-norm (NULL = values only); info_dev [batch] (0 = converged). */
+int scqed_eigh_batched(int device, double *H_dev, int32_t n, int64_t batch, int32_t k,
+                       double *evals_dev, double *evecs_dev, int32_t *info_dev, int32_t solver,
+                       void *stream);
+
+/* paramSweep replacement (numerical_system.py:885-1049): assemble + diagonalise (+ post-ops) for
+ * all points.  Device-buffer form.  post_dev: resonator strips [n_pts, nmax+1+k, k] or NULL. */
+int scqed_sweep_run(scqed_plan *plan, const scqed_sweep_opts *opts, const double *params_dev,
+                    int64_t n_pts, double *evals_dev, double *evecs_dev, double *scalars_dev,
+                    double *post_dev, int32_t *info_dev, void *stream);
+
+/* Same with HOST buffers: copies params in, results out (pinned staging inside the library).
+ * This is the call the Python drop-in makes for one GPU shard. */
+int scqed_sweep_run_host(scqed_plan *plan, const scqed_sweep_opts *opts, const double *params,
+                         int64_t n_pts, double *evals, double *evecs, double *scalars,
+                         double *post, int32_t *info);
+
+/* Kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t scqed_launch_count(void);
+
+/* FP64 peak probe: runs a register-resident DMMA (mma.sync m8n8k4 f64) loop on every SM and
+ * returns TFLOP/s; the roofline denominator for the dense tridiagonalisation. */
+int scqed_probe_fp64_tensor(int device, double *tflops_out);
+int scqed_probe_fp64_fma(int device, double *tflops_out);
+
+const char *scqed_last_error(void);
+const char *scqed_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCQED_H */

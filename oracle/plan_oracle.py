@@ -1,0 +1,275 @@
+"""CPU oracle for the sweep hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this
+module; ``pycqed_b200/`` never does (the product path has no CPU fallback).
+
+It restates, with numpy/scipy, what the reference does at every sweep point:
+
+  coefficients   pyscqed/numerical_system.py:395-437 (``_postsub``) -- here by interpreting the
+                 plan's coefficient program on the host
+  assembly       pyscqed/numerical_system.py:509-594 (``getHamiltonian``): a sum of scaled
+                 Kronecker products in CSR sparse algebra (what QuTiP's ``tensor``/``+``/``*``
+                 do, pyscqed/numerical_system.py:226-251), then ``tidyup(1e-12)`` (:594)
+  eigensolve     pyscqed/util.py:153 ``scipy.linalg.eigh(H, subset_by_index=(0, k-1))``
+                 (LAPACK zheevr), sorted / normalised as util.py:156-176;
+                 pyscqed/util.py:102 ``scipy.sparse.linalg.eigsh`` for the sparse variant
+  resonator      pyscqed/numerical_system.py:736-784 (``getResonatorResponse``)
+  result layout  pyscqed/parameters.py:1060-1068,1146-1157 (``getSweepResult`` transposition)
+
+Third-party arithmetic the reference delegates to and that is not under /root/reference:
+QuTiP 5.0.3.post1 CSR algebra (restated above), SciPy -> LAPACK ``zheevr`` / ARPACK (called
+directly, same entry points as the reference).
+
+Parity pinning: the reference has NO tests or golden vectors for this path,
+so the oracle is pinned against outputs of the reference itself, run unmodified in the build
+container over ``oracle/shims`` -- see ``tests/golden/make_golden.py`` and
+``tests/test_oracle_vs_reference.py``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg
+import scipy.sparse as sp
+import scipy.sparse.linalg
+
+QOBJ_ATOL = 1e-12   # numerical_system.py:19
+
+
+# ------------------------------------------------------------------------------------------------
+# coefficient program
+# ------------------------------------------------------------------------------------------------
+def eval_program(program, params):
+    """Interpret the SSA bytecode for all points at once.
+
+    :param params: [n_pts, n_swept] float64
+    :return: (coef complex128 [n_pts, n_coef], scalars float64 [n_pts, n_scalar])
+    """
+    params = np.asarray(params, dtype=np.float64)
+    if params.ndim != 2 or params.shape[1] != program.n_swept:
+        raise ValueError("params must be [n_pts, %d], got %r" % (program.n_swept, params.shape))
+    n_pts = params.shape[0]
+    regs = np.zeros((program.n_instr, n_pts), dtype=np.float64)
+    with np.errstate(all="ignore"):
+        for i, (op, a, b) in enumerate(program.instr.tolist()):
+            if op == 0:
+                regs[i] = program.consts[a]
+            elif op == 1:
+                regs[i] = params[:, a]
+            elif op == 2:
+                regs[i] = regs[a] + regs[b]
+            elif op == 3:
+                regs[i] = regs[a] - regs[b]
+            elif op == 4:
+                regs[i] = regs[a] * regs[b]
+            elif op == 5:
+                regs[i] = regs[a] / regs[b]
+            elif op == 6:
+                regs[i] = -regs[a]
+            elif op == 7:
+                regs[i] = np.sqrt(regs[a])
+            elif op == 8:
+                regs[i] = np.sin(regs[a])
+            elif op == 9:
+                regs[i] = np.cos(regs[a])
+            elif op == 10:
+                regs[i] = np.exp(regs[a])
+            elif op == 11:
+                regs[i] = np.log(regs[a])
+            elif op == 12:
+                regs[i] = np.power(regs[a], regs[b])
+            elif op == 13:
+                regs[i] = np.power(regs[a], float(b))
+            elif op == 14:
+                regs[i] = np.abs(regs[a])
+            elif op == 15:
+                regs[i] = np.tan(regs[a])
+            elif op == 16:
+                regs[i] = np.arctan(regs[a])
+            elif op == 17:
+                regs[i] = np.tanh(regs[a])
+            elif op == 18:
+                regs[i] = np.sinh(regs[a])
+            elif op == 19:
+                regs[i] = np.cosh(regs[a])
+            else:
+                raise ValueError("unknown opcode %d" % op)
+    coef = np.zeros((n_pts, program.n_coef), dtype=np.complex128)
+    for t in range(program.n_coef):
+        re = regs[program.coef_re[t]] if program.coef_re[t] >= 0 else 0.0
+        im = regs[program.coef_im[t]] if program.coef_im[t] >= 0 else 0.0
+        coef[:, t] = re + 1j * im
+    scal = np.zeros((n_pts, program.n_scalar), dtype=np.float64)
+    for s in range(program.n_scalar):
+        scal[:, s] = regs[program.scalar_regs[s]]
+    return coef, scal
+
+
+# ------------------------------------------------------------------------------------------------
+# assembly
+# ------------------------------------------------------------------------------------------------
+def _tidyup(m, atol=QOBJ_ATOL):
+    m = sp.csr_matrix(m, dtype=np.complex128)
+    re = m.data.real.copy()
+    im = m.data.imag.copy()
+    re[np.abs(re) < atol] = 0.0
+    im[np.abs(im) < atol] = 0.0
+    m.data = re + 1j * im
+    m.eliminate_zeros()
+    return m
+
+
+class PlanOracle:
+    """Holds the Kronecker-expanded term operators (the reference's ``circ_operators`` products)
+    so that a per-point assembly is the same CSR scale-and-add the reference performs."""
+
+    def __init__(self, plan):
+        self.plan = plan
+        self.dims = plan.dims
+        self.n = plan.hilbert_dim
+        self._factors = [sp.csr_matrix(plan.factor_matrix(f)) for f in range(len(plan.factors))]
+        self._eyes = [sp.identity(d, dtype=np.complex128, format="csr") for d in self.dims]
+        self.term_ops = [self._expand(t) for t in plan.terms]
+
+    def _expand(self, fids):
+        out = None
+        for k, fid in enumerate(fids):
+            m = self._eyes[k] if fid < 0 else self._factors[fid]
+            out = m if out is None else sp.kron(out, m, format="csr")
+        return sp.csr_matrix(out)
+
+    def expand_factor(self, fid):
+        ni = self.plan.factors[fid][0]
+        fids = [-1] * len(self.dims)
+        fids[ni] = fid
+        return self._expand(fids)
+
+    def coefficients(self, params):
+        return eval_program(self.plan.program, np.atleast_2d(np.asarray(params, dtype=np.float64)))
+
+    def hamiltonian(self, coef_row, tidy=True):
+        H = None
+        for c, op in zip(coef_row, self.term_ops):
+            H = c * op if H is None else H + c * op
+        H = sp.csr_matrix(H)
+        return _tidyup(H) if tidy else H
+
+    def diag_dense(self, H, k, get_vectors=False):
+        """util.py:127-176."""
+        ret = scipy.linalg.eigh(H.toarray(), eigvals_only=(not get_vectors), subset_by_index=(0, k - 1))
+        if not get_vectors:
+            ret.sort()
+            return ret
+        E, V = ret
+        order = np.argsort(E, kind="stable")
+        E = E[order]
+        V = V[:, order]
+        V = V / np.linalg.norm(V, axis=0, keepdims=True)
+        return E, V
+
+    def diag_sparse(self, H, k, get_vectors=False, **opts):
+        """util.py:76-125 (caller supplies e.g. sigma=-300, tol=0)."""
+        ret = scipy.sparse.linalg.eigsh(sp.csr_matrix(H), k=k, return_eigenvectors=get_vectors, **opts)
+        if not get_vectors:
+            ret.sort()
+            return ret
+        E, V = ret
+        order = np.argsort(E, kind="stable")
+        return E[order], V[:, order] / np.linalg.norm(V[:, order], axis=0, keepdims=True)
+
+    # -- resonator ----------------------------------------------------------------------------
+    def resonator_response(self, E, V, scal_row):
+        """numerical_system.py:736-784, literally (bare-order bookkeeping included)."""
+        spec = self.plan.post["resonator"]
+        gC = scal_row[spec["gC"]]
+        wrl = scal_row[spec["frl"]]
+        qb = scal_row[spec["qb"]]
+        Op = self.expand_factor(spec["op_factor"]) + qb * sp.identity(self.n, dtype=np.complex128, format="csr")
+        return resonator_response(np.asarray(E), V, Op, gC, wrl, spec["nmax"])
+
+    # -- whole sweep -----------------------------------------------------------------------------
+    def sweep(self, params, k, get_vectors=False, resonator=False, sparse_opts=None):
+        params = np.atleast_2d(np.asarray(params, dtype=np.float64))
+        coef, scal = eval_program(self.plan.program, params)
+        n_pts = params.shape[0]
+        Es = np.zeros((n_pts, k))
+        Vs = np.zeros((n_pts, self.n, k), dtype=np.complex128) if get_vectors or resonator else None
+        Rs = []
+        for i in range(n_pts):
+            H = self.hamiltonian(coef[i])
+            if sparse_opts is not None:
+                out = self.diag_sparse(H, k, get_vectors or resonator, **sparse_opts)
+            else:
+                out = self.diag_dense(H, k, get_vectors or resonator)
+            if get_vectors or resonator:
+                Es[i], Vs[i] = out
+                if resonator:
+                    Rs.append(self.resonator_response(Es[i], Vs[i], scal[i]))
+            else:
+                Es[i] = out
+        return {"E": Es, "V": Vs, "Erwa": (np.array(Rs) if resonator else None), "scalars": scal}
+
+
+def resonator_response(E, V, Op, gC, wrl, nmax=100):
+    """RWA strips (numerical_system.py:751-784).  ``V`` is [n, k] (columns = kets)."""
+    E = E - E[0]
+    tmax = len(E)
+    nmax = nmax + 1 + tmax
+    OV = Op @ V
+
+    def mel(i, j):
+        return np.vdot(V[:, i], OV[:, j])
+
+    norm = mel(0, 1)
+    g_list = np.array([mel(i, i + 1) for i in range(tmax - 1)])
+    g_list = gC * np.abs(g_list / norm)
+    order = np.zeros(tmax, dtype=int)
+    diag_bare = np.array([-i * wrl + E[i] for i in range(tmax)])
+    eigensolver_order = np.linalg.eigvalsh(np.diag(diag_bare))
+    for i in range(tmax):
+        index, = np.where(eigensolver_order == diag_bare[i])
+        order[i] = index[0]
+    Erwa = [0.0] * nmax
+    for n in range(nmax):
+        d = np.array([(n - i) * wrl + E[i] for i in range(tmax)])
+        o = np.array([g_list[i] * np.sqrt((n - i) * (n - i > 0)) for i in range(tmax - 1)])
+        e = scipy.linalg.eigvalsh(np.diag(d) + np.diag(o, 1) + np.diag(o, -1))
+        Erwa[n] = np.array([e[i].real for i in order])
+    return np.array(Erwa)
+
+
+# ------------------------------------------------------------------------------------------------
+# comparison helpers used by the parity tests
+# ------------------------------------------------------------------------------------------------
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def cluster_indices(E, rtol=1e-7, atol=1e-9):
+    """Group (near-)degenerate levels: consecutive values closer than atol + rtol*|E|."""
+    groups, cur = [], [0]
+    for i in range(1, len(E)):
+        if abs(E[i] - E[i - 1]) <= atol + rtol * max(abs(E[i]), abs(E[i - 1])):
+            cur.append(i)
+        else:
+            groups.append(cur)
+            cur = [i]
+    groups.append(cur)
+    return groups
+
+
+def subspace_overlap(Va, Vb, E, rtol=1e-7, atol=1e-9):
+    """min over degenerate clusters of the smallest singular value of Va_c^H Vb_c
+    (== |<a|b>| for a non-degenerate level; invariant under phase and rotation inside a
+    degenerate subspace).  A cluster cut by the k-truncation is skipped (its partner is absent)."""
+    worst = 1.0
+    k = Va.shape[1]
+    for g in cluster_indices(np.asarray(E), rtol, atol):
+        if g[-1] == k - 1 and len(g) >= 1 and k < Va.shape[0]:
+            # last cluster may be cut by the truncation -> only testable if isolated; keep singletons
+            if len(g) > 1:
+                continue
+        S = np.linalg.svd(Va[:, g].conj().T @ Vb[:, g], compute_uv=False)
+        worst = min(worst, float(S.min()))
+    return worst

@@ -1,0 +1,256 @@
+"""Lowering: symbolic circuit + operator configuration + sweep spec -> :class:`SweepPlan`.
+
+This is the once-per-sweep replacement of what the reference does at EVERY sweep point:
+``_postsub`` (pyscqed/numerical_system.py:395-437) followed by ``getHamiltonian`` (:509-594).
+The algebra of ``getHamiltonian`` is expanded symbolically here, once:
+
+  Hq = 1/2 Ec (Q+q_b)^T C^-1 (Q+q_b)     -> terms  Q_i Q_j,  Q_i,  identity
+  Hf = 1/2 El (P+phi_b)^T L^-1 (P+phi_b) -> terms  P_i P_j,  P_i,  identity
+  Hj = -1/2 Ej sum_e J_e (e^{+2 pi i Phi_e} Pi_e^+ + e^{-2 pi i Phi_e} Pi_e^-)
+  Hp = -1/2 Ep sum_e V_e (e^{+2 pi i q_e}  Sigma_e^+ + e^{-2 pi i q_e}  Sigma_e^-)
+
+with Pi_e^+- the per-node products of D / D^dagger selected by the SIGN of the branch
+coordinate coefficients exactly as numerical_system.py:529-552 does.
+
+Only public attributes/methods of the reference's ``SymbolicSystem`` are used (the symbolic
+layer is reused, not rebuilt): ``nodes, edges, Rnb, Rinv, node_vector, node_map_rev,
+cooper_disp, fluxon_disp, getInverse*Matrix, get*Vector, getFluxBiasMatrix,
+getParameterFromSymbol, getParametricParametersList, getParametricExpression,
+getParameterValue, getNonSweepParametersDict, getSymbolValuesDict``.
+"""
+from __future__ import annotations
+
+import sympy as sy
+
+from .coefprog import ProgramBuilder
+from .plan import NodeSpec, SweepPlan
+
+
+class LoweringError(Exception):
+    pass
+
+
+def _resolve(expr, SS, swept_names, presub):
+    """Rewrite ``expr`` in terms of the swept INDEPENDENT symbols only.
+
+    After ``_presub`` (numerical_system.py:357-373) the reference's matrices still contain the
+    swept symbols plus every parametric dependent of them (``getSweepParametersDict``,
+    parameters.py:888-906); it fills those in numerically at each point through
+    ``_update_parameterisations`` (parameters.py:1207-1240).  Here dependents are replaced by
+    their defining expressions once, and everything not swept is a number.
+    """
+    expr = sy.sympify(expr)
+    parametric = set(SS.getParametricParametersList())
+    for _ in range(64):
+        expr = expr.subs(presub)
+        todo = {}
+        for sym in expr.free_symbols:
+            name = SS.getParameterFromSymbol(sym)
+            if name in swept_names:
+                continue
+            if name in parametric:
+                todo[sym] = SS.getParametricExpression(name)
+            else:
+                val = SS.getParameterValue(name)
+                if val is None:
+                    raise LoweringError("parameter '%s' has no value" % name)
+                todo[sym] = val
+        if not todo:
+            return expr
+        expr = expr.subs(todo)
+    raise LoweringError("parameterisation expansion did not terminate for %r" % (expr,))
+
+
+def _branch_composition(SS, i):
+    """[(node, sign)] of branch i in node coordinates, parsed like numerical_system.py:519-552."""
+    Pp = SS.Rnb * SS.Rinv * SS.node_vector
+    e = Pp[i]
+    out = []
+    if len(e.atoms()) > 2:            # a sum of coef*symbol terms
+        for arg in e.args:
+            out.append((SS.node_map_rev[arg.args[1]], 1 if arg.args[0] > 0 else -1))
+    else:
+        out.append((SS.node_map_rev[e.args[1]], 1 if e.args[0] > 0 else -1))
+    return out
+
+
+class _TermTable:
+    def __init__(self, n_nodes):
+        self.n_nodes = n_nodes
+        self.factors = []          # (node_index, name)
+        self._fid = {}
+        self.terms = {}            # tuple(factor ids) -> [re_expr, im_expr]
+        self.order = []
+
+    def fid(self, node_index, name):
+        key = (node_index, name)
+        if key not in self._fid:
+            self._fid[key] = len(self.factors)
+            self.factors.append(key)
+        return self._fid[key]
+
+    def add(self, node_factor_names: dict, re_expr, im_expr=0):
+        """node_factor_names: {node_index: factor name}; coefficient = re + i im."""
+        if re_expr == 0 and im_expr == 0:
+            return
+        key = [-1] * self.n_nodes
+        for ni, name in node_factor_names.items():
+            key[ni] = self.fid(ni, name)
+        key = tuple(key)
+        if key not in self.terms:
+            self.terms[key] = [sy.Integer(0), sy.Integer(0)]
+            self.order.append(key)
+        self.terms[key][0] += re_expr
+        self.terms[key][1] += im_expr
+
+
+def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scalars=None,
+                 resonator=None) -> SweepPlan:
+    """Build the plan.
+
+    :param SS: the reference ``SymbolicSystem`` (after ``ndSweep`` if ``swept_names``)
+    :param units: the reference ``Units`` object (``getPrefactor``)
+    :param operator_data: ``{node: {'basis','truncation',...}}`` as kept by ``configureOperator``
+    :param swept_names: independent parameters being swept, in ``addSweep`` order
+    :param scalars: {name: sympy expr or parameter name} extra real per-point outputs
+    :param resonator: {'cpl_node': node, 'nmax': int} to add the Resonator post-op inputs
+    """
+    swept_names = list(swept_names)
+    nodes = list(SS.nodes)
+    N = len(nodes)
+    for node in nodes:
+        if node not in operator_data:
+            raise LoweringError("node %r has no operator configuration (configureOperator)" % (node,))
+
+    if swept_names:
+        presub = SS.getNonSweepParametersDict()
+    else:
+        presub = SS.getSymbolValuesDict()
+    missing = [str(k) for k, v in presub.items() if v is None]
+    if missing:
+        raise LoweringError("parameters without a value: %s" % missing)
+    swept_syms = [SS.getSymbol(n) for n in swept_names]
+
+    def R(expr):
+        return _resolve(expr, SS, swept_names, presub)
+
+    # An oscillator node whose impedance depends on a swept symbol would need its operators
+    # regenerated at every point (numerical_system.py:378-393,435-437).
+    for node, data in operator_data.items():
+        if data["basis"] == "oscillator":
+            z = R(data["impedance"])
+            if z.free_symbols:
+                raise LoweringError(
+                    "oscillator node %r: impedance depends on swept parameter(s) %s; per-point operator "
+                    "regeneration is not supported by this engine yet" % (node, sorted(map(str, z.free_symbols))))
+
+    Ec = units.getPrefactor("Ec")
+    El = units.getPrefactor("El")
+    Ej = units.getPrefactor("Ej")
+    Ep = units.getPrefactor("Ep")
+
+    Cinv = SS.getInverseCapacitanceMatrix().applyfunc(R)
+    Linv = SS.getInverseInductanceMatrix().applyfunc(R)
+    Jvec = SS.getJosephsonVector().applyfunc(R)
+    Pvec = SS.getPhaseSlipVector().applyfunc(R)
+    Qb = SS.getChargeBiasVector().applyfunc(R)
+    Qbt = (SS.Rnb * SS.getChargeBiasVector()).applyfunc(R)
+    Pbm = SS.getFluxBiasMatrix(mode="branch").applyfunc(R)
+    Pbi = SS.getFluxBiasVectorInd().applyfunc(R)
+
+    tt = _TermTable(N)
+    half = sy.Rational(1, 2)
+
+    def quadratic(M, bias, pref, lin_name, sq_name):
+        # pref/2 * sum_ij (O_i + b_i) M_ij (O_j + b_j)
+        for i in range(N):
+            for j in range(N):
+                m = M[i, j]
+                if m == 0:
+                    continue
+                c = half * pref * m
+                if i == j:
+                    tt.add({i: sq_name}, c)
+                else:
+                    tt.add({i: lin_name, j: lin_name}, c)
+                tt.add({i: lin_name}, c * bias[j])
+                tt.add({j: lin_name}, c * bias[i])
+                tt.add({}, c * bias[i] * bias[j])
+
+    quadratic(Cinv, Qb, Ec, "charge", "charge2")
+    quadratic(Linv, Pbi, El, "flux", "flux2")
+
+    def displacement(vec, phase_of, pref, up, down):
+        for e in range(len(SS.edges)):
+            amp = vec[e]
+            if amp == 0:
+                continue
+            comp = _branch_composition(SS, e)
+            ph = 2 * sy.pi * phase_of(e)
+            c = -half * pref * amp
+            cre = c * sy.cos(ph)
+            cim = c * sy.sin(ph)
+            plus = {nodes.index(node): (up if s > 0 else down) for node, s in comp}
+            minus = {nodes.index(node): (up if s < 0 else down) for node, s in comp}
+            tt.add(plus, cre, cim)       # e^{+i ph} * Pi^+
+            tt.add(minus, cre, -cim)     # e^{-i ph} * Pi^-
+
+    displacement(Jvec, lambda e: Pbm[e, e], Ej, "disp", "disp_adj")
+    displacement(Pvec, lambda e: Qbt[e, 0], Ep, "pdisp", "pdisp_adj")
+
+    # ---- node specs -----------------------------------------------------------------------
+    node_specs = []
+    for node in nodes:
+        data = operator_data[node]
+        spec = NodeSpec(node=node, basis=data["basis"], trunc=int(data["truncation"]),
+                        cooper_disp=float(SS.cooper_disp[node]), fluxon_disp=float(SS.fluxon_disp[node]))
+        if data["basis"] == "oscillator":
+            z = float(R(data["impedance"]))
+            spec.impedance_ohm = z * units.getPrefactor("Impe")
+            spec.chg_osc = units.getPrefactor("ChgOsc")
+            spec.flx_osc = units.getPrefactor("FlxOsc")
+        node_specs.append(spec)
+
+    # ---- scalar outputs -------------------------------------------------------------------
+    scalar_names, scalar_exprs = [], []
+
+    def add_scalar(name, expr):
+        if name not in scalar_names:
+            scalar_names.append(name)
+            scalar_exprs.append(sy.sympify(expr))
+
+    for name, expr in (scalars or {}).items():
+        if isinstance(expr, str):
+            expr = SS.getSymbol(expr)
+        add_scalar(name, R(expr))
+
+    post = {}
+    if resonator is not None:
+        # inputs of getResonatorResponse (numerical_system.py:744-749)
+        cpl = resonator["cpl_node"]
+        idx = nodes.index(cpl)
+        add_scalar("gC", R(SS.getSymbol("g%ir" % cpl)))
+        add_scalar("frl", R(SS.getSymbol("f%irl" % cpl)))
+        add_scalar("qb_cpl", Qb[idx])
+        post["resonator"] = {
+            "cpl_node": int(cpl), "node_index": idx, "nmax": int(resonator.get("nmax", 100)),
+            "op_factor": tt.fid(idx, "charge"),
+            "gC": scalar_names.index("gC"), "frl": scalar_names.index("frl"),
+            "qb": scalar_names.index("qb_cpl"),
+        }
+
+    # ---- compile --------------------------------------------------------------------------
+    builder = ProgramBuilder(swept_syms)
+    keys = [k for k in tt.order if not (tt.terms[k][0] == 0 and tt.terms[k][1] == 0)]
+    program = builder.finish([tuple(tt.terms[k]) for k in keys], scalar_exprs, scalar_names)
+    return SweepPlan(
+        nodes=node_specs,
+        factors=list(tt.factors),
+        terms=[list(k) for k in keys],
+        program=program,
+        swept_names=swept_names,
+        sweep_specs=[dict(name=s["name"], start=float(s["start"]), end=float(s["end"]), N=int(s["N"]))
+                     for s in sweep_specs],
+        post=post,
+        meta={"prefactors": {"Ec": Ec, "El": El, "Ej": Ej, "Ep": Ep}},
+    )

@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""Mint the golden fixtures by running the UNMODIFIED reference (``/root/reference/pyscqed``).
+
+The reference has no tests / known answers for its sweep path, and it cannot
+travel to the GPU box, so its outputs are frozen here:
+
+  tests/golden/<cfg>.plan.json   the lowered SweepPlan (factor specs, term table, coefficient
+                                 program) -- input of the GPU path, the oracle and bench.py
+  tests/golden/<cfg>.npz         reference outputs on a reduced grid: params, ``E`` from
+                                 ``paramSweep`` + ``util.diagDenseH`` (or eigsh tol=0 for n>=9261),
+                                 a few Hamiltonians (CSR triplets), ``_postsub`` floats, eigenvector
+                                 samples, resonator ``Erwa``, scalar evaluables
+
+QuTiP is not installed in this image; the reference runs over ``oracle/shims`` (a scipy.sparse
+restatement of the QuTiP calls it makes).  Circuits and parameter values are those of the
+reference's example scripts (file:line cited per config).
+
+Usage:  python tests/golden/make_golden.py [cfg ...]
+"""
+import contextlib
+import io
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("PYSCQED_REFERENCE", "/root/reference")
+
+
+def import_reference():
+    """Import the reference package over the compatibility shims (test infrastructure)."""
+    warnings.filterwarnings("ignore")
+    for p in (os.path.join(ROOT, "oracle", "shims"), REF, ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import pyscqed
+    return pyscqed
+
+
+@contextlib.contextmanager
+def quiet():
+    with contextlib.redirect_stdout(io.StringIO()):
+        yield
+
+
+# ------------------------------------------------------------------------------------------------
+# the five BASELINE.json configs, built with the reference API
+# ------------------------------------------------------------------------------------------------
+def build_transmon(trunc=40):
+    """C1: examples/transmon-example.py:20-37 plus a gate charge (examples/jpsq-example.py:35 style)."""
+    ps = import_reference()
+    with quiet():
+        g = ps.CircuitGraph()
+        g.addBranch(0, 1, "C")
+        g.addBranch(0, 1, "I1")
+        g.addBranch(0, 1, "I2")
+        g.addFluxBias("I1", "Z")
+        g.addChargeBias(1, "g", "Cg")
+        h = ps.NumericalSystem(ps.SymbolicSystem(g))
+        h.configureOperator(1, trunc, "charge")
+        h.setParameterValues("C", 64.568, "I1", 16.1132e-3 / 2, "I2", 16.1132e-3 / 2,
+                             "Cg", 0.0, "phiZ", 0.0, "Qg", 0.0)
+    return h
+
+
+def build_fluxonium(trunc=101):
+    """C2: examples/fluxonium-example.py:25-73 (qubit A + capacitively coupled resonator)."""
+    ps = import_reference()
+    pc = ps.physical_constants
+    EcA, ElA, EjA, frA, ZrA = 1.398e9, 0.523e9 * 0.5, 2.257e9, 6.696, 50.0
+    C = 0.5 * pc.e ** 2 / (pc.h * EcA)
+    L = 0.5 * pc.phi0 ** 2 / (pc.h * ElA * 4 * np.pi ** 2)
+    I = 2 * np.pi * pc.h * EjA / pc.phi0
+    with quiet():
+        g = ps.CircuitGraph()
+        g.addBranch(0, 1, "C")
+        g.addBranch(0, 1, "L")
+        g.addBranch(0, 1, "I")
+        g.addFluxBias("I", "Z")
+        g.coupleResonatorCapacitively(1, "Cc")
+        h = ps.NumericalSystem(ps.SymbolicSystem(g))
+        h.configureOperator(1, trunc, "oscillator")
+        h.setParameterValues("C", C * 1e15 - 0.3, "I", I * 1e6, "L", L * 1e12, "Cc", 0.3,
+                             "f1r", frA, "Z1r", ZrA, "phiZ", 0.5)
+    return h
+
+
+_FAB = dict(Ca=60.0, Jc=3.0, Aj=0.3 ** 2)
+
+
+def build_csfq_3jj(trunc=10):
+    """C3a: grounded 3JJ CSFQ, 2 nodes (examples/csfq-example.py:156-205)."""
+    ps = import_reference()
+    Ca, Jc, Aj = _FAB["Ca"], _FAB["Jc"], _FAB["Aj"]
+    with quiet():
+        g = ps.CircuitGraph()
+        g.addBranch(0, 1, "I1")
+        g.addBranch(0, 1, "C1")
+        g.addBranch(1, 2, "I2")
+        g.addBranch(1, 2, "C2")
+        g.addBranch(1, 2, "Csh")
+        g.addBranch(0, 2, "I3")
+        g.addBranch(0, 2, "C3")
+        g.addFluxBias("I2", "Z")
+        h = ps.NumericalSystem(ps.SymbolicSystem(g))
+        h.configureOperator(1, trunc, "charge")
+        h.configureOperator(2, trunc, "charge")
+        h.setParameterValues("C1", Ca * Aj, "C2", Ca * Aj, "C3", Ca * Aj, "I1", Jc * Aj, "I2", Jc * Aj,
+                             "I3", Jc * Aj, "Csh", 45, "phiZ", 0.5)
+    return h
+
+
+def build_csfq_4jj(trunc=10):
+    """C3b: tunable 4JJ CSFQ, 2 nodes, junction asymmetry d (examples/csfq-example.py:726-847)."""
+    ps = import_reference()
+    import sympy as sy
+    Ca, Jc, Aj = _FAB["Ca"], _FAB["Jc"], _FAB["Aj"]
+    with quiet():
+        g = ps.CircuitGraph()
+        g.addBranch(0, 1, "C1")
+        g.addBranch(0, 1, "I1")
+        g.addBranch(1, 2, "C2a")
+        g.addBranch(1, 2, "I2a")
+        g.addBranch(1, 2, "C2b")
+        g.addBranch(1, 2, "I2b")
+        g.addBranch(1, 2, "Csh")
+        g.addBranch(0, 2, "C3")
+        g.addBranch(0, 2, "I3")
+        g.addFluxBias("I3", "Z")
+        g.addFluxBias("I2a", "Xa")
+        g.addFluxBias("I2b", "Xb")
+        h = ps.NumericalSystem(ps.SymbolicSystem(g))
+        h.configureOperator(1, trunc, "charge")
+        h.configureOperator(2, trunc, "charge")
+        S = h.getSymbolicSystem()
+        S.getSymbols("phiX", symbol_overrides=[sy.symbols(r"\phi_X")])
+        sym = S.getSymbolList()
+        S.addParameterisation("phiXa", 0.5 * sym["phiX"])
+        S.addParameterisation("phiXb", -0.5 * sym["phiX"])
+        S.getSymbols("d", "I2a'", "C2a'", "I2b'", "C2b'",
+                     symbol_overrides=[sy.symbols(r"d"), sy.symbols(r"I'_{a2}"), sy.symbols(r"C'_{a2}"),
+                                       sy.symbols(r"I'_{b2}"), sy.symbols(r"C'_{b2}")])
+        sym = S.getSymbolList()
+        d = sym["d"]
+        S.addParameterisation("C2a", (1 + d) * sym["C2a'"])
+        S.addParameterisation("I2a", (1 + d) * sym["I2a'"])
+        S.addParameterisation("C2b", (1 - d) * sym["C2b'"])
+        S.addParameterisation("I2b", (1 - d) * sym["I2b'"])
+        h.setParameterValues("C1", Ca * Aj, "C2a'", 0.5 * Ca * Aj, "C2b'", 0.5 * Ca * Aj, "C3", Ca * Aj,
+                             "I1", Jc * Aj, "I2a'", 0.5 * Jc * Aj, "I2b'", 0.5 * Jc * Aj, "I3", Jc * Aj,
+                             "Csh", 45, "phiZ", 0.5, "phiX", 0.0, "d", 0.0)
+    return h
+
+
+def build_csfq_floating(trunc=7):
+    """C3c: floating 3JJ CSFQ, 3 nodes (examples/csfq-example.py:432-479) with the alpha
+    parameterisation C2 = alpha C2', I2 = alpha I2' (examples/csfq-example.py:326-337)."""
+    ps = import_reference()
+    import sympy as sy
+    Ca, Jc, Aj = _FAB["Ca"], _FAB["Jc"], _FAB["Aj"]
+    with quiet():
+        g = ps.CircuitGraph()
+        g.addBranch(0, 1, "Cgnd1")
+        g.addBranch(0, 2, "Cgnd2")
+        g.addBranch(0, 3, "Cgnd3")
+        g.addBranch(1, 2, "C1")
+        g.addBranch(1, 2, "I1")
+        g.addBranch(2, 3, "C2")
+        g.addBranch(2, 3, "I2")
+        g.addBranch(2, 3, "Csh")
+        g.addBranch(1, 3, "C3")
+        g.addBranch(1, 3, "I3")
+        g.addFluxBias("I1", "Z")
+        h = ps.NumericalSystem(ps.SymbolicSystem(g))
+        for n in (1, 2, 3):
+            h.configureOperator(n, trunc, "charge")
+        S = h.getSymbolicSystem()
+        S.getSymbols("alpha", "C2'", "I2'",
+                     symbol_overrides=[sy.symbols(r"\alpha"), sy.symbols(r"C'_{2}"), sy.symbols(r"I'_{2}")])
+        sym = S.getSymbolList()
+        S.addParameterisation("C2", sym["alpha"] * sym["C2'"])
+        S.addParameterisation("I2", sym["alpha"] * sym["I2'"])
+        h.setParameterValues("C1", Ca * Aj, "C2'", Ca * Aj, "C3", Ca * Aj, "I1", Jc * Aj, "I2'", Jc * Aj,
+                             "I3", Jc * Aj, "Csh", 45, "Cgnd1", 2, "Cgnd2", 2, "Cgnd3", 2,
+                             "phiZ", 0.5, "alpha", 0.44)
+    return h
+
+
+def build_averin(trunc=20):
+    """C4: Averin coupler (examples/averin-coupler.py:40-44) with the fabrication parameterisation
+    (:265-271) and the DC-SQUID critical current Ic = cos(pi phie) Jc wse w1 (:530-553)."""
+    ps = import_reference()
+    import sympy as sy
+    with quiet():
+        g = ps.CircuitGraph()
+        g.addBranch(0, 1, "Cc")
+        g.addBranch(0, 1, "C1")
+        g.addBranch(0, 1, "Ic")
+        g.addChargeBias(1, "c", "Cg1")
+        h = ps.NumericalSystem(ps.SymbolicSystem(g))
+        h.configureOperator(1, trunc, "charge")
+        s = h.getSymbolicSystem()
+        sym = s.getSymbols("Jc", "Ca", "wse", "w1")
+        s.addParameterisation("Cc", sym["wse"] * sym["w1"] * sym["Ca"])
+        sym2 = s.getSymbols("phie", symbol_overrides=[sy.symbols("\\Phi_e")])
+        s.addParameterisation("Ic", sy.cos(sy.pi * sym2["phie"]) * s.getSymbol("Jc") * s.getSymbol("wse") * s.getSymbol("w1"))
+        h.setParameterValues("wse", 0.1, "w1", 0.15, "Ca", 60, "Jc", 1.5, "Cg1", 1, "C1", 7.7,
+                             "Qc", 0.5, "phie", 0.0)
+    return h
+
+
+def build_fluxonium_atom(trunc=31):
+    """C5: inductively coupled fluxonium pair (examples/fluxonium-atom.py:26-81)."""
+    ps = import_reference()
+    pc = ps.physical_constants
+    Ec, El, Ej = 3.4e9, 1.2e9 * 0.5, 9.4e9
+    C = 0.5 * pc.e ** 2 / (pc.h * Ec) * 1e15
+    L = 0.5 * pc.phi0 ** 2 / (pc.h * El * 4 * np.pi ** 2) * 1e12
+    I = 2 * np.pi * pc.h * Ej / pc.phi0 * 1e6
+    with quiet():
+        g = ps.CircuitGraph()
+        g.addBranch(0, 1, "L1")
+        g.addBranch(0, 1, "I1")
+        g.addBranch(0, 1, "C1")
+        g.addBranch(0, 2, "L2")
+        g.addBranch(0, 2, "I2")
+        g.addBranch(0, 2, "C2")
+        g.coupleBranchesInductively("L1", "L2", "M")
+        g.addFluxBias("I1", "l")
+        g.addFluxBias("I2", "r")
+        h = ps.NumericalSystem(ps.SymbolicSystem(g))
+        h.configureOperator(1, trunc, "oscillator")
+        h.configureOperator(2, trunc, "oscillator")
+        S = h.getSymbolicSystem()
+        S.getSymbols("phi+", "phi-", "L")
+        sym = S.getSymbolList()
+        S.addParameterisation("phil", sym["phi+"] + sym["phi-"])
+        S.addParameterisation("phir", sym["phi+"] - sym["phi-"])
+        S.addParameterisation("M", sym["L"])
+        S.addParameterisation("L1", 2 * sym["L"])
+        S.addParameterisation("L2", 2 * sym["L"])
+        h.setParameterValues("L", L, "C1", C, "I1", I, "C2", C, "I2", I, "phi+", 0.0, "phi-", 0.0)
+    return h
+
+
+# ------------------------------------------------------------------------------------------------
+# running the reference and freezing its outputs
+# ------------------------------------------------------------------------------------------------
+def _csr_triplets(H):
+    m = H.data.as_scipy().tocoo()
+    return m.row.astype(np.int32), m.col.astype(np.int32), m.data.astype(np.complex128)
+
+
+def reference_sweep(h, sweeps, k, get_vectors=False, evaluations=(), sparse_opts=None, timesweep=False):
+    """``paramSweep`` of the reference exactly as a user would drive it
+    (numerical_system.py:860-928); returns per-point records read back from its pickles."""
+    ps = import_reference()
+    with quiet():
+        h.newSweep()
+        for s in sweeps:
+            h.addSweep(s["name"], s["start"], s["end"], s["N"])
+        for name, kw in evaluations:
+            h.addEvaluation(name, **kw)
+        if sparse_opts is not None:
+            h.setDiagConfig(eigvalues=k, get_vectors=get_vectors, sparse=True, sparsesolveropts=sparse_opts)
+        else:
+            h.setDiagConfig(eigvalues=k, get_vectors=get_vectors)
+        t0 = time.time()
+        files = h.paramSweep(timesweep=timesweep)
+        dt = time.time() - t0
+    recs = [ps.util.pickleRead(f) for f in files]
+    for f in files:
+        try:
+            os.remove(f)
+        except OSError:
+            pass
+    return recs, dt
+
+
+def lower(h, sweeps, **kw):
+    from pycqed_b200.lowering import lower_system
+    with quiet():
+        if sweeps:
+            h.SS.ndSweep([h.SS.paramSweepSpec(s["name"], s["start"], s["end"], s["N"]) for s in sweeps])
+    return lower_system(h.SS, h.units, h.operator_data, [s["name"] for s in sweeps], sweeps, **kw)
+
+
+def freeze(name, h, sweeps, k=10, get_vectors=False, evaluations=(), sparse_opts=None, n_h_samples=3,
+           vec_points=(), lower_kw=None, extra_plans=None, store_h=True):
+    """Run the reference on ``sweeps`` and write <name>.npz + <name>.plan.json."""
+    lower_kw = lower_kw or {}
+    t0 = time.time()
+    recs, dt = reference_sweep(h, sweeps, k, get_vectors, evaluations, sparse_opts)
+    out = {}
+    multi = isinstance(recs[0], dict)
+    ham = [r["getHamiltonian"] for r in recs] if multi else recs
+    if get_vectors:
+        E = np.array([np.asarray(r[0], dtype=np.float64) for r in ham])
+        vec_points = list(vec_points) if len(vec_points) else [0]
+        out["vec_points"] = np.asarray(vec_points, dtype=np.int64)
+        out["V"] = np.array([np.stack([v.data.to_array()[:, 0] for v in ham[i][1]], axis=1) for i in vec_points])
+    else:
+        E = np.array([np.asarray(r, dtype=np.float64) for r in ham])
+    out["E"] = E
+    if multi:
+        for key in recs[0]:
+            if key != "getHamiltonian":
+                out["eval_" + key] = np.array([np.asarray(r[key], dtype=np.float64) for r in recs])
+    plan = lower(h, sweeps, **lower_kw)
+    grid = plan.sweep_grid()
+    out["params"] = grid
+    out["swept_names"] = np.array(plan.swept_names)
+    out["k"] = np.int64(k)
+    out["ref_seconds_per_point"] = np.float64(dt / len(recs))
+    # Hamiltonians + _postsub floats at a few points (assembly / coefficient parity)
+    if store_h:
+        idx = sorted(set(np.linspace(0, len(recs) - 1, n_h_samples).astype(int).tolist()))
+        out["h_points"] = np.asarray(idx, dtype=np.int64)
+        with quiet():
+            h.SS.ndSweep([h.SS.paramSweepSpec(s["name"], s["start"], s["end"], s["N"]) for s in sweeps])
+            h._presub()
+            for j, i in enumerate(idx):
+                h._postsub({kk: v[i] for kk, v in h.SS.sweep_grid_c.items()})
+                H = h.getHamiltonian()
+                r, c, v = _csr_triplets(H)
+                out["H%d_row" % j], out["H%d_col" % j], out["H%d_val" % j] = r, c, v
+                out["postsub%d_Cinv" % j] = np.asarray(h.Cinvnp, dtype=np.float64)
+                out["postsub%d_Linv" % j] = np.asarray(h.Linvnp, dtype=np.float64)
+                out["postsub%d_J" % j] = np.asarray(h.Jvecnp, dtype=np.float64)
+                out["postsub%d_Pexp" % j] = np.asarray(h.Pexp_pnp, dtype=np.complex128)
+    out["n"] = np.int64(h.getHilbertSpaceSize())
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    plan.meta["source"] = name
+    plan.save(os.path.join(HERE, name + ".plan.json"))
+    for pname, (hh, sw, kw) in (extra_plans or {}).items():
+        p2 = lower(hh, sw, **(kw or {}))
+        p2.meta["source"] = pname
+        p2.save(os.path.join(HERE, pname + ".plan.json"))
+    print("%-28s n=%-6d pts=%-5d ref %.1f ms/pt  (%.1fs total)" % (
+        name, int(out["n"]), len(recs), 1e3 * dt / len(recs), time.time() - t0), flush=True)
+
+
+def S(name, a, b, n):
+    return {"name": name, "start": a, "end": b, "N": n}
+
+
+def make_c1():
+    freeze("c1_transmon", build_transmon(40), [S("phiZ", -0.5, 0.5, 40), S("Qg", -0.5, 0.5, 25)], k=10)
+    freeze("c1_transmon_vec", build_transmon(40), [S("phiZ", -0.5, 0.5, 5), S("Qg", -0.45, 0.45, 4)], k=10,
+           get_vectors=True, vec_points=[0, 7, 19])
+
+
+def make_c2():
+    freeze("c2_fluxonium", build_fluxonium(101), [S("phiZ", -1.0, 1.0, 201)], k=10,
+           extra_plans={"c2_fluxonium_t200": (build_fluxonium(200), [S("phiZ", -1.0, 1.0, 10000)], None),
+                        "c2_fluxonium_10k": (build_fluxonium(101), [S("phiZ", -1.0, 1.0, 10000)], None)})
+    res = {"resonator": {"cpl_node": 1, "nmax": 100}}
+    freeze("c2_fluxonium_res", build_fluxonium(101), [S("phiZ", -1.0, 1.0, 41)], k=20, get_vectors=True,
+           evaluations=[("Hamiltonian", {}), ("Resonator", {"cpl_node": 1})], vec_points=[0, 10, 30, 31],
+           lower_kw=res,
+           extra_plans={"c2_fluxonium_res_10k": (build_fluxonium(101), [S("phiZ", -1.0, 1.0, 10000)], res)})
+    freeze("c2_fluxonium_t200s", build_fluxonium(200), [S("phiZ", -1.0, 1.0, 9)], k=10)
+
+
+def make_c3():
+    freeze("c3_csfq3jj_t10", build_csfq_3jj(10), [S("phiZ", 0.0, 1.0, 21)], k=10)
+    freeze("c3_csfq4jj_t10", build_csfq_4jj(10), [S("d", 0.0, 0.1, 3), S("phiX", -1.0, 1.0, 11)], k=10,
+           extra_plans={
+               "c3_csfq4jj_t27": (build_csfq_4jj(27), [S("d", 0.0, 0.1, 16), S("phiX", -1.0, 1.0, 64)], None),
+               "c3_csfq4jj_t50": (build_csfq_4jj(50), [S("d", 0.0, 0.1, 16), S("phiX", -1.0, 1.0, 64)], None)})
+    freeze("c3_csfq4jj_t27s", build_csfq_4jj(27), [S("d", 0.0, 0.1, 2), S("phiX", -1.0, 1.0, 2)], k=10,
+           store_h=False)
+    # floating 3-node: exact doublets at phiZ = 0.5 -> vectors stored
+    freeze("c3_csfqfloat_t5", build_csfq_floating(5), [S("alpha", 0.3, 1.0, 3), S("phiZ", 0.45, 0.55, 5)], k=10,
+           get_vectors=True, vec_points=[2, 7, 9])
+    freeze("c3_csfqfloat_t7", build_csfq_floating(7), [S("alpha", 0.3, 1.0, 2), S("phiZ", 0.45, 0.55, 3)], k=10,
+           n_h_samples=2,
+           extra_plans={"c3_csfqfloat_t7_full": (build_csfq_floating(7),
+                                                 [S("alpha", 0.3, 1.0, 16), S("phiZ", 0.45, 0.55, 64)], None),
+                        "c3_csfqfloat_t10_full": (build_csfq_floating(10),
+                                                  [S("alpha", 0.3, 1.0, 16), S("phiZ", 0.45, 0.55, 64)], None)})
+    # n = 9261: the dense reference takes ~1 min/pt; use the reference's sparse path with tol=0
+    # (examples/csfq-example.py:535-553; agrees with dense to 1e-14)
+    freeze("c3_csfqfloat_t10", build_csfq_floating(10), [S("alpha", 0.44, 0.9, 2), S("phiZ", 0.47, 0.5, 2)], k=10,
+           sparse_opts={"sigma": -300, "mode": "normal", "maxiter": None, "tol": 0}, n_h_samples=1)
+
+
+def make_c4():
+    ev = [("Hamiltonian", {}), ("ChargingEnergy", {"node": 1}), ("JosephsonEnergy", {"edge": (0, 1, 2)})]
+    h = build_averin(20)
+    S_ = h.getSymbolicSystem()
+    scal = {"ChargingEnergy_1": None, "JosephsonEnergy_0": None}
+    freeze("c4_averin", h, [S("Qc", -1.0, 1.0, 11), S("phie", -0.5, 0.5, 21)], k=10, evaluations=ev,
+           lower_kw={"scalars": averin_scalars(h)},
+           extra_plans={"c4_averin_full": (build_averin(20), [S("Qc", -1.0, 1.0, 101), S("phie", -0.5, 0.5, 201)],
+                                           {"scalars": averin_scalars(h)})})
+
+
+def averin_scalars(h):
+    """ChargingEnergy(node=1) = 1/2 Cinv_00 Ec and JosephsonEnergy(edge) = J_e Ej
+    (numerical_system.py:696-724) as coefficient-program outputs."""
+    import sympy as sy
+    Cinv = h.SS.getInverseCapacitanceMatrix()
+    J = h.SS.getJosephsonVector()
+    e = h.SS.edges.index((0, 1, 2))
+    return {"ChargingEnergy": sy.Rational(1, 2) * Cinv[0, 0] * h.units.getPrefactor("Ec"),
+            "JosephsonEnergy": J[e] * h.units.getPrefactor("Ej")}
+
+
+def make_c5():
+    freeze("c5_fluxatom_t31", build_fluxonium_atom(31), [S("phi-", 0.0, 1.0, 8)], k=10, n_h_samples=2,
+           extra_plans={"c5_fluxatom_t31_64": (build_fluxonium_atom(31), [S("phi-", 0.0, 1.0, 64)], None),
+                        "c5_fluxatom_t180": (build_fluxonium_atom(180), [S("phi-", 0.0, 1.0, 64)], None)})
+
+
+ALL = {"c1": make_c1, "c2": make_c2, "c3": make_c3, "c4": make_c4, "c5": make_c5}
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or list(ALL)
+    for w in which:
+        ALL[w]()
