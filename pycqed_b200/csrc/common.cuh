@@ -1,0 +1,81 @@
+// common.cuh -- shared helpers for the sm_100a sweep engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace scqed {
+
+typedef double2 cplx;   // interleaved complex128, .x = re, .y = im
+
+#define SCQED_EPS 2.220446049250313e-16
+#define SCQED_SAFMIN 2.2250738585072014e-308
+
+__host__ __device__ __forceinline__ cplx cmake(double re, double im) { return make_double2(re, im); }
+__host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+__host__ __device__ __forceinline__ cplx cmulc(cplx a, cplx b) {
+    return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__host__ __device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+__host__ __device__ __forceinline__ cplx cscale(double s, cplx a) { return make_double2(s * a.x, s * a.y); }
+// acc += a * b
+__device__ __forceinline__ void cfma(cplx &acc, cplx a, cplx b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+// acc += conj(a) * b
+__device__ __forceinline__ void cfmac(cplx &acc, cplx a, cplx b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+// acc -= a * conj(b)
+__device__ __forceinline__ void cfnmac(cplx &acc, cplx a, cplx b) {
+    acc.x = fma(-a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(-a.y, b.x, acc.y); acc.y = fma(a.x, b.y, acc.y);
+}
+__host__ __device__ __forceinline__ double cabs2(cplx a) { return a.x * a.x + a.y * a.y; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ cplx warp_sum(cplx v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    }
+    return v;
+}
+
+// The reference thresholds H at 1e-12, real and imaginary parts separately
+// (pyscqed/numerical_system.py:19,594  Qobj.tidyup).
+__host__ __device__ __forceinline__ cplx tidy(cplx a, double atol) {
+    return make_double2(fabs(a.x) < atol ? 0.0 : a.x, fabs(a.y) < atol ? 0.0 : a.y);
+}
+
+// Device-side copy of a plan's tables (all pointers are device pointers).
+#define SCQED_MAX_NODES 8
+struct PlanDev {
+    int n_nodes;
+    int n;                         // Hilbert dimension = prod dims
+    int dims[SCQED_MAX_NODES];
+    int strides[SCQED_MAX_NODES];  // row-major strides of the composite index
+    int n_factors;
+    const long long *factor_offset;
+    const cplx *factor_data;
+    int n_terms;
+    const int *term_factors;       // [n_terms * n_nodes]
+    int n_swept, n_instr, n_scalar;
+    const int *instr;              // [n_instr * 3]
+    const double *consts;
+    const int *coef_re, *coef_im, *scalar_regs;
+};
+
+}  // namespace scqed

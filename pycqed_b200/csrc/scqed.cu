@@ -1,0 +1,570 @@
+// scqed.cu -- C ABI of the sweep engine (see include/scqed.h for the contract and the reference
+// functions each entry point replaces).  Host-side orchestration only; kernels live in the
+// .cuh files next to this one.
+#include "../../include/scqed.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "coef.cuh"
+#include "assemble.cuh"
+#include "tridiag_eig.cuh"
+#include "resonator.cuh"
+#include "small_eigh.cuh"
+#include "dense_eigh.cuh"
+#include "probe.cuh"
+
+using namespace scqed;
+
+// ------------------------------------------------------------------------------------------------
+// error handling / bookkeeping
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(SCQED_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); p = nullptr; return -1; }
+            want = bytes;
+        }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct scqed_plan {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    PlanDev P;
+    int n_coef_scalar = 0;
+    std::vector<int> factor_node;
+    // device copies of the tables
+    DevBuf tables;
+    // per-call workspaces (grown on demand, reused across calls)
+    DevBuf regs, coef, scal, work, in_params, out_evals, out_evecs, out_post, out_info, out_scal;
+    cudaStream_t own_stream = nullptr;
+};
+
+static int set_device(int device) {
+    CK(cudaSetDevice(device));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_plan **out) {
+    if (!d || !out) return fail(SCQED_EINVAL, "null argument");
+    if (d->n_nodes < 1 || d->n_nodes > SCQED_MAX_NODES) return fail(SCQED_EINVAL, "n_nodes=%d outside 1..%d", d->n_nodes, SCQED_MAX_NODES);
+    if (d->n_terms < 1) return fail(SCQED_EINVAL, "plan has no terms");
+    long long n = 1;
+    for (int k = 0; k < d->n_nodes; ++k) {
+        if (d->dims[k] < 1) return fail(SCQED_EINVAL, "dims[%d]=%d", k, d->dims[k]);
+        n *= d->dims[k];
+        if (n > (1LL << 30)) return fail(SCQED_EINVAL, "Hilbert dimension overflows");
+    }
+    for (int f = 0; f < d->n_factors; ++f)
+        if (d->factor_node[f] < 0 || d->factor_node[f] >= d->n_nodes) return fail(SCQED_EINVAL, "factor %d: bad node", f);
+    for (int t = 0; t < d->n_terms; ++t)
+        for (int k = 0; k < d->n_nodes; ++k) {
+            int f = d->term_factors[t * d->n_nodes + k];
+            if (f >= d->n_factors) return fail(SCQED_EINVAL, "term %d: factor id %d out of range", t, f);
+            if (f >= 0 && d->factor_node[f] != k) return fail(SCQED_EINVAL, "term %d: factor %d is not on node %d", t, f, k);
+        }
+    for (int i = 0; i < d->n_instr; ++i) {
+        int op = d->instr[3 * i], a = d->instr[3 * i + 1], b = d->instr[3 * i + 2];
+        if (op < 0 || op > 19) return fail(SCQED_EINVAL, "instr %d: unknown opcode %d", i, op);
+        if (op == OP_CONST && (a < 0 || a >= d->n_consts)) return fail(SCQED_EINVAL, "instr %d: const index", i);
+        if (op == OP_LOAD && (a < 0 || a >= d->n_swept)) return fail(SCQED_EINVAL, "instr %d: param index", i);
+        if (op >= OP_ADD && (a < 0 || a >= i)) return fail(SCQED_EINVAL, "instr %d: operand a not SSA", i);
+        if (((op >= OP_ADD && op <= OP_DIV) || op == OP_POW) && (b < 0 || b >= i)) return fail(SCQED_EINVAL, "instr %d: operand b not SSA", i);
+    }
+    for (int t = 0; t < d->n_terms; ++t)
+        if (d->coef_re[t] >= d->n_instr || d->coef_im[t] >= d->n_instr) return fail(SCQED_EINVAL, "coef register out of range");
+    for (int s = 0; s < d->n_scalar; ++s)
+        if (d->scalar_regs[s] < 0 || d->scalar_regs[s] >= d->n_instr) return fail(SCQED_EINVAL, "scalar register out of range");
+
+    if (set_device(device)) return SCQED_ECUDA;
+    scqed_plan *pl = new scqed_plan();
+    pl->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete pl; return fail(SCQED_ECUDA, "cudaGetDeviceProperties failed"); }
+    pl->sm_count = prop.multiProcessorCount;
+    pl->smem_optin = prop.sharedMemPerBlockOptin;
+    pl->factor_node.assign(d->factor_node, d->factor_node + d->n_factors);
+
+    // pack all tables into one allocation
+    size_t fac_elems = 0;
+    for (int f = 0; f < d->n_factors; ++f) {
+        size_t dk = d->dims[d->factor_node[f]];
+        size_t end = (size_t)d->factor_offset[f] + dk * dk;
+        if (end > fac_elems) fac_elems = end;
+    }
+    std::vector<unsigned char> host;
+    auto put = [&](const void *src, size_t bytes) {
+        size_t off = (host.size() + 255) & ~(size_t)255;
+        host.resize(off + bytes);
+        if (bytes) memcpy(host.data() + off, src, bytes);
+        return off;
+    };
+    std::vector<long long> foff(d->factor_offset, d->factor_offset + d->n_factors);
+    size_t o_fdata = put(d->factor_data, fac_elems * 16);
+    size_t o_foff = put(foff.data(), foff.size() * 8);
+    size_t o_terms = put(d->term_factors, (size_t)d->n_terms * d->n_nodes * 4);
+    size_t o_instr = put(d->instr, (size_t)d->n_instr * 12);
+    size_t o_consts = put(d->consts, (size_t)d->n_consts * 8);
+    size_t o_cre = put(d->coef_re, (size_t)d->n_terms * 4);
+    size_t o_cim = put(d->coef_im, (size_t)d->n_terms * 4);
+    size_t o_sreg = put(d->scalar_regs, (size_t)d->n_scalar * 4);
+    if (pl->tables.ensure(host.size() + 256)) { delete pl; return fail(SCQED_ENOMEM, "plan tables"); }
+    if (cudaMemcpy(pl->tables.p, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        pl->tables.release(); delete pl; return fail(SCQED_ECUDA, "uploading plan tables failed");
+    }
+    unsigned char *base = (unsigned char *)pl->tables.p;
+    PlanDev &P = pl->P;
+    memset(&P, 0, sizeof(P));
+    P.n_nodes = d->n_nodes;
+    P.n = (int)n;
+    int stride = 1;
+    for (int k = d->n_nodes - 1; k >= 0; --k) { P.dims[k] = d->dims[k]; P.strides[k] = stride; stride *= d->dims[k]; }
+    P.n_factors = d->n_factors;
+    P.factor_data = (const cplx *)(base + o_fdata);
+    P.factor_offset = (const long long *)(base + o_foff);
+    P.n_terms = d->n_terms;
+    P.term_factors = (const int *)(base + o_terms);
+    P.n_swept = d->n_swept; P.n_instr = d->n_instr; P.n_scalar = d->n_scalar;
+    P.instr = (const int *)(base + o_instr);
+    P.consts = (const double *)(base + o_consts);
+    P.coef_re = (const int *)(base + o_cre);
+    P.coef_im = (const int *)(base + o_cim);
+    P.scalar_regs = (const int *)(base + o_sreg);
+    *out = pl;
+    return SCQED_OK;
+}
+
+extern "C" void scqed_plan_destroy(scqed_plan *pl) {
+    if (!pl) return;
+    cudaSetDevice(pl->device);
+    DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->in_params, &pl->out_evals,
+                      &pl->out_evecs, &pl->out_post, &pl->out_info, &pl->out_scal};
+    for (DevBuf *b : bufs) b->release();
+    if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
+    delete pl;
+}
+
+extern "C" int scqed_plan_hilbert_dim(const scqed_plan *pl) { return pl ? pl->P.n : SCQED_EINVAL; }
+extern "C" int64_t scqed_launch_count(void) { return g_launches.load(); }
+extern "C" const char *scqed_last_error(void) { return g_err.c_str(); }
+extern "C" const char *scqed_version(void) { return "scqed 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------
+// K1 / K2
+// ------------------------------------------------------------------------------------------------
+static int run_coef(scqed_plan *pl, const double *params_dev, long long n_pts, cplx *coef_dev, double *scal_dev,
+                    cudaStream_t st) {
+    const PlanDev &P = pl->P;
+    if (pl->regs.ensure((size_t)(P.n_instr > 0 ? P.n_instr : 1) * n_pts * 8)) return fail(SCQED_ENOMEM, "coefficient registers");
+    int threads = 128;
+    long long blocks = (n_pts + threads - 1) / threads;
+    coef_eval_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, params_dev, n_pts, (double *)pl->regs.p, coef_dev, scal_dev);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int scqed_eval_coefficients(scqed_plan *pl, const double *params_dev, int64_t n_pts, double *coef_dev,
+                                       double *scalars_dev, void *stream) {
+    if (!pl || !coef_dev || n_pts < 1) return fail(SCQED_EINVAL, "bad argument");
+    if (pl->P.n_swept > 0 && !params_dev) return fail(SCQED_EINVAL, "params_dev is NULL");
+    if (pl->P.n_scalar > 0 && !scalars_dev) return fail(SCQED_EINVAL, "scalars_dev is NULL but the plan has scalar outputs");
+    if (set_device(pl->device)) return SCQED_ECUDA;
+    return run_coef(pl, params_dev, n_pts, (cplx *)coef_dev, scalars_dev, (cudaStream_t)stream);
+}
+
+static int run_assemble(scqed_plan *pl, const cplx *coef_dev, long long n_pts, int tidyup, cplx *H, cudaStream_t st) {
+    const PlanDev &P = pl->P;
+    long long col_tiles = (P.n + ASM_TC - 1) / ASM_TC, row_tiles = (P.n + ASM_TR - 1) / ASM_TR;
+    long long blocks = n_pts * col_tiles * row_tiles;
+    if (blocks > 2147483647LL) return fail(SCQED_EINVAL, "assembly grid too large; split the batch");
+    assemble_dense_kernel<<<(unsigned)blocks, ASM_TC, (size_t)P.n_terms * 16, st>>>(P, coef_dev, n_pts, tidyup, H);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int scqed_assemble_dense(scqed_plan *pl, const double *params_dev, int64_t n_pts, int32_t tidyup,
+                                    double *H_dev, void *stream) {
+    if (!pl || !H_dev || n_pts < 1) return fail(SCQED_EINVAL, "bad argument");
+    if (pl->P.n_swept > 0 && !params_dev) return fail(SCQED_EINVAL, "params_dev is NULL");
+    if (set_device(pl->device)) return SCQED_ECUDA;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pl->coef.ensure((size_t)n_pts * pl->P.n_terms * 16)) return fail(SCQED_ENOMEM, "coefficients");
+    if (pl->scal.ensure((size_t)n_pts * (pl->P.n_scalar + 1) * 8)) return fail(SCQED_ENOMEM, "scalars");
+    int rc = run_coef(pl, params_dev, n_pts, (cplx *)pl->coef.p, (double *)pl->scal.p, st);
+    if (rc) return rc;
+    // row-major H[i][j]: the kernel's fast index is the column
+    return run_assemble(pl, (const cplx *)pl->coef.p, n_pts, tidyup, (cplx *)H_dev, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// solvers
+// ------------------------------------------------------------------------------------------------
+static bool small_fits(const scqed_plan *pl, int n, int k, int want_vec, int n_terms, SmallLayout *Lout) {
+    SmallLayout L = small_smem_layout(n, k, want_vec, n_terms, pl->smem_optin);
+    if ((size_t)L.total > pl->smem_optin) return false;
+    if (want_vec && L.vb < 1) return false;
+    if (Lout) *Lout = L;
+    return true;
+}
+
+static int run_small(scqed_plan *pl, const PlanDev &P, const cplx *coef, const cplx *Hin, const double *scal,
+                     long long n_pts, int n, int k, int want_vec, int tidyup, const ResonatorArgs &res,
+                     double *evals, cplx *evecs, double *post, int *info, cudaStream_t st) {
+    SmallArgs a;
+    memset(&a, 0, sizeof(a));
+    if (!small_fits(pl, n, k, want_vec, P.n_terms, &a.L)) return fail(SCQED_EUNSUPPORTED, "n=%d k=%d does not fit the fused shared-memory path", n, k);
+    a.P = P; a.coef = coef; a.Hin = Hin; a.scalars = scal; a.n_pts = n_pts; a.n = n; a.k = k;
+    a.want_vec = want_vec; a.tidyup = tidyup; a.evals = evals; a.evecs = evecs; a.info = info;
+    a.res = res; a.post = post;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(small_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
+        attr_set = true;
+    }
+    long long grid = n_pts < pl->sm_count ? n_pts : pl->sm_count;
+    small_eigh_kernel<<<(unsigned)grid, SMALL_THREADS, a.L.total, st>>>(a);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// S2 on a batch of B column-major matrices already resident in A.
+struct DenseWs {
+    cplx *vbuf, *wbuf, *part, *tau;
+    double *dd, *ee, *e2, *Z, *lu;
+    int nseg;
+};
+
+static size_t dense_ws_bytes(int n, int k, int B, int nseg) {
+    size_t per = (size_t)4 * n + (size_t)((n + 7) / 8);
+    size_t b = 0;
+    b += (size_t)B * n * 16 * 3;                 // vbuf, wbuf, tau
+    b += (size_t)B * nseg * n * 16;              // part
+    b += (size_t)B * n * 8 * 3;                  // dd, ee, e2
+    b += (size_t)B * k * n * 8;                  // Z
+    b += (size_t)B * k * per * 8;                // lu
+    return b + 4096;
+}
+
+static void dense_ws_carve(unsigned char *p, int n, int k, int B, int nseg, DenseWs *w) {
+    size_t per = (size_t)4 * n + (size_t)((n + 7) / 8);
+    auto take = [&](size_t bytes) { unsigned char *r = p; p += (bytes + 255) & ~(size_t)255; return r; };
+    w->vbuf = (cplx *)take((size_t)B * n * 16);
+    w->wbuf = (cplx *)take((size_t)B * n * 16);
+    w->tau = (cplx *)take((size_t)B * n * 16);
+    w->part = (cplx *)take((size_t)B * nseg * n * 16);
+    w->dd = (double *)take((size_t)B * n * 8);
+    w->ee = (double *)take((size_t)B * n * 8);
+    w->e2 = (double *)take((size_t)B * n * 8);
+    w->Z = (double *)take((size_t)B * k * n * 8);
+    w->lu = (double *)take((size_t)B * k * per * 8);
+    w->nseg = nseg;
+}
+
+static int dense_nseg(int n, int sm_count, int B) {
+    int rows = (n + D2_HEMV_ROWS - 1) / D2_HEMV_ROWS;
+    int want = (2 * sm_count + rows * B - 1) / (rows * B);
+    if (want < 1) want = 1;
+    if (want > 32) want = 32;
+    return want;
+}
+
+static int run_dense_batch(scqed_plan *pl, int sm_count, cplx *A, int n, int B, int k, int want_vec, int conj_out,
+                           const DenseWs &w, double *evals, cplx *evecs, int *info, cudaStream_t st) {
+    (void)pl;
+    for (int j = 0; j < n - 1; ++j) {
+        int m = n - j - 1;
+        d2_hh_gen<<<dim3(1, B), D2_THREADS, 0, st>>>(A, n, j, w.vbuf, w.dd, w.ee, w.tau);
+        int rows = (m + D2_HEMV_ROWS - 1) / D2_HEMV_ROWS;
+        int nseg = w.nseg;
+        if (nseg > m) nseg = m;
+        int seg = (m + nseg - 1) / nseg;
+        d2_hemv<<<dim3(rows, nseg, B), D2_HEMV_ROWS, (size_t)seg * 16, st>>>(A, n, j, w.vbuf, w.part, nseg);
+        d2_hh_w<<<dim3(1, B), D2_THREADS, 0, st>>>(n, j, w.vbuf, w.part, nseg, w.tau, w.wbuf);
+        int colb = (m + D2_R2_COLS - 1) / D2_R2_COLS;
+        d2_rank2<<<dim3(rows, colb, B), D2_HEMV_ROWS, 0, st>>>(A, n, j, w.vbuf, w.wbuf, w.tau, w.dd);
+        g_launches.fetch_add(4, std::memory_order_relaxed);
+    }
+    CK(cudaGetLastError());
+    tridiag_eig_kernel<<<B, 256, (size_t)k * 8, st>>>(w.dd, w.ee, n, k, want_vec, evals, w.Z, w.lu, k, w.e2, info);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    if (want_vec) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CK(cudaFuncSetAttribute(d2_backtransform, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        if ((size_t)n * 16 > 200 * 1024) return fail(SCQED_EUNSUPPORTED, "n=%d too large for the dense back-transformation", n);
+        d2_backtransform<<<dim3(k, B), D2_THREADS, (size_t)n * 16, st>>>(A, n, k, w.tau, w.Z, evecs, conj_out);
+        LAUNCHED();
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+static int pick_dense_batch(int n, long long n_pts, int k, int sm_count) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
+    size_t budget = free_b / 2;
+    size_t per = (size_t)n * n * 16 + dense_ws_bytes(n, k, 1, 32);
+    long long B = (long long)(budget / per);
+    // enough matrices in flight to fill the SMs during the skinny tail of the reduction
+    long long want = n <= 512 ? 256 : (n <= 1536 ? 64 : (n <= 4096 ? 16 : 4));
+    if (B > want) B = want;
+    if (B > n_pts) B = n_pts;
+    if (B > 65535) B = 65535;
+    if (B < 1) B = 0;
+    (void)sm_count;
+    return (int)B;
+}
+
+extern "C" int scqed_eigh_batched(int device, double *H_dev, int32_t n, int64_t batch, int32_t k, double *evals_dev,
+                                  double *evecs_dev, int32_t *info_dev, int32_t solver, void *stream) {
+    if (!H_dev || !evals_dev || !info_dev || n < 1 || batch < 1 || k < 1 || k > n) return fail(SCQED_EINVAL, "bad argument");
+    if (set_device(device)) return SCQED_ECUDA;
+    cudaStream_t st = (cudaStream_t)stream;
+    scqed_plan tmp;   // only carries device properties + workspaces
+    tmp.device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    tmp.sm_count = prop.multiProcessorCount;
+    tmp.smem_optin = prop.sharedMemPerBlockOptin;
+    memset(&tmp.P, 0, sizeof(tmp.P));
+    int want_vec = evecs_dev != nullptr;
+    ResonatorArgs res;
+    memset(&res, 0, sizeof(res));
+    bool fits = small_fits(&tmp, n, k, want_vec, 1, nullptr);
+    if (solver == 1 && !fits) return fail(SCQED_EUNSUPPORTED, "n=%d k=%d does not fit the fused path", n, k);
+    if (n < 2) solver = 1;
+    int rc;
+    if ((solver == 0 && fits) || solver == 1) {
+        rc = run_small(&tmp, tmp.P, nullptr, (const cplx *)H_dev, nullptr, batch, n, k, want_vec, 0, res, evals_dev,
+                       (cplx *)evecs_dev, nullptr, info_dev, st);
+    } else {
+        int nseg = dense_nseg(n, tmp.sm_count, (int)(batch > 64 ? 64 : batch));
+        long long B = batch > 64 ? 64 : batch;
+        if (tmp.work.ensure(dense_ws_bytes(n, k, (int)B, nseg))) return fail(SCQED_ENOMEM, "dense workspace");
+        DenseWs w;
+        dense_ws_carve((unsigned char *)tmp.work.p, n, k, (int)B, nseg, &w);
+        rc = 0;
+        for (long long b0 = 0; b0 < batch && !rc; b0 += B) {
+            int nb = (int)(batch - b0 < B ? batch - b0 : B);
+            // caller's matrices are row-major = column-major storage of conj(H): same spectrum,
+            // conjugated eigenvectors
+            rc = run_dense_batch(&tmp, tmp.sm_count, (cplx *)H_dev + (size_t)b0 * n * n, n, nb, k, want_vec, 1, w,
+                                 evals_dev + (size_t)b0 * k, evecs_dev ? (cplx *)evecs_dev + (size_t)b0 * k * n : nullptr,
+                                 info_dev + b0, st);
+        }
+        if (!rc) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) rc = fail(SCQED_ECUDA, "dense eigh: %s", cudaGetErrorString(e)); }
+        tmp.work.release();
+    }
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the sweep
+// ------------------------------------------------------------------------------------------------
+static int check_opts(const scqed_plan *pl, const scqed_sweep_opts *o) {
+    if (!o) return fail(SCQED_EINVAL, "opts is NULL");
+    if (o->k < 1 || o->k > pl->P.n) return fail(SCQED_EINVAL, "k=%d outside 1..n=%d", o->k, pl->P.n);
+    if (o->solver < 0 || o->solver > 2) return fail(SCQED_EINVAL, "solver=%d", o->solver);
+    if (o->resonator) {
+        if (!o->want_vectors) return fail(SCQED_EINVAL, "the Resonator evaluable needs eigenvectors (get_vectors=True)");
+        if (o->k > SCQED_RES_KMAX || o->k < 2) return fail(SCQED_EUNSUPPORTED, "resonator strips support 2 <= k <= %d", SCQED_RES_KMAX);
+        if (o->res_op_factor < 0 || o->res_op_factor >= pl->P.n_factors) return fail(SCQED_EINVAL, "res_op_factor");
+        int ns = pl->P.n_scalar;
+        if (o->res_gc < 0 || o->res_gc >= ns || o->res_frl < 0 || o->res_frl >= ns || o->res_qb < 0 || o->res_qb >= ns)
+            return fail(SCQED_EINVAL, "resonator scalar slots out of range");
+        if (o->res_nmax < 0) return fail(SCQED_EINVAL, "res_nmax");
+    }
+    return 0;
+}
+
+extern "C" int scqed_sweep_run(scqed_plan *pl, const scqed_sweep_opts *o, const double *params_dev, int64_t n_pts,
+                               double *evals_dev, double *evecs_dev, double *scalars_dev, double *post_dev,
+                               int32_t *info_dev, void *stream) {
+    if (!pl || !evals_dev || !info_dev || n_pts < 1) return fail(SCQED_EINVAL, "bad argument");
+    if (pl->P.n_swept > 0 && !params_dev) return fail(SCQED_EINVAL, "params_dev is NULL");
+    int rc = check_opts(pl, o);
+    if (rc) return rc;
+    if (o->want_vectors && !evecs_dev && !o->resonator) return fail(SCQED_EINVAL, "want_vectors set but evecs_dev is NULL");
+    if (o->resonator && !post_dev) return fail(SCQED_EINVAL, "resonator set but post_dev is NULL");
+    if (set_device(pl->device)) return SCQED_ECUDA;
+    cudaStream_t st = (cudaStream_t)stream;
+    const PlanDev &P = pl->P;
+    const int n = P.n, k = o->k;
+
+    if (pl->coef.ensure((size_t)n_pts * P.n_terms * 16)) return fail(SCQED_ENOMEM, "coefficients");
+    double *scal = scalars_dev;
+    if (!scal) {
+        if (pl->scal.ensure((size_t)n_pts * (P.n_scalar + 1) * 8)) return fail(SCQED_ENOMEM, "scalars");
+        scal = (double *)pl->scal.p;
+    }
+    rc = run_coef(pl, params_dev, n_pts, (cplx *)pl->coef.p, scal, st);
+    if (rc) return rc;
+
+    ResonatorArgs res;
+    memset(&res, 0, sizeof(res));
+    if (o->resonator) {
+        res.enabled = 1;
+        res.nstrips = o->res_nmax + 1 + k;
+        res.op_factor = o->res_op_factor;
+        res.op_node = pl->factor_node[o->res_op_factor];
+        res.s_gc = o->res_gc; res.s_frl = o->res_frl; res.s_qb = o->res_qb;
+    }
+    bool fits = small_fits(pl, n, k, o->want_vectors, P.n_terms, nullptr);
+    int solver = o->solver;
+    if (solver == 1 && !fits) return fail(SCQED_EUNSUPPORTED, "n=%d k=%d does not fit the fused shared-memory path", n, k);
+    if (solver == 0) solver = fits ? 1 : 2;
+    if (solver == 1) {
+        return run_small(pl, P, (const cplx *)pl->coef.p, nullptr, scal, n_pts, n, k, o->want_vectors, o->tidyup, res,
+                         evals_dev, (cplx *)evecs_dev, post_dev, info_dev, st);
+    }
+    if (o->resonator) return fail(SCQED_EUNSUPPORTED, "the Resonator evaluable is only implemented on the fused path (n <= ~110)");
+    // ---- S2: batches of B matrices through HBM ------------------------------------------------
+    int B = pick_dense_batch(n, n_pts, k, pl->sm_count);
+    if (B < 1) return fail(SCQED_ENOMEM, "not enough device memory for one %d x %d matrix", n, n);
+    int nseg = dense_nseg(n, pl->sm_count, B);
+    size_t a_bytes = (size_t)B * n * n * 16;
+    if (pl->work.ensure(a_bytes + dense_ws_bytes(n, k, B, nseg))) return fail(SCQED_ENOMEM, "dense workspace (B=%d)", B);
+    cplx *A = (cplx *)pl->work.p;
+    DenseWs w;
+    dense_ws_carve((unsigned char *)pl->work.p + ((a_bytes + 255) & ~(size_t)255), n, k, B, nseg, &w);
+    for (long long p0 = 0; p0 < n_pts; p0 += B) {
+        int nb = (int)(n_pts - p0 < B ? n_pts - p0 : B);
+        // Fast index of the assembly kernel = contiguous index of the destination.  The dense path
+        // wants column-major A[i + j*n] = H[i][j]; writing "row-major H^T" is the same bytes, and
+        // H^T = conj(H) element-wise, so assemble conj(H) row-major... simpler: assemble H row-major
+        // and note that, read column-major, the buffer is H^T = conj(H): same eigenvalues, and the
+        // eigenvectors come out conjugated -> conj_out = 1 restores them.
+        rc = run_assemble(pl, (const cplx *)pl->coef.p + (size_t)p0 * P.n_terms, nb, o->tidyup, A, st);
+        if (rc) return rc;
+        rc = run_dense_batch(pl, pl->sm_count, A, n, nb, k, o->want_vectors, 1, w, evals_dev + (size_t)p0 * k,
+                             evecs_dev ? (cplx *)evecs_dev + (size_t)p0 * k * n : nullptr, info_dev + p0, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, const double *params, int64_t n_pts,
+                                    double *evals, double *evecs, double *scalars, double *post, int32_t *info) {
+    if (!pl || !evals || !info || n_pts < 1) return fail(SCQED_EINVAL, "bad argument");
+    int rc = check_opts(pl, o);
+    if (rc) return rc;
+    if (pl->P.n_swept > 0 && !params) return fail(SCQED_EINVAL, "params is NULL");
+    if (o->want_vectors && !evecs && !o->resonator) return fail(SCQED_EINVAL, "want_vectors set but evecs is NULL");
+    if (o->resonator && !post) return fail(SCQED_EINVAL, "resonator set but post is NULL");
+    if (set_device(pl->device)) return SCQED_ECUDA;
+    if (!pl->own_stream) CK(cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking));
+    cudaStream_t st = pl->own_stream;
+    const PlanDev &P = pl->P;
+    const int n = P.n, k = o->k;
+    const int nstrips = o->resonator ? o->res_nmax + 1 + k : 0;
+    size_t b_par = (size_t)n_pts * (P.n_swept > 0 ? P.n_swept : 1) * 8;
+    size_t b_ev = (size_t)n_pts * k * 8;
+    size_t b_vec = (o->want_vectors && (evecs || o->resonator)) ? (size_t)n_pts * k * n * 16 : 0;
+    size_t b_sc = (size_t)n_pts * (P.n_scalar > 0 ? P.n_scalar : 1) * 8;
+    size_t b_post = (size_t)n_pts * nstrips * k * 8;
+    if (pl->in_params.ensure(b_par) || pl->out_evals.ensure(b_ev) || pl->out_info.ensure((size_t)n_pts * 4) ||
+        pl->out_scal.ensure(b_sc) || (b_vec && evecs && pl->out_evecs.ensure(b_vec)) || (b_post && pl->out_post.ensure(b_post)))
+        return fail(SCQED_ENOMEM, "device staging buffers");
+    if (P.n_swept > 0) CK(cudaMemcpyAsync(pl->in_params.p, params, (size_t)n_pts * P.n_swept * 8, cudaMemcpyHostToDevice, st));
+    rc = scqed_sweep_run(pl, o, (const double *)pl->in_params.p, n_pts, (double *)pl->out_evals.p,
+                         evecs ? (double *)pl->out_evecs.p : nullptr, (double *)pl->out_scal.p,
+                         b_post ? (double *)pl->out_post.p : nullptr, (int32_t *)pl->out_info.p, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(evals, pl->out_evals.p, b_ev, cudaMemcpyDeviceToHost, st));
+    if (evecs && b_vec) CK(cudaMemcpyAsync(evecs, pl->out_evecs.p, b_vec, cudaMemcpyDeviceToHost, st));
+    if (scalars && P.n_scalar > 0) CK(cudaMemcpyAsync(scalars, pl->out_scal.p, (size_t)n_pts * P.n_scalar * 8, cudaMemcpyDeviceToHost, st));
+    if (post && b_post) CK(cudaMemcpyAsync(post, pl->out_post.p, b_post, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(info, pl->out_info.p, (size_t)n_pts * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// probes
+// ------------------------------------------------------------------------------------------------
+template <typename K>
+static int run_probe(int device, K kernel, double flops_per_thread_iter, double *out) {
+    if (!out) return fail(SCQED_EINVAL, "null argument");
+    if (set_device(device)) return SCQED_ECUDA;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    double *dummy;
+    CK(cudaMalloc(&dummy, 8));
+    int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    kernel<<<blocks, threads>>>(iters / 10, dummy);
+    CK(cudaDeviceSynchronize());
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        kernel<<<blocks, threads>>>(iters, dummy);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = flops_per_thread_iter * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    g_launches.fetch_add(4, std::memory_order_relaxed);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(dummy);
+    *out = best;
+    return 0;
+}
+
+extern "C" int scqed_probe_fp64_tensor(int device, double *tflops_out) {
+    // 8 DMMA.8x8x4 per iteration per warp: 8 * 2*8*8*4 flops per warp = 4096/32 per thread
+    return run_probe(device, probe_dmma_kernel, 8.0 * 512.0 / 32.0, tflops_out);
+}
+extern "C" int scqed_probe_fp64_fma(int device, double *tflops_out) {
+    return run_probe(device, probe_dfma_kernel, 16.0 * 2.0, tflops_out);
+}

@@ -1,0 +1,318 @@
+"""ctypes binding of ``libscqed.so`` (include/scqed.h) -- the only way numbers are produced.
+
+There is NO CPU fallback: if the CUDA library is missing or no CUDA device is visible, every
+compute entry point raises.  PyTorch is used for device buffers and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libscqed.so")
+
+SOLVER_AUTO, SOLVER_SMALL, SOLVER_DENSE = 0, 1, 2
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class _PlanDesc(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_int32), ("dims", C.POINTER(C.c_int32)),
+        ("n_factors", C.c_int32), ("factor_node", C.POINTER(C.c_int32)),
+        ("factor_offset", C.POINTER(C.c_int64)), ("factor_data", C.POINTER(C.c_double)),
+        ("n_terms", C.c_int32), ("term_factors", C.POINTER(C.c_int32)),
+        ("n_swept", C.c_int32), ("n_instr", C.c_int32), ("instr", C.POINTER(C.c_int32)),
+        ("n_consts", C.c_int32), ("consts", C.POINTER(C.c_double)),
+        ("coef_re", C.POINTER(C.c_int32)), ("coef_im", C.POINTER(C.c_int32)),
+        ("n_scalar", C.c_int32), ("scalar_regs", C.POINTER(C.c_int32)),
+    ]
+
+
+class _SweepOpts(C.Structure):
+    _fields_ = [
+        ("k", C.c_int32), ("want_vectors", C.c_int32), ("solver", C.c_int32), ("tidyup", C.c_int32),
+        ("resonator", C.c_int32), ("res_nmax", C.c_int32), ("res_op_factor", C.c_int32),
+        ("res_gc", C.c_int32), ("res_frl", C.c_int32), ("res_qb", C.c_int32),
+        ("reserved", C.c_int32 * 6),
+    ]
+
+
+#: every symbol include/scqed.h declares (tests check that the library exports all of them)
+EXPORTS = (
+    "scqed_plan_create", "scqed_plan_destroy", "scqed_plan_hilbert_dim", "scqed_eval_coefficients",
+    "scqed_assemble_dense", "scqed_eigh_batched", "scqed_sweep_run", "scqed_sweep_run_host",
+    "scqed_launch_count", "scqed_probe_fp64_tensor", "scqed_probe_fp64_fma", "scqed_last_error",
+    "scqed_version",
+)
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """Load ``libscqed.so`` (built in-tree by ``__graft_entry__.build()``); raises if absent."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(
+                "CUDA extension %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU fallback." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        vp, i32, i64, dp = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p
+        lib.scqed_plan_create.argtypes = [C.POINTER(_PlanDesc), C.c_int, C.POINTER(vp)]
+        lib.scqed_plan_create.restype = C.c_int
+        lib.scqed_plan_destroy.argtypes = [vp]
+        lib.scqed_plan_destroy.restype = None
+        lib.scqed_plan_hilbert_dim.argtypes = [vp]
+        lib.scqed_plan_hilbert_dim.restype = C.c_int
+        lib.scqed_eval_coefficients.argtypes = [vp, dp, i64, dp, dp, vp]
+        lib.scqed_eval_coefficients.restype = C.c_int
+        lib.scqed_assemble_dense.argtypes = [vp, dp, i64, i32, dp, vp]
+        lib.scqed_assemble_dense.restype = C.c_int
+        lib.scqed_eigh_batched.argtypes = [C.c_int, dp, i32, i64, i32, dp, dp, dp, i32, vp]
+        lib.scqed_eigh_batched.restype = C.c_int
+        lib.scqed_sweep_run.argtypes = [vp, C.POINTER(_SweepOpts), dp, i64, dp, dp, dp, dp, dp, vp]
+        lib.scqed_sweep_run.restype = C.c_int
+        lib.scqed_sweep_run_host.argtypes = [vp, C.POINTER(_SweepOpts), dp, i64, dp, dp, dp, dp, dp]
+        lib.scqed_sweep_run_host.restype = C.c_int
+        lib.scqed_launch_count.argtypes = []
+        lib.scqed_launch_count.restype = C.c_int64
+        lib.scqed_probe_fp64_tensor.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        lib.scqed_probe_fp64_tensor.restype = C.c_int
+        lib.scqed_probe_fp64_fma.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        lib.scqed_probe_fp64_fma.restype = C.c_int
+        lib.scqed_last_error.argtypes = []
+        lib.scqed_last_error.restype = C.c_char_p
+        lib.scqed_version.argtypes = []
+        lib.scqed_version.restype = C.c_char_p
+        _lib = lib
+        return lib
+
+
+def _check(rc):
+    if rc != 0:
+        msg = load_library().scqed_last_error().decode("utf-8", "replace")
+        raise EngineError("libscqed error %d: %s" % (rc, msg))
+
+
+def _require_cuda(device=None):
+    import torch
+    if not torch.cuda.is_available():
+        raise EngineError("no CUDA device visible; the sweep engine has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+
+
+def launch_count() -> int:
+    return int(load_library().scqed_launch_count())
+
+
+def probe_fp64(device=0):
+    """(DMMA TFLOP/s, DFMA TFLOP/s) measured with register-resident loops."""
+    lib = load_library()
+    _require_cuda(device)
+    a, b = C.c_double(), C.c_double()
+    _check(lib.scqed_probe_fp64_tensor(int(device), C.byref(a)))
+    _check(lib.scqed_probe_fp64_fma(int(device), C.byref(b)))
+    return a.value, b.value
+
+
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32).reshape(-1))
+
+
+def _ptr(arr, ctype):
+    return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+def _stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class SweepResult:
+    """Results of one sweep on the host (numpy).  ``E`` [n_pts, k]; ``V`` [n_pts, k, n] or None;
+    ``scalars`` {name: [n_pts]}; ``Erwa`` [n_pts, nmax+1+k, k] or None; ``info`` [n_pts]."""
+
+    def __init__(self, E, V, scalars, Erwa, info):
+        self.E, self.V, self.scalars, self.Erwa, self.info = E, V, scalars, Erwa, info
+
+
+class Engine:
+    """A :class:`~pycqed_b200.plan.SweepPlan` uploaded to one GPU."""
+
+    def __init__(self, plan, device=None):
+        self.lib = load_library()
+        self.device = _require_cuda(device)
+        self.plan = plan
+        self.n = plan.hilbert_dim
+        self._handle = C.c_void_p()
+        prog = plan.program
+        dims = _i32(plan.dims)
+        fnode = _i32([f[0] for f in plan.factors])
+        mats = [np.ascontiguousarray(plan.factor_matrix(i), dtype=np.complex128) for i in range(len(plan.factors))]
+        offs, off = [], 0
+        for m in mats:
+            offs.append(off)
+            off += m.size
+        foff = np.ascontiguousarray(np.asarray(offs, dtype=np.int64))
+        fdata = np.concatenate([m.reshape(-1) for m in mats]) if mats else np.zeros(1, dtype=np.complex128)
+        fdata = np.ascontiguousarray(fdata).view(np.float64)
+        terms = _i32(plan.terms)
+        instr = _i32(prog.instr)
+        consts = np.ascontiguousarray(np.asarray(prog.consts, dtype=np.float64))
+        if consts.size == 0:
+            consts = np.zeros(1, dtype=np.float64)
+        cre, cim, sreg = _i32(prog.coef_re), _i32(prog.coef_im), _i32(prog.scalar_regs)
+        if sreg.size == 0:
+            sreg = np.zeros(1, dtype=np.int32)
+        if len(plan.terms) != prog.n_coef:
+            raise EngineError("plan is inconsistent: %d terms but %d coefficients" % (len(plan.terms), prog.n_coef))
+        desc = _PlanDesc(
+            n_nodes=len(plan.dims), dims=_ptr(dims, C.c_int32),
+            n_factors=len(mats), factor_node=_ptr(fnode, C.c_int32),
+            factor_offset=_ptr(foff, C.c_int64), factor_data=_ptr(fdata, C.c_double),
+            n_terms=len(plan.terms), term_factors=_ptr(terms, C.c_int32),
+            n_swept=prog.n_swept, n_instr=prog.n_instr, instr=_ptr(instr, C.c_int32),
+            n_consts=len(prog.consts), consts=_ptr(consts, C.c_double),
+            coef_re=_ptr(cre, C.c_int32), coef_im=_ptr(cim, C.c_int32),
+            n_scalar=prog.n_scalar, scalar_regs=_ptr(sreg, C.c_int32),
+        )
+        _check(self.lib.scqed_plan_create(C.byref(desc), self.device.index, C.byref(self._handle)))
+
+    # ------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self.lib.scqed_plan_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ------------------------------------------------------------------------------------------
+    def _opts(self, k, want_vectors, solver, tidyup, resonator):
+        o = _SweepOpts()
+        o.k, o.want_vectors, o.solver, o.tidyup = int(k), int(bool(want_vectors)), int(solver), int(bool(tidyup))
+        if resonator:
+            spec = self.plan.post.get("resonator")
+            if spec is None:
+                raise EngineError("this plan was lowered without the Resonator evaluable")
+            o.resonator = 1
+            o.res_nmax = int(spec["nmax"])
+            o.res_op_factor = int(spec["op_factor"])
+            o.res_gc, o.res_frl, o.res_qb = int(spec["gC"]), int(spec["frl"]), int(spec["qb"])
+        return o
+
+    def _params_dev(self, params):
+        import torch
+        if isinstance(params, torch.Tensor):
+            p = params.to(device=self.device, dtype=torch.float64).contiguous()
+        else:
+            p = torch.as_tensor(np.ascontiguousarray(params, dtype=np.float64), device=self.device)
+        if p.ndim != 2 or p.shape[1] != self.plan.program.n_swept:
+            raise EngineError("params must be [n_pts, %d]" % self.plan.program.n_swept)
+        return p
+
+    def coefficients(self, params):
+        """K1 on the device: (coef complex [n_pts, n_terms], scalars [n_pts, n_scalar]) as torch tensors."""
+        import torch
+        p = self._params_dev(params)
+        n_pts = p.shape[0]
+        coef = torch.empty((n_pts, len(self.plan.terms)), dtype=torch.complex128, device=self.device)
+        scal = torch.empty((n_pts, max(self.plan.program.n_scalar, 1)), dtype=torch.float64, device=self.device)
+        _check(self.lib.scqed_eval_coefficients(self._handle, p.data_ptr(), n_pts, coef.data_ptr(), scal.data_ptr(), _stream_ptr()))
+        return coef, scal[:, :self.plan.program.n_scalar]
+
+    def assemble_dense(self, params, tidyup=True):
+        """K2: dense H [n_pts, n, n] complex128 torch tensor on the device."""
+        import torch
+        p = self._params_dev(params)
+        n_pts = p.shape[0]
+        H = torch.empty((n_pts, self.n, self.n), dtype=torch.complex128, device=self.device)
+        _check(self.lib.scqed_assemble_dense(self._handle, p.data_ptr(), n_pts, int(bool(tidyup)), H.data_ptr(), _stream_ptr()))
+        return H
+
+    def sweep_device(self, params, k, want_vectors=False, resonator=False, solver=SOLVER_AUTO, tidyup=True):
+        """Device-resident sweep; returns torch tensors (E, V|None, scalars, Erwa|None, info)."""
+        import torch
+        p = self._params_dev(params)
+        n_pts = p.shape[0]
+        o = self._opts(k, want_vectors or resonator, solver, tidyup, resonator)
+        E = torch.empty((n_pts, k), dtype=torch.float64, device=self.device)
+        V = torch.empty((n_pts, k, self.n), dtype=torch.complex128, device=self.device) if want_vectors else None
+        ns = self.plan.program.n_scalar
+        scal = torch.empty((n_pts, max(ns, 1)), dtype=torch.float64, device=self.device)
+        post = None
+        if resonator:
+            post = torch.empty((n_pts, o.res_nmax + 1 + k, k), dtype=torch.float64, device=self.device)
+        info = torch.empty((n_pts,), dtype=torch.int32, device=self.device)
+        _check(self.lib.scqed_sweep_run(
+            self._handle, C.byref(o), p.data_ptr(), n_pts, E.data_ptr(), V.data_ptr() if V is not None else None,
+            scal.data_ptr(), post.data_ptr() if post is not None else None, info.data_ptr(), _stream_ptr()))
+        return E, V, scal[:, :ns], post, info
+
+    def sweep(self, params, k, want_vectors=False, resonator=False, solver=SOLVER_AUTO, tidyup=True,
+              out=None) -> SweepResult:
+        """Host-buffer sweep (the call the drop-in ``paramSweep`` makes): params and results are
+        numpy / pinned host memory, the library does the H2D / D2H copies."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if params.ndim != 2 or params.shape[1] != self.plan.program.n_swept:
+            raise EngineError("params must be [n_pts, %d]" % self.plan.program.n_swept)
+        n_pts = params.shape[0]
+        o = self._opts(k, want_vectors or resonator, solver, tidyup, resonator)
+        ns = self.plan.program.n_scalar
+        out = out or {}
+        E = out.get("E")
+        if E is None:
+            E = np.empty((n_pts, k), dtype=np.float64)
+        V = out.get("V") if want_vectors else None
+        if want_vectors and V is None:
+            V = np.empty((n_pts, k, self.n), dtype=np.complex128)
+        scal = np.empty((n_pts, max(ns, 1)), dtype=np.float64)
+        post = None
+        if resonator:
+            post = out.get("Erwa")
+            if post is None:
+                post = np.empty((n_pts, o.res_nmax + 1 + k, k), dtype=np.float64)
+        info = np.empty((n_pts,), dtype=np.int32)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        _check(self.lib.scqed_sweep_run_host(self._handle, C.byref(o), vp(params), n_pts, vp(E), vp(V), vp(scal),
+                                             vp(post), vp(info)))
+        names = list(self.plan.program.scalar_names)
+        scalars = {nm: scal[:, i].copy() for i, nm in enumerate(names)}
+        return SweepResult(E, V, scalars, post, info)
+
+
+def eigh_batched(H, k, want_vectors=False, solver=SOLVER_AUTO):
+    """Lowest-k eigenpairs of a batch of Hermitian matrices on the device
+    (``diagonalize`` / ``util.diagDenseH`` parity hook).  ``H``: torch complex128 [B, n, n] on a
+    CUDA device; it is overwritten.  Returns (E [B,k], V [B,k,n] | None, info [B])."""
+    import torch
+    lib = load_library()
+    if not (isinstance(H, torch.Tensor) and H.is_cuda and H.dtype == torch.complex128 and H.ndim == 3):
+        raise EngineError("H must be a CUDA complex128 tensor [batch, n, n]")
+    H = H.contiguous()
+    B, n, _ = H.shape
+    E = torch.empty((B, k), dtype=torch.float64, device=H.device)
+    V = torch.empty((B, k, n), dtype=torch.complex128, device=H.device) if want_vectors else None
+    info = torch.empty((B,), dtype=torch.int32, device=H.device)
+    with torch.cuda.device(H.device):
+        _check(lib.scqed_eigh_batched(H.device.index, H.data_ptr(), n, B, k, E.data_ptr(),
+                                      V.data_ptr() if V is not None else None, info.data_ptr(), int(solver), _stream_ptr()))
+    return E, V, info

@@ -1,0 +1,259 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and against the
+golden fixtures produced by the reference itself.
+
+Tolerances are the project's gates (BASELINE.json): eigenvalues 1e-9 relative, eigenvector
+subspace overlap >= 1 - 1e-8, derived quantities (transition energies, resonator strips,
+dispersive shift) to the same tolerance relative to the energy scale they are computed from.
+"""
+import numpy as np
+import pytest
+
+from oracle.plan_oracle import PlanOracle, eval_program, rel_err, subspace_overlap
+from tests.conftest import golden_hamiltonian, load_golden, load_plan
+
+pytestmark = pytest.mark.gpu
+
+E_RTOL = 1e-9
+OVERLAP = 1 - 1e-8
+
+
+@pytest.fixture(scope="module")
+def engine_mod(cuda_device):
+    from pycqed_b200 import engine
+    engine.load_library()
+    return engine
+
+
+def _sample(n_total, cap):
+    return np.unique(np.linspace(0, n_total - 1, min(cap, n_total)).astype(int))
+
+
+# ---------------------------------------------------------------------------------------------
+# K1: coefficient program
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1_transmon", "c2_fluxonium_res", "c3_csfq4jj_t10", "c3_csfqfloat_t5",
+                                  "c4_averin", "c5_fluxatom_t31"])
+def test_coefficient_program(engine_mod, name):
+    g, plan = load_golden(name)
+    coef_ref, scal_ref = eval_program(plan.program, g["params"])
+    with engine_mod.Engine(plan) as eng:
+        coef, scal = eng.coefficients(g["params"])
+    coef, scal = coef.cpu().numpy(), scal.cpu().numpy()
+    scale = np.maximum(np.abs(coef_ref), 1e-300)
+    # same IEEE operations in the same order; libm vs CUDA sin/cos/exp differ by <= 2 ulp
+    assert np.max(np.abs(coef - coef_ref) / np.maximum(scale, np.abs(coef_ref).max() * 1e-3)) < 1e-14
+    if scal_ref.size:
+        assert np.max(np.abs(scal - scal_ref) / np.maximum(np.abs(scal_ref), 1e-300)) < 1e-14
+
+
+# ---------------------------------------------------------------------------------------------
+# K2: dense assembly  (getHamiltonian parity)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1_transmon", "c2_fluxonium", "c3_csfq3jj_t10", "c3_csfq4jj_t10",
+                                  "c3_csfqfloat_t5", "c4_averin", "c5_fluxatom_t31"])
+def test_assemble_dense_matches_reference(engine_mod, name):
+    g, plan = load_golden(name)
+    n = int(g["n"])
+    pts = g["h_points"]
+    with engine_mod.Engine(plan) as eng:
+        H = eng.assemble_dense(g["params"][pts]).cpu().numpy()
+    for j in range(len(pts)):
+        Href = golden_hamiltonian(g, j, n).toarray()
+        scale = max(1.0, np.abs(Href).max())
+        # the reference itself thresholds at 1e-12 (numerical_system.py:19,594)
+        assert np.max(np.abs(H[j] - Href)) <= 4e-12 * scale
+        assert np.max(np.abs(H[j] - H[j].conj().T)) <= 1e-13 * scale
+
+
+# ---------------------------------------------------------------------------------------------
+# eigensolver on raw matrices  (diagonalize / util.diagDenseH parity)
+# ---------------------------------------------------------------------------------------------
+def _random_hermitian(rng, n, batch, real=False):
+    a = rng.standard_normal((batch, n, n))
+    if not real:
+        a = a + 1j * rng.standard_normal((batch, n, n))
+    return (a + a.conj().transpose(0, 2, 1)) / 2
+
+
+@pytest.mark.parametrize("n,k,solver", [(2, 2, 0), (5, 3, 0), (33, 10, 0), (64, 10, 1), (101, 20, 1), (110, 5, 0),
+                                        (101, 10, 2), (130, 10, 0), (257, 12, 2)])
+def test_eigh_batched_random(engine_mod, n, k, solver):
+    import torch
+    rng = np.random.default_rng(1234 + n)
+    H = _random_hermitian(rng, n, 6).astype(np.complex128)
+    E, V, info = engine_mod.eigh_batched(torch.as_tensor(H, device="cuda"), k, want_vectors=True, solver=solver)
+    E, V, info = E.cpu().numpy(), V.cpu().numpy(), info.cpu().numpy()
+    assert not info.any()
+    for b in range(H.shape[0]):
+        w, v = np.linalg.eigh(H[b])
+        scale = np.abs(w).max()
+        assert np.max(np.abs(E[b] - w[:k])) < 1e-12 * scale * n
+        X = V[b].T                                   # [n, k]
+        assert np.max(np.abs(X.conj().T @ X - np.eye(k))) < 1e-10
+        R = H[b] @ X - X * E[b][None, :]
+        assert np.max(np.abs(R)) < 1e-11 * scale * n
+        assert subspace_overlap(X, v[:, :k], w[:k]) >= OVERLAP
+
+
+@pytest.mark.parametrize("solver,n", [(1, 60), (2, 150)])
+def test_eigh_degenerate_and_clustered(engine_mod, solver, n):
+    """Exact doublets / triplets and a tight cluster (the floating-CSFQ trap)."""
+    import torch
+    rng = np.random.default_rng(7)
+    lam = np.sort(rng.uniform(-5, 50, n))
+    lam[:8] = [-10.0, -10.0, -7.5, -7.5, -7.5, -3.0, -3.0 + 1e-11, -1.0]
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    H = (Q * lam[None, :]) @ Q.conj().T
+    H = (H + H.conj().T) / 2
+    k = 8
+    E, V, info = engine_mod.eigh_batched(torch.as_tensor(H[None], device="cuda"), k, want_vectors=True, solver=solver)
+    E, X = E.cpu().numpy()[0], V.cpu().numpy()[0].T
+    assert np.max(np.abs(E - lam[:k])) < 1e-11
+    assert np.max(np.abs(X.conj().T @ X - np.eye(k))) < 1e-9
+    assert np.max(np.abs(H @ X - X * E[None, :])) < 1e-10
+    # projector onto the three exact clusters
+    for grp in ([0, 1], [2, 3, 4], [5, 6]):
+        P = Q[:, grp] @ Q[:, grp].conj().T
+        assert np.max(np.abs(P @ X[:, grp] - X[:, grp])) < 1e-8
+
+
+def test_eigh_values_only_and_diagonal(engine_mod):
+    import torch
+    n = 40
+    H = np.diag(np.arange(n, 0, -1).astype(np.float64)).astype(np.complex128)
+    E, V, info = engine_mod.eigh_batched(torch.as_tensor(H[None], device="cuda"), 5, want_vectors=False)
+    assert V is None
+    assert np.allclose(E.cpu().numpy()[0], [1, 2, 3, 4, 5], rtol=0, atol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------
+# the sweep  (paramSweep parity, against outputs of the reference)
+# ---------------------------------------------------------------------------------------------
+SWEEP_CASES = [
+    # name, max points, solver
+    ("c1_transmon", 1000, 0),
+    ("c4_averin", 231, 0),
+    ("c2_fluxonium", 201, 0),
+    ("c2_fluxonium_t200s", 9, 0),
+    ("c3_csfq3jj_t10", 21, 0),
+    ("c3_csfq4jj_t10", 33, 0),
+    ("c5_fluxatom_t31", 8, 0),
+    ("c3_csfqfloat_t5", 15, 0),
+]
+
+
+@pytest.mark.parametrize("name,cap,solver", SWEEP_CASES)
+def test_sweep_eigenvalues_match_reference(engine_mod, name, cap, solver):
+    g, plan = load_golden(name)
+    k = int(g["k"])
+    idx = _sample(len(g["E"]), cap)
+    with engine_mod.Engine(plan) as eng:
+        res = eng.sweep(g["params"][idx], k, solver=solver)
+    assert not res.info.any()
+    assert rel_err(res.E, g["E"][idx]) < E_RTOL
+    gaps = res.E - res.E[:, :1]
+    gaps_ref = g["E"][idx] - g["E"][idx][:, :1]
+    assert np.max(np.abs(gaps - gaps_ref)) < E_RTOL * np.abs(g["E"]).max()
+
+
+@pytest.mark.parametrize("name", ["c1_transmon_vec", "c2_fluxonium_res", "c3_csfqfloat_t5"])
+def test_sweep_eigenvectors_match_reference(engine_mod, name):
+    g, plan = load_golden(name)
+    k = int(g["k"])
+    pts = g["vec_points"]
+    with engine_mod.Engine(plan) as eng:
+        res = eng.sweep(g["params"][pts], k, want_vectors=True)
+    assert not res.info.any()
+    assert rel_err(res.E, g["E"][pts]) < E_RTOL
+    for j in range(len(pts)):
+        X = res.V[j].T
+        assert np.max(np.abs(X.conj().T @ X - np.eye(k))) < 1e-9
+        assert subspace_overlap(X, g["V"][j], g["E"][pts[j]]) >= OVERLAP
+
+
+def test_sweep_resonator_matches_reference(engine_mod):
+    g, plan = load_golden("c2_fluxonium_res")
+    k = int(g["k"])
+    with engine_mod.Engine(plan) as eng:
+        res = eng.sweep(g["params"], k, want_vectors=True, resonator=True)
+    assert not res.info.any()
+    ref = g["eval_getResonatorResponse"]
+    assert res.Erwa.shape == ref.shape
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(res.Erwa - ref)) < E_RTOL * scale
+
+    def chi(Erwa):   # util.getResonatorShift (util.py:218-240) -> examples/fluxonium-example.py:165,185
+        E = np.swapaxes(Erwa, 1, 2)
+        f = lambda q, nph: E[:, q, nph + q + 1] - E[:, q, nph + q]
+        return f(1, 0) - f(0, 0)
+    # chi is a ~1e-3 GHz difference of ~1e1 GHz strip energies: tolerance relative to those
+    assert np.max(np.abs(chi(res.Erwa) - chi(ref))) < E_RTOL * 10.0
+    # scalar evaluables ride along
+    assert rel_err(res.scalars["gC"], np.full(len(ref), res.scalars["gC"][0])) < 1e-14
+
+
+def test_sweep_scalar_evaluables(engine_mod):
+    g, plan = load_golden("c4_averin")
+    with engine_mod.Engine(plan) as eng:
+        res = eng.sweep(g["params"], int(g["k"]))
+    assert rel_err(res.scalars["ChargingEnergy"], g["eval_getChargingEnergies"]) < 1e-13
+    ref = g["eval_getJosephsonEnergies"]
+    assert np.max(np.abs(res.scalars["JosephsonEnergy"] - ref)) < 1e-13 * np.abs(ref).max()
+
+
+def test_device_and_host_paths_agree(engine_mod):
+    g, plan = load_golden("c2_fluxonium")
+    with engine_mod.Engine(plan) as eng:
+        host = eng.sweep(g["params"][:50], 10, want_vectors=True)
+        E, V, scal, post, info = eng.sweep_device(g["params"][:50], 10, want_vectors=True)
+    assert np.array_equal(host.E, E.cpu().numpy())
+    assert np.array_equal(host.V, V.cpu().numpy())
+
+
+def test_dense_solver_on_small_problem_agrees(engine_mod):
+    """Force the HBM dense path on a problem the fused path also solves."""
+    g, plan = load_golden("c2_fluxonium")
+    idx = _sample(len(g["E"]), 12)
+    with engine_mod.Engine(plan) as eng:
+        a = eng.sweep(g["params"][idx], 10, want_vectors=True, solver=1)
+        b = eng.sweep(g["params"][idx], 10, want_vectors=True, solver=2)
+    assert rel_err(a.E, b.E) < 1e-11
+    assert rel_err(b.E, g["E"][idx]) < E_RTOL
+    for j in range(len(idx)):
+        assert subspace_overlap(a.V[j].T, b.V[j].T, a.E[j]) >= OVERLAP
+
+
+def test_full_size_properties_c2(engine_mod):
+    """BASELINE full size (10 000 points): size-independent properties instead of a CPU re-solve:
+    sortedness, phi -> -phi symmetry of the spectrum, periodicity, finite residual on a sample."""
+    plan = load_plan("c2_fluxonium_10k")
+    grid = plan.sweep_grid()
+    with engine_mod.Engine(plan) as eng:
+        res = eng.sweep(grid, 10)
+        assert not res.info.any()
+        E = res.E
+        assert np.all(np.diff(E, axis=1) >= -1e-9)
+        # H(phiZ) and H(-phiZ) are complex conjugates: identical spectra; grid is symmetric
+        assert np.max(np.abs(E - E[::-1])) < 1e-9 * np.abs(E).max()
+        # period 1 in phiZ: linspace(-1, 1, 10000) contains -1, 1 (and 0 is not on the grid)
+        assert np.max(np.abs(E[0] - E[-1])) < 1e-9 * np.abs(E).max()
+        # residual check on a sample through the dense assembly
+        idx = _sample(len(grid), 16)
+        r2 = eng.sweep(grid[idx], 10, want_vectors=True)
+        H = eng.assemble_dense(grid[idx]).cpu().numpy()
+    for j in range(len(idx)):
+        X = r2.V[j].T
+        assert np.max(np.abs(H[j] @ X - X * r2.E[j][None, :])) < 1e-9 * np.abs(E).max()
+
+
+def test_error_paths(engine_mod):
+    g, plan = load_golden("c2_fluxonium")
+    with engine_mod.Engine(plan) as eng:
+        with pytest.raises(engine_mod.EngineError):
+            eng.sweep(g["params"][:2], 0)
+        with pytest.raises(engine_mod.EngineError):
+            eng.sweep(g["params"][:2], 1000)
+        with pytest.raises(engine_mod.EngineError):
+            eng.sweep(g["params"][:2], 10, resonator=True)      # plan lowered without the evaluable
+        with pytest.raises(engine_mod.EngineError):
+            eng.sweep(np.zeros((3, 5)), 10)                     # wrong number of swept columns
