@@ -44,27 +44,24 @@ struct SmallArgs {
     SmallLayout L;
 };
 
+// two-stage shuffle reductions (blockDim.x <= 1024): warp sums -> smem -> every warp re-reduces
 __device__ __forceinline__ double block_sum(double v, double *red) {
     v = warp_sum(v);
-    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
     __syncthreads();
     if (l == 0) red[w] = v;
     __syncthreads();
-    double s = 0.0;
-    int nw = blockDim.x >> 5;
-    for (int i = 0; i < nw; ++i) s += red[i];
-    return s;
+    double s = l < nw ? red[l] : 0.0;
+    return warp_sum(s);
 }
 __device__ __forceinline__ cplx block_sum(cplx v, double *red) {
     v = warp_sum(v);
-    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
     __syncthreads();
     if (l == 0) { red[2 * w] = v.x; red[2 * w + 1] = v.y; }
     __syncthreads();
-    cplx s = cmake(0.0, 0.0);
-    int nw = blockDim.x >> 5;
-    for (int i = 0; i < nw; ++i) { s.x += red[2 * i]; s.y += red[2 * i + 1]; }
-    return s;
+    cplx s = l < nw ? cmake(red[2 * l], red[2 * l + 1]) : cmake(0.0, 0.0);
+    return warp_sum(s);
 }
 
 __global__ void __launch_bounds__(SMALL_THREADS, 1)

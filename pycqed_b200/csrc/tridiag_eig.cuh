@@ -68,13 +68,15 @@ __device__ int tridiag_bisect(const double *d, const double *e2, int n, int k, c
                               double *lam) {
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
     const double gl = bounds[0], gu = bounds[1], pivmin = bounds[2];
+    // absolute floor like LAPACK dstebz (ABSTOL = ulp * ||T||), a little tighter
+    const double atol = 0.0625 * SCQED_EPS * bounds[3] + 2.0 * pivmin;
     int bad = 0;
     for (int j = w; j < k; j += nw) {
         double lo = gl, hi = gu;
         int it = 0;
         for (; it < 64; ++it) {
             double width = hi - lo;
-            double tol = 2.0 * SCQED_EPS * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin;
+            double tol = 2.0 * SCQED_EPS * fmax(fabs(lo), fabs(hi)) + atol;
             if (width <= tol) break;
             double x = lo + width * ((double)(l + 1) / 33.0);
             int c = sturm_count(d, e2, n, x, pivmin);
@@ -204,7 +206,12 @@ __device__ int tridiag_inverse_iteration(const double *d, const double *e, int n
     const size_t per = (size_t)4 * n + (size_t)((n + 7) / 8);
     const double ortol = 1e-3 * tnorm;   // LAPACK dstein
     int bad = 0;
-    for (int pass = 0; pass < 2; ++pass) {
+    // A purification pass + Gram-Schmidt is only needed when two of the wanted eigenvalues are
+    // closer than LAPACK dstein's ortol; well separated spectra take the short path.
+    bool clustered = false;
+    for (int j = 1; j < k; ++j) clustered |= (fabs(lam[j] - lam[j - 1]) <= ortol);
+    const int npass = clustered ? 2 : 1;
+    for (int pass = 0; pass < npass; ++pass) {
         for (int base = 0; base < k; base += vb) {
             int j = base + (int)threadIdx.x;
             if ((int)threadIdx.x < vb && j < k) {
@@ -233,8 +240,10 @@ __device__ int tridiag_inverse_iteration(const double *d, const double *e, int n
             }
             __syncthreads();
         }
-        if (threadIdx.x < 32) cluster_mgs_warp(n, k, lam, ortol, Z, zld, zs);
-        __syncthreads();
+        if (clustered) {
+            if (threadIdx.x < 32) cluster_mgs_warp(n, k, lam, ortol, Z, zld, zs);
+            __syncthreads();
+        }
     }
     return bad;
 }

@@ -8,7 +8,7 @@ subspaces, resonator strips and scalar evaluables.
 import numpy as np
 import pytest
 
-from oracle.plan_oracle import PlanOracle, eval_program, rel_err, subspace_overlap
+from oracle.plan_oracle import PlanOracle, eig_rel_err, eval_program, rel_err, subspace_overlap
 from tests.conftest import golden_hamiltonian, golden_names, load_golden
 
 # the big cases only check a couple of points to keep the CPU suite in minutes
@@ -44,7 +44,7 @@ def test_eigenvalues_match_reference(name):
     orc = PlanOracle(plan)
     out = orc.sweep(g["params"][idx], k)
     # the gate of the whole project: 1e-9 relative (BASELINE.json); the oracle sits far inside it
-    assert rel_err(out["E"], g["E"][idx]) < 1e-10
+    assert eig_rel_err(out["E"], g["E"][idx]) < 1e-10
     # transition energies E_i - E_0 (absolute, GHz)
     gaps_ref = g["E"][idx] - g["E"][idx][:, :1]
     gaps = out["E"] - out["E"][:, :1]
