@@ -17,6 +17,7 @@
 #include "resonator.cuh"
 #include "small_eigh.cuh"
 #include "dense_eigh.cuh"
+#include "dense_blocked.cuh"
 #include "probe.cuh"
 
 using namespace scqed;
@@ -308,8 +309,10 @@ static void dense_ws_carve(unsigned char *p, int n, int k, int B, int nseg, Dens
 static int dense_nseg(int n, int sm_count, int B) {
     int rows = (n + D2_HEMV_ROWS - 1) / D2_HEMV_ROWS;
     int want = (2 * sm_count + rows * B - 1) / (rows * B);
+    int floor_ = (n + 383) / 384;          // keeps the per-CTA column segment (80 B/col of smem) under 32 KB
+    if (want < floor_) want = floor_;
     if (want < 1) want = 1;
-    if (want > 32) want = 32;
+    if (want > 64) want = 64;
     return want;
 }
 
@@ -347,14 +350,110 @@ static int run_dense_batch(scqed_plan *pl, int sm_count, cplx *A, int n, int B, 
     return 0;
 }
 
+// ---- S2b: blocked zlatrd + DMMA her2k -------------------------------------------------------------
+struct BlkWs {
+    BlkBufs K;
+    double *e2, *Z, *lu;
+    cplx *Ypart;
+};
+
+static size_t blk_ws_bytes(int n, int k, int B, int nseg) {
+    size_t nrb = (n + BLK_ROWS - 1) / BLK_ROWS, np = (n - 1 + BLK_NB - 1) / BLK_NB;
+    size_t per = (size_t)4 * n + (size_t)((n + 7) / 8);
+    size_t b = 0;
+    b += (size_t)B * n * BLK_NB * 16 * 3;          // Vp, Wp, G
+    b += (size_t)B * n * 16 * 2;                   // acol, tau
+    b += (size_t)B * nrb * 8;                      // normpart
+    b += (size_t)B * nseg * n * 16;                // part
+    b += (size_t)B * nrb * n * 16;                 // cpart
+    b += (size_t)B * nrb * BLK_NB * 16 * 2;        // s1part, s2part
+    b += (size_t)B * nrb * nseg * 8;               // vAvpart
+    b += (size_t)B * np * BLK_NB * BLK_NB * 16;    // Tbuf
+    b += (size_t)B * n * 8 * 3;                    // dd, ee, e2
+    b += (size_t)B * k * n * 8;                    // Z
+    b += (size_t)B * k * per * 8;                  // lu
+    b += (size_t)B * nrb * BLK_NB * k * 16;        // Ypart
+    return b + 24 * 256 + 4096;
+}
+
+static void blk_ws_carve(unsigned char *p, cplx *A, int n, int k, int B, int nseg, BlkWs *w) {
+    size_t nrb = (n + BLK_ROWS - 1) / BLK_ROWS, np = (n - 1 + BLK_NB - 1) / BLK_NB;
+    size_t per = (size_t)4 * n + (size_t)((n + 7) / 8);
+    auto take = [&](size_t bytes) { unsigned char *r = p; p += (bytes + 255) & ~(size_t)255; return r; };
+    BlkBufs &K = w->K;
+    K.A = A;
+    K.Vp = (cplx *)take((size_t)B * n * BLK_NB * 16);
+    K.Wp = (cplx *)take((size_t)B * n * BLK_NB * 16);
+    K.G = (cplx *)take((size_t)B * n * BLK_NB * 16);
+    K.acol = (cplx *)take((size_t)B * n * 16);
+    K.tau = (cplx *)take((size_t)B * n * 16);
+    K.normpart = (double *)take((size_t)B * nrb * 8);
+    K.part = (cplx *)take((size_t)B * nseg * n * 16);
+    K.cpart = (cplx *)take((size_t)B * nrb * n * 16);
+    K.s1part = (cplx *)take((size_t)B * nrb * BLK_NB * 16);
+    K.s2part = (cplx *)take((size_t)B * nrb * BLK_NB * 16);
+    K.vAvpart = (double *)take((size_t)B * nrb * nseg * 8);
+    K.Tbuf = (cplx *)take((size_t)B * np * BLK_NB * BLK_NB * 16);
+    K.dd = (double *)take((size_t)B * n * 8);
+    K.ee = (double *)take((size_t)B * n * 8);
+    w->e2 = (double *)take((size_t)B * n * 8);
+    w->Z = (double *)take((size_t)B * k * n * 8);
+    w->lu = (double *)take((size_t)B * k * per * 8);
+    w->Ypart = (cplx *)take((size_t)B * nrb * BLK_NB * k * 16);
+    K.n = n; K.nseg = nseg; K.nrb = (int)nrb; K.npanels = (int)np;
+}
+
+static int run_dense_blocked_batch(cplx *A, int n, int B, int k, int want_vec, int conj_out, BlkWs &w, double *evals,
+                                   cplx *evecs, int *info, cudaStream_t st) {
+    BlkBufs K = w.K;
+    K.A = A;
+    if (k > BLK_KMAX && want_vec) return fail(SCQED_EUNSUPPORTED, "blocked dense path supports k <= %d eigenvectors", BLK_KMAX);
+    const int seg_max = (n + K.nseg - 1) / K.nseg;
+    blk_w_nextcol<<<dim3(K.nrb, B), BLK_ROWS, 0, st>>>(K, -1, -1);
+    LAUNCHED();
+    for (int p = 0; p < K.npanels; ++p) {
+        const int j0 = p * BLK_NB;
+        const int nbp = (n - 1) - j0 < BLK_NB ? (n - 1) - j0 : BLK_NB;
+        for (int i = 0; i < nbp; ++i) {
+            blk_reflect_hemv<<<dim3(K.nrb, K.nseg, B), BLK_ROWS, (size_t)seg_max * 16 * 5, st>>>(K, j0 + i, i);
+            blk_w_nextcol<<<dim3(K.nrb, B), BLK_ROWS, 0, st>>>(K, j0 + i, i);
+        }
+        g_launches.fetch_add(2 * nbp, std::memory_order_relaxed);
+        const int j1 = j0 + nbp;
+        if (p + 1 < K.npanels && j1 < n) {
+            int tiles = (n - j1 + H2K_TILE - 1) / H2K_TILE;
+            blk_her2k_dmma<<<dim3(tiles, tiles, B), 256, 0, st>>>(K, j1, nbp);
+            LAUNCHED();
+        }
+    }
+    CK(cudaGetLastError());
+    tridiag_eig_kernel<<<B, 256, (size_t)k * 8, st>>>(K.dd, K.ee, n, k, want_vec, evals, w.Z, w.lu, k, w.e2, info);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    if (want_vec) {
+        blk_build_T<<<dim3(K.npanels, B), 32, 0, st>>>(K);
+        size_t total = (size_t)B * k * n;
+        blk_init_x<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w.Z, evecs, total);
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+        for (int p = K.npanels - 1; p >= 0; --p) {
+            blk_bt_dots<<<dim3(K.nrb, B), BLK_ROWS, 0, st>>>(K, p, k, evecs, w.Ypart);
+            blk_bt_apply<<<dim3(K.nrb, B), BLK_ROWS, (size_t)2 * BLK_NB * k * 16, st>>>(K, p, k, evecs, w.Ypart);
+        }
+        g_launches.fetch_add(2 * K.npanels, std::memory_order_relaxed);
+        if (conj_out) { blk_conj_x<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(evecs, total); LAUNCHED(); }
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
 static int pick_dense_batch(int n, long long n_pts, int k, int sm_count) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
     size_t budget = free_b / 2;
-    size_t per = (size_t)n * n * 16 + dense_ws_bytes(n, k, 1, 32);
+    size_t per = (size_t)n * n * 16 + blk_ws_bytes(n, k, 1, 64) + dense_ws_bytes(n, k, 1, 64);
     long long B = (long long)(budget / per);
     // enough matrices in flight to fill the SMs during the skinny tail of the reduction
-    long long want = n <= 512 ? 256 : (n <= 1536 ? 64 : (n <= 4096 ? 16 : 4));
+    long long want = n <= 512 ? 256 : (n <= 1536 ? 64 : (n <= 4096 ? 32 : 8));
     if (B > want) B = want;
     if (B > n_pts) B = n_pts;
     if (B > 65535) B = 65535;
@@ -386,19 +485,25 @@ extern "C" int scqed_eigh_batched(int device, double *H_dev, int32_t n, int64_t 
         rc = run_small(&tmp, tmp.P, nullptr, (const cplx *)H_dev, nullptr, batch, n, k, want_vec, 0, res, evals_dev,
                        (cplx *)evecs_dev, nullptr, info_dev, st);
     } else {
-        int nseg = dense_nseg(n, tmp.sm_count, (int)(batch > 64 ? 64 : batch));
-        long long B = batch > 64 ? 64 : batch;
-        if (tmp.work.ensure(dense_ws_bytes(n, k, (int)B, nseg))) return fail(SCQED_ENOMEM, "dense workspace");
+        long long B = batch > 32 ? 32 : batch;
+        int nseg = dense_nseg(n, tmp.sm_count, (int)B);
+        const bool blocked = solver != 3;
+        size_t wsb = blocked ? blk_ws_bytes(n, k, (int)B, nseg) : dense_ws_bytes(n, k, (int)B, nseg);
+        if (tmp.work.ensure(wsb)) return fail(SCQED_ENOMEM, "dense workspace");
         DenseWs w;
-        dense_ws_carve((unsigned char *)tmp.work.p, n, k, (int)B, nseg, &w);
+        BlkWs bw;
+        if (blocked) blk_ws_carve((unsigned char *)tmp.work.p, nullptr, n, k, (int)B, nseg, &bw);
+        else dense_ws_carve((unsigned char *)tmp.work.p, n, k, (int)B, nseg, &w);
         rc = 0;
         for (long long b0 = 0; b0 < batch && !rc; b0 += B) {
             int nb = (int)(batch - b0 < B ? batch - b0 : B);
             // caller's matrices are row-major = column-major storage of conj(H): same spectrum,
             // conjugated eigenvectors
-            rc = run_dense_batch(&tmp, tmp.sm_count, (cplx *)H_dev + (size_t)b0 * n * n, n, nb, k, want_vec, 1, w,
-                                 evals_dev + (size_t)b0 * k, evecs_dev ? (cplx *)evecs_dev + (size_t)b0 * k * n : nullptr,
-                                 info_dev + b0, st);
+            cplx *Ab = (cplx *)H_dev + (size_t)b0 * n * n;
+            double *ev = evals_dev + (size_t)b0 * k;
+            cplx *vec = evecs_dev ? (cplx *)evecs_dev + (size_t)b0 * k * n : nullptr;
+            rc = blocked ? run_dense_blocked_batch(Ab, n, nb, k, want_vec, 1, bw, ev, vec, info_dev + b0, st)
+                         : run_dense_batch(&tmp, tmp.sm_count, Ab, n, nb, k, want_vec, 1, w, ev, vec, info_dev + b0, st);
         }
         if (!rc) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) rc = fail(SCQED_ECUDA, "dense eigh: %s", cudaGetErrorString(e)); }
         tmp.work.release();
@@ -412,7 +517,7 @@ extern "C" int scqed_eigh_batched(int device, double *H_dev, int32_t n, int64_t 
 static int check_opts(const scqed_plan *pl, const scqed_sweep_opts *o) {
     if (!o) return fail(SCQED_EINVAL, "opts is NULL");
     if (o->k < 1 || o->k > pl->P.n) return fail(SCQED_EINVAL, "k=%d outside 1..n=%d", o->k, pl->P.n);
-    if (o->solver < 0 || o->solver > 2) return fail(SCQED_EINVAL, "solver=%d", o->solver);
+    if (o->solver < 0 || o->solver > 3) return fail(SCQED_EINVAL, "solver=%d", o->solver);
     if (o->resonator) {
         if (!o->want_vectors) return fail(SCQED_EINVAL, "the Resonator evaluable needs eigenvectors (get_vectors=True)");
         if (o->k > SCQED_RES_KMAX || o->k < 2) return fail(SCQED_EUNSUPPORTED, "resonator strips support 2 <= k <= %d", SCQED_RES_KMAX);
@@ -467,25 +572,28 @@ extern "C" int scqed_sweep_run(scqed_plan *pl, const scqed_sweep_opts *o, const 
     }
     if (o->resonator) return fail(SCQED_EUNSUPPORTED, "the Resonator evaluable is only implemented on the fused path (n <= ~110)");
     // ---- S2: batches of B matrices through HBM ------------------------------------------------
+    const bool blocked = solver != 3;
     int B = pick_dense_batch(n, n_pts, k, pl->sm_count);
     if (B < 1) return fail(SCQED_ENOMEM, "not enough device memory for one %d x %d matrix", n, n);
     int nseg = dense_nseg(n, pl->sm_count, B);
-    size_t a_bytes = (size_t)B * n * n * 16;
-    if (pl->work.ensure(a_bytes + dense_ws_bytes(n, k, B, nseg))) return fail(SCQED_ENOMEM, "dense workspace (B=%d)", B);
+    size_t a_bytes = ((size_t)B * n * n * 16 + 255) & ~(size_t)255;
+    size_t wsb = blocked ? blk_ws_bytes(n, k, B, nseg) : dense_ws_bytes(n, k, B, nseg);
+    if (pl->work.ensure(a_bytes + wsb)) return fail(SCQED_ENOMEM, "dense workspace (B=%d)", B);
     cplx *A = (cplx *)pl->work.p;
     DenseWs w;
-    dense_ws_carve((unsigned char *)pl->work.p + ((a_bytes + 255) & ~(size_t)255), n, k, B, nseg, &w);
+    BlkWs bw;
+    if (blocked) blk_ws_carve((unsigned char *)pl->work.p + a_bytes, A, n, k, B, nseg, &bw);
+    else dense_ws_carve((unsigned char *)pl->work.p + a_bytes, n, k, B, nseg, &w);
     for (long long p0 = 0; p0 < n_pts; p0 += B) {
         int nb = (int)(n_pts - p0 < B ? n_pts - p0 : B);
-        // Fast index of the assembly kernel = contiguous index of the destination.  The dense path
-        // wants column-major A[i + j*n] = H[i][j]; writing "row-major H^T" is the same bytes, and
-        // H^T = conj(H) element-wise, so assemble conj(H) row-major... simpler: assemble H row-major
-        // and note that, read column-major, the buffer is H^T = conj(H): same eigenvalues, and the
-        // eigenvectors come out conjugated -> conj_out = 1 restores them.
+        // The assembly writes row-major H.  Read column-major, that buffer is H^T = conj(H): same
+        // eigenvalues, conjugated eigenvectors -> conj_out = 1 restores them.
         rc = run_assemble(pl, (const cplx *)pl->coef.p + (size_t)p0 * P.n_terms, nb, o->tidyup, A, st);
         if (rc) return rc;
-        rc = run_dense_batch(pl, pl->sm_count, A, n, nb, k, o->want_vectors, 1, w, evals_dev + (size_t)p0 * k,
-                             evecs_dev ? (cplx *)evecs_dev + (size_t)p0 * k * n : nullptr, info_dev + p0, st);
+        double *ev = evals_dev + (size_t)p0 * k;
+        cplx *vec = evecs_dev ? (cplx *)evecs_dev + (size_t)p0 * k * n : nullptr;
+        rc = blocked ? run_dense_blocked_batch(A, n, nb, k, o->want_vectors, 1, bw, ev, vec, info_dev + p0, st)
+                     : run_dense_batch(pl, pl->sm_count, A, n, nb, k, o->want_vectors, 1, w, ev, vec, info_dev + p0, st);
         if (rc) return rc;
     }
     return 0;

@@ -105,18 +105,21 @@ struct TriLU {
     unsigned char *swp;
 };
 
+// The three routines below walk long arrays that may live in global memory (n up to ~10^4 on the
+// HBM dense path); every loop loads the operands of iteration i+1 before the dependent arithmetic
+// of iteration i, so the critical path is the division chain, not the memory latency.
 __device__ __forceinline__ void trilu_factor(const double *__restrict__ d, const double *__restrict__ e,
                                              int n, double lambda, double eps3, TriLU W) {
     double u = d[0] - lambda;
     double v = n > 1 ? e[0] : 0.0;
+    double ei_n = n > 1 ? e[0] : 0.0, di_n = n > 1 ? d[1] : 0.0, en_n = n > 2 ? e[1] : 0.0;
     for (int i = 1; i < n; ++i) {
-        double ei = e[i - 1];
-        double en = i < n - 1 ? e[i] : 0.0;
+        const double ei = ei_n, di = di_n - lambda, en = en_n;
+        if (i + 1 < n) { ei_n = e[i]; di_n = d[i + 1]; en_n = i + 2 < n ? e[i + 1] : 0.0; }
         if (u == 0.0 && ei == 0.0) u = eps3;
         if (fabs(ei) >= fabs(u)) {          // pivot on row i
             double xu = u / ei;
             W.mul[i] = xu; W.swp[i] = 1;
-            double di = d[i] - lambda;
             W.u0[i - 1] = ei; W.u1[i - 1] = di; W.u2[i - 1] = en;
             u = v - xu * di;
             v = -xu * en;
@@ -124,7 +127,7 @@ __device__ __forceinline__ void trilu_factor(const double *__restrict__ d, const
             double xu = ei / u;
             W.mul[i] = xu; W.swp[i] = 0;
             W.u0[i - 1] = u; W.u1[i - 1] = v; W.u2[i - 1] = 0.0;
-            u = d[i] - lambda - xu * v;
+            u = di - xu * v;
             v = en;
         }
     }
@@ -134,19 +137,28 @@ __device__ __forceinline__ void trilu_factor(const double *__restrict__ d, const
 
 // z <- U^-1 L^-1 P z   (apply_l = 0 skips the L^-1 P part: first iteration from a random start)
 __device__ __forceinline__ void trilu_solve(int n, TriLU W, double *z, int zs, double eps3, bool apply_l) {
-    if (apply_l) {
+    if (apply_l && n > 1) {
+        double cur = z[0];
+        double m_n = W.mul[1], z_n = z[zs];
+        unsigned char s_n = W.swp[1];
         for (int i = 1; i < n; ++i) {
-            double a = z[(i - 1) * zs], b = z[i * zs];
-            if (W.swp[i]) { z[(i - 1) * zs] = b; z[i * zs] = a - W.mul[i] * b; }
-            else          { z[i * zs] = b - W.mul[i] * a; }
+            const double m_i = m_n, b = z_n;
+            const unsigned char s_i = s_n;
+            if (i + 1 < n) { m_n = W.mul[i + 1]; s_n = W.swp[i + 1]; z_n = z[(size_t)(i + 1) * zs]; }
+            if (s_i) { z[(size_t)(i - 1) * zs] = b; cur = cur - m_i * b; }
+            else     { z[(size_t)(i - 1) * zs] = cur; cur = b - m_i * cur; }
         }
+        z[(size_t)(n - 1) * zs] = cur;
     }
     double z1 = 0.0, z2 = 0.0;
+    double p_n = W.u0[n - 1], u1_n = W.u1[n - 1], u2_n = W.u2[n - 1], r_n = z[(size_t)(n - 1) * zs];
     for (int i = n - 1; i >= 0; --i) {
-        double p = W.u0[i];
+        double p = p_n;
+        const double u1 = u1_n, u2 = u2_n, r = r_n;
+        if (i > 0) { p_n = W.u0[i - 1]; u1_n = W.u1[i - 1]; u2_n = W.u2[i - 1]; r_n = z[(size_t)(i - 1) * zs]; }
         if (fabs(p) < eps3 * 1e-3) p = copysign(eps3, p == 0.0 ? 1.0 : p);
-        double zi = (z[i * zs] - W.u1[i] * z1 - W.u2[i] * z2) / p;
-        z[i * zs] = zi;
+        double zi = (r - u1 * z1 - u2 * z2) / p;
+        z[(size_t)i * zs] = zi;
         z2 = z1; z1 = zi;
     }
 }

@@ -76,7 +76,8 @@ def _random_hermitian(rng, n, batch, real=False):
 
 
 @pytest.mark.parametrize("n,k,solver", [(2, 2, 0), (5, 3, 0), (33, 10, 0), (64, 10, 1), (101, 20, 1), (110, 5, 0),
-                                        (101, 10, 2), (130, 10, 0), (257, 12, 2)])
+                                        (101, 10, 2), (130, 10, 0), (257, 12, 2), (3, 2, 2), (34, 5, 2), (65, 8, 2),
+                                        (200, 10, 2), (517, 10, 2), (101, 10, 3), (257, 12, 3)])
 def test_eigh_batched_random(engine_mod, n, k, solver):
     import torch
     rng = np.random.default_rng(1234 + n)
@@ -95,7 +96,7 @@ def test_eigh_batched_random(engine_mod, n, k, solver):
         assert subspace_overlap(X, v[:, :k], w[:k]) >= OVERLAP
 
 
-@pytest.mark.parametrize("solver,n", [(1, 60), (2, 150)])
+@pytest.mark.parametrize("solver,n", [(1, 60), (2, 150), (3, 150), (2, 400)])
 def test_eigh_degenerate_and_clustered(engine_mod, solver, n):
     """Exact doublets / triplets and a tight cluster (the floating-CSFQ trap)."""
     import torch
@@ -223,10 +224,12 @@ def test_dense_solver_on_small_problem_agrees(engine_mod):
     with engine_mod.Engine(plan) as eng:
         a = eng.sweep(g["params"][idx], 10, want_vectors=True, solver=1)
         b = eng.sweep(g["params"][idx], 10, want_vectors=True, solver=2)
-    assert rel_err(a.E, b.E) < 1e-11
-    assert rel_err(b.E, g["E"][idx]) < E_RTOL
-    for j in range(len(idx)):
-        assert subspace_overlap(a.V[j].T, b.V[j].T, a.E[j]) >= OVERLAP
+        c = eng.sweep(g["params"][idx], 10, want_vectors=True, solver=3)
+    for other in (b, c):
+        assert rel_err(a.E, other.E) < 1e-11
+        assert rel_err(other.E, g["E"][idx]) < E_RTOL
+        for j in range(len(idx)):
+            assert subspace_overlap(a.V[j].T, other.V[j].T, a.E[j]) >= OVERLAP
 
 
 def test_full_size_properties_c2(engine_mod):

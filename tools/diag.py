@@ -62,3 +62,17 @@ def perf():
 if __name__ == "__main__":
     if "vec" in sys.argv: vec_diag("c3_csfqfloat_t5")
     if "perf" in sys.argv: perf()
+
+def one(name, k, vec, npts, solver=0):
+    plan = SweepPlan.load(os.path.join(G, name + ".plan.json"))
+    grid = plan.sweep_grid()
+    reps = int(np.ceil(npts / len(grid)))
+    grid = np.tile(grid, (reps, 1))[:npts]
+    with engine.Engine(plan) as eng:
+        p = torch.as_tensor(grid, device="cuda")
+        ms = timeit(lambda: eng.sweep_device(p, k, want_vectors=vec, solver=solver), reps=1)
+        print("%s n=%d pts=%d device %.2f ms (%.2f pts/s)" % (name, plan.hilbert_dim, npts, ms, npts / ms * 1e3))
+
+if __name__ == "__main__" and "one" in sys.argv:
+    i = sys.argv.index("one")
+    one(sys.argv[i + 1], int(sys.argv[i + 2]), bool(int(sys.argv[i + 3])), int(sys.argv[i + 4]))
