@@ -72,6 +72,15 @@ struct PlanDev {
     const cplx *factor_data;
     int n_terms;
     const int *term_factors;       // [n_terms * n_nodes]
+    // matrix-free view: every factor as ELL rows (ell_w[f] entries per row, padded with value 0)
+    const int *ell_w;              // [n_factors]
+    const long long *ell_off;      // [n_factors] offset into ell_cols / ell_vals
+    const int *ell_cols;
+    const cplx *ell_vals;
+    const double *fac_rowsum;      // [n_factors] max_i sum_j |F[i][j]|  (infinity norm)
+    // per term: number of non-identity nodes nn (<= 3), their node ids and factor ids: [n_terms * 7]
+    const int *term_meta;
+    int max_term_nn;
     int n_swept, n_instr, n_scalar;
     const int *instr;              // [n_instr * 3]
     const double *consts;

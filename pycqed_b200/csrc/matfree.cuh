@@ -1,0 +1,476 @@
+// matfree.cuh -- S3: matrix-free lowest-k eigensolver on the Kronecker structure
+//     H(p) = sum_t c_t(p) * kron_k F_{t,k}
+// Chebyshev-filtered block subspace iteration (ChebFSI): no matrix is ever formed.
+//
+// Replaces the reference's sparse path, which materialises every Kronecker product as an n x n
+// CSR matrix (pyscqed/numerical_system.py:226-251) and calls ARPACK, usually in shift-invert
+// mode through a SuperLU factorisation (pyscqed/util.py:76-125, examples/csfq-example.py:509-553).
+// Shift-invert has no matrix-free analogue; a polynomial filter does.
+//
+// Per outer iteration and sweep point (block of b = k + guard vectors):
+//   mf_cheb_smem / mf_cheb_step : Y = p_m(H) X, degree-m Chebyshev polynomial that damps
+//                                 [theta_b, ub] (K3: the Kronecker mat-vec; for diagonal / shift
+//                                 factors the whole filter of one vector runs out of shared
+//                                 memory, two n-vectors, zero HBM traffic)
+//   mf_orth                     : CGS2 orthonormalisation of Y
+//   mf_matvec, mf_gram          : HX = H X,  G = X^H HX  (b x b)
+//   small_eigh_kernel           : eigen-decomposition of G (the fused small-n solver)
+//   mf_rotate, mf_converge      : Ritz vectors, residual norms, per-point convergence flags
+//
+// Algorithmic traffic of one block mat-vec in HBM/L2: 32 n b bytes (read X, write Y); flops
+// 8 n b sum_t prod_k w_{t,k} with w = non-zeros per row of each factor.
+#pragma once
+#include "common.cuh"
+
+namespace scqed {
+
+#define MF_BMAX 32
+#define MF_THREADS 256
+
+struct MfArgs {
+    PlanDev P;
+    const cplx *coef;      // [n_pts][n_terms]
+    int n, b, k;
+    long long n_pts;
+    double *fpar;          // [n_pts][4]: lo, ub, a0, spare
+    int *active;           // [n_pts]
+    int *n_active;         // [1]
+    double *theta;         // [n_pts][b]
+    double *rnorm2;        // [n_pts][b]
+};
+
+// (H x)[i] for one sweep point; x may live in shared or global memory.
+__device__ __forceinline__ cplx mf_apply(const PlanDev &P, const cplx *__restrict__ coef, const cplx *x, int i) {
+    int id[SCQED_MAX_NODES];
+#pragma unroll
+    for (int k = 0; k < SCQED_MAX_NODES; ++k)
+        if (k < P.n_nodes) id[k] = (i / P.strides[k]) % P.dims[k];
+    cplx acc = cmake(0.0, 0.0);
+    for (int t = 0; t < P.n_terms; ++t) {
+        const int *tm = P.term_meta + t * 7;
+        const int nn = __ldg(tm);
+        const cplx c = coef[t];
+        if (nn == 0) { cfma(acc, c, x[i]); continue; }
+        const int k0 = __ldg(tm + 1), f0 = __ldg(tm + 4);
+        const int w0 = __ldg(P.ell_w + f0);
+        const long long o0 = __ldg(P.ell_off + f0) + (long long)id[k0] * w0;
+        const int s0 = P.strides[k0], b0 = i - id[k0] * s0;
+        if (nn == 1) {
+            cplx sum = cmake(0.0, 0.0);
+            for (int a = 0; a < w0; ++a) {
+                cplx v = __ldg(P.ell_vals + o0 + a);
+                int col = __ldg(P.ell_cols + o0 + a);
+                cfma(sum, v, x[b0 + col * s0]);
+            }
+            cfma(acc, c, sum);
+            continue;
+        }
+        const int k1 = __ldg(tm + 2), f1 = __ldg(tm + 5);
+        const int w1 = __ldg(P.ell_w + f1);
+        const long long o1 = __ldg(P.ell_off + f1) + (long long)id[k1] * w1;
+        const int s1 = P.strides[k1], b1 = b0 - id[k1] * s1;
+        if (nn == 2) {
+            cplx sum = cmake(0.0, 0.0);
+            for (int a = 0; a < w0; ++a) {
+                cplx va = __ldg(P.ell_vals + o0 + a);
+                if (va.x == 0.0 && va.y == 0.0) continue;
+                int ca = __ldg(P.ell_cols + o0 + a);
+                cplx inner = cmake(0.0, 0.0);
+                for (int q = 0; q < w1; ++q) {
+                    cplx vq = __ldg(P.ell_vals + o1 + q);
+                    int cq = __ldg(P.ell_cols + o1 + q);
+                    cfma(inner, vq, x[b1 + ca * s0 + cq * s1]);
+                }
+                cfma(sum, va, inner);
+            }
+            cfma(acc, c, sum);
+            continue;
+        }
+        const int k2 = __ldg(tm + 3), f2 = __ldg(tm + 6);
+        const int w2 = __ldg(P.ell_w + f2);
+        const long long o2 = __ldg(P.ell_off + f2) + (long long)id[k2] * w2;
+        const int s2 = P.strides[k2], b2 = b1 - id[k2] * s2;
+        cplx sum = cmake(0.0, 0.0);
+        for (int a = 0; a < w0; ++a) {
+            cplx va = __ldg(P.ell_vals + o0 + a);
+            if (va.x == 0.0 && va.y == 0.0) continue;
+            int ca = __ldg(P.ell_cols + o0 + a);
+            for (int q = 0; q < w1; ++q) {
+                cplx vq = __ldg(P.ell_vals + o1 + q);
+                if (vq.x == 0.0 && vq.y == 0.0) continue;
+                int cq = __ldg(P.ell_cols + o1 + q);
+                cplx vaq = cmul(va, vq);
+                cplx inner = cmake(0.0, 0.0);
+                for (int r = 0; r < w2; ++r) {
+                    cplx vr = __ldg(P.ell_vals + o2 + r);
+                    int cr = __ldg(P.ell_cols + o2 + r);
+                    cfma(inner, vr, x[b2 + ca * s0 + cq * s1 + cr * s2]);
+                }
+                cfma(sum, vaq, inner);
+            }
+        }
+        cfma(acc, c, sum);
+    }
+    return acc;
+}
+
+// diagonal element H[i][i]
+__device__ __forceinline__ double mf_diag(const PlanDev &P, const cplx *__restrict__ coef, int i) {
+    int id[SCQED_MAX_NODES];
+#pragma unroll
+    for (int k = 0; k < SCQED_MAX_NODES; ++k)
+        if (k < P.n_nodes) id[k] = (i / P.strides[k]) % P.dims[k];
+    double acc = 0.0;
+    for (int t = 0; t < P.n_terms; ++t) {
+        cplx prod = coef[t];
+        for (int k = 0; k < P.n_nodes; ++k) {
+            int f = __ldg(P.term_factors + t * P.n_nodes + k);
+            if (f >= 0) {
+                const cplx *F = P.factor_data + __ldg(P.factor_offset + f);
+                prod = cmul(prod, __ldg(F + id[k] * P.dims[k] + id[k]));
+            }
+        }
+        acc += prod.x;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ double mf_hash_uniform(unsigned long long s) {
+    s ^= s >> 33; s *= 0xff51afd7ed558ccdULL; s ^= s >> 33; s *= 0xc4ceb9fe1a85ec53ULL; s ^= s >> 33;
+    return ((double)(s >> 11) * (1.0 / 9007199254740992.0)) * 2.0 - 1.0;
+}
+
+// ---- start block: unit vectors at the b smallest diagonal entries + small noise; Gershgorin-type
+// upper bound ub = sum_t |c_t| prod_k ||F_tk||_inf.   grid (n_pts), block MF_THREADS.
+// dscr: [n_pts][n] scratch for the diagonal.
+__global__ void __launch_bounds__(MF_THREADS)
+mf_prepare(MfArgs a, cplx *X, double *dscr) {
+    __shared__ double sval[MF_THREADS];
+    __shared__ int sidx[MF_THREADS];
+    __shared__ int chosen[MF_BMAX];
+    const long long p = blockIdx.x;
+    const int n = a.n, b = a.b, tid = threadIdx.x;
+    const cplx *coef = a.coef + p * a.P.n_terms;
+    double *d = dscr + p * n;
+    for (int i = tid; i < n; i += blockDim.x) d[i] = mf_diag(a.P, coef, i);
+    if (tid == 0) {
+        double ub = 0.0;
+        for (int t = 0; t < a.P.n_terms; ++t) {
+            double m = sqrt(cabs2(coef[t]));
+            for (int k = 0; k < a.P.n_nodes; ++k) {
+                int f = a.P.term_factors[t * a.P.n_nodes + k];
+                if (f >= 0) m *= a.P.fac_rowsum[f];
+            }
+            ub += m;
+        }
+        a.fpar[p * 4 + 1] = ub;
+        a.active[p] = 1;
+    }
+    __syncthreads();
+    for (int j = 0; j < b; ++j) {          // b rounds of block-wide argmin
+        double best = 1e300; int bi = -1;
+        for (int i = tid; i < n; i += blockDim.x) if (d[i] < best) { best = d[i]; bi = i; }
+        sval[tid] = best; sidx[tid] = bi;
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if (tid < s && (sval[tid + s] < sval[tid] || (sval[tid + s] == sval[tid] && sidx[tid + s] >= 0 && sidx[tid + s] < sidx[tid]))) {
+                sval[tid] = sval[tid + s]; sidx[tid] = sidx[tid + s];
+            }
+            __syncthreads();
+        }
+        if (tid == 0) { chosen[j] = sidx[0]; if (sidx[0] >= 0) d[sidx[0]] = 1e300; }
+        __syncthreads();
+    }
+    for (int j = 0; j < b; ++j) {
+        cplx *x = X + (p * b + j) * n;
+        const int c = chosen[j];
+        for (int i = tid; i < n; i += blockDim.x) {
+            double r = 1e-2 * mf_hash_uniform(((unsigned long long)(p + 1) << 40) ^ ((unsigned long long)(j + 1) << 24) ^ (unsigned long long)i);
+            x[i] = cmake(r + (i == c ? 1.0 : 0.0), 0.0);
+        }
+    }
+}
+
+// ---- HX = H X.  grid (ceil(n/MF_THREADS), b, n_pts) --------------------------------------------------
+__global__ void __launch_bounds__(MF_THREADS)
+mf_matvec(MfArgs a, const cplx *__restrict__ X, cplx *__restrict__ HX) {
+    const long long p = blockIdx.z;
+    if (!a.active[p]) return;
+    const int j = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const cplx *x = X + (p * a.b + j) * a.n;
+    HX[(p * a.b + j) * a.n + i] = mf_apply(a.P, a.coef + p * a.P.n_terms, x, i);
+}
+
+// Chebyshev scalars: e, c from (lo, ub); sigma_1 = e / (a0 - c)
+struct ChebPar { double e, c, sigma1; };
+__device__ __forceinline__ ChebPar cheb_par(const double *fp) {
+    ChebPar q;
+    q.e = 0.5 * (fp[1] - fp[0]);
+    q.c = 0.5 * (fp[1] + fp[0]);
+    q.sigma1 = q.e / (fp[2] - q.c);
+    return q;
+}
+
+// ---- whole filter of one vector in shared memory.  grid (b, n_pts), dyn smem 2*n*16 -----------------
+__global__ void __launch_bounds__(512)
+mf_cheb_smem(MfArgs a, const cplx *__restrict__ X, cplx *__restrict__ Y, int deg) {
+    extern __shared__ cplx sbuf[];
+    const long long p = blockIdx.y;
+    if (!a.active[p]) return;
+    const int j = blockIdx.x, n = a.n, tid = threadIdx.x, T = blockDim.x;
+    const cplx *coef = a.coef + p * a.P.n_terms;
+    cplx *prev = sbuf, *cur = sbuf + n;
+    const cplx *x = X + (p * a.b + j) * n;
+    for (int i = tid; i < n; i += T) prev[i] = x[i];
+    __syncthreads();
+    const ChebPar q = cheb_par(a.fpar + p * 4);
+    double sigma = q.sigma1;
+    {
+        const double s = q.sigma1 / q.e;
+        for (int i = tid; i < n; i += T) {
+            cplx h = mf_apply(a.P, coef, prev, i);
+            cplx xi = prev[i];
+            cur[i] = cmake(s * (h.x - q.c * xi.x), s * (h.y - q.c * xi.y));
+        }
+    }
+    __syncthreads();
+    for (int m = 2; m <= deg; ++m) {
+        const double sigma2 = 1.0 / (2.0 / q.sigma1 - sigma);
+        const double s = 2.0 * sigma2 / q.e, t = sigma * sigma2;
+        for (int i = tid; i < n; i += T) {
+            cplx h = mf_apply(a.P, coef, cur, i);
+            cplx yi = cur[i], pi = prev[i];
+            prev[i] = cmake(s * (h.x - q.c * yi.x) - t * pi.x, s * (h.y - q.c * yi.y) - t * pi.y);
+        }
+        __syncthreads();
+        cplx *tmp = prev; prev = cur; cur = tmp;
+        sigma = sigma2;
+    }
+    cplx *y = Y + (p * a.b + j) * n;
+    for (int i = tid; i < n; i += T) y[i] = cur[i];
+}
+
+// ---- one Chebyshev step through global memory (large n).  grid (ceil(n/T), b, n_pts).
+// m == 1: out = s1 (H x - c x);  m >= 2: prev <- s (H cur - c cur) - t prev   (in place in prev)
+__global__ void __launch_bounds__(MF_THREADS)
+mf_cheb_step(MfArgs a, const cplx *__restrict__ cur, cplx *prev, int m) {
+    const long long p = blockIdx.z;
+    if (!a.active[p]) return;
+    const int j = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x, n = a.n;
+    if (i >= n) return;
+    const ChebPar q = cheb_par(a.fpar + p * 4);
+    const cplx *y = cur + (p * a.b + j) * n;
+    cplx h = mf_apply(a.P, a.coef + p * a.P.n_terms, y, i);
+    cplx yi = y[i];
+    cplx *o = prev + (p * a.b + j) * n;
+    if (m == 1) {
+        const double s = q.sigma1 / q.e;
+        o[i] = cmake(s * (h.x - q.c * yi.x), s * (h.y - q.c * yi.y));
+    } else {
+        double sigma = q.sigma1;
+        for (int u = 2; u < m; ++u) sigma = 1.0 / (2.0 / q.sigma1 - sigma);
+        const double sigma2 = 1.0 / (2.0 / q.sigma1 - sigma);
+        const double s = 2.0 * sigma2 / q.e, t = sigma * sigma2;
+        cplx pi = o[i];
+        o[i] = cmake(s * (h.x - q.c * yi.x) - t * pi.x, s * (h.y - q.c * yi.y) - t * pi.y);
+    }
+}
+
+__device__ __forceinline__ double mf_block_sum(double v, double *red) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double s = l < nw ? red[l] : 0.0;
+    return warp_sum(s);
+}
+
+// ---- CGS2 orthonormalisation of the block (in place).  grid (n_pts), block 512 -----------------------
+__global__ void __launch_bounds__(512)
+mf_orth(MfArgs a, cplx *Y, int *info) {
+    __shared__ double red[32];
+    __shared__ double sdot[MF_BMAX][2];
+    const long long p = blockIdx.x;
+    if (!a.active[p]) return;
+    const int n = a.n, b = a.b, tid = threadIdx.x, T = blockDim.x;
+    const int w = tid >> 5, l = tid & 31, nw = T >> 5;
+    __shared__ double swarp[16][MF_BMAX][2];
+    for (int j = 0; j < b; ++j) {
+        cplx *y = Y + (p * b + j) * n;
+        double nrm0 = 0.0;
+        for (int pass = 0; pass < 2 && j > 0; ++pass) {
+            // all dots <y_q, y_j>, q < j, in one sweep (register accumulators, chunks of 8)
+            for (int q0 = 0; q0 < j; q0 += 8) {
+                cplx acc[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] = cmake(0.0, 0.0);
+                for (int i = tid; i < n; i += T) {
+                    cplx yi = y[i];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (q0 + u < j) cfmac(acc[u], Y[(p * b + q0 + u) * n + i], yi);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    cplx s = warp_sum(acc[u]);
+                    if (l == 0 && q0 + u < j) { swarp[w][q0 + u][0] = s.x; swarp[w][q0 + u][1] = s.y; }
+                }
+            }
+            __syncthreads();
+            if (tid < j) {
+                double sx = 0.0, sy = 0.0;
+                for (int ww = 0; ww < nw; ++ww) { sx += swarp[ww][tid][0]; sy += swarp[ww][tid][1]; }
+                sdot[tid][0] = sx; sdot[tid][1] = sy;
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += T) {
+                cplx yi = y[i];
+                for (int q = 0; q < j; ++q) {
+                    cplx yq = Y[(p * b + q) * n + i];
+                    cplx dq = cmake(sdot[q][0], sdot[q][1]);
+                    yi.x -= yq.x * dq.x - yq.y * dq.y;
+                    yi.y -= yq.x * dq.y + yq.y * dq.x;
+                }
+                y[i] = yi;
+            }
+            __syncthreads();
+        }
+        double s = 0.0;
+        for (int i = tid; i < n; i += T) s += cabs2(y[i]);
+        s = mf_block_sum(s, red);
+        (void)nrm0;
+        if (!(s > 1e-280)) {                      // rank deficient: should not happen; flag it
+            if (tid == 0) info[p] = 2;
+            s = 1.0;
+        }
+        const double sc = 1.0 / sqrt(s);
+        for (int i = tid; i < n; i += T) { cplx yi = y[i]; y[i] = cmake(yi.x * sc, yi.y * sc); }
+        __syncthreads();
+    }
+}
+
+// ---- G[a_][c] = <x_a, hx_c>.  grid (b, n_pts), block 256.  G row-major [n_pts][b][b] -----------------
+__global__ void __launch_bounds__(MF_THREADS)
+mf_gram(MfArgs a, const cplx *__restrict__ X, const cplx *__restrict__ HX, cplx *__restrict__ G) {
+    __shared__ double swarp[MF_THREADS / 32][MF_BMAX][2];
+    const long long p = blockIdx.y;
+    const int ia = blockIdx.x, n = a.n, b = a.b, tid = threadIdx.x, T = blockDim.x;
+    const int w = tid >> 5, l = tid & 31, nw = T >> 5;
+    if (!a.active[p]) return;
+    const cplx *xa = X + (p * b + ia) * n;
+    for (int c0 = 0; c0 < b; c0 += 8) {
+        cplx acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = cmake(0.0, 0.0);
+        for (int i = tid; i < n; i += T) {
+            cplx xi = xa[i];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (c0 + u < b) cfmac(acc[u], xi, HX[(p * b + c0 + u) * n + i]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            cplx s = warp_sum(acc[u]);
+            if (l == 0 && c0 + u < b) { swarp[w][c0 + u][0] = s.x; swarp[w][c0 + u][1] = s.y; }
+        }
+    }
+    __syncthreads();
+    if (tid < b) {
+        double sx = 0.0, sy = 0.0;
+        for (int ww = 0; ww < nw; ++ww) { sx += swarp[ww][tid][0]; sy += swarp[ww][tid][1]; }
+        G[(p * b + ia) * b + tid] = cmake(sx, sy);
+    }
+}
+
+// symmetrise G in place (Hermitian part): grid (n_pts), block b*b threads (<= 1024)
+__global__ void mf_symmetrize(MfArgs a, cplx *G) {
+    const long long p = blockIdx.x;
+    const int b = a.b, r = threadIdx.x / b, c = threadIdx.x % b;
+    if (r >= b) return;
+    cplx x = G[(p * b + r) * b + c], y = G[(p * b + c) * b + r];
+    __syncthreads();
+    G[(p * b + r) * b + c] = cmake(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
+}
+
+// ---- Xn = X S, HXn = HX S; residual norms.  S[a_][j] = evec[j][a_].  grid (ceil(n/T), n_pts) --------
+__global__ void __launch_bounds__(MF_THREADS)
+mf_rotate(MfArgs a, const cplx *__restrict__ X, const cplx *__restrict__ HX, const cplx *__restrict__ S,
+          cplx *__restrict__ Xn, cplx *__restrict__ HXn) {
+    __shared__ cplx sS[MF_BMAX * MF_BMAX];
+    __shared__ double swarp[MF_THREADS / 32][MF_BMAX];
+    const long long p = blockIdx.y;
+    if (!a.active[p]) return;
+    const int n = a.n, b = a.b, tid = threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + tid;
+    const int w = tid >> 5, l = tid & 31, nw = blockDim.x >> 5;
+    for (int q = tid; q < b * b; q += blockDim.x) sS[q] = S[p * b * b + q];     // [j][a]
+    __syncthreads();
+    const double *th = a.theta + p * b;
+    for (int j0 = 0; j0 < b; j0 += 8) {
+        cplx ax[8], ah[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { ax[u] = cmake(0.0, 0.0); ah[u] = cmake(0.0, 0.0); }
+        if (i < n) {
+            for (int q = 0; q < b; ++q) {
+                cplx xq = X[(p * b + q) * n + i], hq = HX[(p * b + q) * n + i];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (j0 + u < b) { cplx s = sS[(j0 + u) * b + q]; cfma(ax[u], xq, s); cfma(ah[u], hq, s); }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            double r2 = 0.0;
+            if (j0 + u < b && i < n) {
+                Xn[(p * b + j0 + u) * n + i] = ax[u];
+                HXn[(p * b + j0 + u) * n + i] = ah[u];
+                double t = th[j0 + u];
+                double rx = ah[u].x - t * ax[u].x, ry = ah[u].y - t * ax[u].y;
+                r2 = rx * rx + ry * ry;
+            }
+            r2 = warp_sum(r2);
+            if (l == 0 && j0 + u < b) swarp[w][j0 + u] = r2;
+        }
+    }
+    __syncthreads();
+    if (tid < b) {
+        double s = 0.0;
+        for (int ww = 0; ww < nw; ++ww) s += swarp[ww][tid];
+        atomicAdd(a.rnorm2 + p * b + tid, s);
+    }
+}
+
+// ---- convergence + next filter window.  grid (ceil(n_pts/128)), block 128 ---------------------------
+__global__ void mf_converge(MfArgs a, double tol, int *info) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n_pts || !a.active[p]) return;
+    const int b = a.b, k = a.k;
+    const double *th = a.theta + p * b;
+    double *r2 = a.rnorm2 + p * b;
+    bool conv = true;
+    for (int j = 0; j < k; ++j) conv &= (sqrt(r2[j]) <= tol * fmax(1.0, fabs(th[j])));
+    for (int j = 0; j < b; ++j) r2[j] = 0.0;
+    double lo = th[b - 1], a0 = th[0], ub = a.fpar[p * 4 + 1];
+    if (!(lo > a0)) lo = a0 + 1e-6 * (ub - a0);
+    if (!(ub > lo)) ub = lo + 1.0;
+    a.fpar[p * 4 + 0] = lo;
+    a.fpar[p * 4 + 1] = ub;
+    a.fpar[p * 4 + 2] = a0;
+    if (conv) { a.active[p] = 0; info[p] = 0; }
+    else atomicAdd(a.n_active, 1);
+}
+
+// ---- outputs: first k Ritz pairs.  grid (ceil(n*k/256), n_pts) -----------------------------------------
+__global__ void mf_output(MfArgs a, const cplx *__restrict__ X, double *__restrict__ evals, cplx *__restrict__ evecs) {
+    const long long p = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x, n = a.n, k = a.k, b = a.b;
+    if (q < k) evals[p * k + q] = a.theta[p * b + q];
+    if (evecs && q < n * k) {
+        int j = q / n, i = q - j * n;
+        evecs[(p * k + j) * n + i] = X[(p * b + j) * n + i];
+    }
+}
+
+}  // namespace scqed

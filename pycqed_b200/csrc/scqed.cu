@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -18,6 +19,7 @@
 #include "small_eigh.cuh"
 #include "dense_eigh.cuh"
 #include "dense_blocked.cuh"
+#include "matfree.cuh"
 #include "probe.cuh"
 
 using namespace scqed;
@@ -72,6 +74,7 @@ struct scqed_plan {
     size_t smem_optin = 0;
     PlanDev P;
     int n_coef_scalar = 0;
+    long long mf_work_per_row = 0;     // complex MACs per output element of the matrix-free mat-vec
     std::vector<int> factor_node;
     // device copies of the tables
     DevBuf tables;
@@ -151,6 +154,59 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     size_t o_cre = put(d->coef_re, (size_t)d->n_terms * 4);
     size_t o_cim = put(d->coef_im, (size_t)d->n_terms * 4);
     size_t o_sreg = put(d->scalar_regs, (size_t)d->n_scalar * 4);
+    // ELL view of the factors + per-term metadata for the matrix-free mat-vec
+    std::vector<int> ell_w(d->n_factors > 0 ? d->n_factors : 1, 0);
+    std::vector<long long> ell_off(d->n_factors > 0 ? d->n_factors : 1, 0);
+    std::vector<int> ell_cols;
+    std::vector<double> ell_vals;      // interleaved complex
+    std::vector<double> rowsum(d->n_factors > 0 ? d->n_factors : 1, 0.0);
+    for (int f = 0; f < d->n_factors; ++f) {
+        const int dk = d->dims[d->factor_node[f]];
+        const double *F = d->factor_data + 2 * (size_t)d->factor_offset[f];
+        int w = 0;
+        double rs = 0.0;
+        for (int i = 0; i < dk; ++i) {
+            int cnt = 0;
+            double sum = 0.0;
+            for (int j = 0; j < dk; ++j) {
+                double re = F[2 * ((size_t)i * dk + j)], im = F[2 * ((size_t)i * dk + j) + 1];
+                if (re != 0.0 || im != 0.0) { ++cnt; sum += std::sqrt(re * re + im * im); }
+            }
+            if (cnt > w) w = cnt;
+            if (sum > rs) rs = sum;
+        }
+        if (w < 1) w = 1;
+        ell_w[f] = w; ell_off[f] = (long long)ell_cols.size(); rowsum[f] = rs;
+        for (int i = 0; i < dk; ++i) {
+            int cnt = 0;
+            for (int j = 0; j < dk; ++j) {
+                double re = F[2 * ((size_t)i * dk + j)], im = F[2 * ((size_t)i * dk + j) + 1];
+                if (re != 0.0 || im != 0.0) { ell_cols.push_back(j); ell_vals.push_back(re); ell_vals.push_back(im); ++cnt; }
+            }
+            for (; cnt < w; ++cnt) { ell_cols.push_back(i); ell_vals.push_back(0.0); ell_vals.push_back(0.0); }
+        }
+    }
+    std::vector<int> term_meta((size_t)d->n_terms * 7, 0);
+    int max_nn = 0;
+    for (int t = 0; t < d->n_terms; ++t) {
+        int nn = 0;
+        for (int k = 0; k < d->n_nodes; ++k) {
+            int f = d->term_factors[t * d->n_nodes + k];
+            if (f >= 0) {
+                if (nn < 3) { term_meta[(size_t)t * 7 + 1 + nn] = k; term_meta[(size_t)t * 7 + 4 + nn] = f; }
+                ++nn;
+            }
+        }
+        term_meta[(size_t)t * 7] = nn;
+        if (nn > max_nn) max_nn = nn;
+    }
+    if (ell_cols.empty()) { ell_cols.push_back(0); ell_vals.push_back(0.0); ell_vals.push_back(0.0); }
+    size_t o_ellw = put(ell_w.data(), ell_w.size() * 4);
+    size_t o_elloff = put(ell_off.data(), ell_off.size() * 8);
+    size_t o_ellc = put(ell_cols.data(), ell_cols.size() * 4);
+    size_t o_ellv = put(ell_vals.data(), ell_vals.size() * 8);
+    size_t o_rowsum = put(rowsum.data(), rowsum.size() * 8);
+    size_t o_tmeta = put(term_meta.data(), term_meta.size() * 4);
     if (pl->tables.ensure(host.size() + 256)) { delete pl; return fail(SCQED_ENOMEM, "plan tables"); }
     if (cudaMemcpy(pl->tables.p, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         pl->tables.release(); delete pl; return fail(SCQED_ECUDA, "uploading plan tables failed");
@@ -167,6 +223,22 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     P.factor_offset = (const long long *)(base + o_foff);
     P.n_terms = d->n_terms;
     P.term_factors = (const int *)(base + o_terms);
+    P.ell_w = (const int *)(base + o_ellw);
+    P.ell_off = (const long long *)(base + o_elloff);
+    P.ell_cols = (const int *)(base + o_ellc);
+    P.ell_vals = (const cplx *)(base + o_ellv);
+    P.fac_rowsum = (const double *)(base + o_rowsum);
+    P.term_meta = (const int *)(base + o_tmeta);
+    P.max_term_nn = max_nn;
+    pl->mf_work_per_row = 0;
+    for (int t = 0; t < d->n_terms; ++t) {
+        long long wprod = 1;
+        for (int k = 0; k < d->n_nodes; ++k) {
+            int f = d->term_factors[t * d->n_nodes + k];
+            if (f >= 0) wprod *= ell_w[f];
+        }
+        pl->mf_work_per_row += wprod;
+    }
     P.n_swept = d->n_swept; P.n_instr = d->n_instr; P.n_scalar = d->n_scalar;
     P.instr = (const int *)(base + o_instr);
     P.consts = (const double *)(base + o_consts);
@@ -462,6 +534,124 @@ static int pick_dense_batch(int n, long long n_pts, int k, int sm_count) {
     return (int)B;
 }
 
+// ---- S3: matrix-free Chebyshev-filtered subspace iteration -------------------------------------------
+static int run_small(scqed_plan *pl, const PlanDev &P, const cplx *coef, const cplx *Hin, const double *scal,
+                     long long n_pts, int n, int k, int want_vec, int tidyup, const ResonatorArgs &res,
+                     double *evals, cplx *evecs, double *post, int *info, cudaStream_t st);
+
+static int mf_block_size(int n, int k) {
+    int b = k + 6;
+    b = (b + 3) & ~3;
+    if (b > MF_BMAX) b = MF_BMAX;
+    if (b > n) b = n;
+    return b;
+}
+
+static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, int k, int want_vec, double *evals,
+                       cplx *evecs, int *info, cudaStream_t st, int deg, int maxit, double tol) {
+    const PlanDev &P = pl->P;
+    const int n = P.n;
+    if (P.max_term_nn > 3) return fail(SCQED_EUNSUPPORTED, "matrix-free path supports terms with at most 3 non-identity factors");
+    const int b = mf_block_size(n, k);
+    if (b < k) return fail(SCQED_EUNSUPPORTED, "matrix-free path supports k <= %d", MF_BMAX);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
+    const size_t per_pt = (size_t)4 * b * n * 16 + (size_t)n * 8 + (size_t)2 * b * b * 16 + (size_t)2 * b * 8 + 64;
+    long long chunk = (long long)((free_b / 2) / per_pt);
+    if (chunk < 1) return fail(SCQED_ENOMEM, "not enough device memory for one matrix-free block (n=%d, b=%d)", n, b);
+    if (chunk > n_pts) chunk = n_pts;
+    if (chunk > 16384) chunk = 16384;
+    if (pl->work.ensure((size_t)chunk * per_pt + 16 * 256)) return fail(SCQED_ENOMEM, "matrix-free workspace");
+    unsigned char *wp = (unsigned char *)pl->work.p;
+    auto take = [&](size_t bytes) { unsigned char *r = wp; wp += (bytes + 255) & ~(size_t)255; return r; };
+    cplx *bufX = (cplx *)take((size_t)chunk * b * n * 16), *bufY = (cplx *)take((size_t)chunk * b * n * 16);
+    cplx *bufH = (cplx *)take((size_t)chunk * b * n * 16), *bufHn = (cplx *)take((size_t)chunk * b * n * 16);
+    double *dscr = (double *)take((size_t)chunk * n * 8);
+    cplx *G = (cplx *)take((size_t)chunk * b * b * 16), *S = (cplx *)take((size_t)chunk * b * b * 16);
+    double *theta = (double *)take((size_t)chunk * b * 8), *rn2 = (double *)take((size_t)chunk * b * 8);
+    double *fpar = (double *)take((size_t)chunk * 4 * 8);
+    int *active = (int *)take((size_t)chunk * 4), *n_active = (int *)take(256), *info_s1 = (int *)take((size_t)chunk * 4);
+    const bool smem_filter = (size_t)2 * n * 16 <= 220 * 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(mf_cheb_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+        attr_set = true;
+    }
+    ResonatorArgs nores;
+    memset(&nores, 0, sizeof(nores));
+    PlanDev Pg;                         // dummy plan for the b x b Rayleigh-Ritz solves (Hin path)
+    memset(&Pg, 0, sizeof(Pg));
+    const int rowblocks = (n + MF_THREADS - 1) / MF_THREADS;
+
+    for (long long p0 = 0; p0 < n_pts; p0 += chunk) {
+        const long long np = n_pts - p0 < chunk ? n_pts - p0 : chunk;
+        MfArgs a;
+        a.P = P; a.coef = coef_all + (size_t)p0 * P.n_terms; a.n = n; a.b = b; a.k = k; a.n_pts = np;
+        a.fpar = fpar; a.active = active; a.n_active = n_active; a.theta = theta; a.rnorm2 = rn2;
+        int *info_c = info + p0;
+        CK(cudaMemsetAsync(rn2, 0, (size_t)np * b * 8, st));
+        CK(cudaMemsetAsync(info_c, 1, (size_t)np * 4, st));
+        cplx *X = bufX, *Y = bufY, *H = bufH, *Hn = bufHn;
+        mf_prepare<<<(unsigned)np, MF_THREADS, 0, st>>>(a, X, dscr);
+        LAUNCHED();
+        // Rayleigh-Ritz on block R (orthonormalised in place): leaves Ritz vectors in X, H X in H
+        auto rayleigh_ritz = [&](cplx *R) -> int {
+            mf_orth<<<(unsigned)np, 512, 0, st>>>(a, R, info_c);
+            mf_matvec<<<dim3(rowblocks, b, (unsigned)np), MF_THREADS, 0, st>>>(a, R, H);
+            mf_gram<<<dim3(b, (unsigned)np), MF_THREADS, 0, st>>>(a, R, H, G);
+            mf_symmetrize<<<(unsigned)np, b * b, 0, st>>>(a, G);
+            g_launches.fetch_add(4, std::memory_order_relaxed);
+            int rc = run_small(pl, Pg, nullptr, G, nullptr, np, b, b, 1, 0, nores, theta, S, nullptr, info_s1, st);
+            if (rc) return rc;
+            cplx *dst = (R == X) ? Y : X;
+            mf_rotate<<<dim3(rowblocks, (unsigned)np), MF_THREADS, 0, st>>>(a, R, H, S, dst, Hn);
+            cudaMemsetAsync(n_active, 0, 4, st);
+            mf_converge<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(a, tol, info_c);
+            g_launches.fetch_add(2, std::memory_order_relaxed);
+            // after rotation the Ritz vectors live in dst; make X point at them
+            if (dst != X) { Y = X; X = dst; }
+            cplx *t = H; H = Hn; Hn = t;
+            return 0;
+        };
+        int rc = rayleigh_ritz(X);
+        if (rc) return rc;
+        CK(cudaGetLastError());
+        for (int it = 0; it < maxit; ++it) {
+            int h_active = 0;
+            CK(cudaMemcpyAsync(&h_active, n_active, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (h_active == 0) break;
+            cplx *R;
+            if (smem_filter) {
+                mf_cheb_smem<<<dim3(b, (unsigned)np), 512, (size_t)2 * n * 16, st>>>(a, X, Y, deg);
+                LAUNCHED();
+                R = Y;
+            } else {
+                // Y_0 = X, Y_1 -> Y, then alternate in place
+                mf_cheb_step<<<dim3(rowblocks, b, (unsigned)np), MF_THREADS, 0, st>>>(a, X, Y, 1);
+                cplx *cur = Y, *prev = X;
+                for (int m = 2; m <= deg; ++m) {
+                    mf_cheb_step<<<dim3(rowblocks, b, (unsigned)np), MF_THREADS, 0, st>>>(a, cur, prev, m);
+                    cplx *t = cur; cur = prev; prev = t;
+                }
+                g_launches.fetch_add(deg, std::memory_order_relaxed);
+                R = cur;
+            }
+            // make the filtered block the "X" buffer for the Rayleigh-Ritz bookkeeping
+            if (R != X) { cplx *t = X; X = R; Y = t; }
+            rc = rayleigh_ritz(X);
+            if (rc) return rc;
+            CK(cudaGetLastError());
+        }
+        unsigned ob = (unsigned)(((size_t)n * k + 255) / 256);
+        mf_output<<<dim3(ob, (unsigned)np), 256, 0, st>>>(a, X, evals + (size_t)p0 * k,
+                                                        (want_vec && evecs) ? evecs + (size_t)p0 * k * n : nullptr);
+        LAUNCHED();
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
 extern "C" int scqed_eigh_batched(int device, double *H_dev, int32_t n, int64_t batch, int32_t k, double *evals_dev,
                                   double *evecs_dev, int32_t *info_dev, int32_t solver, void *stream) {
     if (!H_dev || !evals_dev || !info_dev || n < 1 || batch < 1 || k < 1 || k > n) return fail(SCQED_EINVAL, "bad argument");
@@ -517,7 +707,7 @@ extern "C" int scqed_eigh_batched(int device, double *H_dev, int32_t n, int64_t 
 static int check_opts(const scqed_plan *pl, const scqed_sweep_opts *o) {
     if (!o) return fail(SCQED_EINVAL, "opts is NULL");
     if (o->k < 1 || o->k > pl->P.n) return fail(SCQED_EINVAL, "k=%d outside 1..n=%d", o->k, pl->P.n);
-    if (o->solver < 0 || o->solver > 3) return fail(SCQED_EINVAL, "solver=%d", o->solver);
+    if (o->solver < 0 || o->solver > 4) return fail(SCQED_EINVAL, "solver=%d", o->solver);
     if (o->resonator) {
         if (!o->want_vectors) return fail(SCQED_EINVAL, "the Resonator evaluable needs eigenvectors (get_vectors=True)");
         if (o->k > SCQED_RES_KMAX || o->k < 2) return fail(SCQED_EUNSUPPORTED, "resonator strips support 2 <= k <= %d", SCQED_RES_KMAX);
@@ -565,12 +755,19 @@ extern "C" int scqed_sweep_run(scqed_plan *pl, const scqed_sweep_opts *o, const 
     bool fits = small_fits(pl, n, k, o->want_vectors, P.n_terms, nullptr);
     int solver = o->solver;
     if (solver == 1 && !fits) return fail(SCQED_EUNSUPPORTED, "n=%d k=%d does not fit the fused shared-memory path", n, k);
-    if (solver == 0) solver = fits ? 1 : 2;
+    if (solver == 0) {
+        if (fits) solver = 1;
+        else if (!o->resonator && P.max_term_nn <= 3 && o->k + 6 <= MF_BMAX && (n > 4096 || pl->mf_work_per_row <= n / 2)) solver = 4;
+        else solver = 2;
+    }
     if (solver == 1) {
         return run_small(pl, P, (const cplx *)pl->coef.p, nullptr, scal, n_pts, n, k, o->want_vectors, o->tidyup, res,
                          evals_dev, (cplx *)evecs_dev, post_dev, info_dev, st);
     }
     if (o->resonator) return fail(SCQED_EUNSUPPORTED, "the Resonator evaluable is only implemented on the fused path (n <= ~110)");
+    if (solver == 4)
+        return run_matfree(pl, (const cplx *)pl->coef.p, n_pts, k, o->want_vectors, evals_dev, (cplx *)evecs_dev, info_dev, st,
+                           60, 60, 1e-10);
     // ---- S2: batches of B matrices through HBM ------------------------------------------------
     const bool blocked = solver != 3;
     int B = pick_dense_batch(n, n_pts, k, pl->sm_count);

@@ -178,6 +178,37 @@ def test_sweep_eigenvectors_match_reference(engine_mod, name):
         assert residual_norms(H, res.E[j], X).max() < 1e-11 * scale
 
 
+MATFREE_CASES = [
+    ("c3_csfq4jj_t10", 33), ("c3_csfqfloat_t5", 15), ("c5_fluxatom_t31", 8), ("c3_csfq4jj_t27s", 4),
+    ("c3_csfqfloat_t7", 6), ("c3_csfqfloat_t10", 4), ("c2_fluxonium_t200s", 9),
+]
+
+
+@pytest.mark.parametrize("name,cap", MATFREE_CASES)
+def test_matrix_free_solver_matches_reference(engine_mod, name, cap):
+    """S3 (Chebyshev-filtered subspace iteration on the Kronecker mat-vec) against the reference's
+    eigenvalues; n = 9261 uses the global-memory filter, the others the shared-memory one."""
+    g, plan = load_golden(name)
+    k = int(g["k"])
+    idx = _sample(len(g["E"]), cap)
+    with engine_mod.Engine(plan) as eng:
+        res = eng.sweep(g["params"][idx], k, want_vectors=True, solver=engine_mod.SOLVER_MATFREE)
+    assert not res.info.any()
+    assert eig_rel_err(res.E, g["E"][idx]) < E_RTOL
+    orc = PlanOracle(plan)
+    coef, _ = eval_program(plan.program, g["params"][idx])
+    for j in range(min(len(idx), 3)):
+        X = res.V[j].T
+        assert np.max(np.abs(X.conj().T @ X - np.eye(k))) < 1e-9
+        H = orc.hamiltonian(coef[j])
+        assert residual_norms(H, res.E[j], X).max() < 1e-8 * abs(H).max()
+    if "V" in g:
+        pts = [int(np.nonzero(idx == p)[0][0]) for p in g["vec_points"] if p in idx]
+        for jj, p in zip(pts, [p for p in g["vec_points"] if p in idx]):
+            vi = list(g["vec_points"]).index(p)
+            assert subspace_overlap(res.V[jj].T, g["V"][vi], g["E"][p]) >= OVERLAP
+
+
 def test_sweep_resonator_matches_reference(engine_mod):
     g, plan = load_golden("c2_fluxonium_res")
     k = int(g["k"])

@@ -76,3 +76,22 @@ def one(name, k, vec, npts, solver=0):
 if __name__ == "__main__" and "one" in sys.argv:
     i = sys.argv.index("one")
     one(sys.argv[i + 1], int(sys.argv[i + 2]), bool(int(sys.argv[i + 3])), int(sys.argv[i + 4]))
+
+def mf():
+    for name, npts in [("c3_csfq4jj_t10", 1024), ("c3_csfqfloat_t5", 1024), ("c3_csfqfloat_t7_full", 1024), ("c3_csfq4jj_t27", 1024),
+                       ("c3_csfqfloat_t10_full", 256), ("c3_csfq4jj_t50", 256), ("c5_fluxatom_t31_64", 64), ("c5_fluxatom_t180", 8)]:
+        plan = SweepPlan.load(os.path.join(G, name + ".plan.json"))
+        grid = plan.sweep_grid()
+        reps = int(np.ceil(npts / len(grid)))
+        grid = np.tile(grid, (reps, 1))[:npts]
+        with engine.Engine(plan) as eng:
+            p = torch.as_tensor(grid, device="cuda")
+            l0 = engine.launch_count()
+            ms = timeit(lambda: eng.sweep_device(p, 10, want_vectors=True, solver=4), reps=1)
+            l1 = engine.launch_count()
+            E, V, sc, post, info = eng.sweep_device(p, 10, want_vectors=True, solver=4)
+            print("%-24s n=%-6d pts=%-5d matfree %.1f ms (%.1f pts/s) launches/run %d bad=%d" % (
+                name, plan.hilbert_dim, npts, ms, npts / ms * 1e3, (l1 - l0) // 2, int((info != 0).sum().item())), flush=True)
+
+if __name__ == "__main__" and "mf" in sys.argv:
+    mf()
