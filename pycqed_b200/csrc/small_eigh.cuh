@@ -64,6 +64,205 @@ __device__ __forceinline__ cplx block_sum(cplx v, double *red) {
     return warp_sum(s);
 }
 
+// ---- scalar helpers shared by the complex-Hermitian and the real-symmetric code paths --------------
+__device__ __forceinline__ double nzero(double) { return 0.0; }
+__device__ __forceinline__ cplx nzero(cplx) { return cmake(0.0, 0.0); }
+__device__ __forceinline__ double none(double) { return 1.0; }
+__device__ __forceinline__ cplx none(cplx) { return cmake(1.0, 0.0); }
+__device__ __forceinline__ double nconj(double a) { return a; }
+__device__ __forceinline__ cplx nconj(cplx a) { return cconj(a); }
+__device__ __forceinline__ double nmul(double a, double b) { return a * b; }
+__device__ __forceinline__ cplx nmul(cplx a, cplx b) { return cmul(a, b); }
+__device__ __forceinline__ double nadd(double a, double b) { return a + b; }
+__device__ __forceinline__ cplx nadd(cplx a, cplx b) { return cadd(a, b); }
+__device__ __forceinline__ double nsub(double a, double b) { return a - b; }
+__device__ __forceinline__ cplx nsub(cplx a, cplx b) { return csub(a, b); }
+__device__ __forceinline__ double nscale(double s, double a) { return s * a; }
+__device__ __forceinline__ cplx nscale(double s, cplx a) { return cscale(s, a); }
+__device__ __forceinline__ void nfma(double &acc, double a, double b) { acc = fma(a, b, acc); }
+__device__ __forceinline__ void nfma(cplx &acc, cplx a, cplx b) { cfma(acc, a, b); }
+__device__ __forceinline__ void nfmac(double &acc, double a, double b) { acc = fma(a, b, acc); }     // += conj(a) b
+__device__ __forceinline__ void nfmac(cplx &acc, cplx a, cplx b) { cfmac(acc, a, b); }
+__device__ __forceinline__ void nfnmac(double &acc, double a, double b) { acc = fma(-a, b, acc); }   // -= a conj(b)
+__device__ __forceinline__ void nfnmac(cplx &acc, cplx a, cplx b) { cfnmac(acc, a, b); }
+__device__ __forceinline__ double nabs2(double a) { return a * a; }
+__device__ __forceinline__ double nabs2(cplx a) { return cabs2(a); }
+__device__ __forceinline__ double nre(double a) { return a; }
+__device__ __forceinline__ double nre(cplx a) { return a.x; }
+__device__ __forceinline__ bool niszero(double a) { return a == 0.0; }
+__device__ __forceinline__ bool niszero(cplx a) { return a.x == 0.0 && a.y == 0.0; }
+__device__ __forceinline__ double nshfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ cplx nshfl(cplx v, int src) {
+    return cmake(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+// zlarfg / dlarfg: reflector scalars from alpha and the squared norm of the tail
+__device__ __forceinline__ void reflector_scalars(double alpha, double xn, double &tau, double &beta, double &sc) {
+    if (xn == 0.0) { tau = 0.0; beta = alpha; sc = 0.0; return; }
+    beta = -copysign(sqrt(alpha * alpha + xn), alpha);
+    tau = (beta - alpha) / beta;
+    sc = 1.0 / (alpha - beta);
+}
+__device__ __forceinline__ void reflector_scalars(cplx alpha, double xn, cplx &tau, double &beta, cplx &sc) {
+    if (xn == 0.0 && alpha.y == 0.0) { tau = cmake(0.0, 0.0); beta = alpha.x; sc = cmake(0.0, 0.0); return; }
+    beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xn), alpha.x);
+    tau = cmake((beta - alpha.x) / beta, -alpha.y / beta);
+    cplx den = cmake(alpha.x - beta, alpha.y);
+    double dn = 1.0 / cabs2(den);
+    sc = cmake(den.x * dn, -den.y * dn);
+}
+
+#define SMALL_RQ 4      // rows per lane of the serial warp: n <= 32 * SMALL_RQ
+
+// Warp 0: turn column `col` (col[0] = diagonal, col[1] = alpha, col[2..m) = tail) -- after
+// subtracting the pending rank-2 update  vc[r] conj(w0) + wq[r] conj(vc[0]=1)  when `upd` -- into the
+// next reflector.  Writes vnext[0..m-1) (vnext[0] = 1), keeps it in col[1..m), and d/e/tau of column jn.
+template <typename T>
+__device__ __forceinline__ void warp_next_reflector(T *col, int m, bool upd, const T *vc, T w0, const T *wq,
+                                                    T *vnext, double *dv, double *ev, T *tau, int jn) {
+    const int l = threadIdx.x & 31;
+    T c[SMALL_RQ];
+    double xn = 0.0;
+#pragma unroll
+    for (int q = 0; q < SMALL_RQ; ++q) {
+        int r = l + 32 * q;
+        c[q] = nzero(T());
+        if (r < m) {
+            T x = col[r];
+            if (upd) { nfnmac(x, vc[r], w0); x = nsub(x, wq[q]); }
+            c[q] = x;
+            if (r >= 2) xn += nabs2(x);
+        }
+    }
+    xn = warp_sum(xn);
+    const T diag = nshfl(c[0], 0);
+    if (m < 2) {                                   // 1 x 1 trailing block: only the diagonal is left
+        if (l == 0) { dv[jn] = nre(diag); ev[jn] = 0.0; }
+        return;
+    }
+    const T alpha = nshfl(c[0], 1);
+    T tj, sc;
+    double beta;
+    reflector_scalars(alpha, xn, tj, beta, sc);
+    const bool zero = niszero(tj);
+#pragma unroll
+    for (int q = 0; q < SMALL_RQ; ++q) {
+        int r = l + 32 * q;
+        if (r >= 1 && r < m) {
+            T v = r == 1 ? none(T()) : (zero ? nzero(T()) : nmul(c[q], sc));
+            vnext[r - 1] = v;
+            col[r] = v;                            // reflector kept for the back-transformation
+        }
+    }
+    if (l == 0) { col[0] = diag; dv[jn] = nre(diag); ev[jn] = beta; tau[jn] = tj; }
+}
+
+// Householder tridiagonalisation of the full-storage column-major matrix A (n <= 128), LAPACK
+// z/d-hetd2 'L' arithmetic, restructured so that one pass over the trailing block applies the
+// PENDING rank-2 update of step j-1 and accumulates A v_j of step j, and the O(m) work between
+// passes runs on one warp: two block barriers per column instead of nine.
+template <typename T>
+__device__ void small_tridiag(T *A, int n, double *dv, double *ev, T *tau, T *vbuf, T *wbuf, T *part) {
+    const int tid = threadIdx.x, NT = blockDim.x, l = tid & 31;
+    T *vcur = vbuf, *vprev = vbuf + n, *wprev = wbuf, *wcur = wbuf + n;
+    if (tid < 32) warp_next_reflector<T>(A, n, false, vcur, nzero(T()), nullptr, vcur, dv, ev, tau, 0);
+    __syncthreads();
+    for (int j = 0; j < n - 1; ++j) {
+        const int m = n - j - 1;
+        T *A22 = A + (size_t)(j + 1) * (n + 1);
+        int S = NT / m; if (S > SMALL_SMAX) S = SMALL_SMAX; if (S < 1) S = 1;
+        const int seg = (m + S - 1) / S;
+        const int s = tid / m, r = tid - s * m;
+        if (s < S) {
+            const int c0 = s * seg, c1 = min(m, c0 + seg);
+            T acc = nzero(T());
+            if (j > 0) {
+                const T vr = vprev[r + 1], wr = wprev[r + 1];
+                for (int c = c0; c < c1; ++c) {
+                    T x = A22[r + (size_t)c * n];
+                    nfnmac(x, vr, wprev[c + 1]);
+                    nfnmac(x, wr, vprev[c + 1]);
+                    A22[r + (size_t)c * n] = x;
+                    nfma(acc, x, vcur[c]);
+                }
+            } else {
+                for (int c = c0; c < c1; ++c) nfma(acc, A22[r + (size_t)c * n], vcur[c]);
+            }
+            part[s * m + r] = acc;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const T tj = tau[j];
+            T pr[SMALL_RQ], wq[SMALL_RQ];
+            T dot = nzero(T());
+#pragma unroll
+            for (int q = 0; q < SMALL_RQ; ++q) {
+                int rr = l + 32 * q;
+                pr[q] = nzero(T());
+                if (rr < m) {
+                    T sum = nzero(T());
+                    for (int u = 0; u < S; ++u) sum = nadd(sum, part[u * m + rr]);
+                    pr[q] = nmul(tj, sum);
+                    nfmac(dot, pr[q], vcur[rr]);                 // p^H v
+                }
+            }
+            dot = warp_sum(dot);
+            const T a2 = nmul(nscale(-0.5, tj), dot);            // -1/2 tau (p^H v)
+#pragma unroll
+            for (int q = 0; q < SMALL_RQ; ++q) {
+                int rr = l + 32 * q;
+                wq[q] = nzero(T());
+                if (rr < m) { wq[q] = nadd(pr[q], nmul(a2, vcur[rr])); wcur[rr] = wq[q]; }
+            }
+            const T w0 = nshfl(wq[0], 0);
+            // column j+1 with this step's update applied -> reflector j+1 (or the last diagonal)
+            warp_next_reflector<T>(A22, m, true, vcur, w0, wq, vprev /* becomes vcur */, dv, ev, tau, j + 1);
+        }
+        __syncthreads();
+        T *t = vcur; vcur = vprev; vprev = t;
+        t = wcur; wcur = wprev; wprev = t;
+    }
+}
+
+// x = H(0) H(1) ... H(n-2) z for k vectors; one warp per vector, no block barriers.
+// X is complex [k][n]; the real-symmetric path only touches the real parts.
+template <typename T>
+__device__ void small_backtransform(const T *A, int n, const T *tau, cplx *X, int k) {
+    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31, nw = blockDim.x >> 5;
+    for (int jv = w; jv < k; jv += nw) {
+        cplx *x = X + (size_t)jv * n;
+        for (int j = n - 2; j >= 0; --j) {
+            const T tj = tau[j];
+            if (niszero(tj)) continue;
+            const int m = n - j - 1;
+            const T *v = A + (j + 1) + (size_t)j * n;
+            cplx *xs = x + j + 1;
+            if constexpr (sizeof(T) == sizeof(double)) {
+                const double *vd = (const double *)v;
+                const double td = nre(tj);
+                double dot = 0.0;
+                for (int r = l; r < m; r += 32) dot = fma(r == 0 ? 1.0 : vd[r], xs[r].x, dot);
+                dot = warp_sum(dot) * td;
+                for (int r = l; r < m; r += 32) xs[r].x = fma(-dot, r == 0 ? 1.0 : vd[r], xs[r].x);
+            } else {
+                const cplx *vc = (const cplx *)v;
+                const cplx tc = *(const cplx *)&tj;
+                cplx dot = cmake(0.0, 0.0);
+                for (int r = l; r < m; r += 32) cfmac(dot, r == 0 ? cmake(1.0, 0.0) : vc[r], xs[r]);   // v^H x
+                dot = warp_sum(dot);
+                cplx f = cmul(tc, dot);
+                for (int r = l; r < m; r += 32) {
+                    cplx t = xs[r], vr = r == 0 ? cmake(1.0, 0.0) : vc[r];
+                    t.x -= f.x * vr.x - f.y * vr.y;
+                    t.y -= f.x * vr.y + f.y * vr.x;
+                    xs[r] = t;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(SMALL_THREADS, 1)
 small_eigh_kernel(SmallArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -107,78 +306,25 @@ small_eigh_kernel(SmallArgs a) {
         }
         __syncthreads();
 
-        // ---- Householder tridiagonalisation (LAPACK zhetd2, UPLO='L') ---------------------------
-        for (int j = 0; j < n - 1; ++j) {
-            const int m = n - j - 1;                        // trailing dimension; rows j+1 .. n-1
-            cplx *col = A + (j + 1) + (size_t)j * n;        // x = A[j+1:n, j]
-            double xn = 0.0;
-            for (int r = 1 + tid; r < m; r += T) xn += cabs2(col[r]);
-            xn = block_sum(xn, red);
-            cplx alpha = col[0];
-            cplx tj;
-            double beta;
-            if (xn == 0.0 && alpha.y == 0.0) {
-                tj = cmake(0.0, 0.0);
-                beta = alpha.x;
-            } else {
-                beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xn), alpha.x);
-                tj = cmake((beta - alpha.x) / beta, -alpha.y / beta);
+        // ---- real-symmetric fast path: H(p) exactly real (after the reference's 1e-12 tidy-up the
+        // single-phase oscillator Hamiltonians are) -> compact to doubles, 4x fewer flops ------------
+        int has_imag = 0;
+        for (int idx = tid; idx < n * n; idx += T) has_imag |= (A[idx].y != 0.0);
+        const bool is_real = !__syncthreads_or(has_imag);
+        if (is_real) {
+            double *Ar = (double *)A;
+            for (int base = 0; base < n * n; base += T) {       // in-place compaction, ascending chunks
+                int idx = base + tid;
+                double x = idx < n * n ? A[idx].x : 0.0;
+                __syncthreads();
+                if (idx < n * n) Ar[idx] = x;
+                __syncthreads();
             }
-            // v = x / (alpha - beta), v[0] = 1
-            cplx den = cmake(alpha.x - beta, alpha.y);
-            double dn = 1.0 / cabs2(den);
-            cplx sc = cmake(den.x * dn, -den.y * dn);
-            __syncthreads();                                // everyone has read col[0]
-            for (int r = tid; r < m; r += T) {
-                cplx v = r == 0 ? cmake(1.0, 0.0) : ((tj.x == 0.0 && tj.y == 0.0) ? cmake(0.0, 0.0) : cmul(col[r], sc));
-                vv[r] = v;
-                col[r] = v;                                 // keep the reflector for the back-transform
-            }
-            if (tid == 0) {
-                dv[j] = A[j + (size_t)j * n].x;
-                ev[j] = beta;
-                tau[j] = tj;
-            }
-            __syncthreads();
-            if (tj.x == 0.0 && tj.y == 0.0) continue;
-
-            // p = tau * A22 v : thread (r, s) sums a column segment of row r
-            cplx *A22 = A + (j + 1) + (size_t)(j + 1) * n;
-            int S = T / m; if (S > SMALL_SMAX) S = SMALL_SMAX; if (S < 1) S = 1;
-            const int seg = (m + S - 1) / S;
-            const int r = tid % m, s = tid / m;
-            if (s < S) {
-                int c0 = s * seg, c1 = min(m, c0 + seg);
-                cplx acc = cmake(0.0, 0.0);
-                for (int c = c0; c < c1; ++c) cfma(acc, A22[r + (size_t)c * n], vv[c]);
-                part[s * m + r] = acc;
-            }
-            __syncthreads();
-            cplx pr = cmake(0.0, 0.0), dot = cmake(0.0, 0.0);
-            if (tid < m) {
-                for (int q = 0; q < S; ++q) pr = cadd(pr, part[q * m + tid]);
-                pr = cmul(tj, pr);
-                cfmac(dot, pr, vv[tid]);                   // p^H v
-            }
-            dot = block_sum(dot, red);
-            // alpha2 = -1/2 tau (p^H v);  w = p + alpha2 v
-            cplx a2 = cmul(cmake(-0.5 * tj.x, -0.5 * tj.y), dot);
-            if (tid < m) ww[tid] = cadd(pr, cmul(a2, vv[tid]));
-            __syncthreads();
-            // A22 -= v w^H + w v^H
-            if (s < S) {
-                int c0 = s * seg, c1 = min(m, c0 + seg);
-                cplx vr = vv[r], wr = ww[r];
-                for (int c = c0; c < c1; ++c) {
-                    cplx x = A22[r + (size_t)c * n];
-                    cfnmac(x, vr, ww[c]);
-                    cfnmac(x, wr, vv[c]);
-                    A22[r + (size_t)c * n] = x;
-                }
-            }
-            __syncthreads();
+            small_tridiag<double>(Ar, n, dv, ev, (double *)tau, (double *)vv, (double *)ww, (double *)part);
+        } else {
+            small_tridiag<cplx>(A, n, dv, ev, tau, vv, ww, part);
         }
-        if (tid == 0) { dv[n - 1] = A[(n - 1) + (size_t)(n - 1) * n].x; ev[n - 1] = 0.0; }
+        if (tid == 0) ev[n - 1] = 0.0;
         __syncthreads();
         for (int i = tid; i < n; i += T) e2[i] = ev[i] * ev[i];
         __syncthreads();
@@ -195,30 +341,8 @@ small_eigh_kernel(SmallArgs a) {
             __syncthreads();
             bad |= tridiag_inverse_iteration(dv, ev, n, k, lam, bounds[3], (double *)X, 2 * n, 2, lu, L.vb,
                                              (unsigned long long)p + 1ULL);
-            // Q = H(0) H(1) ... H(n-2): apply H(n-2) first.  One warp per vector, no block syncs.
-            const int w = tid >> 5, l = tid & 31, nw = T >> 5;
-            for (int jv = w; jv < k; jv += nw) {
-                cplx *x = X + (size_t)jv * n;
-                for (int j = n - 2; j >= 0; --j) {
-                    cplx tj = tau[j];
-                    if (tj.x == 0.0 && tj.y == 0.0) continue;
-                    const int m = n - j - 1;
-                    const cplx *v = A + (j + 1) + (size_t)j * n;
-                    cplx *xs = x + j + 1;
-                    cplx dot = cmake(0.0, 0.0);
-                    for (int r = l; r < m; r += 32) cfmac(dot, v[r], xs[r]);   // v^H x
-                    dot = warp_sum(dot);
-                    cplx f = cmul(tj, dot);
-                    for (int r = l; r < m; r += 32) {
-                        cplx t = xs[r];
-                        cplx vr = v[r];
-                        t.x -= f.x * vr.x - f.y * vr.y;
-                        t.y -= f.x * vr.y + f.y * vr.x;
-                        xs[r] = t;
-                    }
-                    __syncwarp();
-                }
-            }
+            if (is_real) small_backtransform<double>((const double *)A, n, (const double *)tau, X, k);
+            else small_backtransform<cplx>(A, n, tau, X, k);
             __syncthreads();
             if (a.evecs) {
                 cplx *out = a.evecs + (size_t)p * k * n;
@@ -247,8 +371,8 @@ static inline SmallLayout small_smem_layout(int n, int k, int want_vec, int n_te
     L.off_e = take((size_t)n * 8);
     L.off_e2 = take((size_t)n * 8);
     L.off_tau = take((size_t)n * 16);
-    L.off_v = take((size_t)n * 16);
-    L.off_w = take((size_t)n * 16);
+    L.off_v = take((size_t)2 * n * 16);      // current + previous reflector
+    L.off_w = take((size_t)2 * n * 16);
     size_t part = (size_t)SMALL_THREADS;
     if (part < (size_t)n_terms) part = n_terms;
     L.off_part = take(part * 16);
