@@ -66,7 +66,8 @@ typedef struct {
     int32_t want_vectors;     /* get_vectors                                                 */
     int32_t solver;           /* 0 auto, 1 fused small (H in smem), 2 dense blocked (HBM, DMMA),
                                  3 dense unblocked (HBM, reference implementation),
-                                 4 matrix-free Chebyshev-filtered subspace iteration        */
+                                 4 matrix-free Chebyshev-filtered subspace iteration,
+                                 5 small path as ONE fused kernel (1 = phase pipeline)       */
     int32_t tidyup;           /* 1: threshold H entries at 1e-12 like Qobj.tidyup (:594)     */
     /* Resonator evaluable (numerical_system.py:736-784 getResonatorResponse); needs vectors */
     int32_t resonator;        /* 0/1                                                         */

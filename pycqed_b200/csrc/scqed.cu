@@ -17,6 +17,7 @@
 #include "tridiag_eig.cuh"
 #include "resonator.cuh"
 #include "small_eigh.cuh"
+#include "small_split.cuh"
 #include "dense_eigh.cuh"
 #include "dense_blocked.cuh"
 #include "matfree.cuh"
@@ -75,6 +76,8 @@ struct scqed_plan {
     PlanDev P;
     int n_coef_scalar = 0;
     long long mf_work_per_row = 0;     // complex MACs per output element of the matrix-free mat-vec
+    int s1_real_mode = -1;             // fused small path: -1 unknown, 0 complex Hermitian, 1 real symmetric
+    DevBuf s1work, s1vec;
     std::vector<int> factor_node;
     // device copies of the tables
     DevBuf tables;
@@ -252,7 +255,7 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
 extern "C" void scqed_plan_destroy(scqed_plan *pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
-    DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->in_params, &pl->out_evals,
+    DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->s1work, &pl->s1vec, &pl->in_params, &pl->out_evals,
                       &pl->out_evecs, &pl->out_post, &pl->out_info, &pl->out_scal};
     for (DevBuf *b : bufs) b->release();
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
@@ -343,6 +346,126 @@ static int run_small(scqed_plan *pl, const PlanDev &P, const cplx *coef, const c
     LAUNCHED();
     CK(cudaGetLastError());
     return 0;
+}
+
+// ---- S1 as a phase pipeline (small_split.cuh) ------------------------------------------------------------
+static bool split_fits(const scqed_plan *pl, int n, int k, int n_terms) {
+    if (n > 32 * SMALL_RQ || k > 32 || n < 2) return false;
+    return S1Smem<cplx>::bytes(n, n_terms, 512) <= pl->smem_optin;
+}
+
+template <typename T>
+static int s1_launch_tridiag(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t st) {
+    const int threads = sizeof(T) == sizeof(double) ? 256 : 512;
+    const size_t smem = S1Smem<T>::bytes(a.n, n_terms, threads);
+    CK(cudaFuncSetAttribute(s1_tridiag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s1_tridiag_kernel<T>, threads, smem));
+    if (occ < 1) return fail(SCQED_EUNSUPPORTED, "small tridiagonalisation kernel does not fit (n=%d)", a.n);
+    long long grid = (long long)occ * pl->sm_count;
+    if (grid > a.n_pts) grid = a.n_pts;
+    s1_tridiag_kernel<T><<<(unsigned)grid, threads, smem, st>>>(a);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, const cplx *Hin, const double *scal,
+                           long long n_pts, int n, int k, int want_vec, int tidyup, const ResonatorArgs &res,
+                           double *evals, cplx *evecs, double *post, int *info, cudaStream_t st) {
+    const bool need_vec = want_vec || res.enabled;
+    long long chunk = n_pts < 16384 ? n_pts : 16384;
+    // a plan whose realness is unknown is probed on a small first chunk
+    long long first = (pl->s1_real_mode < 0 && !Hin) ? (long long)2 * pl->sm_count : chunk;
+    if (first > chunk) first = chunk;
+    const long long G = chunk * k;
+    size_t bytes = 0;
+    auto need = [&](size_t b) { size_t r = bytes; bytes += (b + 255) & ~(size_t)255; return r; };
+    size_t o_dd = need((size_t)chunk * n * 8), o_ee = need((size_t)chunk * n * 8), o_e2 = need((size_t)chunk * n * 8);
+    size_t o_bnd = need((size_t)chunk * 4 * 8), o_tau = need((size_t)chunk * n * 16), o_lam = need((size_t)chunk * k * 8);
+    size_t o_flags = need((size_t)chunk * 4), o_cnt = need(256);
+    size_t o_V = 0, o_lu = 0, o_swp = 0, o_zw = 0;
+    if (need_vec) {
+        o_V = need((size_t)chunk * n * n * 16);
+        o_lu = need((size_t)4 * n * G * 8);
+        o_swp = need((size_t)n * G);
+        o_zw = need((size_t)n * G * 8);
+    }
+    if (pl->s1work.ensure(bytes)) return fail(SCQED_ENOMEM, "small-path workspace (%zu MB)", bytes >> 20);
+    unsigned char *base = (unsigned char *)pl->s1work.p;
+    cplx *vec_tmp = nullptr;
+    if (need_vec && !evecs) {
+        if (pl->s1vec.ensure((size_t)chunk * k * n * 16)) return fail(SCQED_ENOMEM, "small-path eigenvector staging");
+        vec_tmp = (cplx *)pl->s1vec.p;
+    }
+    S1Args a;
+    memset(&a, 0, sizeof(a));
+    a.P = P; a.n = n; a.k = k; a.tidyup = tidyup; a.want_vec = need_vec;
+    a.W.dd = (double *)(base + o_dd); a.W.ee = (double *)(base + o_ee); a.W.e2 = (double *)(base + o_e2);
+    a.W.bnd = (double *)(base + o_bnd); a.W.tau = (cplx *)(base + o_tau); a.W.lam = (double *)(base + o_lam);
+    a.W.flags = (int *)(base + o_flags);
+    (void)o_cnt;
+    if (need_vec) {
+        a.W.Vst = base + o_V; a.W.lu = (double *)(base + o_lu); a.W.swp = base + o_swp; a.W.zw = (double *)(base + o_zw);
+    }
+    for (long long p0 = 0; p0 < n_pts;) {
+        const long long np = (p0 == 0 ? first : chunk) < n_pts - p0 ? (p0 == 0 ? first : chunk) : n_pts - p0;
+        a.n_pts = np;
+        a.coef = coef ? coef + (size_t)p0 * P.n_terms : nullptr;
+        a.Hin = Hin ? Hin + (size_t)p0 * n * n : nullptr;
+        a.info = info + p0;
+        const long long Gc = np * k;
+        CK(cudaMemsetAsync(a.info, 0, (size_t)np * 4, st));
+        bool real_mode = false;
+        if (pl->s1_real_mode != 0) {
+            int rc = s1_launch_tridiag<double>(pl, a, P.n_terms, st);
+            if (rc) return rc;
+            int h_cnt = 0;
+            std::vector<int> hflags((size_t)np);
+            CK(cudaMemcpyAsync(hflags.data(), a.W.flags, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (long long q = 0; q < np; ++q) h_cnt += hflags[(size_t)q] != 0;
+            real_mode = (h_cnt == 0);
+            if (!Hin) pl->s1_real_mode = real_mode ? 1 : 0;
+        }
+        if (!real_mode) {
+            int rc = s1_launch_tridiag<cplx>(pl, a, P.n_terms, st);
+            if (rc) return rc;
+        }
+        const long long warps = np * k;
+        s1_bisect_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(a, nullptr, evals + (size_t)p0 * k);
+        LAUNCHED();
+        if (need_vec) {
+            const int ppw = 32 / k;
+            const long long iw = (np + ppw - 1) / ppw;
+            s1_invit_kernel<<<(unsigned)((iw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, Gc);
+            cplx *vout = evecs ? evecs + (size_t)p0 * k * n : vec_tmp;
+            if (real_mode) {
+                const long long bw = np * ((k + 7) / 8);
+                s1_backtr_kernel<double, 8><<<(unsigned)((bw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, Gc, vout);
+            } else {
+                const long long bw = np * ((k + 3) / 4);
+                s1_backtr_kernel<cplx, 4><<<(unsigned)((bw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, Gc, vout);
+            }
+            g_launches.fetch_add(2, std::memory_order_relaxed);
+            if (res.enabled) {
+                s1_resonator_kernel<<<(unsigned)np, 128, 0, st>>>(a, res, nullptr, scal + (size_t)p0 * P.n_scalar, vout,
+                                                              post + (size_t)p0 * res.nstrips * k);
+                LAUNCHED();
+            }
+        }
+        CK(cudaGetLastError());
+        p0 += np;
+    }
+    return 0;
+}
+
+static int run_small_any(scqed_plan *pl, const PlanDev &P, const cplx *coef, const cplx *Hin, const double *scal,
+                         long long n_pts, int n, int k, int want_vec, int tidyup, const ResonatorArgs &res,
+                         double *evals, cplx *evecs, double *post, int *info, cudaStream_t st, bool monolithic) {
+    if (!monolithic && split_fits(pl, n, k, P.n_terms))
+        return run_small_split(pl, P, coef, Hin, scal, n_pts, n, k, want_vec, tidyup, res, evals, evecs, post, info, st);
+    return run_small(pl, P, coef, Hin, scal, n_pts, n, k, want_vec, tidyup, res, evals, evecs, post, info, st);
 }
 
 // S2 on a batch of B column-major matrices already resident in A.
@@ -601,7 +724,7 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
             mf_gram<<<dim3(b, (unsigned)np), MF_THREADS, 0, st>>>(a, R, H, G);
             mf_symmetrize<<<(unsigned)np, b * b, 0, st>>>(a, G);
             g_launches.fetch_add(4, std::memory_order_relaxed);
-            int rc = run_small(pl, Pg, nullptr, G, nullptr, np, b, b, 1, 0, nores, theta, S, nullptr, info_s1, st);
+            int rc = run_small_any(pl, Pg, nullptr, G, nullptr, np, b, b, 1, 0, nores, theta, S, nullptr, info_s1, st, false);
             if (rc) return rc;
             cplx *dst = (R == X) ? Y : X;
             mf_rotate<<<dim3(rowblocks, (unsigned)np), MF_THREADS, 0, st>>>(a, R, H, S, dst, Hn);
@@ -667,13 +790,16 @@ extern "C" int scqed_eigh_batched(int device, double *H_dev, int32_t n, int64_t 
     int want_vec = evecs_dev != nullptr;
     ResonatorArgs res;
     memset(&res, 0, sizeof(res));
-    bool fits = small_fits(&tmp, n, k, want_vec, 1, nullptr);
+    bool fits = (solver != 5 && split_fits(&tmp, n, k, 1)) || small_fits(&tmp, n, k, want_vec, 1, nullptr);
     if (solver == 1 && !fits) return fail(SCQED_EUNSUPPORTED, "n=%d k=%d does not fit the fused path", n, k);
     if (n < 2) solver = 1;
     int rc;
-    if ((solver == 0 && fits) || solver == 1) {
-        rc = run_small(&tmp, tmp.P, nullptr, (const cplx *)H_dev, nullptr, batch, n, k, want_vec, 0, res, evals_dev,
-                       (cplx *)evecs_dev, nullptr, info_dev, st);
+    if (solver == 5 && !fits) return fail(SCQED_EUNSUPPORTED, "n=%d k=%d does not fit the fused path", n, k);
+    if ((solver == 0 && fits) || solver == 1 || solver == 5) {
+        rc = run_small_any(&tmp, tmp.P, nullptr, (const cplx *)H_dev, nullptr, batch, n, k, want_vec, 0, res, evals_dev,
+                           (cplx *)evecs_dev, nullptr, info_dev, st, solver == 5);
+        if (!rc) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) rc = fail(SCQED_ECUDA, "small eigh: %s", cudaGetErrorString(e)); }
+        tmp.s1work.release(); tmp.s1vec.release();
     } else {
         long long B = batch > 32 ? 32 : batch;
         int nseg = dense_nseg(n, tmp.sm_count, (int)B);
@@ -707,7 +833,7 @@ extern "C" int scqed_eigh_batched(int device, double *H_dev, int32_t n, int64_t 
 static int check_opts(const scqed_plan *pl, const scqed_sweep_opts *o) {
     if (!o) return fail(SCQED_EINVAL, "opts is NULL");
     if (o->k < 1 || o->k > pl->P.n) return fail(SCQED_EINVAL, "k=%d outside 1..n=%d", o->k, pl->P.n);
-    if (o->solver < 0 || o->solver > 4) return fail(SCQED_EINVAL, "solver=%d", o->solver);
+    if (o->solver < 0 || o->solver > 5) return fail(SCQED_EINVAL, "solver=%d", o->solver);
     if (o->resonator) {
         if (!o->want_vectors) return fail(SCQED_EINVAL, "the Resonator evaluable needs eigenvectors (get_vectors=True)");
         if (o->k > SCQED_RES_KMAX || o->k < 2) return fail(SCQED_EUNSUPPORTED, "resonator strips support 2 <= k <= %d", SCQED_RES_KMAX);
@@ -752,17 +878,18 @@ extern "C" int scqed_sweep_run(scqed_plan *pl, const scqed_sweep_opts *o, const 
         res.op_node = pl->factor_node[o->res_op_factor];
         res.s_gc = o->res_gc; res.s_frl = o->res_frl; res.s_qb = o->res_qb;
     }
-    bool fits = small_fits(pl, n, k, o->want_vectors, P.n_terms, nullptr);
+    bool fits = (o->solver != 5 && !(o->resonator && o->k > SCQED_RES_KMAX) && split_fits(pl, n, k, P.n_terms)) ||
+                small_fits(pl, n, k, o->want_vectors, P.n_terms, nullptr);
     int solver = o->solver;
-    if (solver == 1 && !fits) return fail(SCQED_EUNSUPPORTED, "n=%d k=%d does not fit the fused shared-memory path", n, k);
+    if ((solver == 1 || solver == 5) && !fits) return fail(SCQED_EUNSUPPORTED, "n=%d k=%d does not fit the fused shared-memory path", n, k);
     if (solver == 0) {
         if (fits) solver = 1;
         else if (!o->resonator && P.max_term_nn <= 3 && o->k + 6 <= MF_BMAX && (n > 4096 || pl->mf_work_per_row <= n / 2)) solver = 4;
         else solver = 2;
     }
-    if (solver == 1) {
-        return run_small(pl, P, (const cplx *)pl->coef.p, nullptr, scal, n_pts, n, k, o->want_vectors, o->tidyup, res,
-                         evals_dev, (cplx *)evecs_dev, post_dev, info_dev, st);
+    if (solver == 1 || solver == 5) {
+        return run_small_any(pl, P, (const cplx *)pl->coef.p, nullptr, scal, n_pts, n, k, o->want_vectors, o->tidyup, res,
+                             evals_dev, (cplx *)evecs_dev, post_dev, info_dev, st, solver == 5);
     }
     if (o->resonator) return fail(SCQED_EUNSUPPORTED, "the Resonator evaluable is only implemented on the fused path (n <= ~110)");
     if (solver == 4)

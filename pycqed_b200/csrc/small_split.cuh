@@ -1,0 +1,340 @@
+// small_split.cuh -- S1 (n <= ~110) as a pipeline of phase kernels, each launched with the
+// parallelism its phase has.  H(p) still lives only in shared memory; what crosses HBM between the
+// phases is O(n) per point (d, e, tau, eigenvalues) plus the Householder reflectors when
+// eigenvectors are requested (n^2 values per point, written once, read once).
+//
+//   s1_tridiag_kernel   1 CTA per point (2 per SM on the real-symmetric path): assemble (K2) +
+//                       Householder tridiagonalisation (small_tridiag, small_eigh.cuh)
+//   s1_bisect_kernel    1 warp per (point, eigenvalue): Sturm multisection
+//   s1_invit_kernel     1 thread per (point, vector): tridiagonal inverse iteration, workspace
+//                       interleaved over threads so that every access is coalesced
+//   s1_backtr_kernel    1 warp per (point, group of 8 vectors): x = Q z, vectors held in
+//                       registers, each reflector read once per group
+//   s1_resonator_kernel 1 CTA per point: RWA strips (K7)
+//
+// The monolithic small_eigh_kernel did all of this in one CTA per point and spent most of its time
+// in phases that keep 10 threads or 10 warps of 512 threads busy (ncu: 37 % barrier stalls).
+#pragma once
+#include "common.cuh"
+#include "assemble.cuh"
+#include "tridiag_eig.cuh"
+#include "resonator.cuh"
+#include "small_eigh.cuh"
+
+namespace scqed {
+
+struct S1Ws {                 // device workspace for a chunk of P points
+    double *dd, *ee, *e2;     // [P][n]
+    double *bnd;              // [P][4]
+    cplx *tau;                // [P][n]   (real mode: doubles in the same slots)
+    void *Vst;                // [P][n*n] T   reflectors (column-major copy of A after the reduction)
+    double *lam;              // [P][k]
+    double *lu;               // [4][n][G] interleaved
+    unsigned char *swp;       // [n][G]
+    double *zw;               // [n][G]    interleaved tridiagonal eigenvectors
+    int *flags;               // [P] 1 = point is not real (real mode only)
+};
+
+struct S1Args {
+    PlanDev P;
+    const cplx *coef;
+    const cplx *Hin;
+    long long n_pts;
+    int n, k, tidyup, want_vec;
+    S1Ws W;
+    int *info;
+};
+
+// ---- phase A -----------------------------------------------------------------------------------------
+template <typename T> struct S1Smem {
+    static size_t bytes(int n, int n_terms, int nthreads) {
+        size_t o = (size_t)n * n * sizeof(T);
+        o = (o + 15) & ~(size_t)15;
+        o += (size_t)n * 8 * 2 + 16;                    // dv, ev
+        o += (size_t)n * sizeof(T) + 16;                // tau
+        o += (size_t)4 * n * sizeof(T) + 32;            // vbuf, wbuf
+        size_t part = (size_t)nthreads * sizeof(T);
+        size_t cf = (size_t)n_terms * 16;
+        o += (part > cf ? part : cf) + 16;
+        o += 96 * 8 + 4 * 8 + 64;                       // red, bounds
+        return o;
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(sizeof(T) == sizeof(double) ? 256 : 512)
+s1_tridiag_kernel(S1Args a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int n = a.n, tid = threadIdx.x, NT = blockDim.x;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { unsigned char *r = smem + o; o += (bytes + 15) & ~(size_t)15; return r; };
+    T *A = (T *)take((size_t)n * n * sizeof(T));
+    double *dv = (double *)take((size_t)n * 8);
+    double *ev = (double *)take((size_t)n * 8);
+    T *tau = (T *)take((size_t)n * sizeof(T));
+    T *vbuf = (T *)take((size_t)2 * n * sizeof(T));
+    T *wbuf = (T *)take((size_t)2 * n * sizeof(T));
+    size_t partb = (size_t)NT * sizeof(T), cfb = (size_t)a.P.n_terms * 16;
+    T *part = (T *)take(partb > cfb ? partb : cfb);
+    double *red = (double *)take(96 * 8);
+    double *bounds = (double *)take(4 * 8);
+    constexpr bool REAL = sizeof(T) == sizeof(double);
+
+    for (long long p = blockIdx.x; p < a.n_pts; p += gridDim.x) {
+        int not_real = 0;
+        if (a.Hin) {
+            const cplx *Hp = a.Hin + (size_t)p * n * n;
+            for (int idx = tid; idx < n * n; idx += NT) {
+                int i = idx / n, j = idx - i * n;              // row-major source, coalesced
+                cplx v = Hp[idx];
+                if constexpr (REAL) { not_real |= (v.y != 0.0); ((double *)A)[i + j * n] = v.x; }
+                else ((cplx *)A)[i + j * n] = v;
+            }
+        } else {
+            cplx *s_coef = (cplx *)part;
+            for (int t = tid; t < a.P.n_terms; t += NT) s_coef[t] = a.coef[p * a.P.n_terms + t];
+            __syncthreads();
+            for (int idx = tid; idx < n * n; idx += NT) {
+                int j = idx / n, i = idx - j * n;               // column-major destination
+                int id[SCQED_MAX_NODES], jd[SCQED_MAX_NODES];
+                digits(a.P, i, id);
+                digits(a.P, j, jd);
+                cplx v = h_element(a.P, s_coef, id, jd);
+                if (a.tidyup) v = tidy(v, 1e-12);
+                if constexpr (REAL) { not_real |= (v.y != 0.0); ((double *)A)[idx] = v.x; }
+                else ((cplx *)A)[idx] = v;
+            }
+        }
+        not_real = __syncthreads_or(not_real);
+        if (REAL) {
+            if (tid == 0) a.W.flags[p] = not_real;
+            if (not_real) continue;                              // host re-runs this point in complex mode
+        }
+        small_tridiag<T>(A, n, dv, ev, tau, vbuf, wbuf, part);
+        if (tid == 0) ev[n - 1] = 0.0;
+        __syncthreads();
+        tridiag_bounds(dv, ev, n, bounds, red);
+        for (int i = tid; i < n; i += NT) {
+            double e = ev[i];
+            a.W.dd[p * n + i] = dv[i];
+            a.W.ee[p * n + i] = e;
+            a.W.e2[p * n + i] = e * e;
+            ((T *)a.W.tau)[p * n + i] = tau[i];
+        }
+        if (tid < 4) a.W.bnd[p * 4 + tid] = bounds[tid];
+        if (a.want_vec) {
+            T *dst = (T *)a.W.Vst + (size_t)p * n * n;
+            for (int idx = tid; idx < n * n; idx += NT) dst[idx] = A[idx];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- phase B: one warp per (point, eigenvalue) -----------------------------------------------------------
+__global__ void __launch_bounds__(256)
+s1_bisect_kernel(S1Args a, const int *__restrict__ skip, double *__restrict__ evals) {
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int l = threadIdx.x & 31, n = a.n, k = a.k;
+    if (gw >= a.n_pts * k) return;
+    const long long p = gw / k;
+    const int j = (int)(gw - p * k);
+    if (skip && skip[p]) return;
+    const double *d = a.W.dd + p * n, *e2 = a.W.e2 + p * n, *bnd = a.W.bnd + p * 4;
+    const double gl = bnd[0], gu = bnd[1], pivmin = bnd[2];
+    const double atol = 0.0625 * SCQED_EPS * bnd[3] + 2.0 * pivmin;
+    double lo = gl, hi = gu;
+    int it = 0;
+    for (; it < 64; ++it) {
+        double width = hi - lo;
+        double tol = 2.0 * SCQED_EPS * fmax(fabs(lo), fabs(hi)) + atol;
+        if (width <= tol) break;
+        double x = lo + width * ((double)(l + 1) / 33.0);
+        int c = sturm_count(d, e2, n, x, pivmin);
+        unsigned above = __ballot_sync(0xffffffffu, c >= j + 1);
+        double nlo, nhi;
+        if (above == 0u) { nlo = __shfl_sync(0xffffffffu, x, 31); nhi = hi; }
+        else {
+            int first = __ffs(above) - 1;
+            nhi = __shfl_sync(0xffffffffu, x, first);
+            double xl = __shfl_sync(0xffffffffu, x, first > 0 ? first - 1 : 0);
+            nlo = first > 0 ? xl : lo;
+        }
+        if (!(nhi - nlo < width)) { lo = nlo; hi = nhi; break; }
+        lo = nlo; hi = nhi;
+    }
+    if (l == 0) {
+        double v = 0.5 * (lo + hi);
+        a.W.lam[p * k + j] = v;
+        evals[p * k + j] = v;
+        if (it >= 64) atomicOr(a.info + p, 1);
+    }
+}
+
+// ---- phase C: one thread per (point, vector); the k vectors of a point sit in one warp -------------------
+__global__ void __launch_bounds__(128)
+s1_invit_kernel(S1Args a, const int *__restrict__ skip, long long G) {
+    const int k = a.k, n = a.n, l = threadIdx.x & 31;
+    const int ppw = 32 / k;                                     // points per warp
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int slot = l / k, j = l - slot * k;
+    const long long p = warp * ppw + slot;
+    const bool act = slot < ppw && p < a.n_pts && !(skip && skip[p]);
+    const long long g = act ? p * k + j : 0;
+    const double *d = a.W.dd + (act ? p : 0) * n, *e = a.W.ee + (act ? p : 0) * n;
+    const double *lam = a.W.lam + (act ? p : 0) * k;
+    const double tnorm = a.W.bnd[(act ? p : 0) * 4 + 3];
+    const double eps3 = fmax(SCQED_EPS * tnorm, SCQED_SAFMIN * 1e16);
+    const double ortol = 1e-3 * tnorm;
+    TriLU W = { a.W.lu + g, a.W.lu + (size_t)n * G + g, a.W.lu + (size_t)2 * n * G + g, a.W.lu + (size_t)3 * n * G + g,
+                a.W.swp + g, (int)G };
+    double *z = a.W.zw + g;
+    const int zs = (int)G;
+    int bad = 0;
+    bool clustered = false;
+    if (act) for (int q = 1; q < k; ++q) clustered |= (fabs(lam[q] - lam[q - 1]) <= ortol);
+    double lj = act ? lam[j] : 0.0;
+    if (act && j > 0 && fabs(lj - lam[j - 1]) <= 10.0 * SCQED_EPS * fabs(lj)) lj += 10.0 * eps3 * (j & 1 ? 1.0 : 0.5);
+    const unsigned any_clustered = __ballot_sync(0xffffffffu, act && clustered);
+    const int npass = any_clustered ? 2 : 1;
+    for (int pass = 0; pass < npass; ++pass) {
+        if (act && (pass == 0 || clustered)) {
+            trilu_factor(d, e, n, lj, eps3, W);
+            if (pass == 0) {
+                unsigned long long s = ((unsigned long long)p + 1ULL) * 0x9E3779B97F4A7C15ULL + (unsigned long long)(j + 1) * 0xD1B54A32D192ED03ULL;
+                for (int i = 0; i < n; ++i) z[(size_t)i * zs] = lcg_uniform(s);
+                trilu_solve(n, W, z, zs, eps3, false);
+                double gr = normalize_serial(n, z, zs);
+                for (int it = 0; it < 2; ++it) {
+                    trilu_solve(n, W, z, zs, eps3, true);
+                    gr = normalize_serial(n, z, zs);
+                }
+                if (!(gr * eps3 * n > 1e-6)) bad = 1;
+            } else {
+                trilu_solve(n, W, z, zs, eps3, true);
+                normalize_serial(n, z, zs);
+            }
+        }
+        if (any_clustered) {
+            // modified Gram-Schmidt inside each eigenvalue cluster, sequential in j
+            for (int jj = 1; jj < k; ++jj) {
+                __syncwarp();
+                if (act && clustered && j == jj) {
+                    int start = jj;
+                    while (start > 0 && fabs(lam[start] - lam[start - 1]) <= ortol) --start;
+                    for (int q = start; q < jj; ++q) {
+                        const double *zq = a.W.zw + (p * k + q);
+                        double dot = 0.0;
+                        for (int i = 0; i < n; ++i) dot = fma(zq[(size_t)i * zs], z[(size_t)i * zs], dot);
+                        for (int i = 0; i < n; ++i) z[(size_t)i * zs] = fma(-dot, zq[(size_t)i * zs], z[(size_t)i * zs]);
+                    }
+                    if (start < jj) normalize_serial(n, z, zs);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (act && bad) atomicOr(a.info + p, 1);
+}
+
+// ---- phase D: x = Q z.  One warp per (point, group of KV vectors) ------------------------------------------
+template <typename T, int S1_KV>
+__global__ void __launch_bounds__(128)
+s1_backtr_kernel(S1Args a, const int *__restrict__ skip, long long G, cplx *__restrict__ evecs) {
+    const int n = a.n, k = a.k, l = threadIdx.x & 31;
+    const int groups = (k + S1_KV - 1) / S1_KV;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= a.n_pts * groups) return;
+    const long long p = warp / groups;
+    const int g0 = (int)(warp - p * groups) * S1_KV;
+    if (skip && skip[p]) return;
+    const int kv = min(S1_KV, k - g0);
+    T x[SMALL_RQ][S1_KV];
+#pragma unroll
+    for (int q = 0; q < SMALL_RQ; ++q) {
+        int i = l + 32 * q;
+#pragma unroll
+        for (int u = 0; u < S1_KV; ++u) {
+            double zv = (i < n && u < kv) ? a.W.zw[(size_t)i * G + (p * k + g0 + u)] : 0.0;
+            if constexpr (sizeof(T) == sizeof(double)) x[q][u] = zv; else x[q][u] = cmake(zv, 0.0);
+        }
+    }
+    const T *V = (const T *)a.W.Vst + (size_t)p * n * n;
+    const T *tau = (const T *)a.W.tau + p * n;
+    // reflector j lives in column j, rows j+1..n-1 (v[j+1] = 1 stored explicitly)
+    T vn[SMALL_RQ];
+    auto load_col = [&](int j, T *dst) {
+#pragma unroll
+        for (int q = 0; q < SMALL_RQ; ++q) {
+            int i = l + 32 * q;
+            dst[q] = (j >= 0 && i > j && i < n) ? V[(size_t)j * n + i] : nzero(T());
+        }
+    };
+    load_col(n - 2, vn);
+    for (int j = n - 2; j >= 0; --j) {
+        T v[SMALL_RQ];
+#pragma unroll
+        for (int q = 0; q < SMALL_RQ; ++q) v[q] = vn[q];
+        const T tj = tau[j];
+        load_col(j - 1, vn);                                   // prefetch the next reflector
+        if (niszero(tj)) continue;
+        T dot[S1_KV];
+#pragma unroll
+        for (int u = 0; u < S1_KV; ++u) {
+            dot[u] = nzero(T());
+#pragma unroll
+            for (int q = 0; q < SMALL_RQ; ++q) nfmac(dot[u], v[q], x[q][u]);      // v^H x
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < S1_KV; ++u) {
+                if constexpr (sizeof(T) == sizeof(double)) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
+                else {
+                    cplx *dc = (cplx *)&dot[u];
+                    dc->x += __shfl_xor_sync(0xffffffffu, dc->x, o);
+                    dc->y += __shfl_xor_sync(0xffffffffu, dc->y, o);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < S1_KV; ++u) {
+            const T f = nmul(tj, dot[u]);
+#pragma unroll
+            for (int q = 0; q < SMALL_RQ; ++q) x[q][u] = nsub(x[q][u], nmul(f, v[q]));
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < SMALL_RQ; ++q) {
+        int i = l + 32 * q;
+        if (i >= n) continue;
+#pragma unroll
+        for (int u = 0; u < S1_KV; ++u) {
+            if (u >= kv) continue;
+            cplx out;
+            if constexpr (sizeof(T) == sizeof(double)) out = cmake(x[q][u], 0.0); else out = x[q][u];
+            evecs[((size_t)p * k + g0 + u) * n + i] = out;
+        }
+    }
+}
+
+// ---- phase E: resonator strips, one CTA per point -------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+s1_resonator_kernel(S1Args a, ResonatorArgs R, const int *__restrict__ skip, const double *__restrict__ scalars,
+                    const cplx *__restrict__ evecs, double *__restrict__ post) {
+    __shared__ double scratch[8 * SCQED_RES_KMAX];
+    const long long p = blockIdx.x;
+    if (skip && skip[p]) return;
+    resonator_strips(a.P, R, scalars + p * a.P.n_scalar, a.W.lam + p * a.k, evecs + (size_t)p * a.k * a.n, a.n, a.k,
+                     scratch, post + (size_t)p * R.nstrips * a.k);
+}
+
+// complement of the flags (second, complex pass only handles the flagged points)
+__global__ void s1_invert_flags(const int *__restrict__ flags, int *__restrict__ skip, long long n, int *__restrict__ count) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int f = flags[i];
+    skip[i] = !f;
+    if (f) atomicAdd(count, 1);
+}
+
+}  // namespace scqed

@@ -103,6 +103,7 @@ __device__ int tridiag_bisect(const double *d, const double *e2, int n, int k, c
 struct TriLU {
     double *u0, *u1, *u2, *mul;
     unsigned char *swp;
+    int st;      // element stride (1: private contiguous arrays; G: arrays interleaved over G threads)
 };
 
 // The three routines below walk long arrays that may live in global memory (n up to ~10^4 on the
@@ -119,43 +120,43 @@ __device__ __forceinline__ void trilu_factor(const double *__restrict__ d, const
         if (u == 0.0 && ei == 0.0) u = eps3;
         if (fabs(ei) >= fabs(u)) {          // pivot on row i
             double xu = u / ei;
-            W.mul[i] = xu; W.swp[i] = 1;
-            W.u0[i - 1] = ei; W.u1[i - 1] = di; W.u2[i - 1] = en;
+            W.mul[(size_t)(i) * W.st] = xu; W.swp[(size_t)(i) * W.st] = 1;
+            W.u0[(size_t)(i - 1) * W.st] = ei; W.u1[(size_t)(i - 1) * W.st] = di; W.u2[(size_t)(i - 1) * W.st] = en;
             u = v - xu * di;
             v = -xu * en;
         } else {
             double xu = ei / u;
-            W.mul[i] = xu; W.swp[i] = 0;
-            W.u0[i - 1] = u; W.u1[i - 1] = v; W.u2[i - 1] = 0.0;
+            W.mul[(size_t)(i) * W.st] = xu; W.swp[(size_t)(i) * W.st] = 0;
+            W.u0[(size_t)(i - 1) * W.st] = u; W.u1[(size_t)(i - 1) * W.st] = v; W.u2[(size_t)(i - 1) * W.st] = 0.0;
             u = di - xu * v;
             v = en;
         }
     }
     if (u == 0.0) u = eps3;
-    W.u0[n - 1] = u; W.u1[n - 1] = 0.0; W.u2[n - 1] = 0.0;
+    W.u0[(size_t)(n - 1) * W.st] = u; W.u1[(size_t)(n - 1) * W.st] = 0.0; W.u2[(size_t)(n - 1) * W.st] = 0.0;
 }
 
 // z <- U^-1 L^-1 P z   (apply_l = 0 skips the L^-1 P part: first iteration from a random start)
 __device__ __forceinline__ void trilu_solve(int n, TriLU W, double *z, int zs, double eps3, bool apply_l) {
     if (apply_l && n > 1) {
         double cur = z[0];
-        double m_n = W.mul[1], z_n = z[zs];
-        unsigned char s_n = W.swp[1];
+        double m_n = W.mul[(size_t)(1) * W.st], z_n = z[zs];
+        unsigned char s_n = W.swp[(size_t)(1) * W.st];
         for (int i = 1; i < n; ++i) {
             const double m_i = m_n, b = z_n;
             const unsigned char s_i = s_n;
-            if (i + 1 < n) { m_n = W.mul[i + 1]; s_n = W.swp[i + 1]; z_n = z[(size_t)(i + 1) * zs]; }
+            if (i + 1 < n) { m_n = W.mul[(size_t)(i + 1) * W.st]; s_n = W.swp[(size_t)(i + 1) * W.st]; z_n = z[(size_t)(i + 1) * zs]; }
             if (s_i) { z[(size_t)(i - 1) * zs] = b; cur = cur - m_i * b; }
             else     { z[(size_t)(i - 1) * zs] = cur; cur = b - m_i * cur; }
         }
         z[(size_t)(n - 1) * zs] = cur;
     }
     double z1 = 0.0, z2 = 0.0;
-    double p_n = W.u0[n - 1], u1_n = W.u1[n - 1], u2_n = W.u2[n - 1], r_n = z[(size_t)(n - 1) * zs];
+    double p_n = W.u0[(size_t)(n - 1) * W.st], u1_n = W.u1[(size_t)(n - 1) * W.st], u2_n = W.u2[(size_t)(n - 1) * W.st], r_n = z[(size_t)(n - 1) * zs];
     for (int i = n - 1; i >= 0; --i) {
         double p = p_n;
         const double u1 = u1_n, u2 = u2_n, r = r_n;
-        if (i > 0) { p_n = W.u0[i - 1]; u1_n = W.u1[i - 1]; u2_n = W.u2[i - 1]; r_n = z[(size_t)(i - 1) * zs]; }
+        if (i > 0) { p_n = W.u0[(size_t)(i - 1) * W.st]; u1_n = W.u1[(size_t)(i - 1) * W.st]; u2_n = W.u2[(size_t)(i - 1) * W.st]; r_n = z[(size_t)(i - 1) * zs]; }
         if (fabs(p) < eps3 * 1e-3) p = copysign(eps3, p == 0.0 ? 1.0 : p);
         double zi = (r - u1 * z1 - u2 * z2) / p;
         z[(size_t)i * zs] = zi;
@@ -228,7 +229,7 @@ __device__ int tridiag_inverse_iteration(const double *d, const double *e, int n
             int j = base + (int)threadIdx.x;
             if ((int)threadIdx.x < vb && j < k) {
                 double *w = lu_ws + per * threadIdx.x;
-                TriLU W = { w, w + n, w + 2 * n, w + 3 * n, (unsigned char *)(w + 4 * n) };
+                TriLU W = { w, w + n, w + 2 * n, w + 3 * n, (unsigned char *)(w + 4 * n), 1 };
                 double *z = Z + (size_t)j * zld;
                 // separate numerically coincident shifts a little (dstein's pertol idea)
                 double lj = lam[j];

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libscqed.so")
 
-SOLVER_AUTO, SOLVER_SMALL, SOLVER_DENSE, SOLVER_DENSE_UNBLOCKED, SOLVER_MATFREE = 0, 1, 2, 3, 4
+SOLVER_AUTO, SOLVER_SMALL, SOLVER_DENSE, SOLVER_DENSE_UNBLOCKED, SOLVER_MATFREE, SOLVER_SMALL_FUSED = 0, 1, 2, 3, 4, 5
 
 
 class EngineError(RuntimeError):

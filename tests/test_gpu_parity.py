@@ -77,7 +77,8 @@ def _random_hermitian(rng, n, batch, real=False):
 
 @pytest.mark.parametrize("n,k,solver", [(2, 2, 0), (5, 3, 0), (33, 10, 0), (64, 10, 1), (101, 20, 1), (110, 5, 0),
                                         (101, 10, 2), (130, 10, 0), (257, 12, 2), (3, 2, 2), (34, 5, 2), (65, 8, 2),
-                                        (200, 10, 2), (517, 10, 2), (101, 10, 3), (257, 12, 3)])
+                                        (200, 10, 2), (517, 10, 2), (101, 10, 3), (257, 12, 3), (64, 10, 5), (101, 20, 5), (97, 32, 1),
+                                        (112, 8, 1)])
 def test_eigh_batched_random(engine_mod, n, k, solver):
     import torch
     rng = np.random.default_rng(1234 + n)
@@ -96,7 +97,7 @@ def test_eigh_batched_random(engine_mod, n, k, solver):
         assert subspace_overlap(X, v[:, :k], w[:k]) >= OVERLAP
 
 
-@pytest.mark.parametrize("solver,n", [(1, 60), (2, 150), (3, 150), (2, 400)])
+@pytest.mark.parametrize("solver,n", [(1, 60), (5, 60), (2, 150), (3, 150), (2, 400)])
 def test_eigh_degenerate_and_clustered(engine_mod, solver, n):
     """Exact doublets / triplets and a tight cluster (the floating-CSFQ trap)."""
     import torch
@@ -116,6 +117,24 @@ def test_eigh_degenerate_and_clustered(engine_mod, solver, n):
     for grp in ([0, 1], [2, 3, 4], [5, 6]):
         P = Q[:, grp] @ Q[:, grp].conj().T
         assert np.max(np.abs(P @ X[:, grp] - X[:, grp])) < 1e-8
+
+
+def test_eigh_real_symmetric_fast_path(engine_mod):
+    """Real symmetric input takes the compacted real path of the small solver."""
+    import torch
+    rng = np.random.default_rng(99)
+    for n, k in [(50, 10), (101, 12)]:
+        H = _random_hermitian(rng, n, 5, real=True).astype(np.complex128)
+        E, V, info = engine_mod.eigh_batched(torch.as_tensor(H, device="cuda"), k, want_vectors=True)
+        E, V = E.cpu().numpy(), V.cpu().numpy()
+        assert not info.cpu().numpy().any()
+        for b in range(5):
+            w, v = np.linalg.eigh(H[b].real)
+            assert np.max(np.abs(E[b] - w[:k])) < 1e-12 * np.abs(w).max() * n
+            X = V[b].T
+            assert np.max(np.abs(X.imag)) == 0.0
+            assert np.max(np.abs(H[b] @ X - X * E[b][None, :])) < 1e-11 * np.abs(w).max() * n
+            assert subspace_overlap(X, v[:, :k].astype(np.complex128), w[:k]) >= OVERLAP
 
 
 def test_eigh_values_only_and_diagonal(engine_mod):
