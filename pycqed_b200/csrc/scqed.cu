@@ -321,7 +321,7 @@ extern "C" int scqed_assemble_dense(scqed_plan *pl, const double *params_dev, in
 // ------------------------------------------------------------------------------------------------
 static bool small_fits(const scqed_plan *pl, int n, int k, int want_vec, int n_terms, SmallLayout *Lout) {
     SmallLayout L = small_smem_layout(n, k, want_vec, n_terms, pl->smem_optin);
-    if ((size_t)L.total > pl->smem_optin) return false;
+    if ((size_t)L.total + 1024 > pl->smem_optin) return false;
     if (want_vec && L.vb < 1) return false;
     if (Lout) *Lout = L;
     return true;
@@ -338,7 +338,7 @@ static int run_small(scqed_plan *pl, const PlanDev &P, const cplx *coef, const c
     a.res = res; a.post = post;
     static bool attr_set = false;
     if (!attr_set) {
-        CK(cudaFuncSetAttribute(small_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
+        CK(cudaFuncSetAttribute(small_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin - 1024));
         attr_set = true;
     }
     long long grid = n_pts < pl->sm_count ? n_pts : pl->sm_count;

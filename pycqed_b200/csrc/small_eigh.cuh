@@ -112,111 +112,148 @@ __device__ __forceinline__ void reflector_scalars(cplx alpha, double xn, cplx &t
     sc = cmake(den.x * dn, -den.y * dn);
 }
 
-#define SMALL_RQ 4      // rows per lane of the serial warp: n <= 32 * SMALL_RQ
+#define SMALL_RQ 4      // n <= 32 * SMALL_RQ = 128 on the small path
+#define SMALL_SER 128   // threads of the serial section (4 warps, one row each)
+#define SMALL_SEGS 8    // column segments of the fused pass (partial sums per row)
 
-// Warp 0: turn column `col` (col[0] = diagonal, col[1] = alpha, col[2..m) = tail) -- after
-// subtracting the pending rank-2 update  vc[r] conj(w0) + wq[r] conj(vc[0]=1)  when `upd` -- into the
-// next reflector.  Writes vnext[0..m-1) (vnext[0] = 1), keeps it in col[1..m), and d/e/tau of column jn.
+__device__ __forceinline__ void ser_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// sum over the 128 threads of the serial section (two named-barrier phases); `slot` = 8 doubles
+__device__ __forceinline__ double ser_sum(double v, double *slot) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = v;
+    ser_barrier();
+    return slot[0] + slot[1] + slot[2] + slot[3];
+}
+
+// Threads 0..127 (row r = tid): turn column `col` (col[0] = diagonal, col[1] = alpha, col[2..m) =
+// tail) -- after subtracting the pending rank-2 update  vc[r] conj(w0) + wr conj(vc[0]=1)  when
+// `upd` -- into the next reflector.  Writes vnext[0..m-1) (vnext[0] = 1), keeps it in col[1..m),
+// and d/e/tau of column jn.  sm: 16 doubles of scratch + 2 T.
 template <typename T>
-__device__ __forceinline__ void warp_next_reflector(T *col, int m, bool upd, const T *vc, T w0, const T *wq,
-                                                    T *vnext, double *dv, double *ev, T *tau, int jn) {
-    const int l = threadIdx.x & 31;
-    T c[SMALL_RQ];
+__device__ __forceinline__ void ser_next_reflector(T *col, int m, bool upd, const T *vc, T w0, T wr,
+                                                   T *vnext, double *dv, double *ev, T *tau, int jn,
+                                                   double *sm, T *sm_t) {
+    const int r = threadIdx.x;
+    T c = nzero(T());
     double xn = 0.0;
-#pragma unroll
-    for (int q = 0; q < SMALL_RQ; ++q) {
-        int r = l + 32 * q;
-        c[q] = nzero(T());
-        if (r < m) {
-            T x = col[r];
-            if (upd) { nfnmac(x, vc[r], w0); x = nsub(x, wq[q]); }
-            c[q] = x;
-            if (r >= 2) xn += nabs2(x);
-        }
+    if (r < m) {
+        c = col[r];
+        if (upd) { nfnmac(c, vc[r], w0); c = nsub(c, wr); }
+        if (r >= 2) xn = nabs2(c);
+        if (r < 2) sm_t[r] = c;                     // diagonal and alpha
     }
-    xn = warp_sum(xn);
-    const T diag = nshfl(c[0], 0);
-    if (m < 2) {                                   // 1 x 1 trailing block: only the diagonal is left
-        if (l == 0) { dv[jn] = nre(diag); ev[jn] = 0.0; }
+    xn = ser_sum(xn, sm + 8);                       // (barrier also publishes sm_t)
+    const T diag = sm_t[0];
+    if (m < 2) {                                    // 1 x 1 trailing block: only the diagonal is left
+        if (r == 0) { dv[jn] = nre(diag); ev[jn] = 0.0; }
         return;
     }
-    const T alpha = nshfl(c[0], 1);
+    const T alpha = sm_t[1];
     T tj, sc;
     double beta;
     reflector_scalars(alpha, xn, tj, beta, sc);
     const bool zero = niszero(tj);
-#pragma unroll
-    for (int q = 0; q < SMALL_RQ; ++q) {
-        int r = l + 32 * q;
-        if (r >= 1 && r < m) {
-            T v = r == 1 ? none(T()) : (zero ? nzero(T()) : nmul(c[q], sc));
-            vnext[r - 1] = v;
-            col[r] = v;                            // reflector kept for the back-transformation
-        }
+    if (r >= 1 && r < m) {
+        T v = r == 1 ? none(T()) : (zero ? nzero(T()) : nmul(c, sc));
+        vnext[r - 1] = v;
+        col[r] = v;                                 // reflector kept for the back-transformation
     }
-    if (l == 0) { col[0] = diag; dv[jn] = nre(diag); ev[jn] = beta; tau[jn] = tj; }
+    if (r == 0) { col[0] = diag; dv[jn] = nre(diag); ev[jn] = beta; tau[jn] = tj; }
 }
 
 // Householder tridiagonalisation of the full-storage column-major matrix A (n <= 128), LAPACK
 // z/d-hetd2 'L' arithmetic, restructured so that one pass over the trailing block applies the
 // PENDING rank-2 update of step j-1 and accumulates A v_j of step j, and the O(m) work between
-// passes runs on one warp: two block barriers per column instead of nine.
+// passes runs on four warps with named barriers: two block barriers per column instead of nine.
 template <typename T>
 __device__ void small_tridiag(T *A, int n, double *dv, double *ev, T *tau, T *vbuf, T *wbuf, T *part) {
-    const int tid = threadIdx.x, NT = blockDim.x, l = tid & 31;
+    __shared__ double ser_sm[24];
+    __shared__ cplx ser_t[2];
+    const int tid = threadIdx.x, NT = blockDim.x;
     T *vcur = vbuf, *vprev = vbuf + n, *wprev = wbuf, *wcur = wbuf + n;
-    if (tid < 32) warp_next_reflector<T>(A, n, false, vcur, nzero(T()), nullptr, vcur, dv, ev, tau, 0);
+    if (tid < SMALL_SER)
+        ser_next_reflector<T>(A, n, false, vcur, nzero(T()), nzero(T()), vcur, dv, ev, tau, 0, ser_sm, (T *)ser_t);
     __syncthreads();
+    // fused pass mapping: warp w -> column segment s = w % 8, row group rg = w / 8; a thread owns
+    // rows lane + 32 q for RPT consecutive q (register tile), so the three broadcast operands of a
+    // column are loaded once per RPT elements and there is no integer division in the loop.
+    constexpr int S = SMALL_SEGS;
+    const int NW = NT >> 5, RG = NW / S > 0 ? NW / S : 1;
+    const int RPT = SMALL_RQ / RG > 0 ? SMALL_RQ / RG : 1;
+    const int wp_ = tid >> 5, lane = tid & 31;
+    const int sidx = wp_ % S, q0 = (wp_ / S) * RPT;
     for (int j = 0; j < n - 1; ++j) {
         const int m = n - j - 1;
         T *A22 = A + (size_t)(j + 1) * (n + 1);
-        int S = NT / m; if (S > SMALL_SMAX) S = SMALL_SMAX; if (S < 1) S = 1;
         const int seg = (m + S - 1) / S;
-        const int s = tid / m, r = tid - s * m;
-        if (s < S) {
-            const int c0 = s * seg, c1 = min(m, c0 + seg);
-            T acc = nzero(T());
-            if (j > 0) {
-                const T vr = vprev[r + 1], wr = wprev[r + 1];
-                for (int c = c0; c < c1; ++c) {
-                    T x = A22[r + (size_t)c * n];
-                    nfnmac(x, vr, wprev[c + 1]);
-                    nfnmac(x, wr, vprev[c + 1]);
-                    A22[r + (size_t)c * n] = x;
-                    nfma(acc, x, vcur[c]);
-                }
-            } else {
-                for (int c = c0; c < c1; ++c) nfma(acc, A22[r + (size_t)c * n], vcur[c]);
+        if (wp_ < S * RG) {
+            const int c0 = sidx * seg, c1 = min(m, c0 + seg);
+            T acc[SMALL_RQ], vr[SMALL_RQ], wr[SMALL_RQ];
+#pragma unroll
+            for (int q = 0; q < SMALL_RQ; ++q) {
+                acc[q] = nzero(T());
+                int r = lane + 32 * (q0 + q);
+                bool on = q < RPT && r < m && j > 0;
+                vr[q] = on ? vprev[r + 1] : nzero(T());
+                wr[q] = on ? wprev[r + 1] : nzero(T());
             }
-            part[s * m + r] = acc;
+            for (int c = c0; c < c1; ++c) {
+                const T vc = vcur[c];
+                const T wpc = j > 0 ? wprev[c + 1] : nzero(T());
+                const T vpc = j > 0 ? vprev[c + 1] : nzero(T());
+#pragma unroll
+                for (int q = 0; q < SMALL_RQ; ++q) {
+                    int r = lane + 32 * (q0 + q);
+                    if (q < RPT && r < m) {
+                        T x = A22[r + (size_t)c * n];
+                        if (j > 0) {
+                            nfnmac(x, vr[q], wpc);
+                            nfnmac(x, wr[q], vpc);
+                            A22[r + (size_t)c * n] = x;
+                        }
+                        nfma(acc[q], x, vc);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < SMALL_RQ; ++q) {
+                int r = lane + 32 * (q0 + q);
+                if (q < RPT && r < m) part[sidx * m + r] = acc[q];
+            }
         }
         __syncthreads();
-        if (tid < 32) {
+        if (tid < SMALL_SER) {
             const T tj = tau[j];
-            T pr[SMALL_RQ], wq[SMALL_RQ];
-            T dot = nzero(T());
-#pragma unroll
-            for (int q = 0; q < SMALL_RQ; ++q) {
-                int rr = l + 32 * q;
-                pr[q] = nzero(T());
-                if (rr < m) {
-                    T sum = nzero(T());
-                    for (int u = 0; u < S; ++u) sum = nadd(sum, part[u * m + rr]);
-                    pr[q] = nmul(tj, sum);
-                    nfmac(dot, pr[q], vcur[rr]);                 // p^H v
-                }
+            T pr = nzero(T());
+            double dx = 0.0, dy = 0.0;
+            if (tid < m) {
+                T sum = nzero(T());
+                for (int u = 0; u < SMALL_SEGS; ++u) sum = nadd(sum, part[u * m + tid]);
+                pr = nmul(tj, sum);
+                T d1 = nzero(T());
+                nfmac(d1, pr, vcur[tid]);                        // p^H v
+                dx = nre(d1);
+                if constexpr (sizeof(T) != sizeof(double)) dy = ((cplx *)&d1)->y;
             }
-            dot = warp_sum(dot);
+            // both components in one pass: pack (dx, dy) through two slots
+            dx = warp_sum(dx); dy = warp_sum(dy);
+            if ((tid & 31) == 0) { ser_sm[tid >> 5] = dx; ser_sm[4 + (tid >> 5)] = dy; }
+            ser_barrier();
+            dx = ser_sm[0] + ser_sm[1] + ser_sm[2] + ser_sm[3];
+            dy = ser_sm[4] + ser_sm[5] + ser_sm[6] + ser_sm[7];
+            T dot;
+            if constexpr (sizeof(T) == sizeof(double)) dot = dx; else dot = cmake(dx, dy);
             const T a2 = nmul(nscale(-0.5, tj), dot);            // -1/2 tau (p^H v)
-#pragma unroll
-            for (int q = 0; q < SMALL_RQ; ++q) {
-                int rr = l + 32 * q;
-                wq[q] = nzero(T());
-                if (rr < m) { wq[q] = nadd(pr[q], nmul(a2, vcur[rr])); wcur[rr] = wq[q]; }
-            }
-            const T w0 = nshfl(wq[0], 0);
+            T wr = nzero(T());
+            if (tid < m) { wr = nadd(pr, nmul(a2, vcur[tid])); wcur[tid] = wr; }
+            if (tid == 0) ((T *)ser_t)[0] = wr;                  // w[0]
+            ser_barrier();
+            const T w0 = ((T *)ser_t)[0];
+            ser_barrier();                                       // ser_t is reused below
             // column j+1 with this step's update applied -> reflector j+1 (or the last diagonal)
-            warp_next_reflector<T>(A22, m, true, vcur, w0, wq, vprev /* becomes vcur */, dv, ev, tau, j + 1);
+            ser_next_reflector<T>(A22, m, true, vcur, w0, wr, vprev /* becomes vcur */, dv, ev, tau, j + 1,
+                                  ser_sm, (T *)ser_t);
         }
         __syncthreads();
         T *t = vcur; vcur = vprev; vprev = t;
@@ -373,8 +410,9 @@ static inline SmallLayout small_smem_layout(int n, int k, int want_vec, int n_te
     L.off_tau = take((size_t)n * 16);
     L.off_v = take((size_t)2 * n * 16);      // current + previous reflector
     L.off_w = take((size_t)2 * n * 16);
-    size_t part = (size_t)SMALL_THREADS;
+    size_t part = (size_t)SMALL_SEGS * n;
     if (part < (size_t)n_terms) part = n_terms;
+    if (part < 64) part = 64;
     L.off_part = take(part * 16);
     L.off_red = take(96 * 8);
     L.off_lam = take((size_t)(k > 0 ? k : 1) * 8);
@@ -384,7 +422,7 @@ static inline SmallLayout small_smem_layout(int n, int k, int want_vec, int n_te
     L.vb = 0;
     if (want_vec) {
         size_t per = ((size_t)4 * n + (size_t)((n + 7) / 8)) * 8;
-        long long room = (long long)max_bytes - (long long)o;
+        long long room = (long long)max_bytes - 1024 - (long long)o;
         int vb = room > 0 ? (int)(room / (long long)per) : 0;
         if (vb > k) vb = k;
         if (vb > SMALL_THREADS) vb = SMALL_THREADS;

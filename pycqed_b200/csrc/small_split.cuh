@@ -53,10 +53,11 @@ template <typename T> struct S1Smem {
         o += (size_t)n * 8 * 2 + 16;                    // dv, ev
         o += (size_t)n * sizeof(T) + 16;                // tau
         o += (size_t)4 * n * sizeof(T) + 32;            // vbuf, wbuf
-        size_t part = (size_t)nthreads * sizeof(T);
+        (void)nthreads;
+        size_t part = (size_t)SMALL_SEGS * n * sizeof(T);
         size_t cf = (size_t)n_terms * 16;
         o += (part > cf ? part : cf) + 16;
-        o += 96 * 8 + 4 * 8 + 64;                       // red, bounds
+        o += 96 * 8 + 4 * 8 + 64 + 1024;                // red, bounds, static shared of small_tridiag
         return o;
     }
 };
@@ -74,7 +75,7 @@ s1_tridiag_kernel(S1Args a) {
     T *tau = (T *)take((size_t)n * sizeof(T));
     T *vbuf = (T *)take((size_t)2 * n * sizeof(T));
     T *wbuf = (T *)take((size_t)2 * n * sizeof(T));
-    size_t partb = (size_t)NT * sizeof(T), cfb = (size_t)a.P.n_terms * 16;
+    size_t partb = (size_t)SMALL_SEGS * n * sizeof(T), cfb = (size_t)a.P.n_terms * 16;
     T *part = (T *)take(partb > cfb ? partb : cfb);
     double *red = (double *)take(96 * 8);
     double *bounds = (double *)take(4 * 8);
@@ -99,7 +100,9 @@ s1_tridiag_kernel(S1Args a) {
                 int id[SCQED_MAX_NODES], jd[SCQED_MAX_NODES];
                 digits(a.P, i, id);
                 digits(a.P, j, jd);
-                cplx v = h_element(a.P, s_coef, id, jd);
+                // H is Hermitian: H[i][j] = conj(H[j][i]).  Evaluating element (j, i) makes the
+                // factor-table reads of consecutive threads (consecutive i) contiguous.
+                cplx v = cconj(h_element(a.P, s_coef, jd, id));
                 if (a.tidyup) v = tidy(v, 1e-12);
                 if constexpr (REAL) { not_real |= (v.y != 0.0); ((double *)A)[idx] = v.x; }
                 else ((cplx *)A)[idx] = v;
