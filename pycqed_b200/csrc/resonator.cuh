@@ -22,47 +22,53 @@ struct ResonatorArgs {
     int s_gc, s_frl, s_qb;   // scalar slots
 };
 
-// all eigenvalues of a symmetric tridiagonal (d[0..n), e[0..n-1)) by implicit QL; ascending on exit
-__device__ inline int tql_eigenvalues(double *d, double *e, int n) {
+// all eigenvalues of a symmetric tridiagonal (d[0..n), e[0..n-1)) by implicit QL; ascending on exit.
+// Elements are `st` doubles apart: st = 1 for private arrays, st = blockDim.x for per-thread
+// columns of a shared-memory tile (conflict-free, and no local-memory traffic).
+__device__ inline int tql_eigenvalues(double *d, double *e, int n, int st) {
+#define D_(i) d[(i) * st]
+#define E_(i) e[(i) * st]
     int fail = 0;
-    e[n - 1] = 0.0;
+    E_(n - 1) = 0.0;
     for (int l = 0; l < n; ++l) {
         int iter = 0, m;
         do {
             for (m = l; m < n - 1; ++m) {
-                double dd = fabs(d[m]) + fabs(d[m + 1]);
-                if (fabs(e[m]) <= SCQED_EPS * dd) break;
+                double dd = fabs(D_(m)) + fabs(D_(m + 1));
+                if (fabs(E_(m)) <= SCQED_EPS * dd) break;
             }
             if (m != l) {
                 if (iter++ == 80) { fail = 1; break; }
-                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double g = (D_(l + 1) - D_(l)) / (2.0 * E_(l));
                 double r = hypot(g, 1.0);
-                g = d[m] - d[l] + e[l] / (g + copysign(r, g));
+                g = D_(m) - D_(l) + E_(l) / (g + copysign(r, g));
                 double s = 1.0, c = 1.0, p = 0.0;
                 int i;
                 for (i = m - 1; i >= l; --i) {
-                    double f = s * e[i], b = c * e[i];
+                    double f = s * E_(i), b = c * E_(i);
                     r = hypot(f, g);
-                    e[i + 1] = r;
-                    if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; break; }
+                    E_(i + 1) = r;
+                    if (r == 0.0) { D_(i + 1) -= p; E_(m) = 0.0; break; }
                     s = f / r; c = g / r;
-                    g = d[i + 1] - p;
-                    r = (d[i] - g) * s + 2.0 * c * b;
+                    g = D_(i + 1) - p;
+                    r = (D_(i) - g) * s + 2.0 * c * b;
                     p = s * r;
-                    d[i + 1] = g + p;
+                    D_(i + 1) = g + p;
                     g = c * r - b;
                 }
                 if (r == 0.0 && i >= l) continue;
-                d[l] -= p; e[l] = g; e[m] = 0.0;
+                D_(l) -= p; E_(l) = g; E_(m) = 0.0;
             }
         } while (m != l);
     }
     for (int i = 1; i < n; ++i) {            // insertion sort
-        double x = d[i];
+        double x = D_(i);
         int j = i - 1;
-        while (j >= 0 && d[j] > x) { d[j + 1] = d[j]; --j; }
-        d[j + 1] = x;
+        while (j >= 0 && D_(j) > x) { D_(j + 1) = D_(j); --j; }
+        D_(j + 1) = x;
     }
+#undef D_
+#undef E_
     return fail;
 }
 
@@ -70,7 +76,7 @@ __device__ inline int tql_eigenvalues(double *d, double *e, int n) {
 // out: [nstrips][k].
 __device__ void resonator_strips(const PlanDev &P, const ResonatorArgs &R, const double *scal,
                                  const double *lam, const cplx *X, int n, int k, double *scratch,
-                                 double *out) {
+                                 double *out, double *qlws = nullptr) {
     cplx *g = (cplx *)scratch;                   // [k]   matrix elements <i|Op|i+1>
     double *glist = scratch + 2 * k;             // [k]
     double *Erel = scratch + 3 * k;              // [k]
@@ -110,15 +116,30 @@ __device__ void resonator_strips(const PlanDev &P, const ResonatorArgs &R, const
         order[i] = rank;
     }
     __syncthreads();
-    for (int s = threadIdx.x; s < R.nstrips; s += blockDim.x) {
-        double d[SCQED_RES_KMAX], e[SCQED_RES_KMAX];
-        for (int i = 0; i < k; ++i) {
-            d[i] = (double)(s - i) * wrl + Erel[i];
-            int q = s - i;
-            e[i] = i < k - 1 ? glist[i] * sqrt((double)(q > 0 ? q : 0)) : 0.0;
+    if (qlws) {
+        // per-thread columns of a shared tile: element i of this thread at qlws[i * T + tid]
+        const int T = blockDim.x;
+        double *d = qlws + threadIdx.x, *e = qlws + (size_t)k * T + threadIdx.x;
+        for (int s = threadIdx.x; s < R.nstrips; s += T) {
+            for (int i = 0; i < k; ++i) {
+                d[i * T] = (double)(s - i) * wrl + Erel[i];
+                int q = s - i;
+                e[i * T] = i < k - 1 ? glist[i] * sqrt((double)(q > 0 ? q : 0)) : 0.0;
+            }
+            tql_eigenvalues(d, e, k, T);
+            for (int i = 0; i < k; ++i) out[(size_t)s * k + i] = d[order[i] * T];
         }
-        tql_eigenvalues(d, e, k);
-        for (int i = 0; i < k; ++i) out[(size_t)s * k + i] = d[order[i]];
+    } else {
+        for (int s = threadIdx.x; s < R.nstrips; s += blockDim.x) {
+            double d[SCQED_RES_KMAX], e[SCQED_RES_KMAX];
+            for (int i = 0; i < k; ++i) {
+                d[i] = (double)(s - i) * wrl + Erel[i];
+                int q = s - i;
+                e[i] = i < k - 1 ? glist[i] * sqrt((double)(q > 0 ? q : 0)) : 0.0;
+            }
+            tql_eigenvalues(d, e, k, 1);
+            for (int i = 0; i < k; ++i) out[(size_t)s * k + i] = d[order[i]];
+        }
     }
     __syncthreads();
 }

@@ -83,7 +83,7 @@ struct scqed_plan {
     DevBuf tables;
     // per-call workspaces (grown on demand, reused across calls)
     DevBuf regs, coef, scal, work, in_params, out_evals, out_evecs, out_post, out_info, out_scal;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
 };
 
 static int set_device(int device) {
@@ -259,6 +259,7 @@ extern "C" void scqed_plan_destroy(scqed_plan *pl) {
                       &pl->out_evecs, &pl->out_post, &pl->out_info, &pl->out_scal};
     for (DevBuf *b : bufs) b->release();
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
+    if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
     delete pl;
 }
 
@@ -945,17 +946,39 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
     if (pl->in_params.ensure(b_par) || pl->out_evals.ensure(b_ev) || pl->out_info.ensure((size_t)n_pts * 4) ||
         pl->out_scal.ensure(b_sc) || (b_vec && evecs && pl->out_evecs.ensure(b_vec)) || (b_post && pl->out_post.ensure(b_post)))
         return fail(SCQED_ENOMEM, "device staging buffers");
+    if (!pl->copy_stream) CK(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = pl->copy_stream;
     if (P.n_swept > 0) CK(cudaMemcpyAsync(pl->in_params.p, params, (size_t)n_pts * P.n_swept * 8, cudaMemcpyHostToDevice, st));
-    rc = scqed_sweep_run(pl, o, (const double *)pl->in_params.p, n_pts, (double *)pl->out_evals.p,
-                         evecs ? (double *)pl->out_evecs.p : nullptr, (double *)pl->out_scal.p,
-                         b_post ? (double *)pl->out_post.p : nullptr, (int32_t *)pl->out_info.p, st);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(evals, pl->out_evals.p, b_ev, cudaMemcpyDeviceToHost, st));
-    if (evecs && b_vec) CK(cudaMemcpyAsync(evecs, pl->out_evecs.p, b_vec, cudaMemcpyDeviceToHost, st));
-    if (scalars && P.n_scalar > 0) CK(cudaMemcpyAsync(scalars, pl->out_scal.p, (size_t)n_pts * P.n_scalar * 8, cudaMemcpyDeviceToHost, st));
-    if (post && b_post) CK(cudaMemcpyAsync(post, pl->out_post.p, b_post, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(info, pl->out_info.p, (size_t)n_pts * 4, cudaMemcpyDeviceToHost, st));
+    // Chunked pipeline: chunk c+1 is solved on the compute stream while the results of chunk c
+    // travel to the host on the copy stream (host buffers should be pinned for real overlap).
+    long long nchunks = n_pts / 2048;
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > 4) nchunks = 4;
+    const long long per = (n_pts + nchunks - 1) / nchunks;
+    double *d_ev = (double *)pl->out_evals.p, *d_sc = (double *)pl->out_scal.p;
+    cplx *d_vec = (evecs && b_vec) ? (cplx *)pl->out_evecs.p : nullptr;
+    double *d_post = b_post ? (double *)pl->out_post.p : nullptr;
+    int32_t *d_info = (int32_t *)pl->out_info.p;
+    const int ns = P.n_scalar;
+    for (long long c0 = 0; c0 < n_pts; c0 += per) {
+        const long long np = n_pts - c0 < per ? n_pts - c0 : per;
+        rc = scqed_sweep_run(pl, o, (const double *)pl->in_params.p + (size_t)c0 * P.n_swept, np, d_ev + (size_t)c0 * k,
+                             d_vec ? (double *)(d_vec + (size_t)c0 * k * n) : nullptr, d_sc + (size_t)c0 * (ns > 0 ? ns : 1),
+                             d_post ? d_post + (size_t)c0 * nstrips * k : nullptr, d_info + c0, st);
+        if (rc) { cudaStreamSynchronize(cs); return rc; }
+        cudaEvent_t evt;
+        CK(cudaEventCreateWithFlags(&evt, cudaEventDisableTiming));
+        CK(cudaEventRecord(evt, st));
+        CK(cudaStreamWaitEvent(cs, evt, 0));
+        CK(cudaEventDestroy(evt));
+        CK(cudaMemcpyAsync(evals + (size_t)c0 * k, d_ev + (size_t)c0 * k, (size_t)np * k * 8, cudaMemcpyDeviceToHost, cs));
+        if (d_vec) CK(cudaMemcpyAsync(evecs + (size_t)2 * c0 * k * n, d_vec + (size_t)c0 * k * n, (size_t)np * k * n * 16, cudaMemcpyDeviceToHost, cs));
+        if (scalars && ns > 0) CK(cudaMemcpyAsync(scalars + (size_t)c0 * ns, d_sc + (size_t)c0 * ns, (size_t)np * ns * 8, cudaMemcpyDeviceToHost, cs));
+        if (post && d_post) CK(cudaMemcpyAsync(post + (size_t)c0 * nstrips * k, d_post + (size_t)c0 * nstrips * k, (size_t)np * nstrips * k * 8, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(info + c0, d_info + c0, (size_t)np * 4, cudaMemcpyDeviceToHost, cs));
+    }
     CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(cs));
     return 0;
 }
 

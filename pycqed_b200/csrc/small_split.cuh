@@ -328,7 +328,7 @@ s1_resonator_kernel(S1Args a, ResonatorArgs R, const int *__restrict__ skip, con
     const long long p = blockIdx.x;
     if (skip && skip[p]) return;
     resonator_strips(a.P, R, scalars + p * a.P.n_scalar, a.W.lam + p * a.k, evecs + (size_t)p * a.k * a.n, a.n, a.k,
-                     scratch, post + (size_t)p * R.nstrips * a.k);
+                     scratch, post + (size_t)p * R.nstrips * a.k, nullptr);   // QL on private (L1-resident) arrays: a shared tile costs occupancy
 }
 
 // complement of the flags (second, complex pass only handles the flagged points)

@@ -15,6 +15,19 @@
 namespace scqed {
 
 
+// 1/t to ~1 ulp: hardware seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps.  |t| >= pivmin
+// (a normal number) is guaranteed by the caller, so neither the seed nor the refinement overflows.
+// An IEEE division expands to ~25 instructions; the Sturm recurrence is nothing but divisions.
+__device__ __forceinline__ double fast_rcp(double t) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(t));
+    double e = fma(-t, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-t, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
 // number of eigenvalues of T that are < x  (LAPACK dlaebz / dstebz recurrence)
 __device__ __forceinline__ int sturm_count(const double *__restrict__ d, const double *__restrict__ e2,
                                            int n, double x, double pivmin) {
@@ -22,7 +35,8 @@ __device__ __forceinline__ int sturm_count(const double *__restrict__ d, const d
     if (fabs(t) < pivmin) t = -pivmin;
     int c = t <= 0.0;
     for (int j = 1; j < n; ++j) {
-        t = d[j] - e2[j - 1] / t - x;
+        const double q = e2[j - 1];
+        t = d[j] - (q == 0.0 ? 0.0 : q * fast_rcp(t)) - x;
         if (fabs(t) < pivmin) t = -pivmin;
         c += (t <= 0.0);
     }
