@@ -118,6 +118,12 @@ int scqed_sweep_run_host(scqed_plan *plan, const scqed_sweep_opts *opts, const d
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t scqed_launch_count(void);
 
+/* Per-kernel device timing for roofline reporting: when enabled, CUDA events are recorded on the
+ * launching stream around the dominant kernel of a path (tag 1: small-path tridiagonalisation, real
+ * symmetric; tag 2: same, complex Hermitian).  scqed_timing_read sums and clears the spans. */
+void scqed_timing_enable(int on);
+int scqed_timing_read(int tag, double *total_ms, int64_t *count);
+
 /* FP64 peak probe: runs a register-resident DMMA (mma.sync m8n8k4 f64) loop on every SM and
  * returns TFLOP/s; the roofline denominator for the dense tridiagonalisation. */
 int scqed_probe_fp64_tensor(int device, double *tflops_out);

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -49,6 +50,23 @@ static int fail(int code, const char *fmt, ...) {
     } while (0)
 
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+// Optional per-kernel timing (bench.py's roofline): CUDA events recorded on the launching stream
+// around the dominant kernel of each path; read back (and reset) with scqed_timing_read().
+static std::atomic<int> g_timing{0};
+struct TimedSpan { cudaEvent_t e0, e1; int tag; };
+static std::vector<TimedSpan> g_spans;
+static void timing_begin(cudaStream_t st, int tag) {
+    if (!g_timing.load()) return;
+    TimedSpan sp; sp.tag = tag;
+    if (cudaEventCreate(&sp.e0) != cudaSuccess || cudaEventCreate(&sp.e1) != cudaSuccess) return;
+    cudaEventRecord(sp.e0, st);
+    g_spans.push_back(sp);
+}
+static void timing_end(cudaStream_t st) {
+    if (!g_timing.load() || g_spans.empty()) return;
+    cudaEventRecord(g_spans.back().e1, st);
+}
 
 struct DevBuf {
     void *p = nullptr;
@@ -265,6 +283,21 @@ extern "C" void scqed_plan_destroy(scqed_plan *pl) {
 
 extern "C" int scqed_plan_hilbert_dim(const scqed_plan *pl) { return pl ? pl->P.n : SCQED_EINVAL; }
 extern "C" int64_t scqed_launch_count(void) { return g_launches.load(); }
+extern "C" void scqed_timing_enable(int on) { g_timing.store(on ? 1 : 0); }
+extern "C" int scqed_timing_read(int tag, double *total_ms, int64_t *count) {
+    if (!total_ms || !count) return fail(SCQED_EINVAL, "null argument");
+    double tot = 0.0; long long cnt = 0;
+    std::vector<TimedSpan> keep;
+    for (auto &sp : g_spans) {
+        if (sp.tag != tag) { keep.push_back(sp); continue; }
+        float ms = 0.f;
+        if (cudaEventSynchronize(sp.e1) == cudaSuccess && cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) { tot += ms; ++cnt; }
+        cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1);
+    }
+    g_spans.swap(keep);
+    *total_ms = tot; *count = cnt;
+    return 0;
+}
 extern "C" const char *scqed_last_error(void) { return g_err.c_str(); }
 extern "C" const char *scqed_version(void) { return "scqed 0.1 (sm_100a)"; }
 
@@ -365,7 +398,9 @@ static int s1_launch_tridiag(scqed_plan *pl, const S1Args &a, int n_terms, cudaS
     if (occ < 1) return fail(SCQED_EUNSUPPORTED, "small tridiagonalisation kernel does not fit (n=%d)", a.n);
     long long grid = (long long)occ * pl->sm_count;
     if (grid > a.n_pts) grid = a.n_pts;
+    timing_begin(st, sizeof(T) == sizeof(double) ? 1 : 2);
     s1_tridiag_kernel<T><<<(unsigned)grid, threads, smem, st>>>(a);
+    timing_end(st);
     LAUNCHED();
     CK(cudaGetLastError());
     return 0;
@@ -418,7 +453,13 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
         const long long Gc = np * k;
         CK(cudaMemsetAsync(a.info, 0, (size_t)np * 4, st));
         bool real_mode = false;
-        if (pl->s1_real_mode != 0) {
+        if (pl->s1_real_mode == 1 && !Hin) {
+            // known real-symmetric plan: no host round trip; a point that turns out complex is
+            // flagged info = -2 by the kernel and the host-level driver re-runs in complex mode
+            int rc = s1_launch_tridiag<double>(pl, a, P.n_terms, st);
+            if (rc) return rc;
+            real_mode = true;
+        } else if (pl->s1_real_mode != 0) {
             int rc = s1_launch_tridiag<double>(pl, a, P.n_terms, st);
             if (rc) return rc;
             int h_cnt = 0;
@@ -428,6 +469,7 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
             for (long long q = 0; q < np; ++q) h_cnt += hflags[(size_t)q] != 0;
             real_mode = (h_cnt == 0);
             if (!Hin) pl->s1_real_mode = real_mode ? 1 : 0;
+            if (!real_mode) CK(cudaMemsetAsync(a.info, 0, (size_t)np * 4, st));
         }
         if (!real_mode) {
             int rc = s1_launch_tridiag<cplx>(pl, a, P.n_terms, st);
@@ -951,15 +993,30 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
     if (P.n_swept > 0) CK(cudaMemcpyAsync(pl->in_params.p, params, (size_t)n_pts * P.n_swept * 8, cudaMemcpyHostToDevice, st));
     // Chunked pipeline: chunk c+1 is solved on the compute stream while the results of chunk c
     // travel to the host on the copy stream (host buffers should be pinned for real overlap).
-    long long nchunks = n_pts / 2048;
+    long long nchunks = n_pts / 5000;       // chunks stay >= ~17 waves of the small-path kernels
     if (nchunks < 1) nchunks = 1;
-    if (nchunks > 4) nchunks = 4;
+    if (nchunks > 8) nchunks = 8;
+    if (const char *envc = getenv("SCQED_HOST_CHUNKS")) { long long v = atoll(envc); if (v >= 1 && v <= 64) nchunks = v < n_pts ? v : n_pts; }
     const long long per = (n_pts + nchunks - 1) / nchunks;
     double *d_ev = (double *)pl->out_evals.p, *d_sc = (double *)pl->out_scal.p;
     cplx *d_vec = (evecs && b_vec) ? (cplx *)pl->out_evecs.p : nullptr;
     double *d_post = b_post ? (double *)pl->out_post.p : nullptr;
     int32_t *d_info = (int32_t *)pl->out_info.p;
     const int ns = P.n_scalar;
+    auto copy_out = [&](long long c0, long long np, cudaEvent_t evt) -> int {
+        CK(cudaStreamWaitEvent(cs, evt, 0));
+        CK(cudaEventDestroy(evt));
+        CK(cudaMemcpyAsync(evals + (size_t)c0 * k, d_ev + (size_t)c0 * k, (size_t)np * k * 8, cudaMemcpyDeviceToHost, cs));
+        if (d_vec) CK(cudaMemcpyAsync(evecs + (size_t)2 * c0 * k * n, d_vec + (size_t)c0 * k * n, (size_t)np * k * n * 16, cudaMemcpyDeviceToHost, cs));
+        if (scalars && ns > 0) CK(cudaMemcpyAsync(scalars + (size_t)c0 * ns, d_sc + (size_t)c0 * ns, (size_t)np * ns * 8, cudaMemcpyDeviceToHost, cs));
+        if (post && d_post) CK(cudaMemcpyAsync(post + (size_t)c0 * nstrips * k, d_post + (size_t)c0 * nstrips * k, (size_t)np * nstrips * k * 8, cudaMemcpyDeviceToHost, cs));
+        CK(cudaMemcpyAsync(info + c0, d_info + c0, (size_t)np * 4, cudaMemcpyDeviceToHost, cs));
+        return 0;
+    };
+    // Enqueue order: compute(c), then the copies of chunk c-1 -- a copy into pageable host memory
+    // blocks the host, and must not delay the next chunk's kernels.
+    long long prev_c0 = -1, prev_np = 0;
+    cudaEvent_t prev_evt = nullptr;
     for (long long c0 = 0; c0 < n_pts; c0 += per) {
         const long long np = n_pts - c0 < per ? n_pts - c0 : per;
         rc = scqed_sweep_run(pl, o, (const double *)pl->in_params.p + (size_t)c0 * P.n_swept, np, d_ev + (size_t)c0 * k,
@@ -969,16 +1026,19 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
         cudaEvent_t evt;
         CK(cudaEventCreateWithFlags(&evt, cudaEventDisableTiming));
         CK(cudaEventRecord(evt, st));
-        CK(cudaStreamWaitEvent(cs, evt, 0));
-        CK(cudaEventDestroy(evt));
-        CK(cudaMemcpyAsync(evals + (size_t)c0 * k, d_ev + (size_t)c0 * k, (size_t)np * k * 8, cudaMemcpyDeviceToHost, cs));
-        if (d_vec) CK(cudaMemcpyAsync(evecs + (size_t)2 * c0 * k * n, d_vec + (size_t)c0 * k * n, (size_t)np * k * n * 16, cudaMemcpyDeviceToHost, cs));
-        if (scalars && ns > 0) CK(cudaMemcpyAsync(scalars + (size_t)c0 * ns, d_sc + (size_t)c0 * ns, (size_t)np * ns * 8, cudaMemcpyDeviceToHost, cs));
-        if (post && d_post) CK(cudaMemcpyAsync(post + (size_t)c0 * nstrips * k, d_post + (size_t)c0 * nstrips * k, (size_t)np * nstrips * k * 8, cudaMemcpyDeviceToHost, cs));
-        CK(cudaMemcpyAsync(info + c0, d_info + c0, (size_t)np * 4, cudaMemcpyDeviceToHost, cs));
+        if (prev_c0 >= 0) { rc = copy_out(prev_c0, prev_np, prev_evt); if (rc) return rc; }
+        prev_c0 = c0; prev_np = np; prev_evt = evt;
     }
+    if (prev_c0 >= 0) { rc = copy_out(prev_c0, prev_np, prev_evt); if (rc) return rc; }
     CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(cs));
+    // a plan assumed real-symmetric produced a complex point: redo the sweep in complex mode (once)
+    bool redo = false;
+    for (long long q = 0; q < n_pts; ++q) if (info[q] == -2) { redo = true; break; }
+    if (redo && pl->s1_real_mode != 0) {
+        pl->s1_real_mode = 0;
+        return scqed_sweep_run_host(pl, o, params, n_pts, evals, evecs, scalars, post, info);
+    }
     return 0;
 }
 

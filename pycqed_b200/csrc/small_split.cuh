@@ -110,8 +110,8 @@ s1_tridiag_kernel(S1Args a) {
         }
         not_real = __syncthreads_or(not_real);
         if (REAL) {
-            if (tid == 0) a.W.flags[p] = not_real;
-            if (not_real) continue;                              // host re-runs this point in complex mode
+            if (tid == 0) { a.W.flags[p] = not_real; if (not_real) a.info[p] = -2; }
+            if (not_real) continue;                              // info = -2: caller re-runs in complex mode
         }
         small_tridiag<T>(A, n, dv, ev, tau, vbuf, wbuf, part);
         if (tid == 0) ev[n - 1] = 0.0;

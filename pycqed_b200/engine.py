@@ -47,7 +47,7 @@ class _SweepOpts(C.Structure):
 EXPORTS = (
     "scqed_plan_create", "scqed_plan_destroy", "scqed_plan_hilbert_dim", "scqed_eval_coefficients",
     "scqed_assemble_dense", "scqed_eigh_batched", "scqed_sweep_run", "scqed_sweep_run_host",
-    "scqed_launch_count", "scqed_probe_fp64_tensor", "scqed_probe_fp64_fma", "scqed_last_error",
+    "scqed_launch_count", "scqed_timing_enable", "scqed_timing_read", "scqed_probe_fp64_tensor", "scqed_probe_fp64_fma", "scqed_last_error",
     "scqed_version",
 )
 
@@ -85,6 +85,10 @@ def load_library():
         lib.scqed_sweep_run_host.restype = C.c_int
         lib.scqed_launch_count.argtypes = []
         lib.scqed_launch_count.restype = C.c_int64
+        lib.scqed_timing_enable.argtypes = [C.c_int]
+        lib.scqed_timing_enable.restype = None
+        lib.scqed_timing_read.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        lib.scqed_timing_read.restype = C.c_int
         lib.scqed_probe_fp64_tensor.argtypes = [C.c_int, C.POINTER(C.c_double)]
         lib.scqed_probe_fp64_tensor.restype = C.c_int
         lib.scqed_probe_fp64_fma.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -112,6 +116,17 @@ def _require_cuda(device=None):
 
 def launch_count() -> int:
     return int(load_library().scqed_launch_count())
+
+
+def timing_enable(on=True):
+    load_library().scqed_timing_enable(1 if on else 0)
+
+
+def timing_read(tag):
+    """(total ms, launches) of the timed kernel spans with this tag since the last read."""
+    ms, cnt = C.c_double(), C.c_int64()
+    _check(load_library().scqed_timing_read(int(tag), C.byref(ms), C.byref(cnt)))
+    return ms.value, cnt.value
 
 
 def probe_fp64(device=0):
