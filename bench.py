@@ -106,6 +106,11 @@ def cpu_baseline(plan, k, vectors, resonator, budget_s=12.0, max_pts=2000):
     strips (numerical_system.py:736-784) -- point by point like the reference's loop
     (numerical_system.py:944-965), on a bounded sample of the same grid."""
     from oracle.plan_oracle import PlanOracle
+    try:        # torchrun exports OMP_NUM_THREADS=1; the baseline may use every host core
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     grid = plan.sweep_grid()
     orc = PlanOracle(plan)
     # calibrate on a few points, then size the sample for ~budget_s
