@@ -81,6 +81,13 @@ struct PlanDev {
     // per term: number of non-identity nodes nn (<= 3), their node ids and factor ids: [n_terms * 7]
     const int *term_meta;
     int max_term_nn;
+    // stencil view (every factor has a single non-zero diagonal: diagonal / shift operators of the
+    // charge basis): term t = c_t * prod_k val_fk[i_k] * x[i + delta_t].  9 ints per term:
+    // nn, k0,k1,k2, tab0,tab1,tab2 (offsets into st_val), delta, original term id; the n_sdiag
+    // terms with delta == 0 come first.
+    int stencil_ok, n_sdiag, n_soff, st_val_total;
+    const int *st_terms;
+    const cplx *st_val;
     int n_swept, n_instr, n_scalar;
     const int *instr;              // [n_instr * 3]
     const double *consts;

@@ -20,6 +20,7 @@
 // Algorithmic traffic of one block mat-vec in HBM/L2: 32 n b bytes (read X, write Y); flops
 // 8 n b sum_t prod_k w_{t,k} with w = non-zeros per row of each factor.
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace scqed {
@@ -249,6 +250,127 @@ mf_cheb_smem(MfArgs a, const cplx *__restrict__ X, cplx *__restrict__ Y, int deg
     }
     cplx *y = Y + (p * a.b + j) * n;
     for (int i = tid; i < n; i += T) y[i] = cur[i];
+}
+
+// ---- stencil filter: every factor has one non-zero diagonal (charge-basis diagonal / shift operators).
+// (H x)[i] = D[i] x[i] + sum_off-terms c_t prod_k val_k[i_k] x[i + delta_t], with D and all tables in
+// shared memory and the digits of a thread's elements in registers.  A thread-block CLUSTER of CS CTAs
+// holds one vector pair: CTA r owns elements [r ns, (r+1) ns) of both Chebyshev vectors and reads the
+// neighbours it needs from its peers' shared memory (DSMEM), so the whole degree-m filter stays on chip
+// for n up to CS * 5500 (CS <= 8): one cluster barrier per Chebyshev step, zero HBM traffic.
+#define MF_MAXE 11          // elements per thread: ns <= MF_MAXE * 512
+namespace cg = cooperative_groups;
+
+template <int CS>
+__global__ void __launch_bounds__(512)
+mf_cheb_stencil(MfArgs a, const cplx *__restrict__ X, cplx *__restrict__ Y, int deg, int ns) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ cplx *peer[2][CS];
+    const int n = a.n, tid = threadIdx.x, T = blockDim.x;
+    const long long p = blockIdx.y;
+    if (!a.active[p]) return;                       // uniform over the cluster (same p)
+    unsigned rank = 0;
+    if constexpr (CS > 1) rank = cg::this_cluster().block_rank();
+    const int j = blockIdx.x / CS;
+    const int i0 = (int)rank * ns;
+    const int nloc = max(0, min(ns, n - i0));
+    cplx *bufA = (cplx *)smraw, *bufB = bufA + ns;
+    double *Dg = (double *)(bufB + ns);
+    cplx *tab = (cplx *)(Dg + ((ns + 1) & ~1));          // keep 16-byte alignment
+    cplx *cf = tab + a.P.st_val_total;
+    int *rec = (int *)(cf + a.P.n_terms);
+    const int nst = a.P.n_sdiag + a.P.n_soff;
+    const cplx *coef = a.coef + p * a.P.n_terms;
+    for (int q = tid; q < a.P.st_val_total; q += T) tab[q] = a.P.st_val[q];
+    for (int q = tid; q < a.P.n_terms; q += T) cf[q] = coef[q];
+    for (int q = tid; q < nst * 9; q += T) rec[q] = a.P.st_terms[q];
+    const cplx *x = X + (p * a.b + j) * n;
+    for (int e = tid; e < nloc; e += T) bufA[e] = x[i0 + e];
+    if (tid < CS) {
+        if constexpr (CS > 1) {
+            peer[0][tid] = cg::this_cluster().map_shared_rank(bufA, tid);
+            peer[1][tid] = cg::this_cluster().map_shared_rank(bufB, tid);
+        } else { peer[0][0] = bufA; peer[1][0] = bufB; }
+    }
+    __syncthreads();
+    // digits of my elements + the diagonal of H
+    int dig[MF_MAXE];
+#pragma unroll
+    for (int q = 0; q < MF_MAXE; ++q) {
+        int e = tid + q * T;
+        dig[q] = 0;
+        if (e < nloc) {
+            int i = i0 + e, packed = 0;
+            for (int k = 0; k < a.P.n_nodes; ++k) packed |= ((i / a.P.strides[k]) % a.P.dims[k]) << (10 * k);
+            dig[q] = packed;
+            double dsum = 0.0;
+            for (int t = 0; t < a.P.n_sdiag; ++t) {
+                const int *r = rec + t * 9;
+                cplx w = cf[r[8]];
+                for (int u = 0; u < r[0]; ++u) w = cmul(w, tab[r[4 + u] + ((packed >> (10 * r[1 + u])) & 1023)]);
+                dsum += w.x;
+            }
+            Dg[e] = dsum;
+        }
+    }
+    const float inv_ns = 1.0f / (float)ns;
+    auto fetch = [&](int which, int i) -> cplx {
+        if constexpr (CS == 1) return peer[which][0][i];
+        else { int r = __float2int_rz(((float)i + 0.5f) * inv_ns); return peer[which][r][i - r * ns]; }
+    };
+    auto apply = [&](int which, const cplx *loc, int q) -> cplx {       // (H v)[i0 + e], v in buffer `which`
+        const int e = tid + q * T, i = i0 + e, packed = dig[q];
+        cplx xi = loc[e];
+        cplx acc = cmake(Dg[e] * xi.x, Dg[e] * xi.y);
+        for (int t = a.P.n_sdiag; t < nst; ++t) {
+            const int *r = rec + t * 9;
+            cplx w = cf[r[8]];
+            for (int u = 0; u < r[0]; ++u) w = cmul(w, tab[r[4 + u] + ((packed >> (10 * r[1 + u])) & 1023)]);
+            if (w.x != 0.0 || w.y != 0.0) cfma(acc, w, fetch(which, i + r[7]));
+        }
+        return acc;
+    };
+    auto csync = [&]() { if constexpr (CS > 1) cg::this_cluster().sync(); else __syncthreads(); };
+    csync();
+    const ChebPar cq = cheb_par(a.fpar + p * 4);
+    double sigma = cq.sigma1;
+    cplx *prev = bufA, *cur = bufB;
+    int wprev = 0, wcur = 1;
+    {
+        const double s = cq.sigma1 / cq.e;
+#pragma unroll
+        for (int q = 0; q < MF_MAXE; ++q) {
+            int e = tid + q * T;
+            if (e < nloc) {
+                cplx h = apply(wprev, prev, q), xi = prev[e];
+                cur[e] = cmake(s * (h.x - cq.c * xi.x), s * (h.y - cq.c * xi.y));
+            }
+        }
+    }
+    csync();
+    for (int m = 2; m <= deg; ++m) {
+        const double sigma2 = 1.0 / (2.0 / cq.sigma1 - sigma);
+        const double s = 2.0 * sigma2 / cq.e, tt = sigma * sigma2;
+#pragma unroll
+        for (int q = 0; q < MF_MAXE; ++q) {
+            int e = tid + q * T;
+            if (e < nloc) {
+                cplx h = apply(wcur, cur, q), yi = cur[e], pi = prev[e];
+                prev[e] = cmake(s * (h.x - cq.c * yi.x) - tt * pi.x, s * (h.y - cq.c * yi.y) - tt * pi.y);
+            }
+        }
+        csync();
+        cplx *tp = prev; prev = cur; cur = tp;
+        int ti = wprev; wprev = wcur; wcur = ti;
+        sigma = sigma2;
+    }
+    cplx *y = Y + (p * a.b + j) * n;
+    for (int e = tid; e < nloc; e += T) y[i0 + e] = cur[e];
+    csync();                                        // peers may still be reading this CTA's buffers
+}
+
+static inline size_t mf_stencil_smem(const PlanDev &P, int ns) {
+    return (size_t)ns * 40 + 16 + (size_t)P.st_val_total * 16 + (size_t)P.n_terms * 16 + (size_t)(P.n_sdiag + P.n_soff) * 36 + 64;
 }
 
 // ---- one Chebyshev step through global memory (large n).  grid (ceil(n/T), b, n_pts).

@@ -222,6 +222,58 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
         if (nn > max_nn) max_nn = nn;
     }
     if (ell_cols.empty()) { ell_cols.push_back(0); ell_vals.push_back(0.0); ell_vals.push_back(0.0); }
+    // ---- stencil view: factors with exactly one non-zero diagonal ------------------------------------
+    std::vector<int> band_off(d->n_factors > 0 ? d->n_factors : 1, 0), tab_off(d->n_factors > 0 ? d->n_factors : 1, 0);
+    std::vector<double> st_val;     // interleaved complex, per factor dk entries: value in row i (column i + off)
+    bool stencil_ok = d->n_nodes <= 3;
+    for (int f = 0; f < d->n_factors && stencil_ok; ++f) {
+        const int dk = d->dims[d->factor_node[f]];
+        const double *F = d->factor_data + 2 * (size_t)d->factor_offset[f];
+        int off = 0; bool have = false;
+        for (int i = 0; i < dk && stencil_ok; ++i)
+            for (int j = 0; j < dk; ++j) {
+                double re = F[2 * ((size_t)i * dk + j)], im = F[2 * ((size_t)i * dk + j) + 1];
+                if (re == 0.0 && im == 0.0) continue;
+                if (!have) { off = j - i; have = true; }
+                else if (j - i != off) { stencil_ok = false; break; }
+            }
+        band_off[f] = off;
+        tab_off[f] = (int)(st_val.size() / 2);
+        for (int i = 0; i < dk; ++i) {
+            int j = i + off;
+            double re = 0.0, im = 0.0;
+            if (j >= 0 && j < dk) { re = F[2 * ((size_t)i * dk + j)]; im = F[2 * ((size_t)i * dk + j) + 1]; }
+            st_val.push_back(re); st_val.push_back(im);
+        }
+    }
+    if (st_val.size() / 2 > 2048) stencil_ok = false;       // tables must fit a corner of shared memory
+    std::vector<int> st_terms;
+    int n_sdiag = 0, n_soff = 0;
+    if (stencil_ok) {
+        std::vector<long long> strides(d->n_nodes, 1);
+        for (int k = d->n_nodes - 2; k >= 0; --k) strides[k] = strides[k + 1] * d->dims[k + 1];
+        for (int pass = 0; pass < 2 && stencil_ok; ++pass)
+            for (int t = 0; t < d->n_terms; ++t) {
+                int nn = 0, ks[3] = {0, 0, 0}, tabs[3] = {0, 0, 0};
+                long long delta = 0;
+                for (int k = 0; k < d->n_nodes; ++k) {
+                    int f = d->term_factors[t * d->n_nodes + k];
+                    if (f < 0) continue;
+                    if (nn >= 3) { stencil_ok = false; break; }
+                    ks[nn] = k; tabs[nn] = tab_off[f]; ++nn;
+                    delta += (long long)band_off[f] * strides[k];
+                }
+                if (!stencil_ok) break;
+                if ((delta == 0) != (pass == 0)) continue;
+                int rec[9] = {nn, ks[0], ks[1], ks[2], tabs[0], tabs[1], tabs[2], (int)delta, t};
+                st_terms.insert(st_terms.end(), rec, rec + 9);
+                if (pass == 0) ++n_sdiag; else ++n_soff;
+            }
+    }
+    if (st_val.empty()) { st_val.push_back(0.0); st_val.push_back(0.0); }
+    if (st_terms.empty()) st_terms.assign(9, 0);
+    size_t o_stt = put(st_terms.data(), st_terms.size() * 4);
+    size_t o_stv = put(st_val.data(), st_val.size() * 8);
     size_t o_ellw = put(ell_w.data(), ell_w.size() * 4);
     size_t o_elloff = put(ell_off.data(), ell_off.size() * 8);
     size_t o_ellc = put(ell_cols.data(), ell_cols.size() * 4);
@@ -251,6 +303,10 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     P.fac_rowsum = (const double *)(base + o_rowsum);
     P.term_meta = (const int *)(base + o_tmeta);
     P.max_term_nn = max_nn;
+    P.stencil_ok = stencil_ok ? 1 : 0;
+    P.n_sdiag = n_sdiag; P.n_soff = n_soff; P.st_val_total = (int)(st_val.size() / 2);
+    P.st_terms = (const int *)(base + o_stt);
+    P.st_val = (const cplx *)(base + o_stv);
     pl->mf_work_per_row = 0;
     for (int t = 0; t < d->n_terms; ++t) {
         long long wprod = 1;
@@ -738,6 +794,26 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
     double *fpar = (double *)take((size_t)chunk * 4 * 8);
     int *active = (int *)take((size_t)chunk * 4), *n_active = (int *)take(256), *info_s1 = (int *)take((size_t)chunk * 4);
     const bool smem_filter = (size_t)2 * n * 16 <= 220 * 1024;
+    // stencil filter (banded-monomial factors): smallest cluster whose slices fit shared memory
+    int stencil_cs = 0, stencil_ns = 0;
+    if (P.stencil_ok && !getenv("SCQED_NO_STENCIL")) {
+        bool dims_ok = true;
+        for (int q = 0; q < P.n_nodes; ++q) dims_ok &= P.dims[q] < 1024;
+        for (int cs = 1; cs <= 8 && dims_ok; cs *= 2) {
+            int ns = (n + cs - 1) / cs;
+            if (ns <= MF_MAXE * 512 && mf_stencil_smem(P, ns) <= 220 * 1024) { stencil_cs = cs; stencil_ns = ns; break; }
+        }
+        if (stencil_cs) {
+            static bool st_attr = false;
+            if (!st_attr) {
+                CK(cudaFuncSetAttribute(mf_cheb_stencil<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+                CK(cudaFuncSetAttribute(mf_cheb_stencil<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+                CK(cudaFuncSetAttribute(mf_cheb_stencil<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+                CK(cudaFuncSetAttribute(mf_cheb_stencil<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+                st_attr = true;
+            }
+        }
+    }
     static bool attr_set = false;
     if (!attr_set) {
         CK(cudaFuncSetAttribute(mf_cheb_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
@@ -788,7 +864,26 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
             CK(cudaStreamSynchronize(st));
             if (h_active == 0) break;
             cplx *R;
-            if (smem_filter) {
+            if (stencil_cs > 0) {
+                const size_t smem = mf_stencil_smem(P, stencil_ns);
+                cudaLaunchConfig_t cfg;
+                memset(&cfg, 0, sizeof(cfg));
+                cfg.gridDim = dim3((unsigned)(b * stencil_cs), (unsigned)np, 1);
+                cfg.blockDim = dim3(512, 1, 1);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = stencil_cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                const cplx *Xc = X;
+                if (stencil_cs == 1) CK(cudaLaunchKernelEx(&cfg, mf_cheb_stencil<1>, a, Xc, Y, deg, stencil_ns));
+                else if (stencil_cs == 2) CK(cudaLaunchKernelEx(&cfg, mf_cheb_stencil<2>, a, Xc, Y, deg, stencil_ns));
+                else if (stencil_cs == 4) CK(cudaLaunchKernelEx(&cfg, mf_cheb_stencil<4>, a, Xc, Y, deg, stencil_ns));
+                else CK(cudaLaunchKernelEx(&cfg, mf_cheb_stencil<8>, a, Xc, Y, deg, stencil_ns));
+                LAUNCHED();
+                R = Y;
+            } else if (smem_filter) {
                 mf_cheb_smem<<<dim3(b, (unsigned)np), 512, (size_t)2 * n * 16, st>>>(a, X, Y, deg);
                 LAUNCHED();
                 R = Y;
