@@ -85,7 +85,7 @@ struct PlanDev {
     // charge basis): term t = c_t * prod_k val_fk[i_k] * x[i + delta_t].  9 ints per term:
     // nn, k0,k1,k2, tab0,tab1,tab2 (offsets into st_val), delta, original term id; the n_sdiag
     // terms with delta == 0 come first.
-    int stencil_ok, n_sdiag, n_soff, st_val_total;
+    int stencil_ok, st_pure_shift, n_sdiag, n_soff, st_val_total;
     const int *st_terms;
     const cplx *st_val;
     int n_swept, n_instr, n_scalar;

@@ -153,7 +153,32 @@ mf_prepare(MfArgs a, cplx *X, double *dscr) {
     const int n = a.n, b = a.b, tid = threadIdx.x;
     const cplx *coef = a.coef + p * a.P.n_terms;
     double *d = dscr + p * n;
-    for (int i = tid; i < n; i += blockDim.x) d[i] = mf_diag(a.P, coef, i);
+    double gmax = -1e300;
+    for (int i = tid; i < n; i += blockDim.x) {
+        double di = mf_diag(a.P, coef, i);
+        d[i] = di;
+        if (a.P.stencil_ok) {                       // exact Gershgorin row bound from the stencil form
+            double rs = 0.0;
+            for (int t = a.P.n_sdiag; t < a.P.n_sdiag + a.P.n_soff; ++t) {
+                const int *r = a.P.st_terms + t * 9;
+                double w = sqrt(cabs2(coef[r[8]]));
+                for (int u = 0; u < r[0]; ++u) {
+                    int kk = r[1 + u];
+                    w *= sqrt(cabs2(a.P.st_val[r[4 + u] + (i / a.P.strides[kk]) % a.P.dims[kk]]));
+                }
+                rs += w;
+            }
+            gmax = fmax(gmax, di + rs);
+        }
+    }
+    sval[tid] = gmax;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (tid < s) sval[tid] = fmax(sval[tid], sval[tid + s]);
+        __syncthreads();
+    }
+    gmax = sval[0];
+    __syncthreads();
     if (tid == 0) {
         double ub = 0.0;
         for (int t = 0; t < a.P.n_terms; ++t) {
@@ -164,6 +189,7 @@ mf_prepare(MfArgs a, cplx *X, double *dscr) {
             }
             ub += m;
         }
+        if (a.P.stencil_ok) ub = gmax + 1e-9 * fabs(gmax);
         a.fpar[p * 4 + 1] = ub;
         a.active[p] = 1;
     }
@@ -262,7 +288,7 @@ mf_cheb_smem(MfArgs a, const cplx *__restrict__ X, cplx *__restrict__ Y, int deg
 namespace cg = cooperative_groups;
 
 template <int CS>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 1)
 mf_cheb_stencil(MfArgs a, const cplx *__restrict__ X, cplx *__restrict__ Y, int deg, int ns) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ cplx *peer[2][CS];
@@ -313,6 +339,30 @@ mf_cheb_stencil(MfArgs a, const cplx *__restrict__ X, cplx *__restrict__ Y, int 
             Dg[e] = dsum;
         }
     }
+    // pure-shift plans (every off-diagonal factor entry is 0 or 1): the weight of term t at element i
+    // is c_t or 0 for the whole filter -> one validity bit per (element, term), computed once
+    const bool pure = a.P.st_pure_shift && a.P.n_soff <= 32;
+    unsigned msk[MF_MAXE];
+    if (pure) {
+#pragma unroll
+        for (int q = 0; q < MF_MAXE; ++q) {
+            int e = tid + q * T;
+            unsigned mbits = 0u;
+            if (e < nloc) {
+                const int packed = dig[q];
+                for (int t = a.P.n_sdiag; t < nst; ++t) {
+                    const int *r = rec + t * 9;
+                    bool ok = true;
+                    for (int u = 0; u < r[0]; ++u) {
+                        cplx v = tab[r[4 + u] + ((packed >> (10 * r[1 + u])) & 1023)];
+                        ok &= (v.x != 0.0 || v.y != 0.0);
+                    }
+                    if (ok) mbits |= 1u << (t - a.P.n_sdiag);
+                }
+            }
+            msk[q] = mbits;
+        }
+    }
     const float inv_ns = 1.0f / (float)ns;
     auto fetch = [&](int which, int i) -> cplx {
         if constexpr (CS == 1) return peer[which][0][i];
@@ -322,6 +372,16 @@ mf_cheb_stencil(MfArgs a, const cplx *__restrict__ X, cplx *__restrict__ Y, int 
         const int e = tid + q * T, i = i0 + e, packed = dig[q];
         cplx xi = loc[e];
         cplx acc = cmake(Dg[e] * xi.x, Dg[e] * xi.y);
+        if (pure) {
+            unsigned mbits = msk[q];
+            while (mbits) {
+                const int tb = __ffs(mbits) - 1;
+                mbits &= mbits - 1;
+                const int *r = rec + (a.P.n_sdiag + tb) * 9;
+                cfma(acc, cf[r[8]], fetch(which, i + r[7]));
+            }
+            return acc;
+        }
         for (int t = a.P.n_sdiag; t < nst; ++t) {
             const int *r = rec + t * 9;
             cplx w = cf[r[8]];

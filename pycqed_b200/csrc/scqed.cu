@@ -270,6 +270,20 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
                 if (pass == 0) ++n_sdiag; else ++n_soff;
             }
     }
+    // pure shift: every factor used by an off-diagonal term has only 0/1 entries
+    bool pure_shift = stencil_ok;
+    if (stencil_ok) {
+        for (size_t q = (size_t)n_sdiag; q < (size_t)(n_sdiag + n_soff) && pure_shift; ++q) {
+            const int *r = &st_terms[q * 9];
+            for (int u = 0; u < r[0] && pure_shift; ++u) {
+                int dk = d->dims[r[1 + u]];
+                for (int i = 0; i < dk; ++i) {
+                    double re = st_val[2 * (size_t)(r[4 + u] + i)], im = st_val[2 * (size_t)(r[4 + u] + i) + 1];
+                    if (!((re == 0.0 && im == 0.0) || (re == 1.0 && im == 0.0))) { pure_shift = false; break; }
+                }
+            }
+        }
+    }
     if (st_val.empty()) { st_val.push_back(0.0); st_val.push_back(0.0); }
     if (st_terms.empty()) st_terms.assign(9, 0);
     size_t o_stt = put(st_terms.data(), st_terms.size() * 4);
@@ -304,6 +318,7 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     P.term_meta = (const int *)(base + o_tmeta);
     P.max_term_nn = max_nn;
     P.stencil_ok = stencil_ok ? 1 : 0;
+    P.st_pure_shift = pure_shift ? 1 : 0;
     P.n_sdiag = n_sdiag; P.n_soff = n_soff; P.st_val_total = (int)(st_val.size() / 2);
     P.st_terms = (const int *)(base + o_stt);
     P.st_val = (const cplx *)(base + o_stv);
@@ -1032,7 +1047,7 @@ extern "C" int scqed_sweep_run(scqed_plan *pl, const scqed_sweep_opts *o, const 
     if (o->resonator) return fail(SCQED_EUNSUPPORTED, "the Resonator evaluable is only implemented on the fused path (n <= ~110)");
     if (solver == 4)
         return run_matfree(pl, (const cplx *)pl->coef.p, n_pts, k, o->want_vectors, evals_dev, (cplx *)evecs_dev, info_dev, st,
-                           60, 60, 1e-10);
+                           60, 60, 1e-9);
     // ---- S2: batches of B matrices through HBM ------------------------------------------------
     const bool blocked = solver != 3;
     int B = pick_dense_batch(n, n_pts, k, pl->sm_count);

@@ -95,3 +95,15 @@ def mf():
 
 if __name__ == "__main__" and "mf" in sys.argv:
     mf()
+
+if __name__ == "__main__" and "mfone" in sys.argv:
+    i = sys.argv.index("mfone")
+    name, npts = sys.argv[i + 1], int(sys.argv[i + 2])
+    plan = SweepPlan.load(os.path.join(G, name + ".plan.json"))
+    grid = plan.sweep_grid()
+    reps = int(np.ceil(npts / len(grid)))
+    grid = np.tile(grid, (reps, 1))[:npts]
+    with engine.Engine(plan) as eng:
+        p = torch.as_tensor(grid, device="cuda")
+        ms = timeit(lambda: eng.sweep_device(p, 10, want_vectors=True, solver=4), reps=1)
+        print("%s n=%d pts=%d matfree %.1f ms" % (name, plan.hilbert_dim, npts, ms))
