@@ -58,6 +58,15 @@ typedef struct {
     const int32_t *coef_im;         /* [n_terms]                                             */
     int32_t n_scalar;
     const int32_t *scalar_regs;     /* [n_scalar]                                            */
+    /* Auxiliary operators for the Current / Voltage evaluables (numerical_system.py:596-694):
+     * n_aux extra terms (same factor table), coefficient registers aux_re/aux_im, and n_pairs
+     * requested matrix elements, pair q = (term_begin, term_end, i, j): <i| sum_t c_t kron F |j>. */
+    int32_t n_aux;
+    const int32_t *aux_term_factors; /* [n_aux * n_nodes]                                    */
+    const int32_t *aux_re;          /* [n_aux]                                               */
+    const int32_t *aux_im;          /* [n_aux]                                               */
+    int32_t n_pairs;
+    const int32_t *pairs;           /* [n_pairs * 4]                                         */
 } scqed_plan_desc;
 
 /* Options of one sweep (numerical_system.py:790-804 setDiagConfig + :868-875 addEvaluation). */
@@ -114,6 +123,21 @@ int scqed_sweep_run(scqed_plan *plan, const scqed_sweep_opts *opts, const double
 int scqed_sweep_run_host(scqed_plan *plan, const scqed_sweep_opts *opts, const double *params,
                          int64_t n_pts, double *evals, double *evecs, double *scalars,
                          double *post, int32_t *info);
+
+/* getCurrentMatrixElement / getVoltageMatrixElement replacement (numerical_system.py:656-694):
+ * matrix elements of the plan's auxiliary operators between the eigenvectors of each point.
+ * evecs_dev complex [n_pts, k, n] (as returned by scqed_sweep_run); out_dev complex [n_pts, n_pairs]
+ * (interleaved re, im): <i|Op|j>.  The Current / Voltage evaluables keep the real part (:665,:692);
+ * util.pauliCoefficients (util.py:322-328) uses the complex value. */
+int scqed_matrix_elements(scqed_plan *plan, const double *params_dev, int64_t n_pts, int32_t k,
+                          const double *evecs_dev, double *out_dev, void *stream);
+
+/* util.pauliCoefficients replacement (util.py:300-391): local-basis reduction of the two lowest
+ * levels.  e01_dev [n_pts, 2] = (E0, E1); op_dev complex [n_pts, 4] = the computational-basis
+ * operator in the {|0>, |1>} eigenbasis, row-major (m00, m01, m10, m11); h_dev [n_pts, 3] =
+ * (hx, hy, hz).  float64 throughout (the reference rounds to complex64). */
+int scqed_pauli_coefficients(int device, const double *e01_dev, const double *op_dev, int64_t n_pts,
+                             double *h_dev, void *stream);
 
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t scqed_launch_count(void);

@@ -38,70 +38,57 @@ QOBJ_ATOL = 1e-12   # numerical_system.py:19
 # ------------------------------------------------------------------------------------------------
 # coefficient program
 # ------------------------------------------------------------------------------------------------
-def eval_program(program, params):
-    """Interpret the SSA bytecode for all points at once.
-
-    :param params: [n_pts, n_swept] float64
-    :return: (coef complex128 [n_pts, n_coef], scalars float64 [n_pts, n_scalar])
-    """
+def _run_program(program, params):
+    """Interpret the SSA bytecode for all points at once -> register file [n_instr, n_pts]."""
     params = np.asarray(params, dtype=np.float64)
     if params.ndim != 2 or params.shape[1] != program.n_swept:
         raise ValueError("params must be [n_pts, %d], got %r" % (program.n_swept, params.shape))
     n_pts = params.shape[0]
     regs = np.zeros((program.n_instr, n_pts), dtype=np.float64)
+    unary = {6: np.negative, 7: np.sqrt, 8: np.sin, 9: np.cos, 10: np.exp, 11: np.log, 14: np.abs, 15: np.tan,
+             16: np.arctan, 17: np.tanh, 18: np.sinh, 19: np.cosh}
+    binary = {2: np.add, 3: np.subtract, 4: np.multiply, 5: np.divide, 12: np.power}
     with np.errstate(all="ignore"):
         for i, (op, a, b) in enumerate(program.instr.tolist()):
             if op == 0:
                 regs[i] = program.consts[a]
             elif op == 1:
                 regs[i] = params[:, a]
-            elif op == 2:
-                regs[i] = regs[a] + regs[b]
-            elif op == 3:
-                regs[i] = regs[a] - regs[b]
-            elif op == 4:
-                regs[i] = regs[a] * regs[b]
-            elif op == 5:
-                regs[i] = regs[a] / regs[b]
-            elif op == 6:
-                regs[i] = -regs[a]
-            elif op == 7:
-                regs[i] = np.sqrt(regs[a])
-            elif op == 8:
-                regs[i] = np.sin(regs[a])
-            elif op == 9:
-                regs[i] = np.cos(regs[a])
-            elif op == 10:
-                regs[i] = np.exp(regs[a])
-            elif op == 11:
-                regs[i] = np.log(regs[a])
-            elif op == 12:
-                regs[i] = np.power(regs[a], regs[b])
+            elif op in binary:
+                regs[i] = binary[op](regs[a], regs[b])
+            elif op in unary:
+                regs[i] = unary[op](regs[a])
             elif op == 13:
                 regs[i] = np.power(regs[a], float(b))
-            elif op == 14:
-                regs[i] = np.abs(regs[a])
-            elif op == 15:
-                regs[i] = np.tan(regs[a])
-            elif op == 16:
-                regs[i] = np.arctan(regs[a])
-            elif op == 17:
-                regs[i] = np.tanh(regs[a])
-            elif op == 18:
-                regs[i] = np.sinh(regs[a])
-            elif op == 19:
-                regs[i] = np.cosh(regs[a])
             else:
                 raise ValueError("unknown opcode %d" % op)
-    coef = np.zeros((n_pts, program.n_coef), dtype=np.complex128)
-    for t in range(program.n_coef):
-        re = regs[program.coef_re[t]] if program.coef_re[t] >= 0 else 0.0
-        im = regs[program.coef_im[t]] if program.coef_im[t] >= 0 else 0.0
-        coef[:, t] = re + 1j * im
-    scal = np.zeros((n_pts, program.n_scalar), dtype=np.float64)
+    return regs
+
+
+def _complex_outputs(regs, re_ids, im_ids):
+    out = np.zeros((regs.shape[1], len(re_ids)), dtype=np.complex128)
+    for t in range(len(re_ids)):
+        re = regs[re_ids[t]] if re_ids[t] >= 0 else 0.0
+        im = regs[im_ids[t]] if im_ids[t] >= 0 else 0.0
+        out[:, t] = re + 1j * im
+    return out
+
+
+def eval_program(program, params):
+    """:param params: [n_pts, n_swept] float64
+    :return: (coef complex128 [n_pts, n_coef], scalars float64 [n_pts, n_scalar])
+    """
+    regs = _run_program(program, params)
+    coef = _complex_outputs(regs, program.coef_re, program.coef_im)
+    scal = np.zeros((regs.shape[1], program.n_scalar), dtype=np.float64)
     for s in range(program.n_scalar):
         scal[:, s] = regs[program.scalar_regs[s]]
     return coef, scal
+
+
+def eval_aux_coefficients(program, params):
+    """Coefficients of the auxiliary-operator terms (Current / Voltage evaluables) [n_pts, n_aux]."""
+    return _complex_outputs(_run_program(program, params), program.aux_re, program.aux_im)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -129,6 +116,7 @@ class PlanOracle:
         self._factors = [sp.csr_matrix(plan.factor_matrix(f)) for f in range(len(plan.factors))]
         self._eyes = [sp.identity(d, dtype=np.complex128, format="csr") for d in self.dims]
         self.term_ops = [self._expand(t) for t in plan.terms]
+        self.aux_term_ops = [self._expand(t) for t in getattr(plan, "aux_terms", [])]
 
     def _expand(self, fids):
         out = None
@@ -176,6 +164,32 @@ class PlanOracle:
         order = np.argsort(E, kind="stable")
         return E[order], V[:, order] / np.linalg.norm(V[:, order], axis=0, keepdims=True)
 
+    # -- Current / Voltage operators and their matrix elements ----------------------------------
+    def aux_operator(self, aux_coef_row, op_index):
+        """getCurrentOperator / getVoltageOperator (numerical_system.py:596-654,669-681) as CSR."""
+        op = self.plan.aux_ops[op_index]
+        M = sp.csr_matrix((self.n, self.n), dtype=np.complex128)
+        for t in range(op["term_begin"], op["term_end"]):
+            M = M + aux_coef_row[t] * self.aux_term_ops[t]
+        return sp.csr_matrix(M)
+
+    def matrix_elements(self, params, V):
+        """<V_i|Op|V_j> (complex) for every requested pair, op after op, as ``plan.aux_pairs()`` orders
+        them; ``V`` is [n_pts, n, k].  The reference's evaluables keep ``.real``
+        (numerical_system.py:656-667,683-694)."""
+        params = np.atleast_2d(np.asarray(params, dtype=np.float64))
+        ac = eval_aux_coefficients(self.plan.program, params)
+        out = []
+        for p in range(params.shape[0]):
+            row = []
+            for oi, op in enumerate(self.plan.aux_ops):
+                M = self.aux_operator(ac[p], oi)
+                MV = M @ V[p]
+                for i, j in op["elements"]:
+                    row.append(np.vdot(V[p][:, i], MV[:, j]))
+            out.append(row)
+        return np.asarray(out, dtype=np.complex128)
+
     # -- resonator ----------------------------------------------------------------------------
     def resonator_response(self, E, V, scal_row):
         """numerical_system.py:736-784, literally (bare-order bookkeeping included)."""
@@ -207,6 +221,25 @@ class PlanOracle:
             else:
                 Es[i] = out
         return {"E": Es, "V": Vs, "Erwa": (np.array(Rs) if resonator else None), "scalars": scal}
+
+
+def pauli_coefficients(E0, E1, Op):
+    """util.pauliCoefficients (util.py:300-391) in float64 (the reference computes in complex64):
+    local-basis reduction of the two lowest levels.  ``Op`` [n_pts, 2, 2] is the computational-basis
+    operator in the {|0>, |1>} eigenbasis.  Returns hx, hy, hz."""
+    ox = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+    oy = np.array([[0, -1j], [1j, 0]], dtype=np.complex128)
+    oz = np.array([[1, 0], [0, -1]], dtype=np.complex128)
+    hx, hy, hz = [], [], []
+    for i in range(len(E0)):
+        _, Vl = np.linalg.eigh(np.asarray(Op[i], dtype=np.complex128))
+        Vl = np.array([np.abs(Vl[0, k]) / Vl[0, k] * Vl[:, k] for k in (0, 1)])
+        U = Vl.T
+        Hq = U.conj().T @ np.diag([E0[i], E1[i]]).astype(np.complex128) @ U
+        hx.append(np.real(0.5 * np.trace(Hq @ ox)))
+        hy.append(np.real(0.5 * np.trace(Hq @ oy)))
+        hz.append(np.real(0.5 * np.trace(Hq @ oz)))
+    return np.array(hx), np.array(hy), np.array(hz)
 
 
 def resonator_response(E, V, Op, gC, wrl, nmax=100):

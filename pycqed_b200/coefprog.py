@@ -53,6 +53,8 @@ class CoefProgram:
     coef_im: np.ndarray                    # int32 [n_coef]
     scalar_regs: np.ndarray                # int32 [n_scalar]
     scalar_names: list = field(default_factory=list)
+    aux_re: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int32))   # auxiliary-operator terms
+    aux_im: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int32))
 
     @property
     def n_instr(self) -> int:
@@ -76,6 +78,8 @@ class CoefProgram:
             "coef_im": self.coef_im.astype(int).tolist(),
             "scalar_regs": self.scalar_regs.astype(int).tolist(),
             "scalar_names": list(self.scalar_names),
+            "aux_re": self.aux_re.astype(int).tolist(),
+            "aux_im": self.aux_im.astype(int).tolist(),
         }
 
     @staticmethod
@@ -88,6 +92,8 @@ class CoefProgram:
             coef_im=np.asarray(d["coef_im"], dtype=np.int32),
             scalar_regs=np.asarray(d["scalar_regs"], dtype=np.int32),
             scalar_names=list(d.get("scalar_names", [])),
+            aux_re=np.asarray(d.get("aux_re", []), dtype=np.int32),
+            aux_im=np.asarray(d.get("aux_im", []), dtype=np.int32),
         )
 
 
@@ -207,14 +213,18 @@ class ProgramBuilder:
             return self._emit(unary[e.func], self.compile(e.args[0]), 0)
         raise NotImplementedError("cannot lower sympy node %r (%s) to the coefficient program" % (e, type(e)))
 
-    def finish(self, coef_pairs, scalar_exprs=(), scalar_names=()) -> CoefProgram:
-        """``coef_pairs``: iterable of (re_expr, im_expr); ``scalar_exprs``: real expressions."""
-        cre, cim = [], []
-        for re_e, im_e in coef_pairs:
-            re_e = sy.sympify(re_e)
-            im_e = sy.sympify(im_e)
-            cre.append(-1 if re_e == 0 else self.compile(re_e))
-            cim.append(-1 if im_e == 0 else self.compile(im_e))
+    def finish(self, coef_pairs, scalar_exprs=(), scalar_names=(), aux_pairs=()) -> CoefProgram:
+        """``coef_pairs`` / ``aux_pairs``: iterables of (re_expr, im_expr); ``scalar_exprs``: real expressions."""
+        def regs(pairs):
+            rr, ii = [], []
+            for re_e, im_e in pairs:
+                re_e = sy.sympify(re_e)
+                im_e = sy.sympify(im_e)
+                rr.append(-1 if re_e == 0 else self.compile(re_e))
+                ii.append(-1 if im_e == 0 else self.compile(im_e))
+            return rr, ii
+        cre, cim = regs(coef_pairs)
+        are, aim = regs(aux_pairs)
         sregs = [self.compile(s) for s in scalar_exprs]
         instr = np.asarray(self.instr, dtype=np.int32).reshape(-1, 3)
         return CoefProgram(
@@ -225,4 +235,6 @@ class ProgramBuilder:
             coef_im=np.asarray(cim, dtype=np.int32),
             scalar_regs=np.asarray(sregs, dtype=np.int32),
             scalar_names=list(scalar_names),
+            aux_re=np.asarray(are, dtype=np.int32),
+            aux_im=np.asarray(aim, dtype=np.int32),
         )

@@ -29,7 +29,8 @@ __device__ __forceinline__ double powi(double x, int n) {
 
 __global__ void __launch_bounds__(128)
 coef_eval_kernel(PlanDev P, const double *__restrict__ params, long long n_pts,
-                 double *__restrict__ regs, cplx *__restrict__ coef, double *__restrict__ scalars) {
+                 double *__restrict__ regs, cplx *__restrict__ coef, double *__restrict__ scalars,
+                 cplx *__restrict__ auxcoef) {
     long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pts) return;
     const double *prm = params + p * P.n_swept;
@@ -73,6 +74,14 @@ coef_eval_kernel(PlanDev P, const double *__restrict__ params, long long n_pts,
     }
     for (int s = 0; s < P.n_scalar; ++s)
         scalars[p * P.n_scalar + s] = regs[(long long)__ldg(P.scalar_regs + s) * n_pts + p];
+    if (auxcoef) {
+        for (int t = 0; t < P.n_aux; ++t) {
+            int ir = __ldg(P.aux_re + t), ii = __ldg(P.aux_im + t);
+            double re = ir >= 0 ? regs[(long long)ir * n_pts + p] : 0.0;
+            double im = ii >= 0 ? regs[(long long)ii * n_pts + p] : 0.0;
+            auxcoef[p * P.n_aux + t] = cmake(re, im);
+        }
+    }
 }
 
 }  // namespace scqed

@@ -88,6 +88,12 @@ struct PlanDev {
     int stencil_ok, st_pure_shift, n_sdiag, n_soff, st_val_total;
     const int *st_terms;
     const cplx *st_val;
+    // auxiliary operators (Current / Voltage evaluables): extra terms with their own coefficients,
+    // and the list of requested matrix elements <i| sum_{t in [tb, te)} c_t kron F |j>
+    int n_aux, n_pairs;
+    const int *aux_meta;           // [n_aux * 7] like term_meta
+    const int *aux_re, *aux_im;    // [n_aux] coefficient registers
+    const int *pairs;              // [n_pairs * 4]: tb, te, i, j
     int n_swept, n_instr, n_scalar;
     const int *instr;              // [n_instr * 3]
     const double *consts;

@@ -41,14 +41,15 @@ struct MfArgs {
 };
 
 // (H x)[i] for one sweep point; x may live in shared or global memory.
-__device__ __forceinline__ cplx mf_apply(const PlanDev &P, const cplx *__restrict__ coef, const cplx *x, int i) {
+__device__ __forceinline__ cplx mf_apply_terms(const PlanDev &P, const int *__restrict__ meta, int t_begin, int t_end,
+                                               const cplx *__restrict__ coef, const cplx *x, int i) {
     int id[SCQED_MAX_NODES];
 #pragma unroll
     for (int k = 0; k < SCQED_MAX_NODES; ++k)
         if (k < P.n_nodes) id[k] = (i / P.strides[k]) % P.dims[k];
     cplx acc = cmake(0.0, 0.0);
-    for (int t = 0; t < P.n_terms; ++t) {
-        const int *tm = P.term_meta + t * 7;
+    for (int t = t_begin; t < t_end; ++t) {
+        const int *tm = meta + t * 7;
         const int nn = __ldg(tm);
         const cplx c = coef[t];
         if (nn == 0) { cfma(acc, c, x[i]); continue; }
@@ -113,6 +114,33 @@ __device__ __forceinline__ cplx mf_apply(const PlanDev &P, const cplx *__restric
         cfma(acc, c, sum);
     }
     return acc;
+}
+
+__device__ __forceinline__ cplx mf_apply(const PlanDev &P, const cplx *__restrict__ coef, const cplx *x, int i) {
+    return mf_apply_terms(P, P.term_meta, 0, P.n_terms, coef, x, i);
+}
+
+// K7b: matrix elements of auxiliary operators between eigenvectors (Current / Voltage evaluables,
+// pyscqed/numerical_system.py:596-694; util.py:322-328): out[p][q] = <x_i| Op_q |x_j> (complex).  One warp per (point, pair).
+__global__ void __launch_bounds__(128)
+aux_matel_kernel(PlanDev P, const cplx *__restrict__ auxcoef, const cplx *__restrict__ evecs, long long n_pts, int k,
+                 cplx *__restrict__ out) {
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int l = threadIdx.x & 31;
+    if (gw >= n_pts * P.n_pairs) return;
+    const long long p = gw / P.n_pairs;
+    const int q = (int)(gw - p * P.n_pairs);
+    const int tb = __ldg(P.pairs + 4 * q), te = __ldg(P.pairs + 4 * q + 1);
+    const int i1 = __ldg(P.pairs + 4 * q + 2), i2 = __ldg(P.pairs + 4 * q + 3);
+    const cplx *xi = evecs + ((size_t)p * k + i1) * P.n, *xj = evecs + ((size_t)p * k + i2) * P.n;
+    const cplx *cf = auxcoef + p * P.n_aux;
+    cplx acc = cmake(0.0, 0.0);
+    for (int a_ = l; a_ < P.n; a_ += 32) {
+        cplx y = mf_apply_terms(P, P.aux_meta, tb, te, cf, xj, a_);
+        cfmac(acc, xi[a_], y);
+    }
+    acc = warp_sum(acc);
+    if (l == 0) out[p * P.n_pairs + q] = acc;
 }
 
 // diagonal element H[i][i]

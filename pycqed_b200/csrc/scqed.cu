@@ -23,6 +23,7 @@
 #include "dense_blocked.cuh"
 #include "matfree.cuh"
 #include "probe.cuh"
+#include "pauli.cuh"
 
 using namespace scqed;
 
@@ -95,7 +96,8 @@ struct scqed_plan {
     int n_coef_scalar = 0;
     long long mf_work_per_row = 0;     // complex MACs per output element of the matrix-free mat-vec
     int s1_real_mode = -1;             // fused small path: -1 unknown, 0 complex Hermitian, 1 real symmetric
-    DevBuf s1work, s1vec;
+    DevBuf s1work, s1vec, auxc;
+    int pair_max_index = -1;
     std::vector<int> factor_node;
     // device copies of the tables
     DevBuf tables;
@@ -151,6 +153,7 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     pl->sm_count = prop.multiProcessorCount;
     pl->smem_optin = prop.sharedMemPerBlockOptin;
     pl->factor_node.assign(d->factor_node, d->factor_node + d->n_factors);
+    for (int q = 0; q < d->n_pairs; ++q) { int m = d->pairs[4 * q + 2] > d->pairs[4 * q + 3] ? d->pairs[4 * q + 2] : d->pairs[4 * q + 3]; if (m > pl->pair_max_index) pl->pair_max_index = m; }
 
     // pack all tables into one allocation
     size_t fac_elems = 0;
@@ -206,6 +209,25 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
             }
             for (; cnt < w; ++cnt) { ell_cols.push_back(i); ell_vals.push_back(0.0); ell_vals.push_back(0.0); }
         }
+    }
+    if (d->n_aux < 0 || d->n_pairs < 0) return fail(SCQED_EINVAL, "negative aux counts");
+    std::vector<int> aux_meta((size_t)(d->n_aux > 0 ? d->n_aux : 1) * 7, 0);
+    for (int t = 0; t < d->n_aux; ++t) {
+        int nn = 0;
+        for (int k = 0; k < d->n_nodes; ++k) {
+            int f = d->aux_term_factors[t * d->n_nodes + k];
+            if (f >= d->n_factors || (f >= 0 && d->factor_node[f] != k)) return fail(SCQED_EINVAL, "aux term %d: bad factor", t);
+            if (f >= 0) {
+                if (nn >= 3) return fail(SCQED_EUNSUPPORTED, "aux term %d has more than 3 non-identity factors", t);
+                aux_meta[(size_t)t * 7 + 1 + nn] = k; aux_meta[(size_t)t * 7 + 4 + nn] = f; ++nn;
+            }
+        }
+        aux_meta[(size_t)t * 7] = nn;
+        if (d->aux_re[t] >= d->n_instr || d->aux_im[t] >= d->n_instr) return fail(SCQED_EINVAL, "aux coefficient register out of range");
+    }
+    for (int q = 0; q < d->n_pairs; ++q) {
+        const int32_t *pr = d->pairs + 4 * q;
+        if (pr[0] < 0 || pr[1] > d->n_aux || pr[0] > pr[1] || pr[2] < 0 || pr[3] < 0) return fail(SCQED_EINVAL, "pair %d malformed", q);
     }
     std::vector<int> term_meta((size_t)d->n_terms * 7, 0);
     int max_nn = 0;
@@ -294,6 +316,9 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     size_t o_ellv = put(ell_vals.data(), ell_vals.size() * 8);
     size_t o_rowsum = put(rowsum.data(), rowsum.size() * 8);
     size_t o_tmeta = put(term_meta.data(), term_meta.size() * 4);
+    size_t o_ameta = put(aux_meta.data(), aux_meta.size() * 4);
+    size_t o_are = put(d->aux_re, (size_t)d->n_aux * 4), o_aim = put(d->aux_im, (size_t)d->n_aux * 4);
+    size_t o_pairs = put(d->pairs, (size_t)d->n_pairs * 16);
     if (pl->tables.ensure(host.size() + 256)) { delete pl; return fail(SCQED_ENOMEM, "plan tables"); }
     if (cudaMemcpy(pl->tables.p, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         pl->tables.release(); delete pl; return fail(SCQED_ECUDA, "uploading plan tables failed");
@@ -316,6 +341,10 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     P.ell_vals = (const cplx *)(base + o_ellv);
     P.fac_rowsum = (const double *)(base + o_rowsum);
     P.term_meta = (const int *)(base + o_tmeta);
+    P.n_aux = d->n_aux; P.n_pairs = d->n_pairs;
+    P.aux_meta = (const int *)(base + o_ameta);
+    P.aux_re = (const int *)(base + o_are); P.aux_im = (const int *)(base + o_aim);
+    P.pairs = (const int *)(base + o_pairs);
     P.max_term_nn = max_nn;
     P.stencil_ok = stencil_ok ? 1 : 0;
     P.st_pure_shift = pure_shift ? 1 : 0;
@@ -344,7 +373,7 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
 extern "C" void scqed_plan_destroy(scqed_plan *pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
-    DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->s1work, &pl->s1vec, &pl->in_params, &pl->out_evals,
+    DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->s1work, &pl->s1vec, &pl->auxc, &pl->in_params, &pl->out_evals,
                       &pl->out_evecs, &pl->out_post, &pl->out_info, &pl->out_scal};
     for (DevBuf *b : bufs) b->release();
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
@@ -376,12 +405,43 @@ extern "C" const char *scqed_version(void) { return "scqed 0.1 (sm_100a)"; }
 // K1 / K2
 // ------------------------------------------------------------------------------------------------
 static int run_coef(scqed_plan *pl, const double *params_dev, long long n_pts, cplx *coef_dev, double *scal_dev,
-                    cudaStream_t st) {
+                    cudaStream_t st, cplx *aux_dev = nullptr) {
     const PlanDev &P = pl->P;
     if (pl->regs.ensure((size_t)(P.n_instr > 0 ? P.n_instr : 1) * n_pts * 8)) return fail(SCQED_ENOMEM, "coefficient registers");
     int threads = 128;
     long long blocks = (n_pts + threads - 1) / threads;
-    coef_eval_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, params_dev, n_pts, (double *)pl->regs.p, coef_dev, scal_dev);
+    coef_eval_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, params_dev, n_pts, (double *)pl->regs.p, coef_dev, scal_dev, aux_dev);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int scqed_matrix_elements(scqed_plan *pl, const double *params_dev, int64_t n_pts, int32_t k,
+                                     const double *evecs_dev, double *out_dev, void *stream) {
+    if (!pl || !evecs_dev || !out_dev || n_pts < 1 || k < 1) return fail(SCQED_EINVAL, "bad argument");
+    const PlanDev &P = pl->P;
+    if (P.n_pairs < 1) return fail(SCQED_EINVAL, "the plan has no matrix-element requests");
+    if (P.n_swept > 0 && !params_dev) return fail(SCQED_EINVAL, "params_dev is NULL");
+    if (pl->pair_max_index >= k) return fail(SCQED_EINVAL, "a requested eigenvector index exceeds k=%d", k);
+    CK(cudaSetDevice(pl->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pl->coef.ensure((size_t)n_pts * P.n_terms * 16)) return fail(SCQED_ENOMEM, "coefficients");
+    if (pl->scal.ensure((size_t)n_pts * (P.n_scalar + 1) * 8)) return fail(SCQED_ENOMEM, "scalars");
+    if (pl->auxc.ensure((size_t)n_pts * (P.n_aux + 1) * 16)) return fail(SCQED_ENOMEM, "aux coefficients");
+    int rc = run_coef(pl, params_dev, n_pts, (cplx *)pl->coef.p, (double *)pl->scal.p, st, (cplx *)pl->auxc.p);
+    if (rc) return rc;
+    const long long warps = n_pts * P.n_pairs;
+    aux_matel_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, st>>>(P, (const cplx *)pl->auxc.p, (const cplx *)evecs_dev, n_pts, k, (cplx *)out_dev);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int scqed_pauli_coefficients(int device, const double *e01_dev, const double *op_dev, int64_t n_pts,
+                                        double *h_dev, void *stream) {
+    if (!e01_dev || !op_dev || !h_dev || n_pts < 1) return fail(SCQED_EINVAL, "bad argument");
+    if (set_device(device)) return SCQED_ECUDA;
+    pauli_coef_kernel<<<(unsigned)((n_pts + 127) / 128), 128, 0, (cudaStream_t)stream>>>(e01_dev, (const cplx *)op_dev, n_pts, h_dev);
     LAUNCHED();
     CK(cudaGetLastError());
     return 0;

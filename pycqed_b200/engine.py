@@ -31,6 +31,9 @@ class _PlanDesc(C.Structure):
         ("n_consts", C.c_int32), ("consts", C.POINTER(C.c_double)),
         ("coef_re", C.POINTER(C.c_int32)), ("coef_im", C.POINTER(C.c_int32)),
         ("n_scalar", C.c_int32), ("scalar_regs", C.POINTER(C.c_int32)),
+        ("n_aux", C.c_int32), ("aux_term_factors", C.POINTER(C.c_int32)),
+        ("aux_re", C.POINTER(C.c_int32)), ("aux_im", C.POINTER(C.c_int32)),
+        ("n_pairs", C.c_int32), ("pairs", C.POINTER(C.c_int32)),
     ]
 
 
@@ -46,7 +49,7 @@ class _SweepOpts(C.Structure):
 #: every symbol include/scqed.h declares (tests check that the library exports all of them)
 EXPORTS = (
     "scqed_plan_create", "scqed_plan_destroy", "scqed_plan_hilbert_dim", "scqed_eval_coefficients",
-    "scqed_assemble_dense", "scqed_eigh_batched", "scqed_sweep_run", "scqed_sweep_run_host",
+    "scqed_assemble_dense", "scqed_eigh_batched", "scqed_sweep_run", "scqed_sweep_run_host", "scqed_matrix_elements", "scqed_pauli_coefficients",
     "scqed_launch_count", "scqed_timing_enable", "scqed_timing_read", "scqed_probe_fp64_tensor", "scqed_probe_fp64_fma", "scqed_last_error",
     "scqed_version",
 )
@@ -83,6 +86,10 @@ def load_library():
         lib.scqed_sweep_run.restype = C.c_int
         lib.scqed_sweep_run_host.argtypes = [vp, C.POINTER(_SweepOpts), dp, i64, dp, dp, dp, dp, dp]
         lib.scqed_sweep_run_host.restype = C.c_int
+        lib.scqed_matrix_elements.argtypes = [vp, dp, i64, i32, dp, dp, vp]
+        lib.scqed_matrix_elements.restype = C.c_int
+        lib.scqed_pauli_coefficients.argtypes = [i32, dp, dp, i64, dp, vp]
+        lib.scqed_pauli_coefficients.restype = C.c_int
         lib.scqed_launch_count.argtypes = []
         lib.scqed_launch_count.restype = C.c_int64
         lib.scqed_timing_enable.argtypes = [C.c_int]
@@ -156,8 +163,9 @@ class SweepResult:
     """Results of one sweep on the host (numpy).  ``E`` [n_pts, k]; ``V`` [n_pts, k, n] or None;
     ``scalars`` {name: [n_pts]}; ``Erwa`` [n_pts, nmax+1+k, k] or None; ``info`` [n_pts]."""
 
-    def __init__(self, E, V, scalars, Erwa, info):
+    def __init__(self, E, V, scalars, Erwa, info, matel=None):
         self.E, self.V, self.scalars, self.Erwa, self.info = E, V, scalars, Erwa, info
+        self.matel = matel          # complex [n_pts, n_pairs] (Current / Voltage matrix elements) or None
 
 
 class Engine:
@@ -188,6 +196,14 @@ class Engine:
         cre, cim, sreg = _i32(prog.coef_re), _i32(prog.coef_im), _i32(prog.scalar_regs)
         if sreg.size == 0:
             sreg = np.zeros(1, dtype=np.int32)
+        aux_terms = _i32(plan.aux_terms) if plan.aux_terms else np.zeros(1, dtype=np.int32)
+        aux_re = _i32(prog.aux_re) if len(prog.aux_re) else np.zeros(1, dtype=np.int32)
+        aux_im = _i32(prog.aux_im) if len(prog.aux_im) else np.zeros(1, dtype=np.int32)
+        pair_list = plan.aux_pairs()
+        pairs = _i32(pair_list) if pair_list else np.zeros(4, dtype=np.int32)
+        self.n_pairs = len(pair_list)
+        if len(plan.aux_terms) != len(prog.aux_re):
+            raise EngineError("plan is inconsistent: %d aux terms but %d aux coefficients" % (len(plan.aux_terms), len(prog.aux_re)))
         if len(plan.terms) != prog.n_coef:
             raise EngineError("plan is inconsistent: %d terms but %d coefficients" % (len(plan.terms), prog.n_coef))
         desc = _PlanDesc(
@@ -199,6 +215,9 @@ class Engine:
             n_consts=len(prog.consts), consts=_ptr(consts, C.c_double),
             coef_re=_ptr(cre, C.c_int32), coef_im=_ptr(cim, C.c_int32),
             n_scalar=prog.n_scalar, scalar_regs=_ptr(sreg, C.c_int32),
+            n_aux=len(plan.aux_terms), aux_term_factors=_ptr(aux_terms, C.c_int32),
+            aux_re=_ptr(aux_re, C.c_int32), aux_im=_ptr(aux_im, C.c_int32),
+            n_pairs=len(pair_list), pairs=_ptr(pairs, C.c_int32),
         )
         _check(self.lib.scqed_plan_create(C.byref(desc), self.device.index, C.byref(self._handle)))
 
@@ -263,6 +282,25 @@ class Engine:
         _check(self.lib.scqed_assemble_dense(self._handle, p.data_ptr(), n_pts, int(bool(tidyup)), H.data_ptr(), _stream_ptr()))
         return H
 
+    def matrix_elements(self, params, V):
+        """<i|Op|j> of the plan's auxiliary operators (Current / Voltage evaluables) for every
+        point; ``V`` is the device tensor [n_pts, k, n] returned by :meth:`sweep_device`.  Returns a
+        complex128 device tensor [n_pts, n_pairs] ordered like ``plan.aux_pairs()``."""
+        import torch
+        if self.n_pairs < 1:
+            raise EngineError("this plan was lowered without matrix-element evaluations")
+        p = self._params_dev(params)
+        n_pts = p.shape[0]
+        if isinstance(V, np.ndarray):
+            V = torch.as_tensor(np.ascontiguousarray(V, dtype=np.complex128), device=self.device)
+        if not (isinstance(V, torch.Tensor) and V.is_cuda and V.dtype == torch.complex128 and V.ndim == 3
+                and V.shape[0] == n_pts and V.shape[2] == self.n):
+            raise EngineError("V must be a complex128 array / CUDA tensor [n_pts, k, n] of eigenvectors")
+        V = V.contiguous()
+        out = torch.empty((n_pts, self.n_pairs), dtype=torch.complex128, device=self.device)
+        _check(self.lib.scqed_matrix_elements(self._handle, p.data_ptr(), n_pts, int(V.shape[1]), V.data_ptr(), out.data_ptr(), _stream_ptr()))
+        return out
+
     def sweep_device(self, params, k, want_vectors=False, resonator=False, solver=SOLVER_AUTO, tidyup=True):
         """Device-resident sweep; returns torch tensors (E, V|None, scalars, Erwa|None, info)."""
         import torch
@@ -283,13 +321,24 @@ class Engine:
         return E, V, scal[:, :ns], post, info
 
     def sweep(self, params, k, want_vectors=False, resonator=False, solver=SOLVER_AUTO, tidyup=True,
-              out=None) -> SweepResult:
+              out=None, matrix_elements=False) -> SweepResult:
         """Host-buffer sweep (the call the drop-in ``paramSweep`` makes): params and results are
-        numpy / pinned host memory, the library does the H2D / D2H copies."""
+        numpy / pinned host memory, the library does the H2D / D2H copies.  With
+        ``matrix_elements`` the eigenvectors stay on the device for ``scqed_matrix_elements`` and
+        everything is copied back afterwards."""
         params = np.ascontiguousarray(params, dtype=np.float64)
         if params.ndim != 2 or params.shape[1] != self.plan.program.n_swept:
             raise EngineError("params must be [n_pts, %d]" % self.plan.program.n_swept)
         n_pts = params.shape[0]
+        if matrix_elements:
+            p = self._params_dev(params)
+            E, V, scal, post, info = self.sweep_device(p, k, want_vectors=True, resonator=resonator, solver=solver, tidyup=tidyup)
+            M = self.matrix_elements(p, V)
+            names = list(self.plan.program.scalar_names)
+            scal = scal.cpu().numpy()
+            return SweepResult(E.cpu().numpy(), V.cpu().numpy() if want_vectors else None,
+                               {nm: scal[:, i].copy() for i, nm in enumerate(names)},
+                               post.cpu().numpy() if post is not None else None, info.cpu().numpy(), M.cpu().numpy())
         o = self._opts(k, want_vectors or resonator, solver, tidyup, resonator)
         ns = self.plan.program.n_scalar
         out = out or {}
@@ -312,6 +361,24 @@ class Engine:
         names = list(self.plan.program.scalar_names)
         scalars = {nm: scal[:, i].copy() for i, nm in enumerate(names)}
         return SweepResult(E, V, scalars, post, info)
+
+
+def pauli_coefficients(E0, E1, Op, device=None):
+    """``util.pauliCoefficients`` (util.py:300-391) on the device: ``E0``, ``E1`` [n_pts] and the 2x2
+    computational-basis operators ``Op`` [n_pts, 2, 2] (complex) -> (hx, hy, hz) numpy arrays."""
+    import torch
+    lib = load_library()
+    dev = _require_cuda(device)
+    e01 = torch.as_tensor(np.ascontiguousarray(np.stack([np.asarray(E0, dtype=np.float64), np.asarray(E1, dtype=np.float64)], axis=1)), device=dev)
+    op = torch.as_tensor(np.ascontiguousarray(np.asarray(Op, dtype=np.complex128).reshape(-1, 4)), device=dev)
+    n_pts = e01.shape[0]
+    if op.shape[0] != n_pts:
+        raise EngineError("Op must hold one 2x2 operator per point (%d), got %d" % (n_pts, op.shape[0]))
+    h = torch.empty((n_pts, 3), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.scqed_pauli_coefficients(dev.index, e01.data_ptr(), op.data_ptr(), n_pts, h.data_ptr(), _stream_ptr()))
+    h = h.cpu().numpy()
+    return h[:, 0].copy(), h[:, 1].copy(), h[:, 2].copy()
 
 
 def eigh_batched(H, k, want_vectors=False, solver=SOLVER_AUTO):

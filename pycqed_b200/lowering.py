@@ -105,7 +105,7 @@ class _TermTable:
 
 
 def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scalars=None,
-                 resonator=None) -> SweepPlan:
+                 resonator=None, matrix_elements=()) -> SweepPlan:
     """Build the plan.
 
     :param SS: the reference ``SymbolicSystem`` (after ``ndSweep`` if ``swept_names``)
@@ -114,6 +114,8 @@ def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scala
     :param swept_names: independent parameters being swept, in ``addSweep`` order
     :param scalars: {name: sympy expr or parameter name} extra real per-point outputs
     :param resonator: {'cpl_node': node, 'nmax': int} to add the Resonator post-op inputs
+    :param matrix_elements: [{'kind': 'Voltage', 'node': n, 'elements': [(i, j), ...]} |
+                             {'kind': 'Current', 'edge': e, 'elements': [...]}] (numerical_system.py:596-694)
     """
     swept_names = list(swept_names)
     nodes = list(SS.nodes)
@@ -239,10 +241,69 @@ def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scala
             "qb": scalar_names.index("qb_cpl"),
         }
 
+    # ---- auxiliary operators: Current / Voltage evaluables (numerical_system.py:596-694) -----------
+    aux_keys, aux_coefs, aux_ops = [], [], []
+
+    def aux_add(node_factor_names, re_expr, im_expr=0):
+        key = [-1] * N
+        for ni, name in node_factor_names.items():
+            key[ni] = tt.fid(ni, name)
+        aux_keys.append(key)
+        aux_coefs.append((sy.sympify(re_expr), sy.sympify(im_expr)))
+
+    for spec in matrix_elements:
+        begin = len(aux_keys)
+        if spec["kind"] == "Voltage":
+            node = spec.get("node")
+            if node is None:
+                raise Exception("No node specified for node voltage operator.")
+            if node not in nodes:
+                raise Exception("Node %s is not in the circuit." % repr(node))
+            i = nodes.index(node)
+            c = units.getPrefactor("Vop") * Cinv[i, i]                 # Vop * (Q_i + q_b,i) * C^-1_ii  (:678-681)
+            aux_add({i: "charge"}, c)
+            if Qb[i] != 0:
+                aux_add({}, c * Qb[i])
+            name = "getVoltageMatrixElement"
+        elif spec["kind"] == "Current":
+            edge = spec.get("edge")
+            if isinstance(edge, list):
+                edge = tuple(edge)
+            if edge is None:
+                raise Exception("No edge specified for branch current operator.")
+            if edge not in SS.edges:
+                raise Exception("Edge %s not in the circuit. Check that it is in the right direction." % repr(edge))
+            e = SS.edges.index(edge)
+            comp = _branch_composition(SS, e)
+            if SS.CG.isInductiveEdge(edge):
+                Pp = SS.Rnb * SS.Rinv * SS.node_vector
+                Lb = R(SS.getInverseInductanceMatrix(mode='branch')[e, e])
+                expr = Pp[e]
+                args = expr.args if len(expr.atoms()) > 2 else [expr]
+                for arg in args:                                         # IopL * sum coef * P_node * Linv_b[e,e]  (:608-620)
+                    node = SS.node_map_rev[arg.args[1]]
+                    aux_add({nodes.index(node): "flux"}, units.getPrefactor("IopL") * float(arg.args[0]) * Lb)
+            elif SS.CG.isJosephsonEdge(edge):
+                ph = 2 * sy.pi * Pbm[e, e]
+                amp = half * units.getPrefactor("IopJ") * Jvec[e]      # 0.5j IopJ J (e^{+i ph} Pi+ - e^{-i ph} Pi-)  (:622-652)
+                plus = {nodes.index(node): ("disp" if s_ > 0 else "disp_adj") for node, s_ in comp}
+                minus = {nodes.index(node): ("disp" if s_ < 0 else "disp_adj") for node, s_ in comp}
+                aux_add(plus, -amp * sy.sin(ph), amp * sy.cos(ph))
+                aux_add(minus, -amp * sy.sin(ph), -amp * sy.cos(ph))
+            else:
+                raise Exception("Edge %s is not current-carrying" % repr(edge))
+            name = "getCurrentMatrixElement"
+        else:
+            raise Exception("unknown matrix-element kind %r" % (spec["kind"],))
+        if spec.get("elements") is None:
+            raise Exception("No elements specified for %s matrix elements." % spec["kind"].lower())
+        aux_ops.append({"name": name, "term_begin": begin, "term_end": len(aux_keys),
+                        "elements": [[int(a), int(b)] for a, b in spec["elements"]]})
+
     # ---- compile --------------------------------------------------------------------------
     builder = ProgramBuilder(swept_syms)
     keys = [k for k in tt.order if not (tt.terms[k][0] == 0 and tt.terms[k][1] == 0)]
-    program = builder.finish([tuple(tt.terms[k]) for k in keys], scalar_exprs, scalar_names)
+    program = builder.finish([tuple(tt.terms[k]) for k in keys], scalar_exprs, scalar_names, aux_coefs)
     return SweepPlan(
         nodes=node_specs,
         factors=list(tt.factors),
@@ -252,5 +313,7 @@ def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scala
         sweep_specs=[dict(name=s["name"], start=float(s["start"]), end=float(s["end"]), N=int(s["N"]))
                      for s in sweep_specs],
         post=post,
+        aux_terms=aux_keys,
+        aux_ops=aux_ops,
         meta={"prefactors": {"Ec": Ec, "El": El, "Ej": Ej, "Ep": Ep}},
     )

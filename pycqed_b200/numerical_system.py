@@ -27,8 +27,7 @@ Differences, all deliberate:
   * eigenvectors are :class:`Ket` objects (``.full()``, ``.dims``, ``.norm()``, ``.dag_dot``);
     ``Ket.to_qobj()`` converts when QuTiP is installed.
   * oscillator nodes whose impedance depends on a swept parameter (per-point operator
-    regeneration, :378-393) and the ``Current`` / ``Voltage`` evaluables raise
-    ``NotImplementedError`` for now.
+    regeneration, :378-393) are refused with ``LoweringError`` for now.
 """
 from __future__ import annotations
 
@@ -112,10 +111,11 @@ class HamiltonianMatrix:
 class SweepData:
     """In-memory result of ``paramSweep`` (all points, all evaluables)."""
 
-    def __init__(self, specs, evaluations, E, V, scalars, Erwa, info, dims, timings):
+    def __init__(self, specs, evaluations, E, V, scalars, Erwa, info, dims, timings, matel=None):
         self.specs = specs                 # [{'name','start','end','N'}]
         self.evaluations = evaluations     # [method names in addEvaluation order]
         self.E, self.V, self.scalars, self.Erwa, self.info = E, V, scalars, Erwa, info
+        self.matel = matel or {}           # {'getCurrentMatrixElement': [n_pts, n_elements] float64, ...}
         self.dims = dims
         self.timings = timings
 
@@ -138,6 +138,8 @@ class SweepData:
                 return self.E[i]
             if name == "getResonatorResponse":
                 return self.Erwa[i]
+            if name in self.matel:
+                return self.matel[name][i]
             return self.scalars[name][i]
         if len(self.evaluations) == 1 and key is None:
             return one(self.evaluations[0])
@@ -361,6 +363,34 @@ class NumericalSystem:
     def getPhaseSlipEnergies(self, edge=None):
         return self._energy("PhaseSlipEnergy", self.SS.edges, edge)
 
+    # ---- Current / Voltage operators (numerical_system.py:596-694) --------------------------------
+    def _aux_operator(self, spec):
+        """Dense operator of one Current / Voltage spec at the current parameter values, assembled
+        on the device by the same K1 + K2 kernels as H (its terms become the plan's term table)."""
+        plan = lower_system(self.SS, self.units, self.operator_data, matrix_elements=[dict(spec, elements=[])])
+        with _engine.Engine(plan.aux_as_terms(0), device=self.device) as eng:
+            M = eng.assemble_dense(np.zeros((1, 0)), tidyup=False).cpu().numpy()[0]
+        return HamiltonianMatrix(M, plan.dims)
+
+    def getCurrentOperator(self, edge=None):
+        return self._aux_operator({"kind": "Current", "edge": edge})
+
+    def getVoltageOperator(self, node=None):
+        return self._aux_operator({"kind": "Voltage", "node": node})
+
+    def _aux_matrix_elements(self, spec, V):
+        plan = lower_system(self.SS, self.units, self.operator_data, matrix_elements=[spec])
+        vecs = np.stack([np.asarray(v.full() if hasattr(v, "full") else v, dtype=np.complex128).reshape(-1) for v in V])
+        with _engine.Engine(plan, device=self.device) as eng:
+            M = eng.matrix_elements(np.zeros((1, 0)), np.ascontiguousarray(vecs[None])).cpu().numpy()[0]
+        return np.ascontiguousarray(M.real)
+
+    def getCurrentMatrixElement(self, E, V, edge=None, elements=None):
+        return self._aux_matrix_elements({"kind": "Current", "edge": edge, "elements": elements}, V)
+
+    def getVoltageMatrixElement(self, E, V, node=None, elements=None):
+        return self._aux_matrix_elements({"kind": "Voltage", "node": node, "elements": elements}, V)
+
     # ---- diagonaliser (numerical_system.py:790-810; util.py:76-176) -----------------------------
     def setDiagConfig(self, eigvalues=5, get_vectors=False, sparse=False,
                       sparsesolveropts={"sigma": None, "mode": "normal", "maxiter": None, "tol": 1e-3, "which": "SA"}):
@@ -429,6 +459,7 @@ class NumericalSystem:
         want_h = False
         resonator = None
         scalars = {}
+        matel_specs, matel_methods = [], []
         all_scalars = None
         methods = []
         for entry in self.evaluations:
@@ -452,16 +483,29 @@ class NumericalSystem:
                 if key is None:
                     raise NotImplementedError("%s over all nodes/edges in a sweep: pass node=/edge=" % nm)
                 scalars[entry['eval']] = all_scalars["%s:%r" % (nm, key)]
+            elif nm in ("Current", "Voltage"):
+                spec = dict(kw, kind=nm)
+                spec.setdefault("elements", None)
+                matel_specs.append(spec)
+                matel_methods.append(entry['eval'])
             else:
                 raise NotImplementedError("evaluable '%s' is not implemented on the GPU path yet" % nm)
 
-        plan = lower_system(self.SS, self.units, self.operator_data, names, specs, scalars=scalars, resonator=resonator)
+        plan = lower_system(self.SS, self.units, self.operator_data, names, specs, scalars=scalars, resonator=resonator,
+                            matrix_elements=matel_specs)
         grid = plan.sweep_grid()
         loop_time = time.time()
+        matel = {}
         with _engine.Engine(plan, device=self.device) as eng:
             if want_h or resonator is not None:
-                res = eng.sweep(grid, k, want_vectors=get_vectors, resonator=resonator is not None)
+                res = eng.sweep(grid, k, want_vectors=get_vectors, resonator=resonator is not None,
+                                matrix_elements=bool(matel_specs))
                 E, V, scal, Erwa, info = res.E, res.V, res.scalars, res.Erwa, res.info
+                col = 0
+                for method, op in zip(matel_methods, plan.aux_ops):      # :656-667,683-694 keep the real part
+                    ne = len(op["elements"])
+                    matel[method] = np.ascontiguousarray(res.matel[:, col:col + ne].real)
+                    col += ne
             else:
                 _, sc = eng.coefficients(grid)
                 sc = sc.cpu().numpy()
@@ -472,7 +516,7 @@ class NumericalSystem:
         if info.any():
             raise RuntimeError("eigensolver did not converge at %d sweep point(s)" % int(np.count_nonzero(info)))
         data = SweepData(specs, methods, E, V, scal, Erwa, info, plan.dims,
-                         {"init": loop_time - init_time, "loop": end_time - loop_time})
+                         {"init": loop_time - init_time, "loop": end_time - loop_time}, matel)
         self._init_sweep_data()                                   # :915
         if timesweep:
             print("Parameter Sweep Duration:")

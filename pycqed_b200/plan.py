@@ -67,6 +67,8 @@ class SweepPlan:
     swept_names: list
     sweep_specs: list = field(default_factory=list)   # [{'name','start','end','N'}] in addSweep order
     post: dict = field(default_factory=dict)          # e.g. {'resonator': {...}}
+    aux_terms: list = field(default_factory=list)     # extra operator terms [[factor id per node]]
+    aux_ops: list = field(default_factory=list)       # [{'name', 'term_begin', 'term_end', 'elements': [[i, j]]}]
     meta: dict = field(default_factory=dict)
     _opsets: dict = field(default_factory=dict, repr=False)
 
@@ -91,6 +93,26 @@ class SweepPlan:
 
     def factor_kind(self, fid: int) -> str:
         return ops.classify(self.factor_matrix(fid))
+
+    def aux_pairs(self) -> list:
+        """Flat list [term_begin, term_end, i, j] of all requested matrix elements, op after op."""
+        out = []
+        for op in self.aux_ops:
+            for i, j in op["elements"]:
+                out.append([int(op["term_begin"]), int(op["term_end"]), int(i), int(j)])
+        return out
+
+    def aux_as_terms(self, op_index: int) -> "SweepPlan":
+        """A plan whose term table is auxiliary operator ``op_index`` (so K1 + K2 assemble
+        getCurrentOperator / getVoltageOperator, numerical_system.py:596-654,669-681, like an H)."""
+        op = self.aux_ops[op_index]
+        tb, te = int(op["term_begin"]), int(op["term_end"])
+        prog = self.program
+        sub = CoefProgram(n_swept=prog.n_swept, instr=prog.instr, consts=prog.consts,
+                          coef_re=prog.aux_re[tb:te].copy(), coef_im=prog.aux_im[tb:te].copy(),
+                          scalar_regs=prog.scalar_regs, scalar_names=list(prog.scalar_names))
+        return SweepPlan(nodes=self.nodes, factors=self.factors, terms=[list(t) for t in self.aux_terms[tb:te]],
+                         program=sub, swept_names=self.swept_names, sweep_specs=self.sweep_specs, meta=dict(self.meta))
 
     def sweep_grid(self) -> np.ndarray:
         """[n_pts, n_swept] row-major, C-order over the addSweep order (last = fastest),
@@ -132,6 +154,8 @@ class SweepPlan:
                 for s in self.sweep_specs
             ],
             "post": self.post,
+            "aux_terms": [[int(x) for x in t] for t in self.aux_terms],
+            "aux_ops": self.aux_ops,
             "meta": self.meta,
         }
 
@@ -155,6 +179,8 @@ class SweepPlan:
                 for s in d.get("sweep_specs", [])
             ],
             post=d.get("post", {}),
+            aux_terms=[[int(x) for x in t] for t in d.get("aux_terms", [])],
+            aux_ops=d.get("aux_ops", []),
             meta=d.get("meta", {}),
         )
 

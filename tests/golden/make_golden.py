@@ -248,6 +248,37 @@ def build_fluxonium_atom(trunc=31):
     return h
 
 
+def build_rfsquid(trunc=50):
+    """C6a: RF-SQUID qubit of examples/local-basis-example.py:28-49 (oscillator basis)."""
+    ps = import_reference()
+    Ca, Jc, Aj = 60.0, 3.0, 0.2 * 1.2
+    with quiet():
+        g = ps.CircuitGraph()
+        g.addBranch(0, 1, "C")
+        g.addBranch(0, 1, "L")
+        g.addBranch(0, 1, "I")
+        g.addFluxBias("I", "Z")
+        h = ps.NumericalSystem(ps.SymbolicSystem(g))
+        h.configureOperator(1, trunc, "oscillator")
+        h.setParameterValues("C", Ca * Aj, "I", Jc * Aj, "L", 570.0, "phiZ", 0.5)
+    return h
+
+
+def build_cpb(trunc=20):
+    """C6b: Cooper-pair box of examples/local-basis-example.py:145-170 (charge basis, gate charge)."""
+    ps = import_reference()
+    Ca, Jc, Aj = 60.0, 1.0, 0.1 * 0.1
+    with quiet():
+        g = ps.CircuitGraph()
+        g.addBranch(0, 1, "C")
+        g.addBranch(0, 1, "I")
+        g.addChargeBias(1, "Z", "Cg1")
+        h = ps.NumericalSystem(ps.SymbolicSystem(g))
+        h.configureOperator(1, trunc, "charge")
+        h.setParameterValues("C", Ca * Aj, "I", Jc * Aj, "Cg1", 1.0, "QZ", 0.5)
+    return h
+
+
 # ------------------------------------------------------------------------------------------------
 # running the reference and freezing its outputs
 # ------------------------------------------------------------------------------------------------
@@ -418,7 +449,67 @@ def make_c5():
                         "c5_fluxatom_t180": (build_fluxonium_atom(180), [S("phi-", 0.0, 1.0, 64)], None)})
 
 
-ALL = {"c1": make_c1, "c2": make_c2, "c3": make_c3, "c4": make_c4, "c5": make_c5}
+def _pauli_reference(name, h, sweeps, k, evaluations, matel, basis):
+    """Freeze a sweep with Current / Voltage evaluables plus util.pauliCoefficients
+    (util.py:300-391; examples/local-basis-example.py:98-111,176-203) computed by the reference."""
+    ps = import_reference()
+    freeze(name, h, sweeps, k=k, get_vectors=True, evaluations=evaluations, vec_points=[0, 3],
+           lower_kw={"matrix_elements": matel})
+    recs, _ = reference_sweep(h, sweeps, k, True, evaluations)
+    E = np.array([np.asarray(r["getHamiltonian"][0]) for r in recs]).T           # [k, N]
+    V = np.empty((k, len(recs)), dtype=object)
+    for i, r in enumerate(recs):
+        V[:, i] = r["getHamiltonian"][1]
+    with quiet():
+        if basis[0] == "operator":        # a fixed operator at the initial parameter values
+            h.setParameterValues(*basis[2])
+            Op = h.getCurrentOperator(basis[1])
+            op_dense = Op.data.to_array()
+            hx, hy, hz = ps.util.pauliCoefficients(E, V, Op)
+            m = np.array([[[Op.matrix_element(V[a, i], V[b, i]) for b in (0, 1)] for a in (0, 1)] for i in range(len(recs))])
+        else:                              # subspace operators from the Voltage matrix elements
+            Vii = np.array([r["getVoltageMatrixElement"] for r in recs]).T
+            ops_ = ps.util.createSubspaceOperators(Vii[0], Vii[1], Vii[2], Vii[3])
+            hx, hy, hz = ps.util.pauliCoefficients(E, V, ops_)
+            m = np.array([np.asarray(o) for o in ops_])
+            op_dense = np.zeros((0, 0))
+    path = os.path.join(HERE, name + ".npz")
+    g = dict(np.load(path))
+    g.update(pauli_hx=hx, pauli_hy=hy, pauli_hz=hz, pauli_op=m.astype(np.complex128), pauli_operator=op_dense)
+    np.savez_compressed(path, **g)
+
+
+def make_c6():
+    """Eigenvector consumers: Current / Voltage evaluables and pauliCoefficients."""
+    h = build_rfsquid(50)
+    jj = h.getCircuitGraph().getComponentEdge("I")
+    le = h.getCircuitGraph().getComponentEdge("L")
+    sw = [S("phiZ", 0.49, 0.51, 11)]
+    el = [(0, 0), (0, 1), (1, 1), (2, 0)]
+    _pauli_reference("c6_rfsquid", h, sw, 5,
+                     [("Hamiltonian", {}), ("Current", {"edge": jj, "elements": el}), ("Voltage", {"node": 1, "elements": [(0, 1), (1, 2)]})],
+                     [{"kind": "Current", "edge": list(jj), "elements": el}, {"kind": "Voltage", "node": 1, "elements": [(0, 1), (1, 2)]}],
+                     ("operator", le, ("phiZ", 0.5)))
+    h = build_rfsquid(50)
+    freeze("c6_rfsquid_L", h, sw, k=5, get_vectors=True,
+           evaluations=[("Hamiltonian", {}), ("Current", {"edge": le, "elements": el})], vec_points=[0, 3],
+           lower_kw={"matrix_elements": [{"kind": "Current", "edge": list(le), "elements": el}]})
+    h = build_cpb(20)
+    el4 = [(0, 0), (0, 1), (1, 0), (1, 1)]
+    _pauli_reference("c6_cpb", h, [S("QZ", 0.4, 0.6, 11)], 5,
+                     [("Hamiltonian", {}), ("Voltage", {"node": 1, "elements": el4})],
+                     [{"kind": "Voltage", "node": 1, "elements": el4}], ("subspace",))
+    # multi-node: a junction between two non-ground nodes (two-factor current operator)
+    h = build_csfq_3jj(5)
+    e12 = h.getCircuitGraph().getComponentEdge("I2")
+    freeze("c6_csfq3jj_t5", h, [S("phiZ", 0.45, 0.55, 5)], k=6, get_vectors=True,
+           evaluations=[("Hamiltonian", {}), ("Current", {"edge": e12, "elements": el}), ("Voltage", {"node": 2, "elements": el})],
+           vec_points=[0, 2],
+           lower_kw={"matrix_elements": [{"kind": "Current", "edge": list(e12), "elements": el},
+                                         {"kind": "Voltage", "node": 2, "elements": el}]})
+
+
+ALL = {"c6": make_c6, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c4": make_c4, "c5": make_c5}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(ALL)

@@ -57,12 +57,17 @@ class OracleEngine:
         c, _ = self.coefficients(params)
         return _FakeTensor(np.stack([self.orc.hamiltonian(row, tidy=tidyup).toarray() for row in c.numpy()]))
 
-    def sweep(self, params, k, want_vectors=False, resonator=False, **kw):
+    def sweep(self, params, k, want_vectors=False, resonator=False, matrix_elements=False, **kw):
         from pycqed_b200.engine import SweepResult
-        out = self.orc.sweep(params, k, get_vectors=want_vectors, resonator=resonator)
+        out = self.orc.sweep(params, k, get_vectors=want_vectors or matrix_elements, resonator=resonator)
         V = np.ascontiguousarray(out["V"].transpose(0, 2, 1)) if want_vectors else None
         scal = {nm: out["scalars"][:, i] for i, nm in enumerate(self.plan.program.scalar_names)}
-        return SweepResult(out["E"], V, scal, out["Erwa"], np.zeros(len(out["E"]), dtype=np.int32))
+        M = self.orc.matrix_elements(params, out["V"]) if matrix_elements else None
+        return SweepResult(out["E"], V, scal, out["Erwa"], np.zeros(len(out["E"]), dtype=np.int32), M)
+
+    def matrix_elements(self, params, V):
+        V = V if isinstance(V, np.ndarray) else V.numpy()
+        return _FakeTensor(self.orc.matrix_elements(params, np.asarray(V).transpose(0, 2, 1)))
 
 
 @pytest.fixture()
@@ -157,6 +162,79 @@ def test_vectors_and_resonator_layouts(patched):
     rec = b.record(0)
     assert set(rec) == {"getHamiltonian", "getResonatorResponse"}
     assert isinstance(rec["getHamiltonian"][0], tuple) and len(rec["getHamiltonian"][1]) == 6
+
+
+def test_current_voltage_evaluables(patched):
+    """examples/local-basis-example.py:66-85,176-190: Current / Voltage in a sweep, getSweep layout
+    (n_elements, N); diagonal elements are phase independent and must equal the reference's."""
+    ref, mine, mg = _pair("build_rfsquid", patched, 30)
+    jj = ref.getCircuitGraph().getComponentEdge("I")
+    el = [(0, 0), (1, 1), (0, 1)]
+    ev = [("Hamiltonian", {}), ("Current", {"edge": jj, "elements": el}), ("Voltage", {"node": 1, "elements": el})]
+    a, b = _run_both(ref, mine, mg, [("phiZ", 0.49, 0.51, 5)], 4, True, ev)
+    for evn in ("Current", "Voltage"):
+        _, Ia, _ = ref.getSweep(a, "phiZ", {}, evaluable=evn)
+        _, Ib, _ = mine.getSweep(b, "phiZ", {}, evaluable=evn)
+        assert Ia.shape == Ib.shape == (3, 5)
+        scale = max(1.0, np.abs(Ia).max())
+        assert np.max(np.abs(Ia[:2] - Ib[:2])) < 1e-9 * scale
+        assert np.max(np.abs(np.abs(Ia[2]) - np.abs(Ib[2]))) < 1e-7 * scale       # real eigenvectors: sign only
+    rec = b.record(0)
+    assert set(rec) == {"getHamiltonian", "getCurrentMatrixElement", "getVoltageMatrixElement"}
+    assert rec["getCurrentMatrixElement"].shape == (3,)
+    # error behaviour (numerical_system.py:598-601,660-661,671-674)
+    for h in (ref, mine):
+        with mg.quiet():
+            h.newSweep()
+            h.addSweep("phiZ", 0.49, 0.51, 2)
+            h.addEvaluation("Hamiltonian")
+            h.addEvaluation("Current", edge=(7, 8, 0), elements=el)
+            h.setDiagConfig(eigvalues=3, get_vectors=True)
+        with pytest.raises(Exception, match="not in the circuit"):
+            with mg.quiet():
+                h.paramSweep(timesweep=False)
+        with mg.quiet():
+            h.newSweep()
+            h.addSweep("phiZ", 0.49, 0.51, 2)
+            h.addEvaluation("Hamiltonian")
+            h.addEvaluation("Voltage", node=1)
+            h.setDiagConfig(eigvalues=3, get_vectors=True)
+        with pytest.raises(Exception, match="No elements specified"):
+            with mg.quiet():
+                h.paramSweep(timesweep=False)
+
+
+def test_current_voltage_operators_single_point(patched):
+    ref, mine, mg = _pair("build_csfq_3jj", patched, 3)
+    e12 = ref.getCircuitGraph().getComponentEdge("I2")
+    with mg.quiet():
+        for edge in (e12, ref.getCircuitGraph().getComponentEdge("I1")):
+            A = ref.getCurrentOperator(edge).data.to_array()
+            B = mine.getCurrentOperator(edge).full()
+            assert np.max(np.abs(A - B)) < 1e-12 * max(1.0, np.abs(A).max())
+        A = ref.getVoltageOperator(2).data.to_array()
+        B = mine.getVoltageOperator(2).full()
+        assert np.max(np.abs(A - B)) < 1e-12 * max(1.0, np.abs(A).max())
+        ref.setDiagConfig(eigvalues=4, get_vectors=True)
+        E, V = ref.diagonalize(ref.getHamiltonian())
+        el = [(0, 0), (0, 1), (2, 3)]
+        ma = ref.getCurrentMatrixElement(E, V, edge=e12, elements=el)
+        mb = mine.getCurrentMatrixElement(E, V, edge=e12, elements=el)
+        assert np.max(np.abs(ma - mb)) < 1e-10 * max(1.0, np.abs(ma).max())
+        va = ref.getVoltageMatrixElement(E, V, node=1, elements=el)
+        vb = mine.getVoltageMatrixElement(E, V, node=1, elements=el)
+        assert np.max(np.abs(va - vb)) < 1e-10 * max(1.0, np.abs(va).max())
+    ref2, mine2, mg = _pair("build_rfsquid", patched, 20)
+    le = ref2.getCircuitGraph().getComponentEdge("L")
+    with mg.quiet():
+        A = ref2.getCurrentOperator(le).data.to_array()
+        B = mine2.getCurrentOperator(le).full()
+    assert np.max(np.abs(A - B)) < 1e-11 * max(1.0, np.abs(A).max())
+    for h in (ref2, mine2):
+        with pytest.raises(Exception, match="No edge specified"):
+            h.getCurrentOperator()
+        with pytest.raises(Exception, match="No node specified"):
+            h.getVoltageOperator()
 
 
 def test_single_point_api(patched):

@@ -316,3 +316,81 @@ def test_error_paths(engine_mod):
             eng.sweep(g["params"][:2], 10, resonator=True)      # plan lowered without the evaluable
         with pytest.raises(engine_mod.EngineError):
             eng.sweep(np.zeros((3, 5)), 10)                     # wrong number of swept columns
+
+
+# ---------------------------------------------------------------------------------------------
+# eigenvector consumers: Current / Voltage matrix elements, pauliCoefficients
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c6_rfsquid", "c6_rfsquid_L", "c6_cpb", "c6_csfq3jj_t5"])
+def test_matrix_elements_vs_reference_and_oracle(engine_mod, name):
+    """getCurrentMatrixElement / getVoltageMatrixElement (numerical_system.py:596-694)."""
+    import torch
+    from tests.test_oracle_golden import matel_reference
+    g, plan = load_golden(name)
+    k = int(g["k"])
+    ref = matel_reference(g, plan)
+    pairs = plan.aux_pairs()
+    scale = max(1.0, np.abs(ref).max())
+    orc = PlanOracle(plan)
+    with engine_mod.Engine(plan) as eng:
+        res = eng.sweep(g["params"], k, want_vectors=True, matrix_elements=True)
+        assert not res.info.any()
+        assert eig_rel_err(res.E, g["E"]) < E_RTOL
+        assert res.matel.shape == ref.shape
+        # phase-invariant parts against the reference's own sweep
+        for q, (_, _, i, j) in enumerate(pairs):
+            if i == j:
+                assert np.max(np.abs(res.matel[:, q].real - ref[:, q])) < 1e-9 * scale, (name, q)
+            else:
+                pass  # Re<i|Op|j> depends on the eigenvector phases; checked below on fixed vectors
+        # same eigenvectors in, same numbers out: the kernel on the engine's vectors vs the oracle on them
+        Mo = orc.matrix_elements(g["params"], res.V.transpose(0, 2, 1))
+        assert np.max(np.abs(res.matel - Mo)) < 1e-11 * scale
+        # and on the reference's eigenvectors, against the reference's evaluable output (all elements)
+        for a, p in enumerate(g["vec_points"]):
+            Vd = torch.as_tensor(np.ascontiguousarray(g["V"][a].T[None]), device="cuda")
+            M = eng.matrix_elements(g["params"][p:p + 1], Vd).cpu().numpy()[0]
+            assert np.max(np.abs(M.real - ref[p])) < 1e-9 * scale, (name, p)
+
+
+@pytest.mark.parametrize("name", ["c6_rfsquid", "c6_csfq3jj_t5"])
+def test_aux_operator_assembly(engine_mod, name):
+    """getCurrentOperator / getVoltageOperator as dense matrices through K1 + K2."""
+    from oracle.plan_oracle import eval_aux_coefficients
+    g, plan = load_golden(name)
+    orc = PlanOracle(plan)
+    ac = eval_aux_coefficients(plan.program, g["params"][:3])
+    for oi in range(len(plan.aux_ops)):
+        with engine_mod.Engine(plan.aux_as_terms(oi)) as eng:
+            M = eng.assemble_dense(g["params"][:3], tidyup=False).cpu().numpy()
+        for p in range(3):
+            Mo = orc.aux_operator(ac[p], oi).toarray()
+            assert np.max(np.abs(M[p] - Mo)) < 1e-13 * max(1.0, np.abs(Mo).max())
+            assert np.max(np.abs(M[p] - M[p].conj().T)) < 1e-12 * max(1.0, np.abs(Mo).max())
+
+
+def test_pauli_coefficients(engine_mod):
+    """util.pauliCoefficients (util.py:300-391): golden reference values (complex64 accuracy) and
+    the float64 oracle, plus random Hermitian 2x2 operators with every branch of the kernel."""
+    from oracle.plan_oracle import pauli_coefficients
+    for name in ("c6_rfsquid", "c6_cpb"):
+        g, _ = load_golden(name)
+        E0, E1 = g["E"][:, 0], g["E"][:, 1]
+        hx, hy, hz = engine_mod.pauli_coefficients(E0, E1, g["pauli_op"])
+        ox, oy, oz = pauli_coefficients(E0, E1, g["pauli_op"])
+        scale = np.max(np.abs(g["E"][:, :2]))
+        for a, b, r in ((hx, ox, g["pauli_hx"]), (hy, oy, g["pauli_hy"]), (hz, oz, g["pauli_hz"])):
+            assert np.max(np.abs(a - b)) < 1e-12 * scale
+            assert np.max(np.abs(a - r)) < 2e-5 * scale
+    rng = np.random.default_rng(5)
+    N = 4096
+    a = rng.standard_normal((N, 2, 2)) + 1j * rng.standard_normal((N, 2, 2))
+    Op = (a + a.conj().transpose(0, 2, 1)) / 2
+    Op[:64, 0, 0] = Op[:64, 1, 1]                       # delta == 0
+    Op[64:128, 0, 1] *= 1e-9; Op[64:128, 1, 0] *= 1e-9  # nearly diagonal, both signs of delta
+    E0 = rng.standard_normal(N)
+    E1 = E0 + rng.uniform(0.1, 2.0, N)
+    hx, hy, hz = engine_mod.pauli_coefficients(E0, E1, Op)
+    ox, oy, oz = pauli_coefficients(E0, E1, Op)
+    assert np.max(np.abs(hx - ox)) < 1e-11 and np.max(np.abs(hy - oy)) < 1e-11 and np.max(np.abs(hz - oz)) < 1e-11
+    assert np.max(np.abs(2 * np.sqrt(hx ** 2 + hy ** 2 + hz ** 2) - (E1 - E0))) < 1e-12

@@ -104,3 +104,54 @@ def test_known_anchor_values():
     E = orc.sweep(np.array([[0.0, 0.0]]), 4)["E"][0]
     assert abs((E[1] - E[0]) - 4.0576115556) < 1e-8
     assert abs((E[2] - E[1]) - 3.6746586526) < 1e-8
+
+
+# ---- eigenvector consumers ------------------------------------------
+MATEL_CASES = ["c6_rfsquid", "c6_rfsquid_L", "c6_cpb", "c6_csfq3jj_t5"]
+
+
+def matel_reference(g, plan):
+    """Reference matrix elements [n_pts, n_pairs] ordered like plan.aux_pairs()."""
+    cols = []
+    for op in plan.aux_ops:
+        cols.append(np.asarray(g["eval_" + op["name"]]).reshape(len(g["E"]), -1))
+    return np.concatenate(cols, axis=1)
+
+
+@pytest.mark.parametrize("name", MATEL_CASES)
+def test_current_voltage_matrix_elements_match_reference(name):
+    """numerical_system.py:596-694.  Matrix elements depend on the arbitrary phases of the
+    eigenvectors, so the oracle evaluates them on ITS eigenvectors and the comparison is
+    restricted to phase-invariant quantities: diagonal elements, and |<i|Op|j>| for i != j."""
+    g, plan = load_golden(name)
+    k = int(g["k"])
+    orc = PlanOracle(plan)
+    out = orc.sweep(g["params"], k, get_vectors=True)
+    M = orc.matrix_elements(g["params"], out["V"])
+    ref = matel_reference(g, plan)
+    pairs = plan.aux_pairs()
+    assert M.shape == ref.shape == (len(g["E"]), len(pairs))
+    scale = max(1.0, np.abs(ref).max())
+    for q, (_, _, i, j) in enumerate(pairs):
+        if i == j:
+            assert np.max(np.abs(M[:, q].real - ref[:, q])) < 1e-9 * scale, (name, q)
+            assert np.max(np.abs(M[:, q].imag)) < 1e-9 * scale
+    # with the reference's own eigenvectors every element (real part) must agree
+    for a, p in enumerate(g["vec_points"]):
+        Mv = orc.matrix_elements(g["params"][p:p + 1], g["V"][a][None])[0]
+        assert np.max(np.abs(Mv.real - ref[p])) < 1e-9 * scale, (name, p)
+
+
+@pytest.mark.parametrize("name", ["c6_rfsquid", "c6_cpb"])
+def test_pauli_coefficients_match_reference(name):
+    """util.py:300-391.  The reference computes in complex64, so it is only matched to 1e-5 of the
+    energy scale; the float64 oracle is what the GPU kernel is held to."""
+    from oracle.plan_oracle import pauli_coefficients
+    g, plan = load_golden(name)
+    hx, hy, hz = pauli_coefficients(g["E"][:, 0], g["E"][:, 1], g["pauli_op"])
+    scale = np.max(np.abs(g["E"][:, :2]))
+    for mine, ref in ((hx, g["pauli_hx"]), (hy, g["pauli_hy"]), (hz, g["pauli_hz"])):
+        assert np.max(np.abs(mine - ref)) < 2e-5 * scale
+    # the two-level model reproduces the gap (examples/local-basis-example.py:113-133)
+    gap = 2 * np.sqrt(hx ** 2 + hy ** 2 + hz ** 2)
+    assert np.max(np.abs(gap - (g["E"][:, 1] - g["E"][:, 0]))) < 1e-10 * scale
