@@ -96,7 +96,7 @@ struct scqed_plan {
     int n_coef_scalar = 0;
     long long mf_work_per_row = 0;     // complex MACs per output element of the matrix-free mat-vec
     int s1_real_mode = -1;             // fused small path: -1 unknown, 0 complex Hermitian, 1 real symmetric
-    DevBuf s1work, s1vec, auxc;
+    DevBuf s1work, s1vec, auxc, resvec;
     int pair_max_index = -1;
     std::vector<int> factor_node;
     // device copies of the tables
@@ -373,7 +373,7 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
 extern "C" void scqed_plan_destroy(scqed_plan *pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
-    DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->s1work, &pl->s1vec, &pl->auxc, &pl->in_params, &pl->out_evals,
+    DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->s1work, &pl->s1vec, &pl->auxc, &pl->resvec, &pl->in_params, &pl->out_evals,
                       &pl->out_evecs, &pl->out_post, &pl->out_info, &pl->out_scal};
     for (DevBuf *b : bufs) b->release();
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
@@ -1097,17 +1097,31 @@ extern "C" int scqed_sweep_run(scqed_plan *pl, const scqed_sweep_opts *o, const 
     if ((solver == 1 || solver == 5) && !fits) return fail(SCQED_EUNSUPPORTED, "n=%d k=%d does not fit the fused shared-memory path", n, k);
     if (solver == 0) {
         if (fits) solver = 1;
-        else if (!o->resonator && P.max_term_nn <= 3 && o->k + 6 <= MF_BMAX && (n > 4096 || pl->mf_work_per_row <= n / 2)) solver = 4;
+        else if (P.max_term_nn <= 3 && o->k + 6 <= MF_BMAX && (n > 4096 || pl->mf_work_per_row <= n / 2)) solver = 4;
         else solver = 2;
     }
     if (solver == 1 || solver == 5) {
         return run_small_any(pl, P, (const cplx *)pl->coef.p, nullptr, scal, n_pts, n, k, o->want_vectors, o->tidyup, res,
                              evals_dev, (cplx *)evecs_dev, post_dev, info_dev, st, solver == 5);
     }
-    if (o->resonator) return fail(SCQED_EUNSUPPORTED, "the Resonator evaluable is only implemented on the fused path (n <= ~110)");
-    if (solver == 4)
-        return run_matfree(pl, (const cplx *)pl->coef.p, n_pts, k, o->want_vectors, evals_dev, (cplx *)evecs_dev, info_dev, st,
-                           60, 60, 1e-9);
+    // S2 / S3 with the Resonator evaluable: eigenvectors are needed on the device even when the
+    // caller does not want them back
+    cplx *vecs = (cplx *)evecs_dev;
+    if (o->resonator && !vecs) {
+        if (pl->resvec.ensure((size_t)n_pts * k * n * 16)) return fail(SCQED_ENOMEM, "eigenvector buffer for the Resonator evaluable");
+        vecs = (cplx *)pl->resvec.p;
+    }
+    auto finish = [&]() -> int {
+        if (!o->resonator) return 0;
+        resonator_generic_kernel<<<(unsigned)n_pts, 128, 0, st>>>(P, res, scal, evals_dev, vecs, n, k, post_dev);
+        LAUNCHED();
+        CK(cudaGetLastError());
+        return 0;
+    };
+    if (solver == 4) {
+        rc = run_matfree(pl, (const cplx *)pl->coef.p, n_pts, k, o->want_vectors, evals_dev, vecs, info_dev, st, 60, 60, 1e-9);
+        return rc ? rc : finish();
+    }
     // ---- S2: batches of B matrices through HBM ------------------------------------------------
     const bool blocked = solver != 3;
     int B = pick_dense_batch(n, n_pts, k, pl->sm_count);
@@ -1128,12 +1142,12 @@ extern "C" int scqed_sweep_run(scqed_plan *pl, const scqed_sweep_opts *o, const 
         rc = run_assemble(pl, (const cplx *)pl->coef.p + (size_t)p0 * P.n_terms, nb, o->tidyup, A, st);
         if (rc) return rc;
         double *ev = evals_dev + (size_t)p0 * k;
-        cplx *vec = evecs_dev ? (cplx *)evecs_dev + (size_t)p0 * k * n : nullptr;
+        cplx *vec = vecs ? vecs + (size_t)p0 * k * n : nullptr;
         rc = blocked ? run_dense_blocked_batch(A, n, nb, k, o->want_vectors, 1, bw, ev, vec, info_dev + p0, st)
                      : run_dense_batch(pl, pl->sm_count, A, n, nb, k, o->want_vectors, 1, w, ev, vec, info_dev + p0, st);
         if (rc) return rc;
     }
-    return 0;
+    return finish();
 }
 
 extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, const double *params, int64_t n_pts,

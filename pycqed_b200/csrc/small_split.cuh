@@ -331,6 +331,17 @@ s1_resonator_kernel(S1Args a, ResonatorArgs R, const int *__restrict__ skip, con
                      scratch, post + (size_t)p * R.nstrips * a.k, nullptr);   // QL on private (L1-resident) arrays: a shared tile costs occupancy
 }
 
+// The same post-op behind the HBM dense (S2) and matrix-free (S3) solvers: eigenpairs come from
+// global memory, nothing else is needed.
+__global__ void __launch_bounds__(128)
+resonator_generic_kernel(PlanDev P, ResonatorArgs R, const double *__restrict__ scalars, const double *__restrict__ evals,
+                         const cplx *__restrict__ evecs, int n, int k, double *__restrict__ post) {
+    __shared__ double scratch[8 * SCQED_RES_KMAX];
+    const long long p = blockIdx.x;
+    resonator_strips(P, R, scalars + p * P.n_scalar, evals + p * k, evecs + (size_t)p * k * n, n, k, scratch,
+                     post + (size_t)p * R.nstrips * k, nullptr);
+}
+
 // complement of the flags (second, complex pass only handles the flagged points)
 __global__ void s1_invert_flags(const int *__restrict__ flags, int *__restrict__ skip, long long n, int *__restrict__ count) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -398,6 +398,14 @@ def make_c2():
     freeze("c2_fluxonium_t200s", build_fluxonium(200), [S("phiZ", -1.0, 1.0, 9)], k=10)
 
 
+def make_c2b():
+    """C2 at truncation 200 with the Resonator evaluable: the post-op behind the HBM dense solver."""
+    res = {"resonator": {"cpl_node": 1, "nmax": 30}}
+    freeze("c2_fluxonium_res_t200s", build_fluxonium(200), [S("phiZ", -1.0, 1.0, 7)], k=10, get_vectors=True,
+           evaluations=[("Hamiltonian", {}), ("Resonator", {"cpl_node": 1, "nmax": 30})], vec_points=[0, 3],
+           lower_kw=res, store_h=False)
+
+
 def make_c3():
     freeze("c3_csfq3jj_t10", build_csfq_3jj(10), [S("phiZ", 0.0, 1.0, 21)], k=10)
     freeze("c3_csfq4jj_t10", build_csfq_4jj(10), [S("d", 0.0, 0.1, 3), S("phiX", -1.0, 1.0, 11)], k=10,
@@ -509,7 +517,7 @@ def make_c6():
                                          {"kind": "Voltage", "node": 2, "elements": el}]})
 
 
-ALL = {"c6": make_c6, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c4": make_c4, "c5": make_c5}
+ALL = {"c6": make_c6, "c2b": make_c2b, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c4": make_c4, "c5": make_c5}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(ALL)

@@ -249,6 +249,22 @@ def test_sweep_resonator_matches_reference(engine_mod):
     assert rel_err(res.scalars["gC"], np.full(len(ref), res.scalars["gC"][0])) < 1e-14
 
 
+@pytest.mark.parametrize("name,solver,vectors", [("c2_fluxonium_res", 2, True), ("c2_fluxonium_res", 4, False),
+                                                 ("c2_fluxonium_res_t200s", 0, False), ("c2_fluxonium_res_t200s", 0, True)])
+def test_resonator_behind_dense_and_matrix_free_solvers(engine_mod, name, solver, vectors):
+    """getResonatorResponse (numerical_system.py:736-784) when H does not fit the fused small path."""
+    g, plan = load_golden(name)
+    k = int(g["k"])
+    with engine_mod.Engine(plan) as eng:
+        res = eng.sweep(g["params"], k, want_vectors=vectors, resonator=True, solver=solver)
+    assert not res.info.any()
+    assert eig_rel_err(res.E, g["E"]) < E_RTOL
+    ref = g["eval_getResonatorResponse"]
+    assert res.Erwa.shape == ref.shape
+    assert np.max(np.abs(res.Erwa - ref)) < E_RTOL * np.max(np.abs(ref))
+    assert (res.V is not None) == vectors
+
+
 def test_sweep_scalar_evaluables(engine_mod):
     g, plan = load_golden("c4_averin")
     with engine_mod.Engine(plan) as eng:
