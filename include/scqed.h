@@ -67,6 +67,14 @@ typedef struct {
     const int32_t *aux_im;          /* [n_aux]                                               */
     int32_t n_pairs;
     const int32_t *pairs;           /* [n_pairs * 4]                                         */
+    /* Optional dense real term table for the fused small-n solver (n <= 128): Re H = sum_g r[dense_re[g]] G_g,
+     * Im H = sum_g r[dense_im[g]] G_g with G_g real n x n, element (i, j) at dense_tab[g*n*n + j*n + i];
+     * register -1 = identically zero.  n_dense = 0 disables it (the term table is walked per element). */
+    int32_t n_dense;
+    const double *dense_tab;        /* [n_dense * n * n]                                     */
+    const int32_t *dense_re;        /* [n_dense]                                             */
+    const int32_t *dense_im;        /* [n_dense]                                             */
+    const double *dense_gmax;       /* [n_dense] max |G_g|                                   */
 } scqed_plan_desc;
 
 /* Options of one sweep (numerical_system.py:790-804 setDiagConfig + :868-875 addEvaluation). */

@@ -30,7 +30,7 @@ __device__ __forceinline__ double powi(double x, int n) {
 __global__ void __launch_bounds__(128)
 coef_eval_kernel(PlanDev P, const double *__restrict__ params, long long n_pts,
                  double *__restrict__ regs, cplx *__restrict__ coef, double *__restrict__ scalars,
-                 cplx *__restrict__ auxcoef) {
+                 cplx *__restrict__ auxcoef, double *__restrict__ dcoef) {
     long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pts) return;
     const double *prm = params + p * P.n_swept;
@@ -74,6 +74,14 @@ coef_eval_kernel(PlanDev P, const double *__restrict__ params, long long n_pts,
     }
     for (int s = 0; s < P.n_scalar; ++s)
         scalars[p * P.n_scalar + s] = regs[(long long)__ldg(P.scalar_regs + s) * n_pts + p];
+    if (dcoef) {
+        const int ng = P.n_dense;
+        for (int g = 0; g < ng; ++g) {
+            int ir = __ldg(P.dense_re + g), ii = __ldg(P.dense_im + g);
+            dcoef[p * 2 * ng + g] = ir >= 0 ? regs[(long long)ir * n_pts + p] : 0.0;
+            dcoef[p * 2 * ng + ng + g] = ii >= 0 ? regs[(long long)ii * n_pts + p] : 0.0;
+        }
+    }
     if (auxcoef) {
         for (int t = 0; t < P.n_aux; ++t) {
             int ir = __ldg(P.aux_re + t), ii = __ldg(P.aux_im + t);

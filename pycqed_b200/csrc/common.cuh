@@ -94,6 +94,11 @@ struct PlanDev {
     const int *aux_meta;           // [n_aux * 7] like term_meta
     const int *aux_re, *aux_im;    // [n_aux] coefficient registers
     const int *pairs;              // [n_pairs * 4]: tb, te, i, j
+    // dense real term table of the fused small-n solver: Re H = sum_g alpha_g G_g, Im H = sum_g beta_g G_g
+    int n_dense;
+    const double *dense_tab;       // [n_dense][n*n] column-major
+    const int *dense_re, *dense_im;   // [n_dense] coefficient registers (-1 = zero)
+    const double *dense_gmax;      // [n_dense]
     int n_swept, n_instr, n_scalar;
     const int *instr;              // [n_instr * 3]
     const double *consts;

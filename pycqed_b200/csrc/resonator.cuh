@@ -40,13 +40,13 @@ __device__ inline int tql_eigenvalues(double *d, double *e, int n, int st) {
             if (m != l) {
                 if (iter++ == 80) { fail = 1; break; }
                 double g = (D_(l + 1) - D_(l)) / (2.0 * E_(l));
-                double r = hypot(g, 1.0);
+                double r = sqrt(fma(g, g, 1.0));
                 g = D_(m) - D_(l) + E_(l) / (g + copysign(r, g));
                 double s = 1.0, c = 1.0, p = 0.0;
                 int i;
                 for (i = m - 1; i >= l; --i) {
                     double f = s * E_(i), b = c * E_(i);
-                    r = hypot(f, g);
+                    r = sqrt(fma(f, f, g * g));      // |f|, |g| are O(level spacing): no overflow guard needed
                     E_(i + 1) = r;
                     if (r == 0.0) { D_(i + 1) -= p; E_(m) = 0.0; break; }
                     s = f / r; c = g / r;
@@ -83,7 +83,10 @@ __device__ void resonator_strips(const PlanDev &P, const ResonatorArgs &R, const
     int *order = (int *)(scratch + 4 * k);       // [k]
     const double gC = scal[R.s_gc], wrl = scal[R.s_frl], qb = scal[R.s_qb];
     const int c = R.op_node, dc = P.dims[c], sc = P.strides[c];
-    const cplx *F = P.factor_data + P.factor_offset[R.op_factor];
+    // ELL rows of the coupled node's charge operator (2 non-zeros per row in the oscillator basis,
+    // 1 in the charge basis): the dense row walk was 50x more loads
+    const int fw = __ldg(P.ell_w + R.op_factor);
+    const long long foff = __ldg(P.ell_off + R.op_factor);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (int i = w; i < k - 1; i += nw) {
         const cplx *xi = X + (size_t)i * n, *xj = X + (size_t)(i + 1) * n;
@@ -92,9 +95,10 @@ __device__ void resonator_strips(const PlanDev &P, const ResonatorArgs &R, const
             int ac = (a / sc) % dc;
             int base = a - ac * sc;
             cplx y = cscale(qb, xj[a]);
-            for (int b = 0; b < dc; ++b) {
-                cplx f = __ldg(F + ac * dc + b);
-                if (f.x != 0.0 || f.y != 0.0) cfma(y, f, xj[base + b * sc]);
+            for (int b = 0; b < fw; ++b) {
+                const cplx f = __ldg(P.ell_vals + foff + (long long)ac * fw + b);
+                const int col = __ldg(P.ell_cols + foff + (long long)ac * fw + b);
+                cfma(y, f, xj[base + col * sc]);
             }
             cfmac(acc, xi[a], y);
         }

@@ -96,7 +96,7 @@ struct scqed_plan {
     int n_coef_scalar = 0;
     long long mf_work_per_row = 0;     // complex MACs per output element of the matrix-free mat-vec
     int s1_real_mode = -1;             // fused small path: -1 unknown, 0 complex Hermitian, 1 real symmetric
-    DevBuf s1work, s1vec, auxc, resvec;
+    DevBuf s1work, s1vec, auxc, resvec, dcoef;
     int pair_max_index = -1;
     std::vector<int> factor_node;
     // device copies of the tables
@@ -319,6 +319,14 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     size_t o_ameta = put(aux_meta.data(), aux_meta.size() * 4);
     size_t o_are = put(d->aux_re, (size_t)d->n_aux * 4), o_aim = put(d->aux_im, (size_t)d->n_aux * 4);
     size_t o_pairs = put(d->pairs, (size_t)d->n_pairs * 16);
+    int n_dense = d->n_dense;
+    if (n_dense < 0 || (n_dense > 0 && (!d->dense_tab || !d->dense_re || !d->dense_im || !d->dense_gmax)))
+        { delete pl; return fail(SCQED_EINVAL, "dense term table malformed"); }
+    for (int g = 0; g < n_dense; ++g)
+        if (d->dense_re[g] >= d->n_instr || d->dense_im[g] >= d->n_instr) { delete pl; return fail(SCQED_EINVAL, "dense table register out of range"); }
+    size_t o_dtab = put(d->dense_tab, (size_t)n_dense * n * n * 8);
+    size_t o_dre = put(d->dense_re, (size_t)n_dense * 4), o_dim = put(d->dense_im, (size_t)n_dense * 4);
+    size_t o_dgm = put(d->dense_gmax, (size_t)n_dense * 8);
     if (pl->tables.ensure(host.size() + 256)) { delete pl; return fail(SCQED_ENOMEM, "plan tables"); }
     if (cudaMemcpy(pl->tables.p, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         pl->tables.release(); delete pl; return fail(SCQED_ECUDA, "uploading plan tables failed");
@@ -345,6 +353,10 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     P.aux_meta = (const int *)(base + o_ameta);
     P.aux_re = (const int *)(base + o_are); P.aux_im = (const int *)(base + o_aim);
     P.pairs = (const int *)(base + o_pairs);
+    P.n_dense = n_dense;
+    P.dense_tab = (const double *)(base + o_dtab);
+    P.dense_re = (const int *)(base + o_dre); P.dense_im = (const int *)(base + o_dim);
+    P.dense_gmax = (const double *)(base + o_dgm);
     P.max_term_nn = max_nn;
     P.stencil_ok = stencil_ok ? 1 : 0;
     P.st_pure_shift = pure_shift ? 1 : 0;
@@ -373,7 +385,7 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
 extern "C" void scqed_plan_destroy(scqed_plan *pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
-    DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->s1work, &pl->s1vec, &pl->auxc, &pl->resvec, &pl->in_params, &pl->out_evals,
+    DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->s1work, &pl->s1vec, &pl->auxc, &pl->resvec, &pl->dcoef, &pl->in_params, &pl->out_evals,
                       &pl->out_evecs, &pl->out_post, &pl->out_info, &pl->out_scal};
     for (DevBuf *b : bufs) b->release();
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
@@ -405,12 +417,17 @@ extern "C" const char *scqed_version(void) { return "scqed 0.1 (sm_100a)"; }
 // K1 / K2
 // ------------------------------------------------------------------------------------------------
 static int run_coef(scqed_plan *pl, const double *params_dev, long long n_pts, cplx *coef_dev, double *scal_dev,
-                    cudaStream_t st, cplx *aux_dev = nullptr) {
+                    cudaStream_t st, cplx *aux_dev = nullptr, bool dense = false) {
     const PlanDev &P = pl->P;
     if (pl->regs.ensure((size_t)(P.n_instr > 0 ? P.n_instr : 1) * n_pts * 8)) return fail(SCQED_ENOMEM, "coefficient registers");
     int threads = 128;
     long long blocks = (n_pts + threads - 1) / threads;
-    coef_eval_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, params_dev, n_pts, (double *)pl->regs.p, coef_dev, scal_dev, aux_dev);
+    double *dcoef = nullptr;
+    if (dense && P.n_dense > 0) {
+        if (pl->dcoef.ensure((size_t)n_pts * 2 * P.n_dense * 8)) return fail(SCQED_ENOMEM, "dense-table coefficients");
+        dcoef = (double *)pl->dcoef.p;
+    }
+    coef_eval_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, params_dev, n_pts, (double *)pl->regs.p, coef_dev, scal_dev, aux_dev, dcoef);
     LAUNCHED();
     CK(cudaGetLastError());
     return 0;
@@ -579,6 +596,7 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
         const long long np = (p0 == 0 ? first : chunk) < n_pts - p0 ? (p0 == 0 ? first : chunk) : n_pts - p0;
         a.n_pts = np;
         a.coef = coef ? coef + (size_t)p0 * P.n_terms : nullptr;
+        a.dcoef = (P.n_dense > 0 && !Hin && pl->dcoef.p) ? (const double *)pl->dcoef.p + (size_t)p0 * 2 * P.n_dense : nullptr;
         a.Hin = Hin ? Hin + (size_t)p0 * n * n : nullptr;
         a.info = info + p0;
         const long long Gc = np * k;
@@ -587,11 +605,11 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
         if (pl->s1_real_mode == 1 && !Hin) {
             // known real-symmetric plan: no host round trip; a point that turns out complex is
             // flagged info = -2 by the kernel and the host-level driver re-runs in complex mode
-            int rc = s1_launch_tridiag<double>(pl, a, P.n_terms, st);
+            int rc = s1_launch_tridiag<double>(pl, a, P.n_terms > P.n_dense ? P.n_terms : P.n_dense, st);
             if (rc) return rc;
             real_mode = true;
         } else if (pl->s1_real_mode != 0) {
-            int rc = s1_launch_tridiag<double>(pl, a, P.n_terms, st);
+            int rc = s1_launch_tridiag<double>(pl, a, P.n_terms > P.n_dense ? P.n_terms : P.n_dense, st);
             if (rc) return rc;
             int h_cnt = 0;
             std::vector<int> hflags((size_t)np);
@@ -603,7 +621,7 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
             if (!real_mode) CK(cudaMemsetAsync(a.info, 0, (size_t)np * 4, st));
         }
         if (!real_mode) {
-            int rc = s1_launch_tridiag<cplx>(pl, a, P.n_terms, st);
+            int rc = s1_launch_tridiag<cplx>(pl, a, P.n_terms > P.n_dense ? P.n_terms : P.n_dense, st);
             if (rc) return rc;
         }
         const long long warps = np * k;
@@ -637,7 +655,7 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
 static int run_small_any(scqed_plan *pl, const PlanDev &P, const cplx *coef, const cplx *Hin, const double *scal,
                          long long n_pts, int n, int k, int want_vec, int tidyup, const ResonatorArgs &res,
                          double *evals, cplx *evecs, double *post, int *info, cudaStream_t st, bool monolithic) {
-    if (!monolithic && split_fits(pl, n, k, P.n_terms))
+    if (!monolithic && split_fits(pl, n, k, P.n_terms > P.n_dense ? P.n_terms : P.n_dense))
         return run_small_split(pl, P, coef, Hin, scal, n_pts, n, k, want_vec, tidyup, res, evals, evecs, post, info, st);
     return run_small(pl, P, coef, Hin, scal, n_pts, n, k, want_vec, tidyup, res, evals, evecs, post, info, st);
 }
@@ -1079,7 +1097,7 @@ extern "C" int scqed_sweep_run(scqed_plan *pl, const scqed_sweep_opts *o, const 
         if (pl->scal.ensure((size_t)n_pts * (P.n_scalar + 1) * 8)) return fail(SCQED_ENOMEM, "scalars");
         scal = (double *)pl->scal.p;
     }
-    rc = run_coef(pl, params_dev, n_pts, (cplx *)pl->coef.p, scal, st);
+    rc = run_coef(pl, params_dev, n_pts, (cplx *)pl->coef.p, scal, st, nullptr, true);
     if (rc) return rc;
 
     ResonatorArgs res;
@@ -1091,7 +1109,7 @@ extern "C" int scqed_sweep_run(scqed_plan *pl, const scqed_sweep_opts *o, const 
         res.op_node = pl->factor_node[o->res_op_factor];
         res.s_gc = o->res_gc; res.s_frl = o->res_frl; res.s_qb = o->res_qb;
     }
-    bool fits = (o->solver != 5 && !(o->resonator && o->k > SCQED_RES_KMAX) && split_fits(pl, n, k, P.n_terms)) ||
+    bool fits = (o->solver != 5 && !(o->resonator && o->k > SCQED_RES_KMAX) && split_fits(pl, n, k, P.n_terms > P.n_dense ? P.n_terms : P.n_dense)) ||
                 small_fits(pl, n, k, o->want_vectors, P.n_terms, nullptr);
     int solver = o->solver;
     if ((solver == 1 || solver == 5) && !fits) return fail(SCQED_EUNSUPPORTED, "n=%d k=%d does not fit the fused shared-memory path", n, k);

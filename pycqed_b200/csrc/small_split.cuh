@@ -38,6 +38,7 @@ struct S1Ws {                 // device workspace for a chunk of P points
 struct S1Args {
     PlanDev P;
     const cplx *coef;
+    const double *dcoef;       // [n_pts][2 * n_dense] dense-table coefficients (alpha | beta) or NULL
     const cplx *Hin;
     long long n_pts;
     int n, k, tidyup, want_vec;
@@ -75,7 +76,7 @@ s1_tridiag_kernel(S1Args a) {
     T *tau = (T *)take((size_t)n * sizeof(T));
     T *vbuf = (T *)take((size_t)2 * n * sizeof(T));
     T *wbuf = (T *)take((size_t)2 * n * sizeof(T));
-    size_t partb = (size_t)SMALL_SEGS * n * sizeof(T), cfb = (size_t)a.P.n_terms * 16;
+    size_t partb = (size_t)SMALL_SEGS * n * sizeof(T), cfb = (size_t)(a.P.n_terms > a.P.n_dense ? a.P.n_terms : a.P.n_dense) * 16;
     T *part = (T *)take(partb > cfb ? partb : cfb);
     double *red = (double *)take(96 * 8);
     double *bounds = (double *)take(4 * 8);
@@ -90,6 +91,38 @@ s1_tridiag_kernel(S1Args a) {
                 cplx v = Hp[idx];
                 if constexpr (REAL) { not_real |= (v.y != 0.0); ((double *)A)[i + j * n] = v.x; }
                 else ((cplx *)A)[i + j * n] = v;
+            }
+        } else if (a.dcoef) {
+            // dense real term table: H[i][j] = sum_g (alpha_g + i beta_g) G_g[i][j] on the lower
+            // triangle, mirrored by Hermiticity.  One warp per column, lanes down the column:
+            // every G_g load is a coalesced 8-byte read of the (L2-resident) table.
+            const int NG = a.P.n_dense;
+            double *s_dc = (double *)part;
+            for (int t = tid; t < 2 * NG; t += NT) s_dc[t] = a.dcoef[(size_t)p * 2 * NG + t];
+            __syncthreads();
+            double imw = 0.0;
+            for (int g = 0; g < NG; ++g) imw += fabs(s_dc[NG + g]) * __ldg(a.P.dense_gmax + g);
+            // tidyup zeroes |Im| < 1e-12 (numerical_system.py:19,594): below that the point is real
+            const bool pt_real = a.tidyup ? imw < 1e-12 : imw == 0.0;
+            if (REAL && !pt_real) not_real = 1;
+            else {
+                const size_t nn = (size_t)n * n;
+                const int wp = tid >> 5, lane = tid & 31, NW = NT >> 5;
+                for (int j = wp; j < n; j += NW) {
+                    const double *col = a.P.dense_tab + (size_t)j * n;
+                    for (int i = j + lane; i < n; i += 32) {
+                        double re = 0.0, im = 0.0;
+                        for (int g = 0; g < NG; ++g) {
+                            const double gv = __ldg(col + g * nn + i);
+                            re = fma(s_dc[g], gv, re);
+                            if (!REAL && !pt_real) im = fma(s_dc[NG + g], gv, im);
+                        }
+                        if (a.tidyup) { re = fabs(re) < 1e-12 ? 0.0 : re; im = fabs(im) < 1e-12 ? 0.0 : im; }
+                        if (i == j) im = 0.0;
+                        if constexpr (REAL) { ((double *)A)[i + j * n] = re; ((double *)A)[j + i * n] = re; }
+                        else { ((cplx *)A)[i + j * n] = cmake(re, im); ((cplx *)A)[j + i * n] = cmake(re, -im); }
+                    }
+                }
             }
         } else {
             cplx *s_coef = (cplx *)part;

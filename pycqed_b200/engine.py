@@ -11,6 +11,8 @@ import threading
 
 import numpy as np
 
+from .densetab import build_dense_table
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libscqed.so")
 
@@ -34,6 +36,8 @@ class _PlanDesc(C.Structure):
         ("n_aux", C.c_int32), ("aux_term_factors", C.POINTER(C.c_int32)),
         ("aux_re", C.POINTER(C.c_int32)), ("aux_im", C.POINTER(C.c_int32)),
         ("n_pairs", C.c_int32), ("pairs", C.POINTER(C.c_int32)),
+        ("n_dense", C.c_int32), ("dense_tab", C.POINTER(C.c_double)),
+        ("dense_re", C.POINTER(C.c_int32)), ("dense_im", C.POINTER(C.c_int32)), ("dense_gmax", C.POINTER(C.c_double)),
     ]
 
 
@@ -178,6 +182,10 @@ class Engine:
         self.n = plan.hilbert_dim
         self._handle = C.c_void_p()
         prog = plan.program
+        # small Hilbert spaces: dense real term table for the fused solver (extends the program)
+        dense = None if os.environ.get("SCQED_NO_DENSE_TABLE") else build_dense_table(plan)
+        if dense is not None:
+            prog = dense["program"]
         dims = _i32(plan.dims)
         fnode = _i32([f[0] for f in plan.factors])
         mats = [np.ascontiguousarray(plan.factor_matrix(i), dtype=np.complex128) for i in range(len(plan.factors))]
@@ -219,6 +227,13 @@ class Engine:
             aux_re=_ptr(aux_re, C.c_int32), aux_im=_ptr(aux_im, C.c_int32),
             n_pairs=len(pair_list), pairs=_ptr(pairs, C.c_int32),
         )
+        if dense is not None:
+            dtab = np.ascontiguousarray(dense["table"], dtype=np.float64)
+            dre, dim_, dgm = _i32(dense["re_regs"]), _i32(dense["im_regs"]), np.ascontiguousarray(dense["gmax"], dtype=np.float64)
+            desc.n_dense = int(dtab.shape[0])
+            desc.dense_tab = _ptr(dtab, C.c_double)
+            desc.dense_re, desc.dense_im = _ptr(dre, C.c_int32), _ptr(dim_, C.c_int32)
+            desc.dense_gmax = _ptr(dgm, C.c_double)
         _check(self.lib.scqed_plan_create(C.byref(desc), self.device.index, C.byref(self._handle)))
 
     # ------------------------------------------------------------------------------------------
