@@ -624,8 +624,18 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
             int rc = s1_launch_tridiag<cplx>(pl, a, P.n_terms > P.n_dense ? P.n_terms : P.n_dense, st);
             if (rc) return rc;
         }
-        const long long warps = np * k;
-        s1_bisect_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(a, nullptr, evals + (size_t)p0 * k);
+        // enough (point, eigenvalue) pairs to fill the machine with one thread each: plain bisection
+        // (6.6x less arithmetic); small sweeps keep the 33-way warp multisection (short dependent chain)
+        const int bis_mode = getenv("SCQED_BISECT") ? atoi(getenv("SCQED_BISECT")) : 0;
+        const bool thread_bisect = bis_mode == 2 || (bis_mode == 0 && np * k >= (long long)pl->sm_count * 256 && k <= 32);
+        if (thread_bisect) {
+            const int ppw = 32 / k;
+            const long long bw = (np + ppw - 1) / ppw;
+            s1_bisect_thread_kernel<<<(unsigned)((bw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, evals + (size_t)p0 * k);
+        } else {
+            const long long warps = np * k;
+            s1_bisect_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(a, nullptr, evals + (size_t)p0 * k);
+        }
         LAUNCHED();
         if (need_vec) {
             const int ppw = 32 / k;

@@ -265,6 +265,20 @@ def test_resonator_behind_dense_and_matrix_free_solvers(engine_mod, name, solver
     assert (res.V is not None) == vectors
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("name", ["c1_transmon", "c2_fluxonium_res", "c4_averin", "c6_cpb"])
+def test_both_bisection_kernels(engine_mod, monkeypatch, name, mode):
+    """SCQED_BISECT=1: 33-way warp multisection, =2: one thread per eigenvalue (what large sweeps use)."""
+    monkeypatch.setenv("SCQED_BISECT", mode)
+    g, plan = load_golden(name)
+    k = int(g["k"])
+    with engine_mod.Engine(plan) as eng:
+        res = eng.sweep(g["params"], k, want_vectors=True)
+    assert not res.info.any()
+    assert eig_rel_err(res.E, g["E"]) < E_RTOL
+    assert np.all(np.diff(res.E, axis=1) >= 0)
+
+
 def test_sweep_scalar_evaluables(engine_mod):
     g, plan = load_golden("c4_averin")
     with engine_mod.Engine(plan) as eng:
