@@ -71,10 +71,18 @@ typedef struct {
      * Im H = sum_g r[dense_im[g]] G_g with G_g real n x n, element (i, j) at dense_tab[g*n*n + j*n + i];
      * register -1 = identically zero.  n_dense = 0 disables it (the term table is walked per element). */
     int32_t n_dense;
-    const double *dense_tab;        /* [n_dense * n * n]                                     */
+    int32_t n_dense_diag;           /* the last n_dense_diag matrices are diagonal, stored as n-vectors */
+    const double *dense_tab;        /* [(n_dense - n_dense_diag) * n * n + n_dense_diag * n] */
     const int32_t *dense_re;        /* [n_dense]                                             */
     const int32_t *dense_im;        /* [n_dense]                                             */
     const double *dense_gmax;       /* [n_dense] max |G_g|                                   */
+    /* Nodes solved in a rotated basis (oscillator nodes whose impedance is swept, numerical_system.py:378-393:
+     * the plan's factors of node xform_node[i] are expressed in the eigenbasis of a + a^dagger).  Eigenvectors
+     * are rotated back on that tensor mode with the real orthogonal d x d matrix W_i (row-major,
+     * concatenated in xform_data) before they are returned. */
+    int32_t n_xform;
+    const int32_t *xform_node;      /* [n_xform]                                             */
+    const double *xform_data;       /* concatenated W_i, d_i * d_i doubles each              */
 } scqed_plan_desc;
 
 /* Options of one sweep (numerical_system.py:790-804 setDiagConfig + :868-875 addEvaluation). */
@@ -93,7 +101,9 @@ typedef struct {
     int32_t res_gc;           /* scalar slot of g_C                                          */
     int32_t res_frl;          /* scalar slot of the loaded resonator frequency               */
     int32_t res_qb;           /* scalar slot of the node's charge bias                       */
-    int32_t reserved[6];
+    int32_t raw_basis;        /* 1: leave eigenvectors in the plan's (rotated) basis; the caller runs
+                                 scqed_matrix_elements on them and then scqed_back_transform      */
+    int32_t reserved[5];
 } scqed_sweep_opts;
 
 /* Create / destroy.  Uploads the tables to `device`. */
@@ -139,6 +149,10 @@ int scqed_sweep_run_host(scqed_plan *plan, const scqed_sweep_opts *opts, const d
  * util.pauliCoefficients (util.py:322-328) uses the complex value. */
 int scqed_matrix_elements(scqed_plan *plan, const double *params_dev, int64_t n_pts, int32_t k,
                           const double *evecs_dev, double *out_dev, void *stream);
+
+/* Rotate eigenvectors [n_vectors, n] (complex, in place) from the plan's basis back to the reference's
+ * Fock basis on every node listed in xform_node.  A no-op for plans without rotated nodes. */
+int scqed_back_transform(scqed_plan *plan, double *evecs_dev, int64_t n_vectors, void *stream);
 
 /* util.pauliCoefficients replacement (util.py:300-391): local-basis reduction of the two lowest
  * levels.  e01_dev [n_pts, 2] = (E0, E1); op_dev complex [n_pts, 4] = the computational-basis

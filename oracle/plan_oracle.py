@@ -117,6 +117,15 @@ class PlanOracle:
         self._eyes = [sp.identity(d, dtype=np.complex128, format="csr") for d in self.dims]
         self.term_ops = [self._expand(t) for t in plan.terms]
         self.aux_term_ops = [self._expand(t) for t in getattr(plan, "aux_terms", [])]
+        # nodes lowered in a rotated basis (swept oscillator impedance): T maps plan-basis vectors to
+        # the reference's Fock basis, v = T v'
+        self.T = None
+        xf = plan.node_transforms() if hasattr(plan, "node_transforms") else {}
+        if xf:
+            T = np.ones((1, 1))
+            for k, d in enumerate(self.dims):
+                T = np.kron(T, xf[k] if k in xf else np.eye(d))
+            self.T = T
 
     def _expand(self, fids):
         out = None
@@ -179,6 +188,8 @@ class PlanOracle:
         (numerical_system.py:656-667,683-694)."""
         params = np.atleast_2d(np.asarray(params, dtype=np.float64))
         ac = eval_aux_coefficients(self.plan.program, params)
+        if self.T is not None:                                   # Fock basis in, plan basis inside
+            V = np.einsum("ba,pbk->pak", self.T, np.asarray(V))
         out = []
         for p in range(params.shape[0]):
             row = []
@@ -218,6 +229,8 @@ class PlanOracle:
                 Es[i], Vs[i] = out
                 if resonator:
                     Rs.append(self.resonator_response(Es[i], Vs[i], scal[i]))
+                if self.T is not None:
+                    Vs[i] = self.T @ Vs[i]
             else:
                 Es[i] = out
         return {"E": Es, "V": Vs, "Erwa": (np.array(Rs) if resonator else None), "scalars": scal}

@@ -97,6 +97,8 @@ struct scqed_plan {
     long long mf_work_per_row = 0;     // complex MACs per output element of the matrix-free mat-vec
     int s1_real_mode = -1;             // fused small path: -1 unknown, 0 complex Hermitian, 1 real symmetric
     DevBuf s1work, s1vec, auxc, resvec, dcoef;
+    std::vector<int> xform_node;
+    std::vector<size_t> xform_off;     // byte offsets of W_i^T inside `tables`
     int pair_max_index = -1;
     std::vector<int> factor_node;
     // device copies of the tables
@@ -324,9 +326,25 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
         { delete pl; return fail(SCQED_EINVAL, "dense term table malformed"); }
     for (int g = 0; g < n_dense; ++g)
         if (d->dense_re[g] >= d->n_instr || d->dense_im[g] >= d->n_instr) { delete pl; return fail(SCQED_EINVAL, "dense table register out of range"); }
-    size_t o_dtab = put(d->dense_tab, (size_t)n_dense * n * n * 8);
+    if (d->n_dense_diag < 0 || d->n_dense_diag > n_dense) { delete pl; return fail(SCQED_EINVAL, "n_dense_diag"); }
+    size_t o_dtab = put(d->dense_tab, ((size_t)(n_dense - d->n_dense_diag) * n * n + (size_t)d->n_dense_diag * n) * 8);
     size_t o_dre = put(d->dense_re, (size_t)n_dense * 4), o_dim = put(d->dense_im, (size_t)n_dense * 4);
     size_t o_dgm = put(d->dense_gmax, (size_t)n_dense * 8);
+    if (d->n_xform < 0 || (d->n_xform > 0 && (!d->xform_node || !d->xform_data))) { delete pl; return fail(SCQED_EINVAL, "basis transforms malformed"); }
+    {
+        const double *src = d->xform_data;
+        for (int i = 0; i < d->n_xform; ++i) {
+            const int k = d->xform_node[i];
+            if (k < 0 || k >= d->n_nodes) { delete pl; return fail(SCQED_EINVAL, "xform_node[%d]=%d", i, k); }
+            const int dk = d->dims[k];
+            std::vector<double> wt((size_t)dk * dk);
+            for (int a = 0; a < dk; ++a)
+                for (int b = 0; b < dk; ++b) wt[(size_t)b * dk + a] = src[(size_t)a * dk + b];     // W^T: thread a reads wt[b*d + a]
+            pl->xform_node.push_back(k);
+            pl->xform_off.push_back(put(wt.data(), wt.size() * 8));
+            src += (size_t)dk * dk;
+        }
+    }
     if (pl->tables.ensure(host.size() + 256)) { delete pl; return fail(SCQED_ENOMEM, "plan tables"); }
     if (cudaMemcpy(pl->tables.p, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         pl->tables.release(); delete pl; return fail(SCQED_ECUDA, "uploading plan tables failed");
@@ -353,7 +371,7 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     P.aux_meta = (const int *)(base + o_ameta);
     P.aux_re = (const int *)(base + o_are); P.aux_im = (const int *)(base + o_aim);
     P.pairs = (const int *)(base + o_pairs);
-    P.n_dense = n_dense;
+    P.n_dense = n_dense; P.n_dense_diag = d->n_dense_diag;
     P.dense_tab = (const double *)(base + o_dtab);
     P.dense_re = (const int *)(base + o_dre); P.dense_im = (const int *)(base + o_dim);
     P.dense_gmax = (const double *)(base + o_dgm);
@@ -451,6 +469,48 @@ extern "C" int scqed_matrix_elements(scqed_plan *pl, const double *params_dev, i
     aux_matel_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, st>>>(P, (const cplx *)pl->auxc.p, (const cplx *)evecs_dev, n_pts, k, (cplx *)out_dev);
     LAUNCHED();
     CK(cudaGetLastError());
+    return 0;
+}
+
+// v <- (I x W x I) v on tensor mode `node`, in place: one CTA per (vector, fiber); the fiber of d
+// amplitudes is staged in shared memory, thread a forms sum_b W[a][b] x[b] (W^T stored: coalesced).
+__global__ void __launch_bounds__(128)
+mode_rotate_kernel(cplx *__restrict__ V, long long n_fibers_total, int n, int d, int stride, const double *__restrict__ Wt) {
+    extern __shared__ cplx s_x[];
+    const int fibers_per_vec = n / d;
+    for (long long fb = blockIdx.x; fb < n_fibers_total; fb += gridDim.x) {
+        const long long vec = fb / fibers_per_vec;
+        const int f = (int)(fb - vec * fibers_per_vec);
+        const int left = f / stride, right = f - left * stride;
+        cplx *base = V + (size_t)vec * n + (size_t)left * d * stride + right;
+        for (int b = threadIdx.x; b < d; b += blockDim.x) s_x[b] = base[(size_t)b * stride];
+        __syncthreads();
+        for (int a = threadIdx.x; a < d; a += blockDim.x) {
+            double re = 0.0, im = 0.0;
+            for (int b = 0; b < d; ++b) {
+                const double w = __ldg(Wt + (size_t)b * d + a);
+                re = fma(w, s_x[b].x, re);
+                im = fma(w, s_x[b].y, im);
+            }
+            base[(size_t)a * stride] = cmake(re, im);
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int scqed_back_transform(scqed_plan *pl, double *evecs_dev, int64_t n_vectors, void *stream) {
+    if (!pl || !evecs_dev || n_vectors < 1) return fail(SCQED_EINVAL, "bad argument");
+    if (set_device(pl->device)) return SCQED_ECUDA;
+    const PlanDev &P = pl->P;
+    for (size_t i = 0; i < pl->xform_node.size(); ++i) {
+        const int k = pl->xform_node[i], dk = P.dims[k];
+        const long long fibers = (long long)n_vectors * (P.n / dk);
+        const long long grid = fibers < (long long)pl->sm_count * 16 ? fibers : (long long)pl->sm_count * 16;
+        mode_rotate_kernel<<<(unsigned)grid, 128, (size_t)dk * 16, (cudaStream_t)stream>>>(
+            (cplx *)evecs_dev, fibers, P.n, dk, P.strides[k], (const double *)((const unsigned char *)pl->tables.p + pl->xform_off[i]));
+        LAUNCHED();
+        CK(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -1087,9 +1147,24 @@ static int check_opts(const scqed_plan *pl, const scqed_sweep_opts *o) {
     return 0;
 }
 
+static int sweep_run_impl(scqed_plan *pl, const scqed_sweep_opts *o, const double *params_dev, int64_t n_pts,
+                          double *evals_dev, double *evecs_dev, double *scalars_dev, double *post_dev,
+                          int32_t *info_dev, void *stream);
+
 extern "C" int scqed_sweep_run(scqed_plan *pl, const scqed_sweep_opts *o, const double *params_dev, int64_t n_pts,
                                double *evals_dev, double *evecs_dev, double *scalars_dev, double *post_dev,
                                int32_t *info_dev, void *stream) {
+    int rc = sweep_run_impl(pl, o, params_dev, n_pts, evals_dev, evecs_dev, scalars_dev, post_dev, info_dev, stream);
+    if (rc) return rc;
+    // nodes solved in a rotated basis: eigenvectors go back to the reference's basis (post-ops ran in the rotated one)
+    if (evecs_dev && o->want_vectors && !o->raw_basis && !pl->xform_node.empty())
+        return scqed_back_transform(pl, evecs_dev, n_pts * o->k, stream);
+    return 0;
+}
+
+static int sweep_run_impl(scqed_plan *pl, const scqed_sweep_opts *o, const double *params_dev, int64_t n_pts,
+                          double *evals_dev, double *evecs_dev, double *scalars_dev, double *post_dev,
+                          int32_t *info_dev, void *stream) {
     if (!pl || !evals_dev || !info_dev || n_pts < 1) return fail(SCQED_EINVAL, "bad argument");
     if (pl->P.n_swept > 0 && !params_dev) return fail(SCQED_EINVAL, "params_dev is NULL");
     int rc = check_opts(pl, o);

@@ -101,22 +101,27 @@ s1_tridiag_kernel(S1Args a) {
             for (int t = tid; t < 2 * NG; t += NT) s_dc[t] = a.dcoef[(size_t)p * 2 * NG + t];
             __syncthreads();
             double imw = 0.0;
-            for (int g = 0; g < NG; ++g) imw += fabs(s_dc[NG + g]) * __ldg(a.P.dense_gmax + g);
+            // (diagonal matrices cannot make a Hermitian H complex: only the full ones count)
+            for (int g = 0; g < NG - a.P.n_dense_diag; ++g) imw += fabs(s_dc[NG + g]) * __ldg(a.P.dense_gmax + g);
             // tidyup zeroes |Im| < 1e-12 (numerical_system.py:19,594): below that the point is real
             const bool pt_real = a.tidyup ? imw < 1e-12 : imw == 0.0;
             if (REAL && !pt_real) not_real = 1;
             else {
                 const size_t nn = (size_t)n * n;
                 const int wp = tid >> 5, lane = tid & 31, NW = NT >> 5;
+                const int NF = NG - a.P.n_dense_diag;                  // full matrices, then diagonal ones
+                const double *dg = a.P.dense_tab + (size_t)NF * nn;
                 for (int j = wp; j < n; j += NW) {
                     const double *col = a.P.dense_tab + (size_t)j * n;
                     for (int i = j + lane; i < n; i += 32) {
                         double re = 0.0, im = 0.0;
-                        for (int g = 0; g < NG; ++g) {
+                        for (int g = 0; g < NF; ++g) {
                             const double gv = __ldg(col + g * nn + i);
                             re = fma(s_dc[g], gv, re);
                             if (!REAL && !pt_real) im = fma(s_dc[NG + g], gv, im);
                         }
+                        if (i == j)
+                            for (int g = NF; g < NG; ++g) re = fma(s_dc[g], __ldg(dg + (size_t)(g - NF) * n + i), re);
                         if (a.tidyup) { re = fabs(re) < 1e-12 ? 0.0 : re; im = fabs(im) < 1e-12 ? 0.0 : im; }
                         if (i == j) im = 0.0;
                         if constexpr (REAL) { ((double *)A)[i + j * n] = re; ((double *)A)[j + i * n] = re; }

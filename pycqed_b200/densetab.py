@@ -75,7 +75,8 @@ def build_dense_table(plan, max_n: int = MAX_N):
     """Returns None when the plan is too large, else a dict with
 
     ``program``  the plan's coefficient program with the combination instructions appended,
-    ``table``    float64 [n_g, n*n], element (i, j) of G_g at ``j*n + i`` (column-major),
+    ``table``    float64: the ``n_full`` general matrices, element (i, j) of G_g at ``g*n*n + j*n + i`` (column-major),
+                 followed by the ``n_diag`` purely diagonal ones as n-vectors,
     ``re_regs`` / ``im_regs``  int32 [n_g] registers of alpha_g / beta_g (-1 = identically zero),
     ``gmax``     float64 [n_g] max |G_g| (the kernel's realness test: sum |beta_g| gmax_g < 1e-12).
     """
@@ -164,11 +165,21 @@ def build_dense_table(plan, max_n: int = MAX_N):
         im_regs.append(ii)
     if not table:
         return None
-    tab = np.stack([np.ascontiguousarray(M.T).reshape(-1) for M in table])     # [g][j*n + i]
+    # purely diagonal matrices (charge-basis Q, Q^2; the projector terms of a swept-impedance oscillator)
+    # go last and are stored as n-vectors: they only touch the n diagonal elements
+    is_diag = [not np.any(M - np.diag(np.diag(M))) for M in table]
+    order = [i for i, dg in enumerate(is_diag) if not dg] + [i for i, dg in enumerate(is_diag) if dg]
+    table = [table[i] for i in order]
+    re_regs = [re_regs[i] for i in order]
+    im_regs = [im_regs[i] for i in order]
+    n_diag = int(sum(is_diag))
+    n_full = len(table) - n_diag
+    tab = np.concatenate([np.ascontiguousarray(M.T).reshape(-1) for M in table[:n_full]] +
+                         [np.ascontiguousarray(np.diag(M)).reshape(-1) for M in table[n_full:]] + [np.zeros(0)])
     program = CoefProgram(
         n_swept=prog.n_swept, instr=np.asarray(instr, dtype=np.int32).reshape(-1, 3),
         consts=np.asarray(consts, dtype=np.float64), coef_re=prog.coef_re, coef_im=prog.coef_im,
         scalar_regs=prog.scalar_regs, scalar_names=list(prog.scalar_names), aux_re=prog.aux_re, aux_im=prog.aux_im)
-    return {"program": program, "table": np.ascontiguousarray(tab, dtype=np.float64),
+    return {"program": program, "table": np.ascontiguousarray(tab, dtype=np.float64), "n_full": n_full, "n_diag": n_diag,
             "re_regs": np.asarray(re_regs, dtype=np.int32), "im_regs": np.asarray(im_regs, dtype=np.int32),
             "gmax": np.asarray([np.abs(M).max() for M in table], dtype=np.float64)}

@@ -36,8 +36,9 @@ class _PlanDesc(C.Structure):
         ("n_aux", C.c_int32), ("aux_term_factors", C.POINTER(C.c_int32)),
         ("aux_re", C.POINTER(C.c_int32)), ("aux_im", C.POINTER(C.c_int32)),
         ("n_pairs", C.c_int32), ("pairs", C.POINTER(C.c_int32)),
-        ("n_dense", C.c_int32), ("dense_tab", C.POINTER(C.c_double)),
+        ("n_dense", C.c_int32), ("n_dense_diag", C.c_int32), ("dense_tab", C.POINTER(C.c_double)),
         ("dense_re", C.POINTER(C.c_int32)), ("dense_im", C.POINTER(C.c_int32)), ("dense_gmax", C.POINTER(C.c_double)),
+        ("n_xform", C.c_int32), ("xform_node", C.POINTER(C.c_int32)), ("xform_data", C.POINTER(C.c_double)),
     ]
 
 
@@ -45,15 +46,15 @@ class _SweepOpts(C.Structure):
     _fields_ = [
         ("k", C.c_int32), ("want_vectors", C.c_int32), ("solver", C.c_int32), ("tidyup", C.c_int32),
         ("resonator", C.c_int32), ("res_nmax", C.c_int32), ("res_op_factor", C.c_int32),
-        ("res_gc", C.c_int32), ("res_frl", C.c_int32), ("res_qb", C.c_int32),
-        ("reserved", C.c_int32 * 6),
+        ("res_gc", C.c_int32), ("res_frl", C.c_int32), ("res_qb", C.c_int32), ("raw_basis", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 
 #: every symbol include/scqed.h declares (tests check that the library exports all of them)
 EXPORTS = (
     "scqed_plan_create", "scqed_plan_destroy", "scqed_plan_hilbert_dim", "scqed_eval_coefficients",
-    "scqed_assemble_dense", "scqed_eigh_batched", "scqed_sweep_run", "scqed_sweep_run_host", "scqed_matrix_elements", "scqed_pauli_coefficients",
+    "scqed_assemble_dense", "scqed_eigh_batched", "scqed_sweep_run", "scqed_sweep_run_host", "scqed_matrix_elements", "scqed_pauli_coefficients", "scqed_back_transform",
     "scqed_launch_count", "scqed_timing_enable", "scqed_timing_read", "scqed_probe_fp64_tensor", "scqed_probe_fp64_fma", "scqed_last_error",
     "scqed_version",
 )
@@ -92,6 +93,8 @@ def load_library():
         lib.scqed_sweep_run_host.restype = C.c_int
         lib.scqed_matrix_elements.argtypes = [vp, dp, i64, i32, dp, dp, vp]
         lib.scqed_matrix_elements.restype = C.c_int
+        lib.scqed_back_transform.argtypes = [vp, dp, i64, vp]
+        lib.scqed_back_transform.restype = C.c_int
         lib.scqed_pauli_coefficients.argtypes = [i32, dp, dp, i64, dp, vp]
         lib.scqed_pauli_coefficients.restype = C.c_int
         lib.scqed_launch_count.argtypes = []
@@ -227,10 +230,18 @@ class Engine:
             aux_re=_ptr(aux_re, C.c_int32), aux_im=_ptr(aux_im, C.c_int32),
             n_pairs=len(pair_list), pairs=_ptr(pairs, C.c_int32),
         )
+        xf = plan.node_transforms()
+        self.rotated = bool(xf)
+        if xf:
+            xnode = _i32(sorted(xf))
+            xdata = np.ascontiguousarray(np.concatenate([np.asarray(xf[i], dtype=np.float64).reshape(-1) for i in sorted(xf)]))
+            desc.n_xform = len(xf)
+            desc.xform_node, desc.xform_data = _ptr(xnode, C.c_int32), _ptr(xdata, C.c_double)
         if dense is not None:
             dtab = np.ascontiguousarray(dense["table"], dtype=np.float64)
             dre, dim_, dgm = _i32(dense["re_regs"]), _i32(dense["im_regs"]), np.ascontiguousarray(dense["gmax"], dtype=np.float64)
-            desc.n_dense = int(dtab.shape[0])
+            desc.n_dense = int(dense["n_full"] + dense["n_diag"])
+            desc.n_dense_diag = int(dense["n_diag"])
             desc.dense_tab = _ptr(dtab, C.c_double)
             desc.dense_re, desc.dense_im = _ptr(dre, C.c_int32), _ptr(dim_, C.c_int32)
             desc.dense_gmax = _ptr(dgm, C.c_double)
@@ -299,7 +310,8 @@ class Engine:
 
     def matrix_elements(self, params, V):
         """<i|Op|j> of the plan's auxiliary operators (Current / Voltage evaluables) for every
-        point; ``V`` is the device tensor [n_pts, k, n] returned by :meth:`sweep_device`.  Returns a
+        point; ``V`` is the device tensor [n_pts, k, n] returned by :meth:`sweep_device` (for a plan with
+        rotated nodes: by ``sweep_device(..., raw_basis=True)``, i.e. in the plan's basis).  Returns a
         complex128 device tensor [n_pts, n_pairs] ordered like ``plan.aux_pairs()``."""
         import torch
         if self.n_pairs < 1:
@@ -316,12 +328,21 @@ class Engine:
         _check(self.lib.scqed_matrix_elements(self._handle, p.data_ptr(), n_pts, int(V.shape[1]), V.data_ptr(), out.data_ptr(), _stream_ptr()))
         return out
 
-    def sweep_device(self, params, k, want_vectors=False, resonator=False, solver=SOLVER_AUTO, tidyup=True):
+    def back_transform(self, V):
+        """Rotate eigenvectors [n_pts, k, n] (CUDA complex128, in place) from the plan's basis to the
+        reference's Fock basis (only plans with swept-impedance oscillator nodes have one)."""
+        if self.rotated:
+            _check(self.lib.scqed_back_transform(self._handle, V.data_ptr(), int(V.shape[0] * V.shape[1]), _stream_ptr()))
+        return V
+
+    def sweep_device(self, params, k, want_vectors=False, resonator=False, solver=SOLVER_AUTO, tidyup=True,
+                     raw_basis=False):
         """Device-resident sweep; returns torch tensors (E, V|None, scalars, Erwa|None, info)."""
         import torch
         p = self._params_dev(params)
         n_pts = p.shape[0]
         o = self._opts(k, want_vectors or resonator, solver, tidyup, resonator)
+        o.raw_basis = int(bool(raw_basis))
         E = torch.empty((n_pts, k), dtype=torch.float64, device=self.device)
         V = torch.empty((n_pts, k, self.n), dtype=torch.complex128, device=self.device) if want_vectors else None
         ns = self.plan.program.n_scalar
@@ -347,8 +368,10 @@ class Engine:
         n_pts = params.shape[0]
         if matrix_elements:
             p = self._params_dev(params)
-            E, V, scal, post, info = self.sweep_device(p, k, want_vectors=True, resonator=resonator, solver=solver, tidyup=tidyup)
-            M = self.matrix_elements(p, V)
+            E, V, scal, post, info = self.sweep_device(p, k, want_vectors=True, resonator=resonator, solver=solver,
+                                                       tidyup=tidyup, raw_basis=True)
+            M = self.matrix_elements(p, V)            # operators and vectors both in the plan's basis
+            self.back_transform(V)
             names = list(self.plan.program.scalar_names)
             scal = scal.cpu().numpy()
             return SweepResult(E.cpu().numpy(), V.cpu().numpy() if want_vectors else None,

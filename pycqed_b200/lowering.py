@@ -12,6 +12,12 @@ The algebra of ``getHamiltonian`` is expanded symbolically here, once:
 with Pi_e^+- the per-node products of D / D^dagger selected by the SIGN of the branch
 coordinate coefficients exactly as numerical_system.py:529-552 does.
 
+Oscillator nodes whose impedance depends on a swept parameter ("regen" nodes, which the reference
+rebuilds at every point, numerical_system.py:378-393,435-437) are lowered in the eigenbasis of
+a + a^dagger: their operators become constant unit matrices, the impedance dependence goes into the
+coefficients, and exp(+-i beta(Z) X) becomes one projector term per level
+(:func:`pycqed_b200.operators.oscillator_regen_set`).
+
 Only public attributes/methods of the reference's ``SymbolicSystem`` are used (the symbolic
 layer is reused, not rebuilt): ``nodes, edges, Rnb, Rinv, node_vector, node_map_rev,
 cooper_disp, fluxon_disp, getInverse*Matrix, get*Vector, getFluxBiasMatrix,
@@ -20,6 +26,7 @@ getParameterValue, getNonSweepParametersDict, getSymbolValuesDict``.
 """
 from __future__ import annotations
 
+import numpy as np
 import sympy as sy
 
 from .coefprog import ProgramBuilder
@@ -74,9 +81,55 @@ def _branch_composition(SS, i):
     return out
 
 
+def _expand_regen(regen, node_factor_names, re_expr, im_expr, fresh=False):
+    """Rewrite a term that touches regenerated oscillator nodes: scale by q(Z) / f(Z) powers and expand
+    a displacement operator into projector terms.  Yields (names, re, im).
+
+    ``rg['stale']`` (regen_mode='reference'): the reference's sweep loop regenerates ``circ_operators`` but NOT
+    the ``Qnp`` / ``Pnp`` vectors that ``getHamiltonian`` / ``getVoltageOperator`` / ``getResonatorResponse`` read
+    (numerical_system.py:259-271 are only called from ``prepareOperators``, :302-305, not from ``_postsub``,
+    :435-437), so Q and P stay at the impedance of the last ``setParameterValues`` while D follows the sweep.
+    ``fresh`` marks the one consumer that does read the regenerated operators (``getCurrentOperator``, :608-620)."""
+    names = dict(node_factor_names)
+    scale = sy.Integer(1)
+    disp = None
+    for ni, name in node_factor_names.items():
+        if ni not in regen:
+            continue
+        rg = regen[ni]
+        q, f = (rg["q0"], rg["f0"]) if (rg["stale"] and not fresh) else (rg["q"], rg["f"])
+        if name == "charge":
+            scale *= q
+        elif name == "charge2":
+            scale *= q ** 2
+        elif name == "flux":
+            scale *= f
+        elif name == "flux2":
+            scale *= f ** 2
+        elif name in ("disp", "disp_adj"):
+            if disp is not None:
+                raise LoweringError("a junction between two oscillator nodes whose impedances are both swept is not supported")
+            disp = (ni, +1 if name == "disp" else -1)
+        else:
+            raise LoweringError("phase-slip displacement on an oscillator node with swept impedance is not supported")
+    re_expr, im_expr = scale * re_expr, scale * im_expr
+    if disp is None:
+        yield names, re_expr, im_expr
+        return
+    ni, sgn = disp
+    rg = regen[ni]
+    for m, lam in enumerate(rg["lam"]):
+        ph = rg["beta"] * float(lam)
+        c, s_ = sy.cos(ph), sgn * sy.sin(ph)
+        nm = dict(names)
+        nm[ni] = "proj:%d" % m
+        yield nm, re_expr * c - im_expr * s_, re_expr * s_ + im_expr * c
+
+
 class _TermTable:
-    def __init__(self, n_nodes):
+    def __init__(self, n_nodes, regen=None):
         self.n_nodes = n_nodes
+        self.regen = regen or {}
         self.factors = []          # (node_index, name)
         self._fid = {}
         self.terms = {}            # tuple(factor ids) -> [re_expr, im_expr]
@@ -93,19 +146,24 @@ class _TermTable:
         """node_factor_names: {node_index: factor name}; coefficient = re + i im."""
         if re_expr == 0 and im_expr == 0:
             return
-        key = [-1] * self.n_nodes
-        for ni, name in node_factor_names.items():
-            key[ni] = self.fid(ni, name)
-        key = tuple(key)
-        if key not in self.terms:
-            self.terms[key] = [sy.Integer(0), sy.Integer(0)]
-            self.order.append(key)
-        self.terms[key][0] += re_expr
-        self.terms[key][1] += im_expr
+        if self.regen and any(ni in self.regen for ni in node_factor_names):
+            expanded = list(_expand_regen(self.regen, node_factor_names, sy.sympify(re_expr), sy.sympify(im_expr)))
+        else:
+            expanded = [(node_factor_names, re_expr, im_expr)]
+        for names, re_e, im_e in expanded:
+            key = [-1] * self.n_nodes
+            for ni, name in names.items():
+                key[ni] = self.fid(ni, name)
+            key = tuple(key)
+            if key not in self.terms:
+                self.terms[key] = [sy.Integer(0), sy.Integer(0)]
+                self.order.append(key)
+            self.terms[key][0] += re_e
+            self.terms[key][1] += im_e
 
 
 def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scalars=None,
-                 resonator=None, matrix_elements=()) -> SweepPlan:
+                 resonator=None, matrix_elements=(), regen_mode="consistent") -> SweepPlan:
     """Build the plan.
 
     :param SS: the reference ``SymbolicSystem`` (after ``ndSweep`` if ``swept_names``)
@@ -114,6 +172,10 @@ def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scala
     :param swept_names: independent parameters being swept, in ``addSweep`` order
     :param scalars: {name: sympy expr or parameter name} extra real per-point outputs
     :param resonator: {'cpl_node': node, 'nmax': int} to add the Resonator post-op inputs
+    :param regen_mode: oscillator nodes with swept impedance: 'consistent' (every operator of the node follows
+                       the impedance, i.e. H equals what ``setParameterValues`` + ``getHamiltonian`` give at each
+                       point) or 'reference' (reproduce the reference's sweep loop, which leaves the charge /
+                       flux operators at the pre-sweep impedance; see _expand_regen)
     :param matrix_elements: [{'kind': 'Voltage', 'node': n, 'elements': [(i, j), ...]} |
                              {'kind': 'Current', 'edge': e, 'elements': [...]}] (numerical_system.py:596-694)
     """
@@ -136,15 +198,28 @@ def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scala
     def R(expr):
         return _resolve(expr, SS, swept_names, presub)
 
-    # An oscillator node whose impedance depends on a swept symbol would need its operators
-    # regenerated at every point (numerical_system.py:378-393,435-437).
+    # An oscillator node whose impedance depends on a swept symbol: the reference regenerates its
+    # operators at every point (numerical_system.py:378-393,435-437); here the dependence is moved
+    # into the coefficients (see _expand_regen).
+    from . import operators as _ops
+    regen = {}
     for node, data in operator_data.items():
         if data["basis"] == "oscillator":
             z = R(data["impedance"])
             if z.free_symbols:
-                raise LoweringError(
-                    "oscillator node %r: impedance depends on swept parameter(s) %s; per-point operator "
-                    "regeneration is not supported by this engine yet" % (node, sorted(map(str, z.free_symbols))))
+                zi = z * units.getPrefactor("Impe")
+                z0 = float(sy.sympify(data["impedance"]).subs(SS.getSymbolValuesDict())) * units.getPrefactor("Impe")
+                if regen_mode not in ("consistent", "reference"):
+                    raise LoweringError("regen_mode must be 'consistent' or 'reference'")
+                regen[nodes.index(node)] = {
+                    "stale": regen_mode == "reference",
+                    "q0": float(np.sqrt(1.0 / (2.0 * z0))) * units.getPrefactor("ChgOsc"),
+                    "f0": float(np.sqrt(z0 / 2.0)) * units.getPrefactor("FlxOsc"),
+                    "q": sy.sqrt(1 / (2 * zi)) * units.getPrefactor("ChgOsc"),           # :1076
+                    "f": sy.sqrt(zi / 2) * units.getPrefactor("FlxOsc"),                 # :1077
+                    "beta": float(SS.cooper_disp[node]) * 2.0 * sy.pi / _ops.PHI0 * float(_ops.HBAR) ** 0.5 * sy.sqrt(zi / 2),   # :1078
+                    "lam": _ops.oscillator_regen_set(int(data["truncation"]))["lam"],
+                }
 
     Ec = units.getPrefactor("Ec")
     El = units.getPrefactor("El")
@@ -160,7 +235,7 @@ def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scala
     Pbm = SS.getFluxBiasMatrix(mode="branch").applyfunc(R)
     Pbi = SS.getFluxBiasVectorInd().applyfunc(R)
 
-    tt = _TermTable(N)
+    tt = _TermTable(N, regen)
     half = sy.Rational(1, 2)
 
     def quadratic(M, bias, pref, lin_name, sq_name):
@@ -207,10 +282,12 @@ def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scala
         spec = NodeSpec(node=node, basis=data["basis"], trunc=int(data["truncation"]),
                         cooper_disp=float(SS.cooper_disp[node]), fluxon_disp=float(SS.fluxon_disp[node]))
         if data["basis"] == "oscillator":
-            z = float(R(data["impedance"]))
-            spec.impedance_ohm = z * units.getPrefactor("Impe")
             spec.chg_osc = units.getPrefactor("ChgOsc")
             spec.flx_osc = units.getPrefactor("FlxOsc")
+            if nodes.index(node) in regen:
+                spec.regen = True
+            else:
+                spec.impedance_ohm = float(R(data["impedance"])) * units.getPrefactor("Impe")
         node_specs.append(spec)
 
     # ---- scalar outputs -------------------------------------------------------------------
@@ -233,7 +310,12 @@ def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scala
         idx = nodes.index(cpl)
         add_scalar("gC", R(SS.getSymbol("g%ir" % cpl)))
         add_scalar("frl", R(SS.getSymbol("f%irl" % cpl)))
-        add_scalar("qb_cpl", Qb[idx])
+        # a regenerated node carries the unit charge operator: <i|Q + q_b|j> / q(Z) = <i|Q~ + q_b/q(Z)|j>,
+        # and only ratios of these matrix elements enter (numerical_system.py:755-762)
+        if idx in regen:
+            add_scalar("qb_cpl", Qb[idx] / (regen[idx]["q0"] if regen[idx]["stale"] else regen[idx]["q"]))
+        else:
+            add_scalar("qb_cpl", Qb[idx])
         post["resonator"] = {
             "cpl_node": int(cpl), "node_index": idx, "nmax": int(resonator.get("nmax", 100)),
             "op_factor": tt.fid(idx, "charge"),
@@ -244,12 +326,17 @@ def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scala
     # ---- auxiliary operators: Current / Voltage evaluables (numerical_system.py:596-694) -----------
     aux_keys, aux_coefs, aux_ops = [], [], []
 
-    def aux_add(node_factor_names, re_expr, im_expr=0):
-        key = [-1] * N
-        for ni, name in node_factor_names.items():
-            key[ni] = tt.fid(ni, name)
-        aux_keys.append(key)
-        aux_coefs.append((sy.sympify(re_expr), sy.sympify(im_expr)))
+    def aux_add(node_factor_names, re_expr, im_expr=0, fresh=False):
+        if regen and any(ni in regen for ni in node_factor_names):
+            expanded = list(_expand_regen(regen, node_factor_names, sy.sympify(re_expr), sy.sympify(im_expr), fresh))
+        else:
+            expanded = [(node_factor_names, re_expr, im_expr)]
+        for names, re_e, im_e in expanded:
+            key = [-1] * N
+            for ni, name in names.items():
+                key[ni] = tt.fid(ni, name)
+            aux_keys.append(key)
+            aux_coefs.append((sy.sympify(re_e), sy.sympify(im_e)))
 
     for spec in matrix_elements:
         begin = len(aux_keys)
@@ -282,7 +369,7 @@ def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scala
                 args = expr.args if len(expr.atoms()) > 2 else [expr]
                 for arg in args:                                         # IopL * sum coef * P_node * Linv_b[e,e]  (:608-620)
                     node = SS.node_map_rev[arg.args[1]]
-                    aux_add({nodes.index(node): "flux"}, units.getPrefactor("IopL") * float(arg.args[0]) * Lb)
+                    aux_add({nodes.index(node): "flux"}, units.getPrefactor("IopL") * float(arg.args[0]) * Lb, fresh=True)
             elif SS.CG.isJosephsonEdge(edge):
                 ph = 2 * sy.pi * Pbm[e, e]
                 amp = half * units.getPrefactor("IopJ") * Jvec[e]      # 0.5j IopJ J (e^{+i ph} Pi+ - e^{-i ph} Pi-)  (:622-652)

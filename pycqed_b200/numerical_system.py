@@ -171,6 +171,10 @@ class NumericalSystem:
         self.units = unit
         self.device = device
         self.operator_data = {}
+        #: swept oscillator impedance: 'consistent' = H(p) is what setParameterValues + getHamiltonian give at p;
+        #: 'reference' = reproduce the reference's sweep loop, which keeps the charge / flux operators of the node
+        #: at the pre-sweep impedance (numerical_system.py:259-271 are not re-run by _postsub)
+        self.regen_mode = "consistent"
         self._circ_operators = None
         self._single = None            # (plan, engine) for the current parameter values
         self.setDiagConfig()
@@ -492,7 +496,7 @@ class NumericalSystem:
                 raise NotImplementedError("evaluable '%s' is not implemented on the GPU path yet" % nm)
 
         plan = lower_system(self.SS, self.units, self.operator_data, names, specs, scalars=scalars, resonator=resonator,
-                            matrix_elements=matel_specs)
+                            matrix_elements=matel_specs, regen_mode=self.regen_mode)
         grid = plan.sweep_grid()
         loop_time = time.time()
         matel = {}

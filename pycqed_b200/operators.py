@@ -143,6 +143,31 @@ def oscillator_basis(trunc: int, impedance_ohm: float, chg_osc: float, flx_osc: 
     return tuple(tidyup(x) for x in (Q, P, D, D.conj().T, S, S.conj().T))
 
 
+def oscillator_regen_set(trunc: int) -> dict:
+    """Impedance-independent operator set of an oscillator node in the eigenbasis of X = a^dag + a.
+
+    When the node impedance Z depends on a swept parameter the reference regenerates
+    Q = i sqrt(1/2Z) (a^dag - a), P = sqrt(Z/2) (a^dag + a), D = exp(i beta(Z) X) at EVERY sweep point
+    (numerical_system.py:378-393,435-437,1064-1109).  With X = W diag(lam) W^T (W real orthogonal) the
+    similarity H' = W^T H W has, on this node, only CONSTANT matrices times scalar functions of Z:
+
+        charge -> q(Z) W^T i(a^dag - a) W,   flux -> f(Z) diag(lam),   D -> diag(exp(i beta(Z) lam_m))
+
+    so the Z dependence moves into the coefficient program (the diagonal D becomes one projector
+    term per level) and eigenvectors are rotated back with W after the solve.
+    Returns {'lam', 'W', 'charge', 'flux', 'charge2', 'flux2'} (unit matrices, d = trunc).
+    """
+    a = oscillator_ladder(trunc)
+    ad = a.conj().T
+    X = (ad + a).real
+    lam, W = np.linalg.eigh(X)
+    Qt = 1j * (ad - a)
+    Qp = W.T @ Qt @ W
+    Qp = 0.5 * (Qp + Qp.conj().T)
+    return {"lam": lam, "W": W, "charge": Qp, "flux": np.diag(lam).astype(np.complex128),
+            "charge2": Qp @ Qp, "flux2": np.diag(lam * lam).astype(np.complex128)}
+
+
 def classify(M: np.ndarray) -> str:
     """Structural type of a factor: 'identity', 'diag', 'band1' (|i-j| <= 1) or 'dense'.
 

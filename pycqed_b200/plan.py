@@ -37,12 +37,25 @@ class NodeSpec:
     flx_osc: float = 0.0         # Units.getPrefactor('FlxOsc')
     cooper_disp: float = 1.0
     fluxon_disp: float = 1.0
+    regen: bool = False          # oscillator whose impedance is swept: unit operators in the eigenbasis of a+a^dag
 
     @property
     def dim(self) -> int:
         return ops.node_dimension(self.basis, self.trunc)
 
+    def transform(self):
+        """Real orthogonal W (columns = eigenvectors of a + a^dag) that rotates this node's coordinates
+        back to the Fock basis, or None (see operators.oscillator_regen_set)."""
+        if not self.regen:
+            return None
+        return ops.oscillator_regen_set(self.trunc)["W"]
+
     def operator_set(self) -> dict:
+        if self.regen:
+            if self.basis != "oscillator":
+                raise Exception("only oscillator nodes are regenerated")
+            rs = ops.oscillator_regen_set(self.trunc)
+            return {k: rs[k] for k in ("charge", "flux", "charge2", "flux2")}
         if self.basis == "charge":
             t = ops.charge_basis(self.trunc)
         elif self.basis == "oscillator":
@@ -87,9 +100,18 @@ class SweepPlan:
 
     def factor_matrix(self, fid: int) -> np.ndarray:
         ni, name = self.factors[fid]
+        if name.startswith("proj:"):                      # |m><m| of a regenerated oscillator node
+            d = self.nodes[ni].dim
+            m = np.zeros((d, d), dtype=np.complex128)
+            m[int(name[5:]), int(name[5:])] = 1.0
+            return m
         if ni not in self._opsets:
             self._opsets[ni] = self.nodes[ni].operator_set()
         return self._opsets[ni][name]
+
+    def node_transforms(self) -> dict:
+        """{node index: W} for the nodes solved in a rotated basis (eigenvectors are rotated back)."""
+        return {i: nd.transform() for i, nd in enumerate(self.nodes) if nd.regen}
 
     def factor_kind(self, fid: int) -> str:
         return ops.classify(self.factor_matrix(fid))
@@ -142,7 +164,7 @@ class SweepPlan:
                 {"node": int(n.node), "basis": n.basis, "trunc": int(n.trunc),
                  "impedance_ohm": repr(float(n.impedance_ohm)), "chg_osc": repr(float(n.chg_osc)),
                  "flx_osc": repr(float(n.flx_osc)), "cooper_disp": repr(float(n.cooper_disp)),
-                 "fluxon_disp": repr(float(n.fluxon_disp))}
+                 "fluxon_disp": repr(float(n.fluxon_disp)), "regen": bool(n.regen)}
                 for n in self.nodes
             ],
             "factors": [[int(a), str(b)] for a, b in self.factors],
@@ -165,7 +187,7 @@ class SweepPlan:
             NodeSpec(node=int(n["node"]), basis=n["basis"], trunc=int(n["trunc"]),
                      impedance_ohm=float(n["impedance_ohm"]), chg_osc=float(n["chg_osc"]),
                      flx_osc=float(n["flx_osc"]), cooper_disp=float(n["cooper_disp"]),
-                     fluxon_disp=float(n["fluxon_disp"]))
+                     fluxon_disp=float(n["fluxon_disp"]), regen=bool(n.get("regen", False)))
             for n in d["nodes"]
         ]
         return SweepPlan(

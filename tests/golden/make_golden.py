@@ -517,7 +517,48 @@ def make_c6():
                                          {"kind": "Voltage", "node": 2, "elements": el}]})
 
 
-ALL = {"c6": make_c6, "c2b": make_c2b, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c4": make_c4, "c5": make_c5}
+def make_c7():
+    """Swept oscillator impedance (numerical_system.py:378-393,435-437,1064-1109).
+
+    c7_fluxonium_LphiZ   the reference's own sweep loop over L x phiZ (regen_mode='reference': its loop keeps Q / P
+                         at the pre-sweep impedance), with eigenvectors and the Resonator evaluable
+    c7_fluxonium_C       regen_mode='consistent': reference values from its single-point path
+                         (setParameterValue + getHamiltonian + diagonalize at every grid point)"""
+    h = build_fluxonium(40)
+    L0 = h.getParameterValue("L")
+    res = {"resonator": {"cpl_node": 1, "nmax": 20}, "regen_mode": "reference"}
+    freeze("c7_fluxonium_LphiZ", h, [S("L", 0.8 * L0, 1.3 * L0, 5), S("phiZ", 0.0, 0.5, 4)], k=8, get_vectors=True,
+           evaluations=[("Hamiltonian", {}), ("Resonator", {"cpl_node": 1, "nmax": 20})], vec_points=[0, 7, 19],
+           lower_kw=res, store_h=False)
+    # the pre-sweep impedance enters the plan in this mode, and the reference's sweep leaves the system at
+    # the last grid point: lower again from a fresh system
+    plan = lower(build_fluxonium(40), [S("L", 0.8 * L0, 1.3 * L0, 5), S("phiZ", 0.0, 0.5, 4)], **res)
+    plan.meta["source"] = "c7_fluxonium_LphiZ"
+    plan.save(os.path.join(HERE, "c7_fluxonium_LphiZ.plan.json"))
+    h = build_fluxonium(40)
+    C0 = h.getParameterValue("C")
+    sw = [S("C", 0.7 * C0, 1.2 * C0, 9)]
+    plan = lower(h, sw)
+    grid = plan.sweep_grid()
+    k = 8
+    E, V = [], []
+    with quiet():
+        h.setDiagConfig(eigvalues=k, get_vectors=True)
+        for c in grid[:, 0]:
+            h.setParameterValue("C", float(c))
+            e, v = h.diagonalize(h.getHamiltonian())
+            E.append(np.asarray(e, dtype=np.float64))
+            V.append(np.stack([x.data.to_array()[:, 0] for x in v], axis=1))
+    out = {"E": np.array(E), "V": np.array(V)[[0, 4, 8]], "vec_points": np.array([0, 4, 8]), "params": grid,
+           "swept_names": np.array(plan.swept_names), "k": np.int64(k), "n": np.int64(h.getHilbertSpaceSize()),
+           "ref_seconds_per_point": np.float64(0.0)}
+    np.savez_compressed(os.path.join(HERE, "c7_fluxonium_C.npz"), **out)
+    plan.meta["source"] = "c7_fluxonium_C"
+    plan.save(os.path.join(HERE, "c7_fluxonium_C.plan.json"))
+    print("c7_fluxonium_C               n=%d pts=%d" % (int(out["n"]), len(grid)), flush=True)
+
+
+ALL = {"c6": make_c6, "c7": make_c7, "c2b": make_c2b, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c4": make_c4, "c5": make_c5}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(ALL)

@@ -280,15 +280,58 @@ def test_error_behaviour_matches_reference(patched):
         with pytest.raises(Exception, match="need eigenvectors"):
             with mg.quiet():
                 h.paramSweep(timesweep=False)
-    # swept impedance is refused loudly rather than silently wrong
-    from pycqed_b200.lowering import LoweringError
+
+
+def test_swept_oscillator_impedance_matches_reference(patched):
+    """Sweeping L (or C) of an oscillator-basis node changes its impedance: the reference regenerates the
+    node operators at every point (numerical_system.py:378-393,435-437,1064-1109); the plan keeps
+    constant unit operators in the eigenbasis of a + a^dagger instead.  Eigenvalues, eigenvectors
+    (rotated back), resonator strips and matrix elements must agree."""
+    ref, mine, mg = _pair("build_fluxonium", patched, 24)
+    mine.regen_mode = "reference"          # the reference's loop leaves Q / P at the pre-sweep impedance
+    L0 = ref.getParameterValue("L")
+    ev = [("Hamiltonian", {}), ("Resonator", {"cpl_node": 1, "nmax": 8}),
+          ("Voltage", {"node": 1, "elements": [(0, 0), (1, 1), (0, 1)]})]
+    a, b = _run_both(ref, mine, mg, [("L", 0.8 * L0, 1.3 * L0, 4), ("phiZ", 0.1, 0.5, 3)], 5, True, ev)
+    xa, EVa, _ = ref.getSweep(a, ["L", "phiZ"], {})
+    xb, EVb, _ = mine.getSweep(b, ["L", "phiZ"], {})
+    assert EVa.shape == EVb.shape
+    Ea, Eb = EVa[:, 0].astype(float), EVb[:, 0].astype(float)
+    assert np.max(np.abs(Ea - Eb)) < 1e-9 * np.abs(Ea).max()
+    for i in range(5):
+        for idx in np.ndindex(*EVa.shape[2:]):
+            va = EVa[(i, 1) + idx].data.to_array()[:, 0]
+            vb = EVb[(i, 1) + idx].full()[:, 0]
+            assert abs(abs(np.vdot(va, vb)) - 1.0) < 1e-8
+    _, Ra, _ = ref.getSweep(a, ["L", "phiZ"], {}, evaluable="Resonator")
+    _, Rb, _ = mine.getSweep(b, ["L", "phiZ"], {}, evaluable="Resonator")
+    assert Ra.shape == Rb.shape and np.max(np.abs(Ra - Rb)) < 1e-9 * np.abs(Ra).max()
+    _, Va, _ = ref.getSweep(a, ["L", "phiZ"], {}, evaluable="Voltage")
+    _, Vb, _ = mine.getSweep(b, ["L", "phiZ"], {}, evaluable="Voltage")
+    assert Va.shape == Vb.shape
+    assert np.max(np.abs(Va[:2] - Vb[:2])) < 1e-9 * max(1.0, np.abs(Va).max())
+    assert np.max(np.abs(np.abs(Va[2]) - np.abs(Vb[2]))) < 1e-7 * max(1.0, np.abs(Va).max())
+
+
+def test_swept_impedance_consistent_mode_matches_single_point_path(patched):
+    """Default regen_mode='consistent': at every sweep point H equals the reference's own single-point path
+    (setParameterValues + getHamiltonian + diagonalize), which regenerates ALL operators of the node."""
+    ref, mine, mg = _pair("build_fluxonium", patched, 20)
+    C0 = ref.getParameterValue("C")
     with mg.quiet():
-        mine2.newSweep()
-        mine2.addSweep("L", 1e5, 2e5, 3)
-        mine2.setDiagConfig(eigvalues=4)
-    with pytest.raises(LoweringError, match="impedance depends on swept"):
+        mine.newSweep()
+        mine.addSweep("C", 0.7 * C0, 1.2 * C0, 4)
+        mine.setDiagConfig(eigvalues=5, get_vectors=True)
+        data = mine.paramSweep(timesweep=False)
+    x, EV, _ = mine.getSweep(data, "C", {})
+    ref.setDiagConfig(eigvalues=5, get_vectors=True)
+    for i, c in enumerate(x):
         with mg.quiet():
-            mine2.paramSweep(timesweep=False)
+            ref.setParameterValue("C", float(c))
+            E, V = ref.diagonalize(ref.getHamiltonian())
+        assert np.max(np.abs(np.asarray(E) - EV[:, 0, i].astype(float))) < 1e-9 * np.abs(E).max()
+        for j in range(5):
+            assert abs(abs(np.vdot(V[j].data.to_array()[:, 0], EV[j, 1, i].full()[:, 0])) - 1.0) < 1e-8
 
 
 def test_operator_factors_match_reference():

@@ -279,6 +279,26 @@ def test_both_bisection_kernels(engine_mod, monkeypatch, name, mode):
     assert np.all(np.diff(res.E, axis=1) >= 0)
 
 
+@pytest.mark.parametrize("name,solver", [("c7_fluxonium_LphiZ", 0), ("c7_fluxonium_LphiZ", 2), ("c7_fluxonium_C", 0),
+                                         ("c7_fluxonium_C", 2), ("c7_fluxonium_C", 5)])
+def test_swept_oscillator_impedance(engine_mod, name, solver):
+    """Row f4: operator regeneration of the reference (numerical_system.py:378-393,435-437) replaced by a plan in
+    the eigenbasis of a + a^dagger: projector terms for exp(i beta(Z) X), eigenvectors rotated back on the device."""
+    g, plan = load_golden(name)
+    k = int(g["k"])
+    res_on = "eval_getResonatorResponse" in g
+    with engine_mod.Engine(plan) as eng:
+        assert eng.rotated
+        res = eng.sweep(g["params"], k, want_vectors=True, resonator=res_on, solver=solver)
+    assert not res.info.any()
+    assert eig_rel_err(res.E, g["E"]) < E_RTOL
+    for a, p in enumerate(g["vec_points"]):
+        assert subspace_overlap(res.V[p].T, g["V"][a], g["E"][p]) >= OVERLAP
+    if res_on:
+        ref = g["eval_getResonatorResponse"]
+        assert np.max(np.abs(res.Erwa - ref)) < E_RTOL * np.max(np.abs(ref))
+
+
 def test_sweep_scalar_evaluables(engine_mod):
     g, plan = load_golden("c4_averin")
     with engine_mod.Engine(plan) as eng:

@@ -84,6 +84,17 @@ def test_resonator_matches_reference():
         assert abs(chi(a) - chi(b)) < 1e-9
 
 
+@pytest.mark.parametrize("name", ["c2_fluxonium_res_t200s", "c7_fluxonium_LphiZ"])
+def test_resonator_other_configs(name):
+    """t = 200 (dense solver territory) and the swept-impedance plan (rotated node basis, unit charge operator)."""
+    g, plan = load_golden(name)
+    k = int(g["k"])
+    out = PlanOracle(plan).sweep(g["params"], k, get_vectors=True, resonator=True)
+    ref = g["eval_getResonatorResponse"]
+    assert out["Erwa"].shape == ref.shape
+    assert np.max(np.abs(out["Erwa"] - ref)) < 1e-9 * np.max(np.abs(ref))
+
+
 def test_scalar_evaluables_match_reference():
     g, plan = load_golden("c4_averin")
     _, scal = eval_program(plan.program, g["params"])
