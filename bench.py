@@ -300,8 +300,9 @@ def run_ours(args):
                 "(CUDA events on its stream, recorded by the library, averaged over the timed steps: %.3f ms of the %.3f ms step). "
                 "peak = FP64 DMMA/DFMA rate measured in this run by scqed_probe_fp64_* (DMMA %.1f, DFMA %.1f TFLOP/s; "
                 "MEASURED_PEAKS.json has no FP64 entry). The kernel is latency/barrier bound (n-1 dependent Householder steps on "
-                "a 101x101 matrix), not pipe bound; H never leaves shared memory, HBM traffic is results only "
-                "(%.1f MB/step)." % ("(4/3) n^3" if real else "(16/3) n^3", "real-symmetric" if real else "complex-Hermitian",
+                "a 101x101 matrix), not pipe bound; H never leaves shared memory; `traffic` (ncu dram bytes of this kernel) is the "
+                "n^2 x 8 B of Householder reflectors per point it writes for the back-transformation, i.e. the algorithmic output; "
+                "results leaving the GPU: %.1f MB/step." % ("(4/3) n^3" if real else "(16/3) n^3", "real-symmetric" if real else "complex-Hermitian",
                                      n_pts, kern_ms, ms_per_step, dmma, dfma, d2h / 1e6))
     else:
         kern_ms = ms_per_step
@@ -309,9 +310,19 @@ def run_ours(args):
         kern = "whole step (dense / matrix-free path)"
         note = "no per-kernel span recorded; whole-step time used"
     achieved = flops_pt * n_pts / (kern_ms * 1e-3) / 1e12
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of the same workload
+    # (profiles/r01_s1_tridiag_ncu_summary.csv: one launch over 9704 points), scaled to this launch
+    traffic = None
+    try:
+        if k_real_n + k_cplx_n > 0 and args.workload == "c2_fluxonium_res_10k":
+            rows = dict((r.split(",")[0], r.split(",")) for r in open(os.path.join(ROOT, "profiles", "r01_s1_tridiag_ncu_summary.csv")) if r.count(",") >= 2)
+            mb = float(rows["dram__bytes_read.sum"][2]) + float(rows["dram__bytes_write.sum"][2])
+            traffic = mb * 1e6 / 9704.0 * n_pts
+    except Exception:
+        traffic = None
     roofline = {
         "bound": "tensor", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak, "traffic": None, "kernel_ms_per_step": kern_ms, "kernel_share_of_step": kern_ms / ms_per_step,
+        "frac": achieved / peak, "traffic": traffic, "kernel_ms_per_step": kern_ms, "kernel_share_of_step": kern_ms / ms_per_step,
         "note": note,
         "hbm_peak_gbs_measured": peaks.get("hbm_gbs"),
         "hbm_achieved_gbs_results_only": d2h / (ms_per_step * 1e-3) / 1e9,
