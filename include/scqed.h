@@ -80,6 +80,16 @@ typedef struct {
      * the plan's factors of node xform_node[i] are expressed in the eigenbasis of a + a^dagger).  Eigenvectors
      * are rotated back on that tensor mode with the real orthogonal d x d matrix W_i (row-major,
      * concatenated in xform_data) before they are returned. */
+    /* Optional entry list for scqed_assemble_dense (pattern of H expanded once): entry e is position
+     * ent_key[e] = i*n + j (sorted, distinct) and H[i][j] = sum over pairs q in [ent_ptr[e], ent_ptr[e+1]) of
+     * c[ent_term[q]] * ent_val[q].  ent_dense != 0: the pattern covers >= 25 % of the matrix (one thread per
+     * element, no zero fill pass).  n_entries = 0: walk the term table per element. */
+    int32_t n_entries;
+    int32_t ent_dense;
+    const int64_t *ent_key;         /* [n_entries]                                           */
+    const int32_t *ent_ptr;         /* [n_entries + 1]                                       */
+    const int32_t *ent_term;        /* [ent_ptr[n_entries]]                                  */
+    const double *ent_val;          /* complex [ent_ptr[n_entries]]                          */
     int32_t n_xform;
     const int32_t *xform_node;      /* [n_xform]                                             */
     const double *xform_data;       /* concatenated W_i, d_i * d_i doubles each              */

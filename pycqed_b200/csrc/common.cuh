@@ -99,6 +99,13 @@ struct PlanDev {
     const double *dense_tab;       // [n_dense - n_dense_diag][n*n] column-major, then [n_dense_diag][n]
     const int *dense_re, *dense_im;   // [n_dense] coefficient registers (-1 = zero)
     const double *dense_gmax;      // [n_dense]
+    // entry list of the dense assembly (K2): distinct positions of H and their (term, value) contributions
+    int n_entries, ent_dense;
+    const long long *ent_key;      // [n_entries] i*n + j, sorted
+    const int *ent_ptr;            // [n_entries + 1]
+    const int *ent_term;           // [n_pairs_total]
+    const cplx *ent_val;           // [n_pairs_total]
+    const int *ent_map;            // dense patterns: [n*n] element -> entry (-1 = structural zero)
     int n_swept, n_instr, n_scalar;
     const int *instr;              // [n_instr * 3]
     const double *consts;

@@ -330,6 +330,27 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     size_t o_dtab = put(d->dense_tab, ((size_t)(n_dense - d->n_dense_diag) * n * n + (size_t)d->n_dense_diag * n) * 8);
     size_t o_dre = put(d->dense_re, (size_t)n_dense * 4), o_dim = put(d->dense_im, (size_t)n_dense * 4);
     size_t o_dgm = put(d->dense_gmax, (size_t)n_dense * 8);
+    size_t o_ekey = 0, o_eptr = 0, o_eterm = 0, o_eval = 0, o_emap = 0;
+    if (d->n_entries < 0 || (d->n_entries > 0 && (!d->ent_key || !d->ent_ptr || !d->ent_term || !d->ent_val))) { delete pl; return fail(SCQED_EINVAL, "entry list malformed"); }
+    if (d->n_entries > 0) {
+        const int ne = d->n_entries;
+        const long long np_tot = d->ent_ptr[ne];
+        for (int e = 0; e < ne; ++e) {
+            if (d->ent_key[e] < 0 || d->ent_key[e] >= n * n || (e > 0 && d->ent_key[e] <= d->ent_key[e - 1]) || d->ent_ptr[e + 1] < d->ent_ptr[e])
+                { delete pl; return fail(SCQED_EINVAL, "entry %d malformed", e); }
+        }
+        for (long long q = 0; q < np_tot; ++q)
+            if (d->ent_term[q] < 0 || d->ent_term[q] >= d->n_terms) { delete pl; return fail(SCQED_EINVAL, "entry pair %lld: term out of range", q); }
+        o_ekey = put(d->ent_key, (size_t)ne * 8);
+        o_eptr = put(d->ent_ptr, (size_t)(ne + 1) * 4);
+        o_eterm = put(d->ent_term, (size_t)np_tot * 4);
+        o_eval = put(d->ent_val, (size_t)np_tot * 16);
+        if (d->ent_dense) {
+            std::vector<int> emap((size_t)(n * n), -1);
+            for (int e = 0; e < ne; ++e) emap[(size_t)d->ent_key[e]] = e;
+            o_emap = put(emap.data(), emap.size() * 4);
+        }
+    }
     if (d->n_xform < 0 || (d->n_xform > 0 && (!d->xform_node || !d->xform_data))) { delete pl; return fail(SCQED_EINVAL, "basis transforms malformed"); }
     {
         const double *src = d->xform_data;
@@ -371,6 +392,10 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     P.aux_meta = (const int *)(base + o_ameta);
     P.aux_re = (const int *)(base + o_are); P.aux_im = (const int *)(base + o_aim);
     P.pairs = (const int *)(base + o_pairs);
+    P.n_entries = d->n_entries; P.ent_dense = d->n_entries > 0 && d->ent_dense;
+    P.ent_key = (const long long *)(base + o_ekey); P.ent_ptr = (const int *)(base + o_eptr);
+    P.ent_term = (const int *)(base + o_eterm); P.ent_val = (const cplx *)(base + o_eval);
+    P.ent_map = (const int *)(base + o_emap);
     P.n_dense = n_dense; P.n_dense_diag = d->n_dense_diag;
     P.dense_tab = (const double *)(base + o_dtab);
     P.dense_re = (const int *)(base + o_dre); P.dense_im = (const int *)(base + o_dim);
@@ -535,6 +560,23 @@ extern "C" int scqed_eval_coefficients(scqed_plan *pl, const double *params_dev,
 
 static int run_assemble(scqed_plan *pl, const cplx *coef_dev, long long n_pts, int tidyup, cplx *H, cudaStream_t st) {
     const PlanDev &P = pl->P;
+    if (P.n_entries > 0 && !getenv("SCQED_NO_ENTRY_LIST")) {
+        const size_t nn = (size_t)P.n * P.n;
+        const long long eb = P.ent_dense ? (long long)((nn + 255) / 256) : (P.n_entries + 255) / 256;
+        if (eb <= 65535 && n_pts <= 2147483647LL) {
+            timing_begin(st, 3);
+            if (P.ent_dense) {
+                assemble_mapped_kernel<<<dim3((unsigned)n_pts, (unsigned)eb), 256, (size_t)P.n_terms * 16, st>>>(P, coef_dev, tidyup, H);
+            } else {
+                CK(cudaMemsetAsync(H, 0, (size_t)n_pts * nn * 16, st));
+                assemble_entries_kernel<<<dim3((unsigned)n_pts, (unsigned)eb), 256, (size_t)P.n_terms * 16, st>>>(P, coef_dev, tidyup, H);
+            }
+            timing_end(st);
+            LAUNCHED();
+            CK(cudaGetLastError());
+            return 0;
+        }
+    }
     long long col_tiles = (P.n + ASM_TC - 1) / ASM_TC, row_tiles = (P.n + ASM_TR - 1) / ASM_TR;
     long long blocks = n_pts * col_tiles * row_tiles;
     if (blocks > 2147483647LL) return fail(SCQED_EINVAL, "assembly grid too large; split the batch");

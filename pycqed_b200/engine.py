@@ -12,6 +12,7 @@ import threading
 import numpy as np
 
 from .densetab import build_dense_table
+from .entrytab import build_entry_table
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libscqed.so")
@@ -38,6 +39,8 @@ class _PlanDesc(C.Structure):
         ("n_pairs", C.c_int32), ("pairs", C.POINTER(C.c_int32)),
         ("n_dense", C.c_int32), ("n_dense_diag", C.c_int32), ("dense_tab", C.POINTER(C.c_double)),
         ("dense_re", C.POINTER(C.c_int32)), ("dense_im", C.POINTER(C.c_int32)), ("dense_gmax", C.POINTER(C.c_double)),
+        ("n_entries", C.c_int32), ("ent_dense", C.c_int32), ("ent_key", C.POINTER(C.c_int64)),
+        ("ent_ptr", C.POINTER(C.c_int32)), ("ent_term", C.POINTER(C.c_int32)), ("ent_val", C.POINTER(C.c_double)),
         ("n_xform", C.c_int32), ("xform_node", C.POINTER(C.c_int32)), ("xform_data", C.POINTER(C.c_double)),
     ]
 
@@ -230,6 +233,18 @@ class Engine:
             aux_re=_ptr(aux_re, C.c_int32), aux_im=_ptr(aux_im, C.c_int32),
             n_pairs=len(pair_list), pairs=_ptr(pairs, C.c_int32),
         )
+        # dense assembly (K2, also feeding the HBM dense solver): entry list of the pattern of H.
+        # Only where a dense H is a sane object (<= 2 GB per matrix).
+        ent = None
+        if self.n <= 11000 and not os.environ.get("SCQED_NO_ENTRY_LIST"):
+            ent = build_entry_table(plan)
+        if ent is not None:
+            ekey = np.ascontiguousarray(ent["key"], dtype=np.int64)
+            eptr, eterm = _i32(ent["ptr"]), _i32(ent["term"])
+            evalv = np.ascontiguousarray(ent["val"], dtype=np.complex128).view(np.float64)
+            desc.n_entries, desc.ent_dense = int(ekey.size), int(ent["dense"])
+            desc.ent_key = _ptr(ekey, C.c_int64)
+            desc.ent_ptr, desc.ent_term, desc.ent_val = _ptr(eptr, C.c_int32), _ptr(eterm, C.c_int32), _ptr(evalv, C.c_double)
         xf = plan.node_transforms()
         self.rotated = bool(xf)
         if xf:
