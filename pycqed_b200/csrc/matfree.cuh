@@ -499,11 +499,12 @@ __device__ __forceinline__ double mf_block_sum(double v, double *red) {
 
 // ---- CGS2 orthonormalisation of the block (in place).  grid (n_pts), block 512 -----------------------
 __global__ void __launch_bounds__(512)
-mf_orth(MfArgs a, cplx *Y, int *info) {
+mf_orth(MfArgs a, cplx *Y, int *info, const int *__restrict__ only) {
     __shared__ double red[32];
     __shared__ double sdot[MF_BMAX][2];
     const long long p = blockIdx.x;
     if (!a.active[p]) return;
+    if (only && !only[p]) return;
     const int n = a.n, b = a.b, tid = threadIdx.x, T = blockDim.x;
     const int w = tid >> 5, l = tid & 31, nw = T >> 5;
     __shared__ double swarp[16][MF_BMAX][2];
@@ -558,6 +559,96 @@ mf_orth(MfArgs a, cplx *Y, int *info) {
         const double sc = 1.0 / sqrt(s);
         for (int i = tid; i < n; i += T) { cplx yi = y[i]; y[i] = cmake(yi.x * sc, yi.y * sc); }
         __syncthreads();
+    }
+}
+
+// ---- CholQR: Y <- Y T with T = S R^-1, where S = diag(M)^-1/2 and R^H R = S M S is the Cholesky factor of
+// the column-scaled Gram matrix M = Y^H Y.  Two rounds (CholQR2) orthonormalise a filtered block to machine
+// precision with 2 Gram sweeps + 2 row-parallel updates instead of the b sequential CGS2 steps of mf_orth
+// (one CTA per point, 22 % of the n = 9261 solve).  A point whose scaled Gram matrix is numerically
+// singular (pivot^2 < 1e-10) is flagged in `redo` and orthonormalised by mf_orth afterwards.
+// One warp per point; lane = column.
+__global__ void __launch_bounds__(32)
+mf_chol(MfArgs a, const cplx *__restrict__ M, cplx *__restrict__ Tout, int *__restrict__ redo, int first_round) {
+    __shared__ cplx R[MF_BMAX][MF_BMAX + 1];
+    __shared__ double sc[MF_BMAX];
+    const long long p = blockIdx.x;
+    const int b = a.b, l = threadIdx.x;
+    if (first_round && l == 0) redo[p] = 0;
+    if (!a.active[p]) return;
+    if (!first_round && redo[p]) return;
+    bool bad = false;
+    if (l < b) {
+        const double dg = M[(p * b + l) * b + l].x;
+        bad = !(dg > 1e-280) || !isfinite(dg);
+        sc[l] = bad ? 1.0 : 1.0 / sqrt(dg);
+    }
+    __syncwarp();
+    for (int r = 0; r < b; ++r)
+        if (l < b) { cplx m = M[(p * b + r) * b + l]; const double f = sc[r] * sc[l]; R[r][l] = cmake(m.x * f, m.y * f); }
+    __syncwarp();
+    // upper Cholesky, column l owned by lane l: R[j][l] for j <= l
+    for (int j = 0; j < b; ++j) {
+        if (l >= j && l < b) {
+            cplx v = R[j][l];
+            for (int q = 0; q < j; ++q) { cplx rq = R[q][j], rl = R[q][l]; v.x -= rq.x * rl.x + rq.y * rl.y; v.y -= rq.x * rl.y - rq.y * rl.x; }   // conj(R[q][j]) R[q][l]
+            R[j][l] = v;
+        }
+        __syncwarp();
+        const double piv = R[j][j].x;
+        if (!(piv > 1e-10)) bad = true;
+        const double inv = 1.0 / sqrt(piv > 1e-10 ? piv : 1.0);
+        __syncwarp();
+        if (l >= j && l < b) { cplx v = R[j][l]; R[j][l] = l == j ? cmake(sqrt(piv > 1e-10 ? piv : 1.0), 0.0) : cmake(v.x * inv, v.y * inv); }
+        __syncwarp();
+    }
+    if (__any_sync(0xffffffffu, bad)) { if (l == 0) redo[p] = 1; return; }
+    // X = R^-1 (upper), column l by back substitution; T = S X
+    if (l < b) {
+        cplx x[MF_BMAX];
+#pragma unroll
+        for (int i = 0; i < MF_BMAX; ++i) x[i] = cmake(0.0, 0.0);
+#pragma unroll
+        for (int i = MF_BMAX - 1; i >= 0; --i) {
+            if (i <= l && i < b) {
+                cplx v = i == l ? cmake(1.0, 0.0) : cmake(0.0, 0.0);
+#pragma unroll
+                for (int q = i + 1; q < MF_BMAX; ++q)
+                    if (q <= l) { cplx r = R[i][q]; v.x -= r.x * x[q].x - r.y * x[q].y; v.y -= r.x * x[q].y + r.y * x[q].x; }
+                const double d = 1.0 / R[i][i].x;
+                x[i] = cmake(v.x * d, v.y * d);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MF_BMAX; ++i)
+            if (i < b) Tout[(p * b + i) * b + l] = i <= l ? cmake(x[i].x * sc[i], x[i].y * sc[i]) : cmake(0.0, 0.0);
+    }
+}
+
+// Y[:, j] <- sum_{q <= j} Y[:, q] T[q][j], in place; grid (ceil(n / 256), n_pts), one thread per row.
+template <int BB>
+__global__ void __launch_bounds__(MF_THREADS)
+mf_right_apply(MfArgs a, cplx *__restrict__ Y, const cplx *__restrict__ Tm, const int *__restrict__ redo) {
+    __shared__ cplx sT[BB * BB];
+    const long long p = blockIdx.y;
+    if (!a.active[p] || redo[p]) return;
+    const int n = a.n, b = a.b, tid = threadIdx.x;
+    for (int q = tid; q < b * b; q += blockDim.x) sT[q] = Tm[p * b * b + q];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + tid;
+    if (i >= n) return;
+    cplx y[BB];
+#pragma unroll
+    for (int q = 0; q < BB; ++q) y[q] = q < b ? Y[(p * b + q) * n + i] : cmake(0.0, 0.0);
+#pragma unroll
+    for (int j = BB - 1; j >= 0; --j) {
+        if (j < b) {
+            cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+            for (int q = 0; q < BB; ++q)
+                if (q <= j) cfma(acc, y[q], sT[q * b + j]);
+            Y[(p * b + j) * n + i] = acc;
+        }
     }
 }
 

@@ -983,7 +983,7 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
     if (b < k) return fail(SCQED_EUNSUPPORTED, "matrix-free path supports k <= %d", MF_BMAX);
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
-    const size_t per_pt = (size_t)4 * b * n * 16 + (size_t)n * 8 + (size_t)2 * b * b * 16 + (size_t)2 * b * 8 + 64;
+    const size_t per_pt = (size_t)4 * b * n * 16 + (size_t)n * 8 + (size_t)2 * b * b * 16 + (size_t)2 * b * 8 + 64 + 8;
     long long chunk = (long long)((free_b / 2) / per_pt);
     if (chunk < 1) return fail(SCQED_ENOMEM, "not enough device memory for one matrix-free block (n=%d, b=%d)", n, b);
     if (chunk > n_pts) chunk = n_pts;
@@ -998,6 +998,8 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
     double *theta = (double *)take((size_t)chunk * b * 8), *rn2 = (double *)take((size_t)chunk * b * 8);
     double *fpar = (double *)take((size_t)chunk * 4 * 8);
     int *active = (int *)take((size_t)chunk * 4), *n_active = (int *)take(256), *info_s1 = (int *)take((size_t)chunk * 4);
+    int *redo = (int *)take((size_t)chunk * 4);
+    const bool use_cholqr = !getenv("SCQED_NO_CHOLQR");
     const bool smem_filter = (size_t)2 * n * 16 <= 220 * 1024;
     // stencil filter (banded-monomial factors): smallest cluster whose slices fit shared memory
     int stencil_cs = 0, stencil_ns = 0;
@@ -1043,7 +1045,18 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
         LAUNCHED();
         // Rayleigh-Ritz on block R (orthonormalised in place): leaves Ritz vectors in X, H X in H
         auto rayleigh_ritz = [&](cplx *R) -> int {
-            mf_orth<<<(unsigned)np, 512, 0, st>>>(a, R, info_c);
+            if (use_cholqr) {
+                for (int round = 0; round < 2; ++round) {
+                    mf_gram<<<dim3(b, (unsigned)np), MF_THREADS, 0, st>>>(a, R, R, G);
+                    mf_chol<<<(unsigned)np, 32, 0, st>>>(a, G, S, redo, round == 0);
+                    if (b <= 16) mf_right_apply<16><<<dim3(rowblocks, (unsigned)np), MF_THREADS, 0, st>>>(a, R, S, redo);
+                    else mf_right_apply<32><<<dim3(rowblocks, (unsigned)np), MF_THREADS, 0, st>>>(a, R, S, redo);
+                }
+                mf_orth<<<(unsigned)np, 512, 0, st>>>(a, R, info_c, redo);        // only the flagged points do work
+                g_launches.fetch_add(6, std::memory_order_relaxed);
+            } else {
+                mf_orth<<<(unsigned)np, 512, 0, st>>>(a, R, info_c, nullptr);
+            }
             mf_matvec<<<dim3(rowblocks, b, (unsigned)np), MF_THREADS, 0, st>>>(a, R, H);
             mf_gram<<<dim3(b, (unsigned)np), MF_THREADS, 0, st>>>(a, R, H, G);
             mf_symmetrize<<<(unsigned)np, b * b, 0, st>>>(a, G);
