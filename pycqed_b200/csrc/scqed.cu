@@ -19,6 +19,7 @@
 #include "resonator.cuh"
 #include "small_eigh.cuh"
 #include "small_split.cuh"
+#include "small_packed.cuh"
 #include "dense_eigh.cuh"
 #include "dense_blocked.cuh"
 #include "matfree.cuh"
@@ -633,13 +634,59 @@ static int run_small(scqed_plan *pl, const PlanDev &P, const cplx *coef, const c
 }
 
 // ---- S1 as a phase pipeline (small_split.cuh) ------------------------------------------------------------
-static bool split_fits(const scqed_plan *pl, int n, int k, int n_terms) {
-    if (n > 32 * SMALL_RQ || k > 32 || n < 2) return false;
-    return S1Smem<cplx>::bytes(n, n_terms, 512) <= pl->smem_optin;
+// SCQED_S1_PACKED: 0 = full-storage kernel only (n <= 128), 1 = packed lower triangle for every n,
+// unset = auto: full storage for n <= 128 (faster per matrix: 6.6 vs 9.9 ms on the bench), packed above
+// (the only way 128 < n <= ~212 real symmetric stays on chip: 8x the HBM solver at n = 200)
+static int s1_packed_mode() {
+    const char *e = getenv("SCQED_S1_PACKED");
+    return e ? atoi(e) : 2;
+}
+
+#define S1_NOT_REAL 77001       // internal: 128 < n <= 224 only fits the shared-memory path when H is real
+// real_hint: -1 unknown, 1 known real, 0 known complex
+static bool split_fits(const scqed_plan *pl, int n, int k, int n_terms, int real_hint = -1) {
+    if (k > 32 || n < 2) return false;
+    if (n <= 32 * SMALL_RQ)
+        return S1Smem<cplx>::bytes(n, n_terms, 512) <= pl->smem_optin ||
+               (s1_packed_mode() && S1PSmem<cplx>::bytes(n, n_terms, 256) <= pl->smem_optin);
+    if (n > 224 || real_hint == 0 || !s1_packed_mode()) return false;
+    return S1PSmem<double>::bytes(n, n_terms, 512) <= pl->smem_optin;     // packed lower triangle, real symmetric only
+}
+
+template <typename T, int NQ>
+static int s1p_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t st, bool *launched) {
+    const int threads = NQ <= 4 ? 256 : 512;
+    const size_t smem = S1PSmem<T>::bytes(a.n, n_terms, threads);
+    *launched = false;
+    if (smem > pl->smem_optin) return 0;
+    CK(cudaFuncSetAttribute(s1p_tridiag_kernel<T, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s1p_tridiag_kernel<T, NQ>, threads, smem));
+    if (occ < 1) return 0;
+    long long grid = (long long)occ * pl->sm_count;
+    if (grid > a.n_pts) grid = a.n_pts;
+    timing_begin(st, sizeof(T) == sizeof(double) ? 1 : 2);
+    s1p_tridiag_kernel<T, NQ><<<(unsigned)grid, threads, smem, st>>>(a);
+    timing_end(st);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    *launched = true;
+    return 0;
 }
 
 template <typename T>
 static int s1_launch_tridiag(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t st) {
+    const bool full_fits = a.n <= 32 * SMALL_RQ &&
+        S1Smem<T>::bytes(a.n, n_terms, sizeof(T) == sizeof(double) ? 256 : 512) <= pl->smem_optin;
+    if (s1_packed_mode() == 1 || (s1_packed_mode() == 2 && !full_fits)) {
+        bool launched = false;
+        int rc = 0;
+        if (a.n <= 128) rc = s1p_launch<T, 4>(pl, a, n_terms, st, &launched);
+        else if constexpr (sizeof(T) == sizeof(double)) rc = s1p_launch<T, 7>(pl, a, n_terms, st, &launched);
+        if (rc) return rc;
+        if (launched) return 0;
+        if (a.n > 32 * SMALL_RQ) return fail(SCQED_EUNSUPPORTED, "n=%d does not fit the shared-memory tridiagonalisation", a.n);
+    }
     const int threads = sizeof(T) == sizeof(double) ? 256 : 512;
     const size_t smem = S1Smem<T>::bytes(a.n, n_terms, threads);
     CK(cudaFuncSetAttribute(s1_tridiag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -722,6 +769,7 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
             if (!Hin) pl->s1_real_mode = real_mode ? 1 : 0;
             if (!real_mode) CK(cudaMemsetAsync(a.info, 0, (size_t)np * 4, st));
         }
+        if (!real_mode && n > 32 * SMALL_RQ) return S1_NOT_REAL;       // caller falls back to the HBM solvers
         if (!real_mode) {
             int rc = s1_launch_tridiag<cplx>(pl, a, P.n_terms > P.n_dense ? P.n_terms : P.n_dense, st);
             if (rc) return rc;
@@ -744,7 +792,10 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
             const long long iw = (np + ppw - 1) / ppw;
             s1_invit_kernel<<<(unsigned)((iw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, Gc);
             cplx *vout = evecs ? evecs + (size_t)p0 * k * n : vec_tmp;
-            if (real_mode) {
+            if (real_mode && n > 32 * SMALL_RQ) {
+                const long long bw = np * ((k + 7) / 8);
+                s1_backtr_kernel<double, 8, 7><<<(unsigned)((bw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, Gc, vout);
+            } else if (real_mode) {
                 const long long bw = np * ((k + 7) / 8);
                 s1_backtr_kernel<double, 8><<<(unsigned)((bw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, Gc, vout);
             } else {
@@ -767,7 +818,7 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
 static int run_small_any(scqed_plan *pl, const PlanDev &P, const cplx *coef, const cplx *Hin, const double *scal,
                          long long n_pts, int n, int k, int want_vec, int tidyup, const ResonatorArgs &res,
                          double *evals, cplx *evecs, double *post, int *info, cudaStream_t st, bool monolithic) {
-    if (!monolithic && split_fits(pl, n, k, P.n_terms > P.n_dense ? P.n_terms : P.n_dense))
+    if (!monolithic && split_fits(pl, n, k, P.n_terms > P.n_dense ? P.n_terms : P.n_dense, Hin ? -1 : pl->s1_real_mode))
         return run_small_split(pl, P, coef, Hin, scal, n_pts, n, k, want_vec, tidyup, res, evals, evecs, post, info, st);
     return run_small(pl, P, coef, Hin, scal, n_pts, n, k, want_vec, tidyup, res, evals, evecs, post, info, st);
 }
@@ -1151,12 +1202,18 @@ extern "C" int scqed_eigh_batched(int device, double *H_dev, int32_t n, int64_t 
     if (n < 2) solver = 1;
     int rc;
     if (solver == 5 && !fits) return fail(SCQED_EUNSUPPORTED, "n=%d k=%d does not fit the fused path", n, k);
-    if ((solver == 0 && fits) || solver == 1 || solver == 5) {
+    bool small = (solver == 0 && fits) || solver == 1 || solver == 5;
+    if (small) {
         rc = run_small_any(&tmp, tmp.P, nullptr, (const cplx *)H_dev, nullptr, batch, n, k, want_vec, 0, res, evals_dev,
                            (cplx *)evecs_dev, nullptr, info_dev, st, solver == 5);
-        if (!rc) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) rc = fail(SCQED_ECUDA, "small eigh: %s", cudaGetErrorString(e)); }
+        if (rc == S1_NOT_REAL) {            // 128 < n <= 224 and the matrices are not real: HBM solver instead
+            if (solver != 0) rc = fail(SCQED_EUNSUPPORTED, "n=%d fits the shared-memory path only for real symmetric matrices", n);
+            else small = false;
+        }
+        if (small && !rc) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) rc = fail(SCQED_ECUDA, "small eigh: %s", cudaGetErrorString(e)); }
         tmp.s1work.release(); tmp.s1vec.release();
-    } else {
+    }
+    if (!small) {
         long long B = batch > 32 ? 32 : batch;
         int nseg = dense_nseg(n, tmp.sm_count, (int)B);
         const bool blocked = solver != 3;
@@ -1249,7 +1306,7 @@ static int sweep_run_impl(scqed_plan *pl, const scqed_sweep_opts *o, const doubl
         res.op_node = pl->factor_node[o->res_op_factor];
         res.s_gc = o->res_gc; res.s_frl = o->res_frl; res.s_qb = o->res_qb;
     }
-    bool fits = (o->solver != 5 && !(o->resonator && o->k > SCQED_RES_KMAX) && split_fits(pl, n, k, P.n_terms > P.n_dense ? P.n_terms : P.n_dense)) ||
+    bool fits = (o->solver != 5 && !(o->resonator && o->k > SCQED_RES_KMAX) && split_fits(pl, n, k, P.n_terms > P.n_dense ? P.n_terms : P.n_dense, pl->s1_real_mode)) ||
                 small_fits(pl, n, k, o->want_vectors, P.n_terms, nullptr);
     int solver = o->solver;
     if ((solver == 1 || solver == 5) && !fits) return fail(SCQED_EUNSUPPORTED, "n=%d k=%d does not fit the fused shared-memory path", n, k);
@@ -1259,8 +1316,12 @@ static int sweep_run_impl(scqed_plan *pl, const scqed_sweep_opts *o, const doubl
         else solver = 2;
     }
     if (solver == 1 || solver == 5) {
-        return run_small_any(pl, P, (const cplx *)pl->coef.p, nullptr, scal, n_pts, n, k, o->want_vectors, o->tidyup, res,
-                             evals_dev, (cplx *)evecs_dev, post_dev, info_dev, st, solver == 5);
+        rc = run_small_any(pl, P, (const cplx *)pl->coef.p, nullptr, scal, n_pts, n, k, o->want_vectors, o->tidyup, res,
+                           evals_dev, (cplx *)evecs_dev, post_dev, info_dev, st, solver == 5);
+        if (rc != S1_NOT_REAL) return rc;
+        // 128 < n <= 224 and H is not real symmetric: the packed shared-memory path does not apply
+        if (o->solver == 1) return fail(SCQED_EUNSUPPORTED, "n=%d fits the shared-memory path only for real symmetric H", n);
+        solver = (P.max_term_nn <= 3 && o->k + 6 <= MF_BMAX && pl->mf_work_per_row <= n / 2) ? 4 : 2;
     }
     // S2 / S3 with the Resonator evaluable: eigenvectors are needed on the device even when the
     // caller does not want them back

@@ -311,7 +311,7 @@ s1_invit_kernel(S1Args a, const int *__restrict__ skip, long long G) {
 }
 
 // ---- phase D: x = Q z.  One warp per (point, group of KV vectors) ------------------------------------------
-template <typename T, int S1_KV>
+template <typename T, int S1_KV, int RQ = SMALL_RQ>
 __global__ void __launch_bounds__(128)
 s1_backtr_kernel(S1Args a, const int *__restrict__ skip, long long G, cplx *__restrict__ evecs) {
     const int n = a.n, k = a.k, l = threadIdx.x & 31;
@@ -322,9 +322,9 @@ s1_backtr_kernel(S1Args a, const int *__restrict__ skip, long long G, cplx *__re
     const int g0 = (int)(warp - p * groups) * S1_KV;
     if (skip && skip[p]) return;
     const int kv = min(S1_KV, k - g0);
-    T x[SMALL_RQ][S1_KV];
+    T x[RQ][S1_KV];
 #pragma unroll
-    for (int q = 0; q < SMALL_RQ; ++q) {
+    for (int q = 0; q < RQ; ++q) {
         int i = l + 32 * q;
 #pragma unroll
         for (int u = 0; u < S1_KV; ++u) {
@@ -335,19 +335,19 @@ s1_backtr_kernel(S1Args a, const int *__restrict__ skip, long long G, cplx *__re
     const T *V = (const T *)a.W.Vst + (size_t)p * n * n;
     const T *tau = (const T *)a.W.tau + p * n;
     // reflector j lives in column j, rows j+1..n-1 (v[j+1] = 1 stored explicitly)
-    T vn[SMALL_RQ];
+    T vn[RQ];
     auto load_col = [&](int j, T *dst) {
 #pragma unroll
-        for (int q = 0; q < SMALL_RQ; ++q) {
+        for (int q = 0; q < RQ; ++q) {
             int i = l + 32 * q;
             dst[q] = (j >= 0 && i > j && i < n) ? V[(size_t)j * n + i] : nzero(T());
         }
     };
     load_col(n - 2, vn);
     for (int j = n - 2; j >= 0; --j) {
-        T v[SMALL_RQ];
+        T v[RQ];
 #pragma unroll
-        for (int q = 0; q < SMALL_RQ; ++q) v[q] = vn[q];
+        for (int q = 0; q < RQ; ++q) v[q] = vn[q];
         const T tj = tau[j];
         load_col(j - 1, vn);                                   // prefetch the next reflector
         if (niszero(tj)) continue;
@@ -356,7 +356,7 @@ s1_backtr_kernel(S1Args a, const int *__restrict__ skip, long long G, cplx *__re
         for (int u = 0; u < S1_KV; ++u) {
             dot[u] = nzero(T());
 #pragma unroll
-            for (int q = 0; q < SMALL_RQ; ++q) nfmac(dot[u], v[q], x[q][u]);      // v^H x
+            for (int q = 0; q < RQ; ++q) nfmac(dot[u], v[q], x[q][u]);      // v^H x
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -374,11 +374,11 @@ s1_backtr_kernel(S1Args a, const int *__restrict__ skip, long long G, cplx *__re
         for (int u = 0; u < S1_KV; ++u) {
             const T f = nmul(tj, dot[u]);
 #pragma unroll
-            for (int q = 0; q < SMALL_RQ; ++q) x[q][u] = nsub(x[q][u], nmul(f, v[q]));
+            for (int q = 0; q < RQ; ++q) x[q][u] = nsub(x[q][u], nmul(f, v[q]));
         }
     }
 #pragma unroll
-    for (int q = 0; q < SMALL_RQ; ++q) {
+    for (int q = 0; q < RQ; ++q) {
         int i = l + 32 * q;
         if (i >= n) continue;
 #pragma unroll

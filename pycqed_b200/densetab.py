@@ -1,6 +1,6 @@
 """Dense real term table for the fused small-n solver (S1).
 
-For a Hilbert space that fits one SM's shared memory (n <= 128) the Kronecker term table
+For a Hilbert space that fits one SM's shared memory (n <= 224) the Kronecker term table
 H(p) = sum_t c_t(p) kron_k F_{t,k}  is expanded ONCE on the host into a handful of real n x n
 matrices G_g with real per-point coefficients:
 
@@ -27,7 +27,7 @@ import numpy as np
 from . import coefprog as cp
 from .coefprog import CoefProgram
 
-MAX_N = 128
+MAX_N = 224
 _UNARY = {cp.OP_NEG: lambda x: -x, cp.OP_SQRT: math.sqrt, cp.OP_SIN: math.sin, cp.OP_COS: math.cos,
           cp.OP_EXP: math.exp, cp.OP_LOG: math.log, cp.OP_ABS: abs, cp.OP_TAN: math.tan, cp.OP_ATAN: math.atan,
           cp.OP_TANH: math.tanh, cp.OP_SINH: math.sinh, cp.OP_COSH: math.cosh}

@@ -97,6 +97,52 @@ def test_eigh_batched_random(engine_mod, n, k, solver):
         assert subspace_overlap(X, v[:, :k], w[:k]) >= OVERLAP
 
 
+@pytest.mark.parametrize("packed", ["0", "1"])
+@pytest.mark.parametrize("n,k,real", [(2, 2, True), (7, 3, False), (33, 10, True), (64, 10, False), (101, 20, True),
+                                      (101, 10, False), (128, 8, True), (112, 8, False)])
+def test_small_path_full_and_packed_storage(engine_mod, monkeypatch, n, k, real, packed):
+    """SCQED_S1_PACKED=1 (default): lower-triangle packed shared-memory tridiagonalisation; =0: full storage."""
+    import torch
+    if packed == "0" and n > 118:
+        pytest.skip("n^2 complex128 does not fit one SM's shared memory in full storage")
+    monkeypatch.setenv("SCQED_S1_PACKED", packed)
+    rng = np.random.default_rng(99 + n)
+    H = _random_hermitian(rng, n, 5, real=real).astype(np.complex128)
+    E, V, info = engine_mod.eigh_batched(torch.as_tensor(H, device="cuda"), k, want_vectors=True, solver=1)
+    E, V, info = E.cpu().numpy(), V.cpu().numpy(), info.cpu().numpy()
+    assert not info.any()
+    for b in range(H.shape[0]):
+        w, v = np.linalg.eigh(H[b])
+        scale = np.abs(w).max()
+        assert np.max(np.abs(E[b] - w[:k])) < 1e-12 * scale * n
+        X = V[b].T
+        assert np.max(np.abs(X.conj().T @ X - np.eye(k))) < 1e-10
+        assert np.max(np.abs(H[b] @ X - X * E[b][None, :])) < 1e-11 * scale * n
+
+
+@pytest.mark.parametrize("n,k", [(129, 10), (160, 12), (200, 10), (208, 6)])
+def test_real_symmetric_up_to_224_on_chip(engine_mod, n, k):
+    """128 < n <= ~212: real symmetric matrices stay on the shared-memory path (packed storage); complex
+    ones of the same size fall back to the HBM solver (covered by test_eigh_batched_random)."""
+    import torch
+    rng = np.random.default_rng(5 + n)
+    H = _random_hermitian(rng, n, 4, real=True).astype(np.complex128)
+    for solver in (0, 1):
+        E, V, info = engine_mod.eigh_batched(torch.as_tensor(H, device="cuda"), k, want_vectors=True, solver=solver)
+        E, V, info = E.cpu().numpy(), V.cpu().numpy(), info.cpu().numpy()
+        assert not info.any()
+        for b in range(H.shape[0]):
+            w, v = np.linalg.eigh(H[b])
+            scale = np.abs(w).max()
+            assert np.max(np.abs(E[b] - w[:k])) < 1e-12 * scale * n
+            X = V[b].T
+            assert np.max(np.abs(X.conj().T @ X - np.eye(k))) < 1e-10
+            assert np.max(np.abs(H[b] @ X - X * E[b][None, :])) < 1e-11 * scale * n
+    with pytest.raises(engine_mod.EngineError):
+        Hc = _random_hermitian(rng, n, 2, real=False).astype(np.complex128)
+        engine_mod.eigh_batched(torch.as_tensor(Hc, device="cuda"), k, want_vectors=True, solver=1)
+
+
 @pytest.mark.parametrize("solver,n", [(1, 60), (5, 60), (2, 150), (3, 150), (2, 400)])
 def test_eigh_degenerate_and_clustered(engine_mod, solver, n):
     """Exact doublets / triplets and a tight cluster (the floating-CSFQ trap)."""
