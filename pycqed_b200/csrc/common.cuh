@@ -106,6 +106,11 @@ struct PlanDev {
     const int *ent_term;           // [n_pairs_total]
     const cplx *ent_val;           // [n_pairs_total]
     const int *ent_map;            // dense patterns: [n*n] element -> entry (-1 = structural zero)
+    // two-node plans with dense single-node operators (matfree_d2.cuh): the coupling terms (two non-identity
+    // factors) as a compact term_meta-style list + their original term ids
+    int d2_nmulti;
+    const int *d2_meta;            // [d2_nmulti * 7]
+    const int *d2_cidx;            // [d2_nmulti]
     int n_swept, n_instr, n_scalar;
     const int *instr;              // [n_instr * 3]
     const double *consts;

@@ -1,0 +1,159 @@
+// matfree_d2.cuh -- Kronecker mat-vec for TWO-node plans with dense single-node operators
+// (inductively / capacitively coupled oscillator-basis nodes: the fluxonium atom, C5).
+//
+// mf_apply walks every term per output element; with the oscillator displacement operators D, D^dagger
+// (dense d x d) on both nodes that is four dense mode products of complex arithmetic per mat-vec.
+// Here all single-node terms of node k (charge^2, flux^2, D, D^dagger, constants) are first COMBINED per
+// sweep point into one d_k x d_k matrix
+//        H_k(p) = sum_{t on node k only} c_t(p) F_t            (mf_d2_build, once per point)
+// so that, with x viewed as a d0 x d1 matrix X,
+//        H x  =  H_0 X  +  X H_1^T  +  (coupling terms, sparse factors on both nodes).
+// H_k(p) is Hermitian and for these circuits REAL (c D + conj(c) D^dagger = 2 Re(c D) for symmetric D):
+// two real x complex mode products instead of four complex ones, 4x fewer flops, and the products run
+// as register-tiled GEMM slabs: a CTA owns RB rows of X for one (point, vector); thread = column i1;
+// the H_0 row block and the X row block are staged in shared memory and broadcast, X / H_1 stream
+// coalesced from L2.  Algorithmic work per mat-vec and vector: 2 n (d0 + d1) real-complex MACs
+// (n = d0 d1), traffic 32 n bytes.
+#pragma once
+#include "matfree.cuh"
+
+namespace scqed {
+
+#define D2_RB 16
+
+// H_k(p) for k = 0, 1: re / im planes [n_pts][d0*d0 + d1*d1]; max |Im| accumulated into imax[0].
+__global__ void __launch_bounds__(256)
+mf_d2_build(MfArgs a, double *__restrict__ Hre, double *__restrict__ Him, double *__restrict__ imax) {
+    const long long p = blockIdx.y;
+    const PlanDev &P = a.P;
+    const int d0 = P.dims[0], d1 = P.dims[1];
+    const int tot = d0 * d0 + d1 * d1;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    double my = 0.0;
+    if (e < tot) {
+        const int k = e < d0 * d0 ? 0 : 1;
+        const int dk = k == 0 ? d0 : d1;
+        const int q = k == 0 ? e : e - d0 * d0;
+        const int r = q / dk, c = q - r * dk;
+        const cplx *coef = a.coef + p * P.n_terms;
+        cplx acc = cmake(0.0, 0.0);
+        for (int t = 0; t < P.n_terms; ++t) {
+            const int *tm = P.term_meta + t * 7;
+            const int nn = __ldg(tm);
+            if (nn == 0) { if (k == 0 && r == c) acc = cadd(acc, coef[t]); continue; }
+            if (nn != 1 || __ldg(tm + 1) != k) continue;
+            const cplx f = __ldg(P.factor_data + __ldg(P.factor_offset + __ldg(tm + 4)) + (size_t)r * dk + c);
+            cfma(acc, coef[t], f);
+        }
+        Hre[p * tot + e] = acc.x;
+        Him[p * tot + e] = acc.y;
+        my = fabs(acc.y);
+    }
+    my = fmax(my, __shfl_xor_sync(0xffffffffu, my, 16));
+    my = fmax(my, __shfl_xor_sync(0xffffffffu, my, 8));
+    my = fmax(my, __shfl_xor_sync(0xffffffffu, my, 4));
+    my = fmax(my, __shfl_xor_sync(0xffffffffu, my, 2));
+    my = fmax(my, __shfl_xor_sync(0xffffffffu, my, 1));
+    if ((threadIdx.x & 31) == 0 && my > 0.0) atomicMax((unsigned long long *)imax, (unsigned long long)__double_as_longlong(my));
+}
+
+// MODE 0: HX = H X.  MODE 1: Chebyshev step m (same recurrence as mf_cheb_step), `out` holds y_{m-2} and
+// receives y_m.  grid (ceil(d0 / D2_RB), b, n_pts), block = d1 rounded up to a warp multiple (<= 256).
+template <int MODE, bool REALH>
+__global__ void __launch_bounds__(256)
+mf_d2_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const double *__restrict__ Hre,
+             const double *__restrict__ Him) {
+    extern __shared__ __align__(16) unsigned char d2smem[];
+    const long long p = blockIdx.z;
+    if (!a.active[p]) return;
+    const PlanDev &P = a.P;
+    const int d0 = P.dims[0], d1 = P.dims[1], n = a.n;
+    const int j = blockIdx.y, R0 = blockIdx.x * D2_RB, tid = threadIdx.x;
+    const int rb = min(D2_RB, d0 - R0);
+    const int tot = d0 * d0 + d1 * d1;
+    const double *H0re = Hre + p * tot, *H0im = Him + p * tot;
+    const double *H1re = H0re + (size_t)d0 * d0, *H1im = H0im + (size_t)d0 * d0;
+    // shared: H0 rows [D2_RB][d0] (re, then im when complex), X rows [D2_RB][d1], compact coupling coefficients
+    double *sHre = (double *)d2smem;
+    double *sHim = sHre + (size_t)D2_RB * d0;
+    cplx *sX = (cplx *)(sHim + (REALH ? 0 : (size_t)D2_RB * d0));
+    cplx *sC = sX + (size_t)D2_RB * d1;
+    const cplx *x = X + (p * a.b + j) * n;
+    for (int q = tid; q < rb * d0; q += blockDim.x) {
+        const int r = q / d0, c = q - r * d0;
+        sHre[r * d0 + c] = H0re[(size_t)(R0 + r) * d0 + c];
+        if (!REALH) sHim[r * d0 + c] = H0im[(size_t)(R0 + r) * d0 + c];
+    }
+    for (int q = tid; q < rb * d1; q += blockDim.x) sX[q] = x[(size_t)R0 * d1 + q];
+    for (int q = tid; q < P.d2_nmulti; q += blockDim.x) sC[q] = a.coef[p * P.n_terms + __ldg(P.d2_cidx + q)];
+    __syncthreads();
+    const int i1 = tid;
+    if (i1 >= d1) return;
+    cplx acc[D2_RB];
+#pragma unroll
+    for (int r = 0; r < D2_RB; ++r) acc[r] = cmake(0.0, 0.0);
+    // Y[R0 + r][i1] += sum_b H0[R0 + r][b] X[b][i1]   (X streams coalesced from L2, H0 broadcast from shared memory)
+#pragma unroll 2
+    for (int b = 0; b < d0; ++b) {
+        const cplx xb = x[(size_t)b * d1 + i1];
+#pragma unroll
+        for (int r = 0; r < D2_RB; ++r) {
+            const double hr = sHre[r * d0 + b];
+            acc[r].x = fma(hr, xb.x, acc[r].x);
+            acc[r].y = fma(hr, xb.y, acc[r].y);
+            if (!REALH) {
+                const double hi = sHim[r * d0 + b];
+                acc[r].x = fma(-hi, xb.y, acc[r].x);
+                acc[r].y = fma(hi, xb.x, acc[r].y);
+            }
+        }
+    }
+    // Y[R0 + r][i1] += sum_b X[R0 + r][b] H1[i1][b];  H1 Hermitian: H1[i1][b] = conj(H1[b][i1]) (row b is contiguous)
+#pragma unroll 2
+    for (int b = 0; b < d1; ++b) {
+        const double hr = H1re[(size_t)b * d1 + i1];
+        const double hi = REALH ? 0.0 : -H1im[(size_t)b * d1 + i1];
+#pragma unroll
+        for (int r = 0; r < D2_RB; ++r) {
+            const cplx xv = sX[r * d1 + b];
+            acc[r].x = fma(hr, xv.x, acc[r].x);
+            acc[r].y = fma(hr, xv.y, acc[r].y);
+            if (!REALH) {
+                acc[r].x = fma(-hi, xv.y, acc[r].x);
+                acc[r].y = fma(hi, xv.x, acc[r].y);
+            }
+        }
+    }
+    ChebPar q;
+    double s = 0.0, t = 0.0;
+    if (MODE == 1) {
+        q = cheb_par(a.fpar + p * 4);
+        if (m == 1) s = q.sigma1 / q.e;
+        else {
+            double sigma = q.sigma1;
+            for (int u = 2; u < m; ++u) sigma = 1.0 / (2.0 / q.sigma1 - sigma);
+            const double sigma2 = 1.0 / (2.0 / q.sigma1 - sigma);
+            s = 2.0 * sigma2 / q.e;
+            t = sigma * sigma2;
+        }
+    }
+    cplx *o = out + (p * a.b + j) * n;
+#pragma unroll
+    for (int r = 0; r < D2_RB; ++r) {
+        if (r >= rb) break;
+        const int i = (R0 + r) * d1 + i1;
+        cplx h = acc[r];
+        if (P.d2_nmulti > 0) h = cadd(h, mf_apply_terms(P, P.d2_meta, 0, P.d2_nmulti, sC, x, i));
+        if (MODE == 0) o[i] = h;
+        else {
+            const cplx yi = sX[r * d1 + i1];
+            if (m == 1) o[i] = cmake(s * (h.x - q.c * yi.x), s * (h.y - q.c * yi.y));
+            else {
+                const cplx pi = o[i];
+                o[i] = cmake(s * (h.x - q.c * yi.x) - t * pi.x, s * (h.y - q.c * yi.y) - t * pi.y);
+            }
+        }
+    }
+}
+
+}  // namespace scqed

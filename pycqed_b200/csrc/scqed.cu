@@ -23,6 +23,7 @@
 #include "dense_eigh.cuh"
 #include "dense_blocked.cuh"
 #include "matfree.cuh"
+#include "matfree_d2.cuh"
 #include "probe.cuh"
 #include "pauli.cuh"
 
@@ -101,6 +102,8 @@ struct scqed_plan {
     std::vector<int> xform_node;
     std::vector<size_t> xform_off;     // byte offsets of W_i^T inside `tables`
     int pair_max_index = -1;
+    bool d2_ok = false;                // two-node plan with dense single-node operators: combined mode products
+    DevBuf d2h;
     std::vector<int> factor_node;
     // device copies of the tables
     DevBuf tables;
@@ -319,6 +322,25 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     size_t o_ellv = put(ell_vals.data(), ell_vals.size() * 8);
     size_t o_rowsum = put(rowsum.data(), rowsum.size() * 8);
     size_t o_tmeta = put(term_meta.data(), term_meta.size() * 4);
+    // two-node plans with a dense single-node operator: coupling terms listed separately (matfree_d2.cuh)
+    std::vector<int> d2_meta, d2_cidx;
+    int d2_nmulti = 0;
+    {
+        bool dense_single = false, ok = d->n_nodes == 2 && max_nn <= 2 && d->dims[0] <= 256 && d->dims[1] <= 256;
+        for (int t = 0; t < d->n_terms && ok; ++t) {
+            const int nn = term_meta[(size_t)t * 7];
+            if (nn == 1 && ell_w[term_meta[(size_t)t * 7 + 4]] >= 16) dense_single = true;
+            if (nn == 2) {
+                if ((long long)ell_w[term_meta[(size_t)t * 7 + 4]] * ell_w[term_meta[(size_t)t * 7 + 5]] > 64) ok = false;   // dense coupling: generic path
+                for (int q = 0; q < 7; ++q) d2_meta.push_back(term_meta[(size_t)t * 7 + q]);
+                d2_cidx.push_back(t);
+                ++d2_nmulti;
+            }
+        }
+        pl->d2_ok = ok && dense_single;
+        if (d2_meta.empty()) { d2_meta.assign(7, 0); d2_cidx.assign(1, 0); }
+    }
+    size_t o_d2m = put(d2_meta.data(), d2_meta.size() * 4), o_d2c = put(d2_cidx.data(), d2_cidx.size() * 4);
     size_t o_ameta = put(aux_meta.data(), aux_meta.size() * 4);
     size_t o_are = put(d->aux_re, (size_t)d->n_aux * 4), o_aim = put(d->aux_im, (size_t)d->n_aux * 4);
     size_t o_pairs = put(d->pairs, (size_t)d->n_pairs * 16);
@@ -393,6 +415,7 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     P.aux_meta = (const int *)(base + o_ameta);
     P.aux_re = (const int *)(base + o_are); P.aux_im = (const int *)(base + o_aim);
     P.pairs = (const int *)(base + o_pairs);
+    P.d2_nmulti = d2_nmulti; P.d2_meta = (const int *)(base + o_d2m); P.d2_cidx = (const int *)(base + o_d2c);
     P.n_entries = d->n_entries; P.ent_dense = d->n_entries > 0 && d->ent_dense;
     P.ent_key = (const long long *)(base + o_ekey); P.ent_ptr = (const int *)(base + o_eptr);
     P.ent_term = (const int *)(base + o_eterm); P.ent_val = (const cplx *)(base + o_eval);
@@ -429,7 +452,7 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
 extern "C" void scqed_plan_destroy(scqed_plan *pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
-    DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->s1work, &pl->s1vec, &pl->auxc, &pl->resvec, &pl->dcoef, &pl->in_params, &pl->out_evals,
+    DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->s1work, &pl->s1vec, &pl->auxc, &pl->resvec, &pl->dcoef, &pl->d2h, &pl->in_params, &pl->out_evals,
                       &pl->out_evecs, &pl->out_post, &pl->out_info, &pl->out_scal};
     for (DevBuf *b : bufs) b->release();
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
@@ -1034,7 +1057,8 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
     if (b < k) return fail(SCQED_EUNSUPPORTED, "matrix-free path supports k <= %d", MF_BMAX);
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
-    const size_t per_pt = (size_t)4 * b * n * 16 + (size_t)n * 8 + (size_t)2 * b * b * 16 + (size_t)2 * b * 8 + 64 + 8;
+    const size_t per_pt = (size_t)4 * b * n * 16 + (size_t)n * 8 + (size_t)2 * b * b * 16 + (size_t)2 * b * 8 + 64 + 8 +
+                          (pl->d2_ok ? (size_t)(P.dims[0] * P.dims[0] + P.dims[1] * P.dims[1]) * 16 : 0);
     long long chunk = (long long)((free_b / 2) / per_pt);
     if (chunk < 1) return fail(SCQED_ENOMEM, "not enough device memory for one matrix-free block (n=%d, b=%d)", n, b);
     if (chunk > n_pts) chunk = n_pts;
@@ -1051,7 +1075,7 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
     int *active = (int *)take((size_t)chunk * 4), *n_active = (int *)take(256), *info_s1 = (int *)take((size_t)chunk * 4);
     int *redo = (int *)take((size_t)chunk * 4);
     const bool use_cholqr = !getenv("SCQED_NO_CHOLQR");
-    const bool smem_filter = (size_t)2 * n * 16 <= 220 * 1024;
+    const bool smem_filter = (size_t)2 * n * 16 <= 220 * 1024 && !getenv("SCQED_MF_GLOBAL");     // env: force the global-memory filter (tests)
     // stencil filter (banded-monomial factors): smallest cluster whose slices fit shared memory
     int stencil_cs = 0, stencil_ns = 0;
     if (P.stencil_ok && !getenv("SCQED_NO_STENCIL")) {
@@ -1077,6 +1101,27 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
         CK(cudaFuncSetAttribute(mf_cheb_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
         attr_set = true;
     }
+    // two-node plans with dense single-node operators on the global-memory filter: combined per-point
+    // node Hamiltonians + real mode products (matfree_d2.cuh)
+    const bool use_d2 = pl->d2_ok && !smem_filter && stencil_cs == 0 && !getenv("SCQED_NO_D2");
+    const int d2_tot = P.dims[0] * P.dims[0] + (P.n_nodes > 1 ? P.dims[1] * P.dims[1] : 0);
+    double *d2re = nullptr, *d2im = nullptr, *d2imax = nullptr;
+    size_t d2_smem_real = 0, d2_smem_cplx = 0;
+    if (use_d2) {
+        if (pl->d2h.ensure((size_t)chunk * d2_tot * 16 + 256)) return fail(SCQED_ENOMEM, "combined node Hamiltonians");
+        d2imax = (double *)pl->d2h.p;
+        d2re = (double *)((unsigned char *)pl->d2h.p + 256);
+        d2im = d2re + (size_t)chunk * d2_tot;
+        d2_smem_real = (size_t)D2_RB * P.dims[0] * 8 + (size_t)D2_RB * P.dims[1] * 16 + (size_t)(P.d2_nmulti + 1) * 16;
+        d2_smem_cplx = d2_smem_real + (size_t)D2_RB * P.dims[0] * 8;
+        CK(cudaFuncSetAttribute(mf_d2_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_real));
+        CK(cudaFuncSetAttribute(mf_d2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_real));
+        CK(cudaFuncSetAttribute(mf_d2_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_cplx));
+        CK(cudaFuncSetAttribute(mf_d2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_cplx));
+    }
+    bool d2_real = false;
+    const dim3 d2_grid_base((unsigned)((P.dims[0] + D2_RB - 1) / D2_RB), (unsigned)b, 1);
+    const int d2_threads = P.n_nodes > 1 ? ((P.dims[1] + 31) / 32) * 32 : 32;
     ResonatorArgs nores;
     memset(&nores, 0, sizeof(nores));
     PlanDev Pg;                         // dummy plan for the b x b Rayleigh-Ritz solves (Hin path)
@@ -1094,6 +1139,25 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
         cplx *X = bufX, *Y = bufY, *H = bufH, *Hn = bufHn;
         mf_prepare<<<(unsigned)np, MF_THREADS, 0, st>>>(a, X, dscr);
         LAUNCHED();
+        auto d2_launch = [&](int mode, const cplx *src, cplx *dst, int mstep) {
+            dim3 g(d2_grid_base.x, d2_grid_base.y, (unsigned)np);
+            if (d2_real) {
+                if (mode == 0) mf_d2_kernel<0, true><<<g, d2_threads, d2_smem_real, st>>>(a, src, dst, mstep, d2re, d2im);
+                else mf_d2_kernel<1, true><<<g, d2_threads, d2_smem_real, st>>>(a, src, dst, mstep, d2re, d2im);
+            } else {
+                if (mode == 0) mf_d2_kernel<0, false><<<g, d2_threads, d2_smem_cplx, st>>>(a, src, dst, mstep, d2re, d2im);
+                else mf_d2_kernel<1, false><<<g, d2_threads, d2_smem_cplx, st>>>(a, src, dst, mstep, d2re, d2im);
+            }
+        };
+        if (use_d2) {
+            CK(cudaMemsetAsync(d2imax, 0, 8, st));
+            mf_d2_build<<<dim3((unsigned)((d2_tot + 255) / 256), (unsigned)np), 256, 0, st>>>(a, d2re, d2im, d2imax);
+            LAUNCHED();
+            double h_imax = 0.0;
+            CK(cudaMemcpyAsync(&h_imax, d2imax, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            d2_real = h_imax < 1e-12;        // the reference's tidyup threshold: such an imaginary part is dropped
+        }
         // Rayleigh-Ritz on block R (orthonormalised in place): leaves Ritz vectors in X, H X in H
         auto rayleigh_ritz = [&](cplx *R) -> int {
             if (use_cholqr) {
@@ -1108,7 +1172,8 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
             } else {
                 mf_orth<<<(unsigned)np, 512, 0, st>>>(a, R, info_c, nullptr);
             }
-            mf_matvec<<<dim3(rowblocks, b, (unsigned)np), MF_THREADS, 0, st>>>(a, R, H);
+            if (use_d2) d2_launch(0, R, H, 0);
+            else mf_matvec<<<dim3(rowblocks, b, (unsigned)np), MF_THREADS, 0, st>>>(a, R, H);
             mf_gram<<<dim3(b, (unsigned)np), MF_THREADS, 0, st>>>(a, R, H, G);
             mf_symmetrize<<<(unsigned)np, b * b, 0, st>>>(a, G);
             g_launches.fetch_add(4, std::memory_order_relaxed);
@@ -1158,10 +1223,12 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
                 R = Y;
             } else {
                 // Y_0 = X, Y_1 -> Y, then alternate in place
-                mf_cheb_step<<<dim3(rowblocks, b, (unsigned)np), MF_THREADS, 0, st>>>(a, X, Y, 1);
+                if (use_d2) d2_launch(1, X, Y, 1);
+                else mf_cheb_step<<<dim3(rowblocks, b, (unsigned)np), MF_THREADS, 0, st>>>(a, X, Y, 1);
                 cplx *cur = Y, *prev = X;
                 for (int m = 2; m <= deg; ++m) {
-                    mf_cheb_step<<<dim3(rowblocks, b, (unsigned)np), MF_THREADS, 0, st>>>(a, cur, prev, m);
+                    if (use_d2) d2_launch(1, cur, prev, m);
+                    else mf_cheb_step<<<dim3(rowblocks, b, (unsigned)np), MF_THREADS, 0, st>>>(a, cur, prev, m);
                     cplx *t = cur; cur = prev; prev = t;
                 }
                 g_launches.fetch_add(deg, std::memory_order_relaxed);

@@ -345,6 +345,35 @@ def test_swept_oscillator_impedance(engine_mod, name, solver):
         assert np.max(np.abs(res.Erwa - ref)) < E_RTOL * np.max(np.abs(ref))
 
 
+def test_two_node_dense_mode_products(engine_mod, monkeypatch):
+    """matfree_d2.cuh: per-point combined node Hamiltonians + real mode products (the fluxonium atom above
+    n = 7040).  (a) forced on the 31 x 31 fixture against the reference's eigenvalues, (b) at 180 x 180
+    against the generic term-walking mat-vec on the same points."""
+    g, plan = load_golden("c5_fluxatom_t31")
+    k = int(g["k"])
+    monkeypatch.setenv("SCQED_MF_GLOBAL", "1")
+    with engine_mod.Engine(plan) as eng:
+        res = eng.sweep(g["params"], k, want_vectors=True, solver=4)
+    assert not res.info.any()
+    assert eig_rel_err(res.E, g["E"]) < E_RTOL
+    orc = PlanOracle(plan)
+    coef, _ = eval_program(plan.program, g["params"][:1])
+    H = orc.hamiltonian(coef[0]).toarray()
+    X = res.V[0].T
+    assert np.max(np.abs(H @ X - X * res.E[0][None, :])) < 1e-7 * np.abs(res.E[0]).max()
+    monkeypatch.delenv("SCQED_MF_GLOBAL")
+    plan = load_plan("c5_fluxatom_t180")
+    pts = plan.sweep_grid()[[3, 40]]
+    with engine_mod.Engine(plan) as eng:
+        a = eng.sweep(pts, 6, want_vectors=True)
+        monkeypatch.setenv("SCQED_NO_D2", "1")
+        b = eng.sweep(pts, 6, want_vectors=True)
+    assert not a.info.any() and not b.info.any()
+    assert eig_rel_err(a.E, b.E) < E_RTOL
+    for p in range(2):
+        assert subspace_overlap(a.V[p].T, b.V[p].T, b.E[p]) >= 1 - 1e-7
+
+
 def test_sweep_scalar_evaluables(engine_mod):
     g, plan = load_golden("c4_averin")
     with engine_mod.Engine(plan) as eng:
