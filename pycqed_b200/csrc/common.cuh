@@ -111,6 +111,7 @@ struct PlanDev {
     int d2_nmulti;
     const int *d2_meta;            // [d2_nmulti * 7]
     const int *d2_cidx;            // [d2_nmulti]
+    const int *d2_phase;           // [d2_nmulti] product of the two factors' entries: 0 real, 1 imaginary, 2 mixed
     int n_swept, n_instr, n_scalar;
     const int *instr;              // [n_instr * 3]
     const double *consts;

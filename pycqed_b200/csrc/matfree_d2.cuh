@@ -55,11 +55,40 @@ mf_d2_build(MfArgs a, double *__restrict__ Hre, double *__restrict__ Him, double
     my = fmax(my, __shfl_xor_sync(0xffffffffu, my, 2));
     my = fmax(my, __shfl_xor_sync(0xffffffffu, my, 1));
     if ((threadIdx.x & 31) == 0 && my > 0.0) atomicMax((unsigned long long *)imax, (unsigned long long)__double_as_longlong(my));
+    // coupling terms: real iff (factor-entry product real and c real) or (product imaginary and c imaginary);
+    // d2_phase: 0 real, 1 imaginary, 2 mixed.  Violations raise imax[1].
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const cplx *coef = a.coef + p * P.n_terms;
+        double viol = 0.0;
+        for (int q = 0; q < P.d2_nmulti; ++q) {
+            const cplx c = coef[__ldg(P.d2_cidx + q)];
+            const int ph = __ldg(P.d2_phase + q);
+            const double bad = ph == 0 ? fabs(c.y) : (ph == 1 ? fabs(c.x) : fabs(c.x) + fabs(c.y));
+            viol = fmax(viol, bad);
+        }
+        if (viol > 0.0) atomicMax((unsigned long long *)(imax + 1), (unsigned long long)__double_as_longlong(viol));
+    }
+}
+
+// max |Im X| over the block of every active point -> imax[2]  (decides whether the real-vector kernels apply)
+__global__ void __launch_bounds__(256)
+mf_d2_imag_max(MfArgs a, const cplx *__restrict__ X, double *__restrict__ imax) {
+    const long long p = blockIdx.x;
+    if (!a.active[p]) return;
+    const size_t tot = (size_t)a.b * a.n;
+    const cplx *x = X + p * tot;
+    double my = 0.0;
+    for (size_t i = threadIdx.x; i < tot; i += blockDim.x) my = fmax(my, fabs(x[i].y));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my = fmax(my, __shfl_xor_sync(0xffffffffu, my, o));
+    if ((threadIdx.x & 31) == 0 && my > 0.0) atomicMax((unsigned long long *)(imax + 2), (unsigned long long)__double_as_longlong(my));
 }
 
 // MODE 0: HX = H X.  MODE 1: Chebyshev step m (same recurrence as mf_cheb_step), `out` holds y_{m-2} and
 // receives y_m.  grid (ceil(d0 / D2_RB), b, n_pts), block = d1 rounded up to a warp multiple (<= 256).
-template <int MODE, bool REALH>
+// REALX: H real AND the vectors real (exactly zero imaginary parts, checked by mf_d2_imag_max before every
+// use): the imaginary half of the arithmetic is skipped.
+template <int MODE, bool REALH, bool REALX>
 __global__ void __launch_bounds__(256)
 mf_d2_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const double *__restrict__ Hre,
              const double *__restrict__ Him) {
@@ -100,7 +129,7 @@ mf_d2_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const doubl
         for (int r = 0; r < D2_RB; ++r) {
             const double hr = sHre[r * d0 + b];
             acc[r].x = fma(hr, xb.x, acc[r].x);
-            acc[r].y = fma(hr, xb.y, acc[r].y);
+            if (!REALX) acc[r].y = fma(hr, xb.y, acc[r].y);
             if (!REALH) {
                 const double hi = sHim[r * d0 + b];
                 acc[r].x = fma(-hi, xb.y, acc[r].x);
@@ -117,7 +146,7 @@ mf_d2_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const doubl
         for (int r = 0; r < D2_RB; ++r) {
             const cplx xv = sX[r * d1 + b];
             acc[r].x = fma(hr, xv.x, acc[r].x);
-            acc[r].y = fma(hr, xv.y, acc[r].y);
+            if (!REALX) acc[r].y = fma(hr, xv.y, acc[r].y);
             if (!REALH) {
                 acc[r].x = fma(-hi, xv.y, acc[r].x);
                 acc[r].y = fma(hi, xv.x, acc[r].y);
@@ -144,6 +173,7 @@ mf_d2_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const doubl
         const int i = (R0 + r) * d1 + i1;
         cplx h = acc[r];
         if (P.d2_nmulti > 0) h = cadd(h, mf_apply_terms(P, P.d2_meta, 0, P.d2_nmulti, sC, x, i));
+        if (REALX) h.y = 0.0;
         if (MODE == 0) o[i] = h;
         else {
             const cplx yi = sX[r * d1 + i1];

@@ -323,8 +323,15 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     size_t o_rowsum = put(rowsum.data(), rowsum.size() * 8);
     size_t o_tmeta = put(term_meta.data(), term_meta.size() * 4);
     // two-node plans with a dense single-node operator: coupling terms listed separately (matfree_d2.cuh)
-    std::vector<int> d2_meta, d2_cidx;
+    std::vector<int> d2_meta, d2_cidx, d2_phase;
     int d2_nmulti = 0;
+    auto factor_phase = [&](int f) {          // 0: all entries real, 1: all imaginary, 2: mixed
+        const int dk = d->dims[d->factor_node[f]];
+        const double *fd = d->factor_data + 2 * (size_t)d->factor_offset[f];
+        bool any_re = false, any_im = false;
+        for (size_t e = 0; e < (size_t)dk * dk; ++e) { any_re |= fd[2 * e] != 0.0; any_im |= fd[2 * e + 1] != 0.0; }
+        return any_re && any_im ? 2 : (any_im ? 1 : 0);
+    };
     {
         bool dense_single = false, ok = d->n_nodes == 2 && max_nn <= 2 && d->dims[0] <= 256 && d->dims[1] <= 256;
         for (int t = 0; t < d->n_terms && ok; ++t) {
@@ -334,13 +341,19 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
                 if ((long long)ell_w[term_meta[(size_t)t * 7 + 4]] * ell_w[term_meta[(size_t)t * 7 + 5]] > 64) ok = false;   // dense coupling: generic path
                 for (int q = 0; q < 7; ++q) d2_meta.push_back(term_meta[(size_t)t * 7 + q]);
                 d2_cidx.push_back(t);
+                {
+                    const int pa = factor_phase(term_meta[(size_t)t * 7 + 4]), pb = factor_phase(term_meta[(size_t)t * 7 + 5]);
+                    d2_phase.push_back((pa == 2 || pb == 2) ? 2 : ((pa + pb) & 1));      // i * i = -1 is real
+                }
                 ++d2_nmulti;
             }
         }
         pl->d2_ok = ok && dense_single;
         if (d2_meta.empty()) { d2_meta.assign(7, 0); d2_cidx.assign(1, 0); }
+        if (d2_phase.empty()) d2_phase.assign(1, 0);
     }
     size_t o_d2m = put(d2_meta.data(), d2_meta.size() * 4), o_d2c = put(d2_cidx.data(), d2_cidx.size() * 4);
+    size_t o_d2p = put(d2_phase.data(), d2_phase.size() * 4);
     size_t o_ameta = put(aux_meta.data(), aux_meta.size() * 4);
     size_t o_are = put(d->aux_re, (size_t)d->n_aux * 4), o_aim = put(d->aux_im, (size_t)d->n_aux * 4);
     size_t o_pairs = put(d->pairs, (size_t)d->n_pairs * 16);
@@ -415,7 +428,7 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     P.aux_meta = (const int *)(base + o_ameta);
     P.aux_re = (const int *)(base + o_are); P.aux_im = (const int *)(base + o_aim);
     P.pairs = (const int *)(base + o_pairs);
-    P.d2_nmulti = d2_nmulti; P.d2_meta = (const int *)(base + o_d2m); P.d2_cidx = (const int *)(base + o_d2c);
+    P.d2_nmulti = d2_nmulti; P.d2_meta = (const int *)(base + o_d2m); P.d2_cidx = (const int *)(base + o_d2c); P.d2_phase = (const int *)(base + o_d2p);
     P.n_entries = d->n_entries; P.ent_dense = d->n_entries > 0 && d->ent_dense;
     P.ent_key = (const long long *)(base + o_ekey); P.ent_ptr = (const int *)(base + o_eptr);
     P.ent_term = (const int *)(base + o_eterm); P.ent_val = (const cplx *)(base + o_eval);
@@ -1114,12 +1127,14 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
         d2im = d2re + (size_t)chunk * d2_tot;
         d2_smem_real = (size_t)D2_RB * P.dims[0] * 8 + (size_t)D2_RB * P.dims[1] * 16 + (size_t)(P.d2_nmulti + 1) * 16;
         d2_smem_cplx = d2_smem_real + (size_t)D2_RB * P.dims[0] * 8;
-        CK(cudaFuncSetAttribute(mf_d2_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_real));
-        CK(cudaFuncSetAttribute(mf_d2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_real));
-        CK(cudaFuncSetAttribute(mf_d2_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_cplx));
-        CK(cudaFuncSetAttribute(mf_d2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_cplx));
+        CK(cudaFuncSetAttribute(mf_d2_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_real));
+        CK(cudaFuncSetAttribute(mf_d2_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_real));
+        CK(cudaFuncSetAttribute(mf_d2_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_real));
+        CK(cudaFuncSetAttribute(mf_d2_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_real));
+        CK(cudaFuncSetAttribute(mf_d2_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_cplx));
+        CK(cudaFuncSetAttribute(mf_d2_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_cplx));
     }
-    bool d2_real = false;
+    bool d2_real = false, d2_cpl_real = false, d2_realx = false;
     const dim3 d2_grid_base((unsigned)((P.dims[0] + D2_RB - 1) / D2_RB), (unsigned)b, 1);
     const int d2_threads = P.n_nodes > 1 ? ((P.dims[1] + 31) / 32) * 32 : 32;
     ResonatorArgs nores;
@@ -1141,22 +1156,27 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
         LAUNCHED();
         auto d2_launch = [&](int mode, const cplx *src, cplx *dst, int mstep) {
             dim3 g(d2_grid_base.x, d2_grid_base.y, (unsigned)np);
-            if (d2_real) {
-                if (mode == 0) mf_d2_kernel<0, true><<<g, d2_threads, d2_smem_real, st>>>(a, src, dst, mstep, d2re, d2im);
-                else mf_d2_kernel<1, true><<<g, d2_threads, d2_smem_real, st>>>(a, src, dst, mstep, d2re, d2im);
+            if (d2_real && d2_realx) {
+                if (mode == 0) mf_d2_kernel<0, true, true><<<g, d2_threads, d2_smem_real, st>>>(a, src, dst, mstep, d2re, d2im);
+                else mf_d2_kernel<1, true, true><<<g, d2_threads, d2_smem_real, st>>>(a, src, dst, mstep, d2re, d2im);
+            } else if (d2_real) {
+                if (mode == 0) mf_d2_kernel<0, true, false><<<g, d2_threads, d2_smem_real, st>>>(a, src, dst, mstep, d2re, d2im);
+                else mf_d2_kernel<1, true, false><<<g, d2_threads, d2_smem_real, st>>>(a, src, dst, mstep, d2re, d2im);
             } else {
-                if (mode == 0) mf_d2_kernel<0, false><<<g, d2_threads, d2_smem_cplx, st>>>(a, src, dst, mstep, d2re, d2im);
-                else mf_d2_kernel<1, false><<<g, d2_threads, d2_smem_cplx, st>>>(a, src, dst, mstep, d2re, d2im);
+                if (mode == 0) mf_d2_kernel<0, false, false><<<g, d2_threads, d2_smem_cplx, st>>>(a, src, dst, mstep, d2re, d2im);
+                else mf_d2_kernel<1, false, false><<<g, d2_threads, d2_smem_cplx, st>>>(a, src, dst, mstep, d2re, d2im);
             }
         };
         if (use_d2) {
-            CK(cudaMemsetAsync(d2imax, 0, 8, st));
+            CK(cudaMemsetAsync(d2imax, 0, 32, st));
             mf_d2_build<<<dim3((unsigned)((d2_tot + 255) / 256), (unsigned)np), 256, 0, st>>>(a, d2re, d2im, d2imax);
             LAUNCHED();
-            double h_imax = 0.0;
-            CK(cudaMemcpyAsync(&h_imax, d2imax, 8, cudaMemcpyDeviceToHost, st));
+            double h_imax[2] = {0.0, 0.0};
+            CK(cudaMemcpyAsync(h_imax, d2imax, 16, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            d2_real = h_imax < 1e-12;        // the reference's tidyup threshold: such an imaginary part is dropped
+            d2_real = h_imax[0] < 1e-12;        // the reference's tidyup threshold: such an imaginary part is dropped
+            d2_cpl_real = h_imax[1] == 0.0;     // coupling terms exactly real
+            d2_realx = false;                   // set per outer iteration from max |Im X|
         }
         // Rayleigh-Ritz on block R (orthonormalised in place): leaves Ritz vectors in X, H X in H
         auto rayleigh_ritz = [&](cplx *R) -> int {
@@ -1186,6 +1206,11 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
             g_launches.fetch_add(2, std::memory_order_relaxed);
             // after rotation the Ritz vectors live in dst; make X point at them
             if (dst != X) { Y = X; X = dst; }
+            if (use_d2 && d2_real && d2_cpl_real) {       // are the Ritz vectors exactly real? (read at the next sync)
+                cudaMemsetAsync(d2imax + 2, 0, 8, st);
+                mf_d2_imag_max<<<(unsigned)np, 256, 0, st>>>(a, X, d2imax);
+                LAUNCHED();
+            }
             cplx *t = H; H = Hn; Hn = t;
             return 0;
         };
@@ -1194,9 +1219,12 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
         CK(cudaGetLastError());
         for (int it = 0; it < maxit; ++it) {
             int h_active = 0;
+            double h_ximax = 1.0;
             CK(cudaMemcpyAsync(&h_active, n_active, 4, cudaMemcpyDeviceToHost, st));
+            if (use_d2 && d2_real && d2_cpl_real) CK(cudaMemcpyAsync(&h_ximax, d2imax + 2, 8, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             if (h_active == 0) break;
+            d2_realx = use_d2 && d2_real && d2_cpl_real && h_ximax == 0.0 && !getenv("SCQED_NO_D2_REALX");
             cplx *R;
             if (stencil_cs > 0) {
                 const size_t smem = mf_stencil_smem(P, stencil_ns);
