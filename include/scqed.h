@@ -72,6 +72,8 @@ typedef struct {
      * register -1 = identically zero.  n_dense = 0 disables it (the term table is walked per element). */
     int32_t n_dense;
     int32_t n_dense_diag;           /* the last n_dense_diag matrices are diagonal, stored as n-vectors */
+    int32_t dense_tridiag;          /* 1: every G_g is tridiagonal, i.e. H(p) is Hermitian tridiagonal (single-node
+                                       charge basis): the Householder stage is skipped                        */
     const double *dense_tab;        /* [(n_dense - n_dense_diag) * n * n + n_dense_diag * n] */
     const int32_t *dense_re;        /* [n_dense]                                             */
     const int32_t *dense_im;        /* [n_dense]                                             */

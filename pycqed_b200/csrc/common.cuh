@@ -95,6 +95,7 @@ struct PlanDev {
     const int *aux_re, *aux_im;    // [n_aux] coefficient registers
     const int *pairs;              // [n_pairs * 4]: tb, te, i, j
     // dense real term table of the fused small-n solver: Re H = sum_g alpha_g G_g, Im H = sum_g beta_g G_g
+    int dense_tridiag;             // H(p) is Hermitian tridiagonal for every p
     int n_dense, n_dense_diag;     // the last n_dense_diag are diagonal (n-vectors after the full matrices)
     const double *dense_tab;       // [n_dense - n_dense_diag][n*n] column-major, then [n_dense_diag][n]
     const int *dense_re, *dense_im;   // [n_dense] coefficient registers (-1 = zero)

@@ -433,7 +433,7 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
     P.ent_key = (const long long *)(base + o_ekey); P.ent_ptr = (const int *)(base + o_eptr);
     P.ent_term = (const int *)(base + o_eterm); P.ent_val = (const cplx *)(base + o_eval);
     P.ent_map = (const int *)(base + o_emap);
-    P.n_dense = n_dense; P.n_dense_diag = d->n_dense_diag;
+    P.n_dense = n_dense; P.n_dense_diag = d->n_dense_diag; P.dense_tridiag = n_dense > 0 && d->dense_tridiag;
     P.dense_tab = (const double *)(base + o_dtab);
     P.dense_re = (const int *)(base + o_dre); P.dense_im = (const int *)(base + o_dim);
     P.dense_gmax = (const double *)(base + o_dgm);
@@ -787,7 +787,14 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
         const long long Gc = np * k;
         CK(cudaMemsetAsync(a.info, 0, (size_t)np * 4, st));
         bool real_mode = false;
-        if (pl->s1_real_mode == 1 && !Hin) {
+        const bool direct = P.dense_tridiag && a.dcoef && !Hin;     // H(p) is already tridiagonal: no Householder stage
+        if (direct) {
+            timing_begin(st, 4);
+            s1_direct_tridiag_kernel<<<(unsigned)((np * 32 + 127) / 128), 128, 0, st>>>(a);
+            timing_end(st);
+            LAUNCHED();
+            real_mode = true;
+        } else if (pl->s1_real_mode == 1 && !Hin) {
             // known real-symmetric plan: no host round trip; a point that turns out complex is
             // flagged info = -2 by the kernel and the host-level driver re-runs in complex mode
             int rc = s1_launch_tridiag<double>(pl, a, P.n_terms > P.n_dense ? P.n_terms : P.n_dense, st);
@@ -828,7 +835,10 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
             const long long iw = (np + ppw - 1) / ppw;
             s1_invit_kernel<<<(unsigned)((iw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, Gc);
             cplx *vout = evecs ? evecs + (size_t)p0 * k * n : vec_tmp;
-            if (real_mode && n > 32 * SMALL_RQ) {
+            if (direct) {
+                const long long tot = np * k * n;
+                s1_phase_backtr_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a, Gc, vout);
+            } else if (real_mode && n > 32 * SMALL_RQ) {
                 const long long bw = np * ((k + 7) / 8);
                 s1_backtr_kernel<double, 8, 7><<<(unsigned)((bw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, Gc, vout);
             } else if (real_mode) {

@@ -171,6 +171,109 @@ s1_tridiag_kernel(S1Args a) {
     }
 }
 
+// ---- phase A': H(p) is already Hermitian tridiagonal (single-node charge basis: transmon, Averin coupler) --------
+// No Householder stage at all.  From the dense term table: d_i = H[i][i], s_i = H[i+1][i]; the unitary diagonal
+// similarity D = diag(ph), ph_0 = 1, ph_{i+1} = ph_i s_i / |s_i| turns H into the REAL symmetric tridiagonal
+// T = D^H H D with off-diagonals |s_i| (same spectrum; eigenvectors v = D z).  One warp per point: lanes
+// stride over i, Gershgorin bounds by shuffles, the phase prefix product serially per 32-chunk.
+__global__ void __launch_bounds__(128)
+s1_direct_tridiag_kernel(S1Args a) {
+    const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int l = threadIdx.x & 31, n = a.n;
+    if (p >= a.n_pts) return;
+    const PlanDev &P = a.P;
+    const int NG = P.n_dense, NF = NG - P.n_dense_diag;
+    const double *dc = a.dcoef + (size_t)p * 2 * NG;
+    const size_t nn = (size_t)n * n;
+    const double *dg = P.dense_tab + (size_t)NF * nn;
+    double lo = 1e300, hi = -1e300, emax = 0.0;
+    double prev_e = 0.0;                    // |s_{i-1}| of the lane's first element is fetched by shuffle
+    cplx carry = cmake(1.0, 0.0);           // phase of element (32 q) of this chunk
+    cplx *ph = a.W.tau + p * n;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + l;
+        double d = 0.0, e = 0.0;
+        cplx u = cmake(1.0, 0.0);           // s_i / |s_i|
+        if (i < n) {
+            double sre = 0.0, sim = 0.0;
+            for (int g = 0; g < NF; ++g) {
+                d = fma(dc[g], __ldg(P.dense_tab + g * nn + (size_t)i * n + i), d);
+                if (i + 1 < n) {
+                    const double gv = __ldg(P.dense_tab + g * nn + (size_t)i * n + i + 1);      // G[i+1][i]
+                    sre = fma(dc[g], gv, sre);
+                    sim = fma(dc[NG + g], gv, sim);
+                }
+            }
+            for (int g = NF; g < NG; ++g) d = fma(dc[g], __ldg(dg + (size_t)(g - NF) * n + i), d);
+            if (a.tidyup) {
+                d = fabs(d) < 1e-12 ? 0.0 : d;
+                sre = fabs(sre) < 1e-12 ? 0.0 : sre;
+                sim = fabs(sim) < 1e-12 ? 0.0 : sim;
+            }
+            e = sqrt(sre * sre + sim * sim);
+            if (e > 0.0) u = cmake(sre / e, sim / e);
+            a.W.dd[p * n + i] = d;
+            a.W.ee[p * n + i] = e;
+            a.W.e2[p * n + i] = e * e;
+        }
+        // Gershgorin: |e_{i-1}| + |e_i|
+        double eprev = __shfl_up_sync(0xffffffffu, e, 1);
+        if (l == 0) eprev = prev_e;
+        prev_e = __shfl_sync(0xffffffffu, e, 31);
+        if (i < n) {
+            const double r = (i > 0 ? eprev : 0.0) + (i < n - 1 ? e : 0.0);
+            lo = fmin(lo, d - r); hi = fmax(hi, d + r);
+            emax = fmax(emax, e * e);
+        }
+        // inclusive prefix product of the unit phases inside the chunk (Hillis-Steele), then apply the carry:
+        // ph_{i+1} = carry * u_{i0} ... u_i
+        cplx pref = u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            cplx other = cmake(__shfl_up_sync(0xffffffffu, pref.x, o), __shfl_up_sync(0xffffffffu, pref.y, o));
+            if (l >= o) pref = cmul(pref, other);
+        }
+        cplx excl = cmake(__shfl_up_sync(0xffffffffu, pref.x, 1), __shfl_up_sync(0xffffffffu, pref.y, 1));
+        if (l == 0) excl = cmake(1.0, 0.0);
+        if (i < n) {
+            cplx v = cmul(carry, excl);
+            const double nv = 1.0 / sqrt(v.x * v.x + v.y * v.y);      // keep |ph| = 1 against rounding drift
+            ph[i] = cmake(v.x * nv, v.y * nv);
+        }
+        cplx last = cmake(__shfl_sync(0xffffffffu, pref.x, 31), __shfl_sync(0xffffffffu, pref.y, 31));
+        carry = cmul(carry, last);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    }
+    if (l == 0) {                           // same conventions as tridiag_bounds
+        double tn = fmax(fabs(lo), fabs(hi));
+        double pad = 2.0 * tn * SCQED_EPS * n + 2.0 * SCQED_SAFMIN;
+        a.W.bnd[p * 4 + 0] = lo - pad;
+        a.W.bnd[p * 4 + 1] = hi + pad;
+        a.W.bnd[p * 4 + 2] = fmax(SCQED_SAFMIN * fmax(1.0, emax), SCQED_SAFMIN);
+        a.W.bnd[p * 4 + 3] = tn;
+        a.W.flags[p] = 0;
+    }
+}
+
+// v = D z: eigenvectors of the tridiagonal H from those of T.  One thread per (point, vector, i).
+__global__ void __launch_bounds__(256)
+s1_phase_backtr_kernel(S1Args a, long long G, cplx *__restrict__ evecs) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = a.n, k = a.k;
+    if (idx >= a.n_pts * k * n) return;
+    const long long pv = idx / n;                 // p * k + j
+    const int i = (int)(idx - pv * n);
+    const long long p = pv / k;
+    const double z = a.W.zw[(size_t)i * G + pv];
+    const cplx ph = a.W.tau[p * n + i];
+    evecs[idx] = cmake(z * ph.x, z * ph.y);
+}
+
 // ---- phase B: one warp per (point, eigenvalue) -----------------------------------------------------------
 __global__ void __launch_bounds__(256)
 s1_bisect_kernel(S1Args a, const int *__restrict__ skip, double *__restrict__ evals) {

@@ -180,6 +180,9 @@ def build_dense_table(plan, max_n: int = MAX_N):
         n_swept=prog.n_swept, instr=np.asarray(instr, dtype=np.int32).reshape(-1, 3),
         consts=np.asarray(consts, dtype=np.float64), coef_re=prog.coef_re, coef_im=prog.coef_im,
         scalar_regs=prog.scalar_regs, scalar_names=list(prog.scalar_names), aux_re=prog.aux_re, aux_im=prog.aux_im)
+    ii, jj = np.indices((n, n))
+    tridiagonal = all(not np.any(M[np.abs(ii - jj) > 1]) for M in table[:n_full])
     return {"program": program, "table": np.ascontiguousarray(tab, dtype=np.float64), "n_full": n_full, "n_diag": n_diag,
+            "tridiagonal": bool(tridiagonal and n >= 3),
             "re_regs": np.asarray(re_regs, dtype=np.int32), "im_regs": np.asarray(im_regs, dtype=np.int32),
             "gmax": np.asarray([np.abs(M).max() for M in table], dtype=np.float64)}

@@ -37,7 +37,7 @@ class _PlanDesc(C.Structure):
         ("n_aux", C.c_int32), ("aux_term_factors", C.POINTER(C.c_int32)),
         ("aux_re", C.POINTER(C.c_int32)), ("aux_im", C.POINTER(C.c_int32)),
         ("n_pairs", C.c_int32), ("pairs", C.POINTER(C.c_int32)),
-        ("n_dense", C.c_int32), ("n_dense_diag", C.c_int32), ("dense_tab", C.POINTER(C.c_double)),
+        ("n_dense", C.c_int32), ("n_dense_diag", C.c_int32), ("dense_tridiag", C.c_int32), ("dense_tab", C.POINTER(C.c_double)),
         ("dense_re", C.POINTER(C.c_int32)), ("dense_im", C.POINTER(C.c_int32)), ("dense_gmax", C.POINTER(C.c_double)),
         ("n_entries", C.c_int32), ("ent_dense", C.c_int32), ("ent_key", C.POINTER(C.c_int64)),
         ("ent_ptr", C.POINTER(C.c_int32)), ("ent_term", C.POINTER(C.c_int32)), ("ent_val", C.POINTER(C.c_double)),
@@ -245,6 +245,7 @@ class Engine:
             desc.n_entries, desc.ent_dense = int(ekey.size), int(ent["dense"])
             desc.ent_key = _ptr(ekey, C.c_int64)
             desc.ent_ptr, desc.ent_term, desc.ent_val = _ptr(eptr, C.c_int32), _ptr(eterm, C.c_int32), _ptr(evalv, C.c_double)
+        self.tridiagonal = bool(dense is not None and dense["tridiagonal"] and not os.environ.get("SCQED_NO_TRIDIAG_SHORTCUT"))
         xf = plan.node_transforms()
         self.rotated = bool(xf)
         if xf:
@@ -257,6 +258,7 @@ class Engine:
             dre, dim_, dgm = _i32(dense["re_regs"]), _i32(dense["im_regs"]), np.ascontiguousarray(dense["gmax"], dtype=np.float64)
             desc.n_dense = int(dense["n_full"] + dense["n_diag"])
             desc.n_dense_diag = int(dense["n_diag"])
+            desc.dense_tridiag = int(dense["tridiagonal"] and not os.environ.get("SCQED_NO_TRIDIAG_SHORTCUT"))
             desc.dense_tab = _ptr(dtab, C.c_double)
             desc.dense_re, desc.dense_im = _ptr(dre, C.c_int32), _ptr(dim_, C.c_int32)
             desc.dense_gmax = _ptr(dgm, C.c_double)

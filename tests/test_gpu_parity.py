@@ -374,6 +374,36 @@ def test_two_node_dense_mode_products(engine_mod, monkeypatch):
         assert subspace_overlap(a.V[p].T, b.V[p].T, b.E[p]) >= 1 - 1e-7
 
 
+@pytest.mark.parametrize("name", ["c1_transmon_vec", "c4_averin", "c6_cpb"])
+def test_tridiagonal_hamiltonians_skip_householder(engine_mod, monkeypatch, name):
+    """Single-node charge-basis circuits have a Hermitian tridiagonal H: d, |e| and the
+    diagonal phase similarity come straight from the term table (s1_direct_tridiag_kernel).  Same answers as
+    the Householder route and as the reference, eigenvectors included (complex phases for the transmon)."""
+    g, plan = load_golden(name)
+    k = int(g["k"])
+    with engine_mod.Engine(plan) as eng:
+        assert eng.tridiagonal
+        a = eng.sweep(g["params"], k, want_vectors=True)
+    monkeypatch.setenv("SCQED_NO_TRIDIAG_SHORTCUT", "1")
+    with engine_mod.Engine(plan) as eng:
+        assert not eng.tridiagonal
+        b = eng.sweep(g["params"], k, want_vectors=True)
+    assert not a.info.any() and not b.info.any()
+    assert eig_rel_err(a.E, g["E"]) < E_RTOL and eig_rel_err(a.E, b.E) < E_RTOL
+    orc = PlanOracle(plan)
+    coef, _ = eval_program(plan.program, g["params"])
+    for p in range(0, len(g["params"]), max(1, len(g["params"]) // 7)):
+        H = orc.hamiltonian(coef[p]).toarray()
+        X = a.V[p].T
+        scale = max(1.0, np.abs(a.E[p]).max())
+        assert np.max(np.abs(H @ X - X * a.E[p][None, :])) < 1e-9 * scale
+        assert np.max(np.abs(X.conj().T @ X - np.eye(k))) < 1e-10
+        assert subspace_overlap(X, b.V[p].T, b.E[p]) >= OVERLAP
+    if "V" in g:
+        for j, p in enumerate(g["vec_points"]):
+            assert subspace_overlap(a.V[p].T, g["V"][j], g["E"][p]) >= OVERLAP
+
+
 def test_sweep_scalar_evaluables(engine_mod):
     g, plan = load_golden("c4_averin")
     with engine_mod.Engine(plan) as eng:
