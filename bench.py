@@ -146,8 +146,10 @@ def run_reference(args):
     k, vectors, resonator = args.k, not args.no_vectors, (not args.no_resonator) and "resonator" in plan.post
     times, vals = [], []
     base = None
+    # each step is a bounded sample of the workload; the whole run stays within ~2 minutes
+    budget = min(args.ref_budget, 120.0 / max(1, args.warmup + args.steps))
     for i in range(args.warmup + args.steps):
-        base = cpu_baseline(plan, k, vectors, resonator, budget_s=args.ref_budget)
+        base = cpu_baseline(plan, k, vectors, resonator, budget_s=budget)
         if i >= args.warmup:
             vals.append(base["value"])
     v = float(np.mean(vals))
