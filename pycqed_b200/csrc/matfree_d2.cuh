@@ -15,6 +15,7 @@
 // coalesced from L2.  Algorithmic work per mat-vec and vector: 2 n (d0 + d1) real-complex MACs
 // (n = d0 d1), traffic 32 n bytes.
 #pragma once
+#include <type_traits>
 #include "matfree.cuh"
 
 namespace scqed {
@@ -183,6 +184,89 @@ mf_d2_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const doubl
                 o[i] = cmake(s * (h.x - q.c * yi.x) - t * pi.x, s * (h.y - q.c * yi.y) - t * pi.y);
             }
         }
+    }
+}
+
+// The whole degree-`deg` Chebyshev filter of one vector out of shared memory (n <= ~7000), two-node form with
+// REAL combined node Hamiltonians: H0, H1 and both n-vectors live on chip; y = H0 X + X H1^T + coupling costs
+// (d0 + d1) real MACs per element instead of four complex dense mode products through the ELL tables.
+// grid (b, n_pts), block 512.  REALX: the vector is exactly real (imaginary half skipped, half the footprint).
+template <bool REALX>
+__global__ void __launch_bounds__(512)
+mf_cheb_smem_d2(MfArgs a, const cplx *__restrict__ X, cplx *__restrict__ Y, int deg, const double *__restrict__ Hre) {
+    extern __shared__ __align__(16) unsigned char d2f[];
+    typedef typename std::conditional<REALX, double, cplx>::type V;
+    const long long p = blockIdx.y;
+    if (!a.active[p]) return;
+    const PlanDev &P = a.P;
+    const int j = blockIdx.x, n = a.n, tid = threadIdx.x, T = blockDim.x;
+    const int d0 = P.dims[0], d1 = P.dims[1], d1p = d1 | 1;             // odd pitch: conflict-free H1 rows
+    // 16-byte objects first: coupling coefficients, (REALX) complex copy of the vector for the coupling terms,
+    // the two vectors; then the real node Hamiltonians
+    cplx *sC = (cplx *)d2f;
+    cplx *sx = sC + P.d2_nmulti + 1;
+    V *prev = (V *)(sx + ((REALX && P.d2_nmulti > 0) ? n : 0));
+    V *cur = prev + n + (REALX ? (n & 1) : 0);                          // keep 16-byte alignment
+    double *sH0 = (double *)(cur + n + (REALX ? (n & 1) : 0));          // [d0][d0]
+    double *sH1 = sH0 + (size_t)d0 * d0;                                // [d1][d1p]
+    const double *Hp = Hre + p * ((size_t)d0 * d0 + (size_t)d1 * d1);
+    for (int q = tid; q < d0 * d0; q += T) sH0[q] = Hp[q];
+    for (int q = tid; q < d1 * d1; q += T) sH1[(q / d1) * d1p + (q % d1)] = Hp[(size_t)d0 * d0 + q];
+    for (int q = tid; q < P.d2_nmulti; q += T) sC[q] = a.coef[p * P.n_terms + __ldg(P.d2_cidx + q)];
+    const cplx *x = X + (p * a.b + j) * n;
+    for (int i = tid; i < n; i += T) {
+        if constexpr (REALX) prev[i] = x[i].x; else prev[i] = x[i];
+    }
+    __syncthreads();
+    const ChebPar q = cheb_par(a.fpar + p * 4);
+    double sigma = q.sigma1;
+    for (int m = 1; m <= deg; ++m) {
+        // m == 1: cur = s1 (H - c) prev;   m >= 2: prev <- s (H - c) cur - t prev, then swap
+        const V *src = m == 1 ? prev : cur;
+        V *dst = m == 1 ? cur : prev;
+        double s, t = 0.0, sigma2 = sigma;
+        if (m == 1) s = q.sigma1 / q.e;
+        else { sigma2 = 1.0 / (2.0 / q.sigma1 - sigma); s = 2.0 * sigma2 / q.e; t = sigma * sigma2; }
+        if (REALX && P.d2_nmulti > 0) {
+            for (int i = tid; i < n; i += T) sx[i] = cmake(((const double *)src)[i], 0.0);
+            __syncthreads();
+        }
+        for (int i = tid; i < n; i += T) {
+            const int i0 = i / d1, i1 = i - i0 * d1;
+            double hr = 0.0, hi = 0.0;
+            const double *h0 = sH0 + (size_t)i0 * d0;
+            for (int b = 0; b < d0; ++b) {
+                if constexpr (REALX) hr = fma(h0[b], src[b * d1 + i1], hr);
+                else { const cplx v = src[b * d1 + i1]; hr = fma(h0[b], v.x, hr); hi = fma(h0[b], v.y, hi); }
+            }
+            const double *h1 = sH1 + (size_t)i1 * d1p;
+            const V *row = src + (size_t)i0 * d1;
+            for (int b = 0; b < d1; ++b) {
+                if constexpr (REALX) hr = fma(h1[b], row[b], hr);
+                else { const cplx v = row[b]; hr = fma(h1[b], v.x, hr); hi = fma(h1[b], v.y, hi); }
+            }
+            if (P.d2_nmulti > 0) {
+                cplx c;
+                if constexpr (REALX) c = mf_apply_terms(P, P.d2_meta, 0, P.d2_nmulti, sC, sx, i);
+                else c = mf_apply_terms(P, P.d2_meta, 0, P.d2_nmulti, sC, (const cplx *)src, i);
+                hr += c.x; hi += c.y;
+            }
+            if constexpr (REALX) {
+                const double yi = src[i];
+                dst[i] = m == 1 ? s * (hr - q.c * yi) : s * (hr - q.c * yi) - t * dst[i];
+            } else {
+                const cplx yi = src[i];
+                if (m == 1) dst[i] = cmake(s * (hr - q.c * yi.x), s * (hi - q.c * yi.y));
+                else { const cplx pi = dst[i]; dst[i] = cmake(s * (hr - q.c * yi.x) - t * pi.x, s * (hi - q.c * yi.y) - t * pi.y); }
+            }
+        }
+        __syncthreads();
+        if (m >= 2) { V *tmp = prev; prev = cur; cur = tmp; }
+        sigma = sigma2;
+    }
+    cplx *y = Y + (p * a.b + j) * n;
+    for (int i = tid; i < n; i += T) {
+        if constexpr (REALX) y[i] = cmake(cur[i], 0.0); else y[i] = cur[i];
     }
 }
 

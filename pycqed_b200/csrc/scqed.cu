@@ -1126,7 +1126,7 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
     }
     // two-node plans with dense single-node operators on the global-memory filter: combined per-point
     // node Hamiltonians + real mode products (matfree_d2.cuh)
-    const bool use_d2 = pl->d2_ok && !smem_filter && stencil_cs == 0 && !getenv("SCQED_NO_D2");
+    const bool use_d2 = pl->d2_ok && stencil_cs == 0 && !getenv("SCQED_NO_D2");
     const int d2_tot = P.dims[0] * P.dims[0] + (P.n_nodes > 1 ? P.dims[1] * P.dims[1] : 0);
     double *d2re = nullptr, *d2im = nullptr, *d2imax = nullptr;
     size_t d2_smem_real = 0, d2_smem_cplx = 0;
@@ -1256,7 +1256,20 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
                 LAUNCHED();
                 R = Y;
             } else if (smem_filter) {
-                mf_cheb_smem<<<dim3(b, (unsigned)np), 512, (size_t)2 * n * 16, st>>>(a, X, Y, deg);
+                // two-node dense form with real node Hamiltonians: H0, H1 on chip next to the two vectors
+                const size_t hbytes = ((size_t)P.dims[0] * P.dims[0] + (size_t)(P.n_nodes > 1 ? P.dims[1] * (P.dims[1] | 1) : 0) + 2) * 8 +
+                                      (size_t)(P.d2_nmulti + 2) * 16;
+                const size_t sm_rx = (size_t)2 * n * 8 + hbytes + (P.d2_nmulti > 0 ? (size_t)n * 16 : 0) + 64;
+                const size_t sm_cx = (size_t)2 * n * 16 + hbytes + 64;
+                if (use_d2 && d2_real && d2_realx && sm_rx <= 220 * 1024) {
+                    CK(cudaFuncSetAttribute(mf_cheb_smem_d2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rx));
+                    mf_cheb_smem_d2<true><<<dim3(b, (unsigned)np), 512, sm_rx, st>>>(a, X, Y, deg, d2re);
+                } else if (use_d2 && d2_real && sm_cx <= 220 * 1024) {
+                    CK(cudaFuncSetAttribute(mf_cheb_smem_d2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cx));
+                    mf_cheb_smem_d2<false><<<dim3(b, (unsigned)np), 512, sm_cx, st>>>(a, X, Y, deg, d2re);
+                } else {
+                    mf_cheb_smem<<<dim3(b, (unsigned)np), 512, (size_t)2 * n * 16, st>>>(a, X, Y, deg);
+                }
                 LAUNCHED();
                 R = Y;
             } else {
