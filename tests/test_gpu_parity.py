@@ -460,6 +460,46 @@ def test_full_size_properties_c2(engine_mod):
         assert np.max(np.abs(H[j] @ X - X * r2.E[j][None, :])) < 1e-9 * np.abs(E).max()
 
 
+def _mirror_index(plan, flip):
+    """Flat grid index of the point with the listed sweep axes mirrored (C-order over addSweep order)."""
+    shape = [int(sp["N"]) for sp in plan.sweep_specs]
+    idx = np.indices(shape)
+    for ax in flip:
+        idx[ax] = shape[ax] - 1 - idx[ax]
+    return np.ravel_multi_index([i.reshape(-1) for i in idx], shape)
+
+
+@pytest.mark.parametrize("name,k,flips,n_res", [
+    ("c1_transmon", 10, [[0], [1]], 12),              # E(phiZ, Qg) = E(-phiZ, Qg) = E(phiZ, -Qg): symmetric grids
+    ("c4_averin_full", 10, [[0], [1]], 12),           # 20 301 points: Qc -> -Qc, phie -> -phie
+    ("c3_csfq4jj_t27", 10, [[1]], 3),                 # 1024 points, n = 3025: phiX -> -phiX
+    ("c3_csfqfloat_t7_full", 10, [[1]], 3),           # 1024 points, n = 3375: phiZ mirrored about 0.5
+    ("c5_fluxatom_t31_64", 10, [[0]], 4),             # phi- in [0, 1]: period 1 and even
+])
+def test_full_size_properties_other_configs(engine_mod, name, k, flips, n_res):
+    """The other BASELINE grids at full size: sortedness, the mirror symmetries of each sweep axis (H at the
+    mirrored point is the complex conjugate or a unitary image of H: same spectrum), residuals ||H v - E v||
+    through the dense assembly on a sample, and orthonormality."""
+    plan = load_plan(name)
+    grid = plan.sweep_grid()
+    with engine_mod.Engine(plan) as eng:
+        res = eng.sweep(grid, k)
+        assert not res.info.any()
+        E = res.E
+        scale = np.abs(E).max()
+        assert np.all(np.diff(E, axis=1) >= -1e-9 * scale)
+        for flip in flips:
+            assert np.max(np.abs(E - E[_mirror_index(plan, flip)])) < 1e-9 * scale, (name, flip)
+        idx = _sample(len(grid), n_res)
+        r2 = eng.sweep(grid[idx], k, want_vectors=True)
+        assert np.max(np.abs(r2.E - E[idx])) < 1e-9 * scale
+        H = eng.assemble_dense(grid[idx]).cpu().numpy()
+    for j in range(len(idx)):
+        X = r2.V[j].T
+        assert np.max(np.abs(H[j] @ X - X * r2.E[j][None, :])) < 1e-8 * scale
+        assert np.max(np.abs(X.conj().T @ X - np.eye(k))) < 1e-9
+
+
 def test_error_paths(engine_mod):
     g, plan = load_golden("c2_fluxonium")
     with engine_mod.Engine(plan) as eng:
