@@ -764,14 +764,38 @@ __global__ void mf_converge(MfArgs a, double tol, int *info) {
 }
 
 // ---- outputs: first k Ritz pairs.  grid (ceil(n*k/256), n_pts) -----------------------------------------
-__global__ void mf_output(MfArgs a, const cplx *__restrict__ X, double *__restrict__ evals, cplx *__restrict__ evecs) {
+// `oidx` (optional): position of local point p in the caller's arrays (coarse-to-fine ordering, see run_matfree)
+__global__ void mf_output(MfArgs a, const cplx *__restrict__ X, double *__restrict__ evals, cplx *__restrict__ evecs,
+                          const int *__restrict__ oidx) {
     const long long p = blockIdx.y;
+    const long long po = oidx ? oidx[p] : p;
     const int q = blockIdx.x * blockDim.x + threadIdx.x, n = a.n, k = a.k, b = a.b;
-    if (q < k) evals[p * k + q] = a.theta[p * b + q];
+    if (q < k) evals[po * k + q] = a.theta[p * b + q];
     if (evecs && q < n * k) {
         int j = q / n, i = q - j * n;
-        evecs[(p * k + j) * n + i] = X[(p * b + j) * n + i];
+        evecs[(po * k + j) * n + i] = X[(p * b + j) * n + i];
     }
+}
+
+// coarse-to-fine start: X[p] = Xsrc[src[p]] (the converged Ritz block of the nearest already-solved sweep point)
+__global__ void __launch_bounds__(256)
+mf_init_from(MfArgs a, cplx *__restrict__ X, const cplx *__restrict__ Xsrc, const int *__restrict__ src) {
+    const long long p = blockIdx.y;
+    const size_t tot = (size_t)a.b * a.n;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < tot) X[p * tot + i] = Xsrc[(size_t)src[p] * tot + i];
+}
+
+__global__ void mf_gather_coef(const cplx *__restrict__ in, cplx *__restrict__ out, const int *__restrict__ perm, long long n_pts, int n_terms) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pts * n_terms) return;
+    const long long p = i / n_terms;
+    out[i] = in[(long long)perm[p] * n_terms + (i - p * n_terms)];
+}
+
+__global__ void mf_scatter_info(const int *__restrict__ in, int *__restrict__ out, const int *__restrict__ perm, long long n_pts) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_pts) out[perm[p]] = in[p];
 }
 
 }  // namespace scqed

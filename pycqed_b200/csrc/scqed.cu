@@ -102,6 +102,7 @@ struct scqed_plan {
     std::vector<int> xform_node;
     std::vector<size_t> xform_off;     // byte offsets of W_i^T inside `tables`
     int pair_max_index = -1;
+    DevBuf mfwarm;
     bool d2_ok = false;                // two-node plan with dense single-node operators: combined mode products
     DevBuf d2h;
     std::vector<int> factor_node;
@@ -465,7 +466,7 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
 extern "C" void scqed_plan_destroy(scqed_plan *pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
-    DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->s1work, &pl->s1vec, &pl->auxc, &pl->resvec, &pl->dcoef, &pl->d2h, &pl->in_params, &pl->out_evals,
+    DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->s1work, &pl->s1vec, &pl->auxc, &pl->resvec, &pl->dcoef, &pl->d2h, &pl->mfwarm, &pl->in_params, &pl->out_evals,
                       &pl->out_evecs, &pl->out_post, &pl->out_info, &pl->out_scal};
     for (DevBuf *b : bufs) b->release();
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
@@ -1071,8 +1072,71 @@ static int mf_block_size(int n, int k) {
     return b;
 }
 
+// Warm start hooks of one run_matfree_core call (all optional):
+//   oidx      [n_pts] where each local point goes in evals / evecs (info stays local)
+//   keep_x    receives the converged Ritz blocks [n_pts][b][n]
+//   init_x / init_src   start blocks: X[p] = init_x[init_src[p]]
+struct MfWarm { const int *oidx; cplx *keep_x; const cplx *init_x; const int *init_src; };
+
+static int run_matfree_core(scqed_plan *pl, const cplx *coef_all, long long n_pts, int k, int want_vec, double *evals,
+                            cplx *evecs, int *info, cudaStream_t st, int deg, int maxit, double tol, const MfWarm &warm);
+
+// Coarse-to-fine sweep: every MF_STRIDE-th point of the (flattened) grid is solved from scratch, the others
+// start from the converged Ritz block of their nearest solved neighbour.  Neighbouring sweep points have
+// nearly the same low-energy subspace, so the filtered subspace iteration needs 2-4 outer iterations
+// instead of ~10; the accuracy criterion (residual <= tol) is unchanged.
+#define MF_STRIDE 8
 static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, int k, int want_vec, double *evals,
                        cplx *evecs, int *info, cudaStream_t st, int deg, int maxit, double tol) {
+    const PlanDev &P = pl->P;
+    const MfWarm none = {nullptr, nullptr, nullptr, nullptr};
+    // small sweeps: the two passes would each under-fill the GPU and pay their own iteration latencies
+    if (n_pts < 16 * MF_STRIDE || n_pts > 2000000000LL || getenv("SCQED_NO_WARM_START"))
+        return run_matfree_core(pl, coef_all, n_pts, k, want_vec, evals, evecs, info, st, deg, maxit, tol, none);
+    const int b = mf_block_size(P.n, k);
+    if (b < k) return fail(SCQED_EUNSUPPORTED, "matrix-free path supports k <= %d", MF_BMAX);
+    const long long nc = (n_pts + MF_STRIDE - 1) / MF_STRIDE, nf = n_pts - nc;
+    std::vector<int> perm((size_t)n_pts), src((size_t)(nf > 0 ? nf : 1));
+    for (long long c = 0; c < nc; ++c) perm[(size_t)c] = (int)(c * MF_STRIDE);
+    long long q = nc;
+    for (long long p = 0; p < n_pts; ++p) {
+        if (p % MF_STRIDE == 0) continue;
+        long long lo = p / MF_STRIDE, hi = lo + 1;                       // nearest solved neighbour in grid order
+        long long pick = (hi < nc && (hi * MF_STRIDE - p) < (p - lo * MF_STRIDE)) ? hi : lo;
+        perm[(size_t)q] = (int)p;
+        src[(size_t)(q - nc)] = (int)pick;
+        ++q;
+    }
+    const size_t xblk = (size_t)b * P.n * 16;
+    const size_t bytes = (size_t)n_pts * P.n_terms * 16 + (size_t)n_pts * 4 * 3 + (size_t)nc * xblk + 1024;
+    if (pl->mfwarm.ensure(bytes)) return fail(SCQED_ENOMEM, "warm-start buffers (%zu MB)", bytes >> 20);
+    unsigned char *wp = (unsigned char *)pl->mfwarm.p;
+    auto take = [&](size_t nb) { unsigned char *r = wp; wp += (nb + 255) & ~(size_t)255; return r; };
+    cplx *xkeep = (cplx *)take((size_t)nc * xblk);
+    cplx *coefp = (cplx *)take((size_t)n_pts * P.n_terms * 16);
+    int *d_perm = (int *)take((size_t)n_pts * 4), *d_src = (int *)take((size_t)(nf > 0 ? nf : 1) * 4), *infop = (int *)take((size_t)n_pts * 4);
+    CK(cudaMemcpyAsync(d_perm, perm.data(), (size_t)n_pts * 4, cudaMemcpyHostToDevice, st));
+    if (nf > 0) CK(cudaMemcpyAsync(d_src, src.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                                           // perm / src are stack-owned host vectors
+    const long long tot = n_pts * P.n_terms;
+    mf_gather_coef<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(coef_all, coefp, d_perm, n_pts, P.n_terms);
+    LAUNCHED();
+    MfWarm wc = {d_perm, xkeep, nullptr, nullptr};
+    int rc = run_matfree_core(pl, coefp, nc, k, want_vec, evals, evecs, infop, st, deg, maxit, tol, wc);
+    if (rc) return rc;
+    if (nf > 0) {
+        MfWarm wf = {d_perm + nc, nullptr, xkeep, d_src};
+        rc = run_matfree_core(pl, coefp + (size_t)nc * P.n_terms, nf, k, want_vec, evals, evecs, infop + nc, st, deg, maxit, tol, wf);
+        if (rc) return rc;
+    }
+    mf_scatter_info<<<(unsigned)((n_pts + 255) / 256), 256, 0, st>>>(infop, info, d_perm, n_pts);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int run_matfree_core(scqed_plan *pl, const cplx *coef_all, long long n_pts, int k, int want_vec, double *evals,
+                            cplx *evecs, int *info, cudaStream_t st, int deg, int maxit, double tol, const MfWarm &warm) {
     const PlanDev &P = pl->P;
     const int n = P.n;
     if (P.max_term_nn > 3) return fail(SCQED_EUNSUPPORTED, "matrix-free path supports terms with at most 3 non-identity factors");
@@ -1164,6 +1228,11 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
         cplx *X = bufX, *Y = bufY, *H = bufH, *Hn = bufHn;
         mf_prepare<<<(unsigned)np, MF_THREADS, 0, st>>>(a, X, dscr);
         LAUNCHED();
+        if (warm.init_x) {
+            const size_t xt = (size_t)b * n;
+            mf_init_from<<<dim3((unsigned)((xt + 255) / 256), (unsigned)np), 256, 0, st>>>(a, X, warm.init_x, warm.init_src + p0);
+            LAUNCHED();
+        }
         auto d2_launch = [&](int mode, const cplx *src, cplx *dst, int mstep) {
             dim3 g(d2_grid_base.x, d2_grid_base.y, (unsigned)np);
             if (d2_real && d2_realx) {
@@ -1292,8 +1361,12 @@ static int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, in
             CK(cudaGetLastError());
         }
         unsigned ob = (unsigned)(((size_t)n * k + 255) / 256);
-        mf_output<<<dim3(ob, (unsigned)np), 256, 0, st>>>(a, X, evals + (size_t)p0 * k,
-                                                        (want_vec && evecs) ? evecs + (size_t)p0 * k * n : nullptr);
+        if (warm.keep_x) CK(cudaMemcpyAsync(warm.keep_x + (size_t)p0 * b * n, X, (size_t)np * b * n * 16, cudaMemcpyDeviceToDevice, st));
+        if (warm.oidx)
+            mf_output<<<dim3(ob, (unsigned)np), 256, 0, st>>>(a, X, evals, (want_vec && evecs) ? evecs : nullptr, warm.oidx + p0);
+        else
+            mf_output<<<dim3(ob, (unsigned)np), 256, 0, st>>>(a, X, evals + (size_t)p0 * k,
+                                                            (want_vec && evecs) ? evecs + (size_t)p0 * k * n : nullptr, nullptr);
         LAUNCHED();
         CK(cudaGetLastError());
     }
