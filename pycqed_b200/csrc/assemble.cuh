@@ -76,41 +76,67 @@ assemble_dense_kernel(PlanDev P, const cplx *__restrict__ coef_all, long long n_
 // The pattern of H is the same at every sweep point.  Sparse patterns (charge-basis circuits: 0.2-3 %
 // non-zeros): the batch is zero-filled at memset speed and one thread per ENTRY writes
 // sum_q c[term_q] * val_q -- every structural non-zero is written exactly once, 16 n^2 B/pt of HBM
-// writes and no per-element term walk.  grid = (points, entry blocks).
+// writes and no per-element term walk.  grid = (point groups, entry blocks).
+#define ASM_PG 8      // points served by one block: the pattern tables are read once per ASM_PG points
 __global__ void __launch_bounds__(256)
-assemble_entries_kernel(PlanDev P, const cplx *__restrict__ coef_all, int tidyup, cplx *__restrict__ H) {
-    extern __shared__ cplx s_coef[];
-    const long long p = blockIdx.x;
-    for (int t = threadIdx.x; t < P.n_terms; t += blockDim.x) s_coef[t] = coef_all[p * P.n_terms + t];
+assemble_entries_kernel(PlanDev P, const cplx *__restrict__ coef_all, long long n_pts, int tidyup, cplx *__restrict__ H) {
+    extern __shared__ cplx s_coef[];                       // [ASM_PG][n_terms]
+    const long long p0 = (long long)blockIdx.x * ASM_PG;
+    const int npg = (int)(n_pts - p0 < ASM_PG ? n_pts - p0 : ASM_PG);
+    const int nt = P.n_terms;
+    for (int t = threadIdx.x; t < npg * nt; t += blockDim.x) s_coef[t] = coef_all[p0 * nt + t];
     __syncthreads();
     const int e = blockIdx.y * blockDim.x + threadIdx.x;
     if (e >= P.n_entries) return;
     const int q0 = __ldg(P.ent_ptr + e), q1 = __ldg(P.ent_ptr + e + 1);
-    cplx acc = cmake(0.0, 0.0);
-    for (int q = q0; q < q1; ++q) cfma(acc, s_coef[__ldg(P.ent_term + q)], __ldg(P.ent_val + q));
-    if (tidyup) acc = tidy(acc, 1e-12);
-    H[(size_t)p * P.n * P.n + (size_t)__ldg(P.ent_key + e)] = acc;
+    cplx acc[ASM_PG];
+#pragma unroll
+    for (int g = 0; g < ASM_PG; ++g) acc[g] = cmake(0.0, 0.0);
+    for (int q = q0; q < q1; ++q) {
+        const int t = __ldg(P.ent_term + q);
+        const cplx v = __ldg(P.ent_val + q);
+#pragma unroll
+        for (int g = 0; g < ASM_PG; ++g)
+            if (g < npg) cfma(acc[g], s_coef[g * nt + t], v);
+    }
+    const size_t nn = (size_t)P.n * P.n, key = (size_t)__ldg(P.ent_key + e);
+#pragma unroll
+    for (int g = 0; g < ASM_PG; ++g)
+        if (g < npg) H[(size_t)(p0 + g) * nn + key] = tidyup ? tidy(acc[g], 1e-12) : acc[g];
 }
 
 // Dense patterns (oscillator displacement operators): one thread per ELEMENT, fully coalesced 16-byte
-// stores, element -> entry through a 4-byte map; structural zeros are written directly.
+// stores, element -> entry through a 4-byte map; structural zeros are written directly.  A block serves
+// ASM_PG consecutive points: the entry's (term, value) pairs are read once and applied to the ASM_PG
+// coefficient rows staged in shared memory, so the table traffic per stored element drops ASM_PG-fold.
 __global__ void __launch_bounds__(256)
-assemble_mapped_kernel(PlanDev P, const cplx *__restrict__ coef_all, int tidyup, cplx *__restrict__ H) {
-    extern __shared__ cplx s_coef[];
-    const long long p = blockIdx.x;
-    for (int t = threadIdx.x; t < P.n_terms; t += blockDim.x) s_coef[t] = coef_all[p * P.n_terms + t];
+assemble_mapped_kernel(PlanDev P, const cplx *__restrict__ coef_all, long long n_pts, int tidyup, cplx *__restrict__ H) {
+    extern __shared__ cplx s_coef[];                       // [ASM_PG][n_terms]
+    const long long p0 = (long long)blockIdx.x * ASM_PG;
+    const int npg = (int)(n_pts - p0 < ASM_PG ? n_pts - p0 : ASM_PG);
+    const int nt = P.n_terms;
+    for (int t = threadIdx.x; t < npg * nt; t += blockDim.x) s_coef[t] = coef_all[p0 * nt + t];
     __syncthreads();
     const size_t nn = (size_t)P.n * P.n;
     const size_t idx = (size_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (idx >= nn) return;
     const int e = __ldg(P.ent_map + idx);
-    cplx acc = cmake(0.0, 0.0);
+    cplx acc[ASM_PG];
+#pragma unroll
+    for (int g = 0; g < ASM_PG; ++g) acc[g] = cmake(0.0, 0.0);
     if (e >= 0) {
         const int q0 = __ldg(P.ent_ptr + e), q1 = __ldg(P.ent_ptr + e + 1);
-        for (int q = q0; q < q1; ++q) cfma(acc, s_coef[__ldg(P.ent_term + q)], __ldg(P.ent_val + q));
-        if (tidyup) acc = tidy(acc, 1e-12);
+        for (int q = q0; q < q1; ++q) {
+            const int t = __ldg(P.ent_term + q);
+            const cplx v = __ldg(P.ent_val + q);
+#pragma unroll
+            for (int g = 0; g < ASM_PG; ++g)
+                if (g < npg) cfma(acc[g], s_coef[g * nt + t], v);
+        }
     }
-    H[(size_t)p * nn + idx] = acc;
+#pragma unroll
+    for (int g = 0; g < ASM_PG; ++g)
+        if (g < npg) H[(size_t)(p0 + g) * nn + idx] = tidyup ? tidy(acc[g], 1e-12) : acc[g];
 }
 
 }  // namespace scqed

@@ -604,10 +604,10 @@ static int run_assemble(scqed_plan *pl, const cplx *coef_dev, long long n_pts, i
         if (eb <= 65535 && n_pts <= 2147483647LL) {
             timing_begin(st, 3);
             if (P.ent_dense) {
-                assemble_mapped_kernel<<<dim3((unsigned)n_pts, (unsigned)eb), 256, (size_t)P.n_terms * 16, st>>>(P, coef_dev, tidyup, H);
+                assemble_mapped_kernel<<<dim3((unsigned)((n_pts + ASM_PG - 1) / ASM_PG), (unsigned)eb), 256, (size_t)ASM_PG * P.n_terms * 16, st>>>(P, coef_dev, n_pts, tidyup, H);
             } else {
                 CK(cudaMemsetAsync(H, 0, (size_t)n_pts * nn * 16, st));
-                assemble_entries_kernel<<<dim3((unsigned)n_pts, (unsigned)eb), 256, (size_t)P.n_terms * 16, st>>>(P, coef_dev, tidyup, H);
+                assemble_entries_kernel<<<dim3((unsigned)((n_pts + ASM_PG - 1) / ASM_PG), (unsigned)eb), 256, (size_t)ASM_PG * P.n_terms * 16, st>>>(P, coef_dev, n_pts, tidyup, H);
             }
             timing_end(st);
             LAUNCHED();
