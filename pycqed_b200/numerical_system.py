@@ -395,6 +395,35 @@ class NumericalSystem:
     def getVoltageMatrixElement(self, E, V, node=None, elements=None):
         return self._aux_matrix_elements({"kind": "Voltage", "node": node, "elements": elements}, V)
 
+    # ---- small conveniences of the reference API ---------------------------------------------------
+    def prepareOperators(self):
+        """numerical_system.py:302-305.  Operators are device tables built from the plan; nothing to expand."""
+        self._invalidate()
+
+    def sparsity(self, op):
+        """numerical_system.py:99-100: 1 - nnz / n^2."""
+        a = op.full() if hasattr(op, "full") else np.asarray(op.data.to_array())
+        return 1 - np.count_nonzero(a) / self.getHilbertSpaceSize() ** 2
+
+    def getOperatorList(self, node):
+        """(Q, P, D, Ddag, S, Sdag) of one node as dense arrays (numerical_system.py:162-182)."""
+        if node not in self.getNodeList():
+            raise Exception("Node '%i' is not a valid circuit node." % node)
+        plan, _ = self._single_plan()
+        ops = plan.nodes[self.getNodeIndex(node)].operator_set()
+        return tuple(ops[kind] for kind in ("charge", "flux", "disp", "disp_adj", "pdisp", "pdisp_adj"))
+
+    def getResonatorResponse(self, E, V, nmax=100, cpl_node=None):
+        """numerical_system.py:736-784 at the current parameter values.  The strips are computed on the device from
+        the eigenpairs of H at these values (``E`` / ``V`` only fix how many levels enter, as in a sweep)."""
+        if cpl_node is None:
+            return None
+        k = len(E)
+        plan = lower_system(self.SS, self.units, self.operator_data, resonator={"cpl_node": cpl_node, "nmax": nmax})
+        with _engine.Engine(plan, device=self.device) as eng:
+            res = eng.sweep(np.zeros((1, 0)), k, want_vectors=True, resonator=True)
+        return res.Erwa[0]
+
     # ---- diagonaliser (numerical_system.py:790-810; util.py:76-176) -----------------------------
     def setDiagConfig(self, eigvalues=5, get_vectors=False, sparse=False,
                       sparsesolveropts={"sigma": None, "mode": "normal", "maxiter": None, "tol": 1e-3, "which": "SA"}):

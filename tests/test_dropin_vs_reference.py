@@ -257,6 +257,27 @@ def test_single_point_api(patched):
     assert np.max(np.abs(qa - mine.circ_operators[1]["charge"].full())) < 1e-12
 
 
+def test_single_point_conveniences(patched):
+    ref, mine, mg = _pair("build_fluxonium", patched, 18)
+    with mg.quiet():
+        ref.setDiagConfig(eigvalues=5, get_vectors=True)
+        E, V = ref.diagonalize(ref.getHamiltonian())
+        Ra = ref.getResonatorResponse(np.asarray(E), V, nmax=9, cpl_node=1)
+        Rb = mine.getResonatorResponse(np.asarray(E), V, nmax=9, cpl_node=1)
+        assert mine.getResonatorResponse(np.asarray(E), V) is None
+    assert Ra.shape == Rb.shape == (9 + 1 + 5, 5)
+    assert np.max(np.abs(Ra - Rb)) < 1e-9 * np.abs(Ra).max()
+    with mg.quiet():
+        la = [x.data.to_array() for x in ref.getOperatorList(1)]
+        lb = mine.getOperatorList(1)
+    for a, b in zip(la, lb):
+        assert np.max(np.abs(a - b)) < 1e-11 * max(1.0, np.abs(a).max())
+    with mg.quiet():
+        sa, sb = ref.sparsity(ref.getHamiltonian()), mine.sparsity(mine.getHamiltonian())
+    assert abs(sa - sb) < 1e-12
+    mine.prepareOperators()
+
+
 def test_error_behaviour_matches_reference(patched):
     ref, mine, mg = _pair("build_transmon", patched, 5)
     for h in (ref, mine):
