@@ -821,7 +821,7 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
         // enough (point, eigenvalue) pairs to fill the machine with one thread each: plain bisection
         // (6.6x less arithmetic); small sweeps keep the 33-way warp multisection (short dependent chain)
         const int bis_mode = getenv("SCQED_BISECT") ? atoi(getenv("SCQED_BISECT")) : 0;
-        const bool thread_bisect = bis_mode == 2 || (bis_mode == 0 && np * k >= (long long)pl->sm_count * 256 && k <= 32);
+        const bool thread_bisect = bis_mode == 2 || (bis_mode == 0 && np * k >= 4096 && k <= 32);
         if (thread_bisect) {
             const int ppw = 32 / k;
             const long long bw = (np + ppw - 1) / ppw;
@@ -1590,8 +1590,33 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
     long long nchunks = n_pts / 5000;       // chunks stay >= ~17 waves of the small-path kernels
     if (nchunks < 1) nchunks = 1;
     if (nchunks > 8) nchunks = 8;
+    double geom = 0.0;
+    if (nchunks == 2) { nchunks = 3; geom = 0.6; }      // measured best on the bench workload: 12.9 -> 11.9 ms end to end
     if (const char *envc = getenv("SCQED_HOST_CHUNKS")) { long long v = atoll(envc); if (v >= 1 && v <= 64) nchunks = v < n_pts ? v : n_pts; }
     const long long per = (n_pts + nchunks - 1) / nchunks;
+    // Chunk sizes.  Default: equal.  SCQED_HOST_GEOM=r (0 < r < 1): geometric, chunk i+1 = r * chunk i, so that the
+    // copy of chunk i hides behind the (shorter) solve of chunk i+1 and only a small last copy is exposed.
+    std::vector<long long> sizes;
+    {
+        double r = geom;
+        if (const char *eg = getenv("SCQED_HOST_GEOM")) r = atof(eg);
+        else if (getenv("SCQED_HOST_CHUNKS")) r = 0.0;
+        if (r > 0.05 && r < 0.999 && nchunks > 1) {
+            double tot = 0.0, w = 1.0;
+            for (long long c = 0; c < nchunks; ++c) { tot += w; w *= r; }
+            long long left = n_pts;
+            w = 1.0;
+            for (long long c = 0; c < nchunks && left > 0; ++c) {
+                long long sz = c == nchunks - 1 ? left : (long long)(n_pts * (w / tot) + 0.5);
+                if (sz < 1) sz = 1;
+                if (sz > left) sz = left;
+                sizes.push_back(sz); left -= sz; w *= r;
+            }
+            if (left > 0) sizes.back() += left;
+        } else {
+            for (long long c0 = 0; c0 < n_pts; c0 += per) sizes.push_back(n_pts - c0 < per ? n_pts - c0 : per);
+        }
+    }
     double *d_ev = (double *)pl->out_evals.p, *d_sc = (double *)pl->out_scal.p;
     cplx *d_vec = (evecs && b_vec) ? (cplx *)pl->out_evecs.p : nullptr;
     double *d_post = b_post ? (double *)pl->out_post.p : nullptr;
@@ -1611,8 +1636,9 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
     // blocks the host, and must not delay the next chunk's kernels.
     long long prev_c0 = -1, prev_np = 0;
     cudaEvent_t prev_evt = nullptr;
-    for (long long c0 = 0; c0 < n_pts; c0 += per) {
-        const long long np = n_pts - c0 < per ? n_pts - c0 : per;
+    long long c0 = 0;
+    for (size_t ci = 0; ci < sizes.size(); c0 += sizes[ci], ++ci) {
+        const long long np = sizes[ci];
         rc = scqed_sweep_run(pl, o, (const double *)pl->in_params.p + (size_t)c0 * P.n_swept, np, d_ev + (size_t)c0 * k,
                              d_vec ? (double *)(d_vec + (size_t)c0 * k * n) : nullptr, d_sc + (size_t)c0 * (ns > 0 ? ns : 1),
                              d_post ? d_post + (size_t)c0 * nstrips * k : nullptr, d_info + c0, st);
