@@ -71,6 +71,46 @@ mf_d2_build(MfArgs a, double *__restrict__ Hre, double *__restrict__ Him, double
     }
 }
 
+// Tighter spectral upper bound from the combined node Hamiltonians: ||H|| <= ||H0||_inf + ||H1||_inf + sum over
+// coupling terms |c| ||F_a||_inf ||F_b||_inf.  The term-by-term bound of mf_prepare counts charge^2 and flux^2
+// separately although their off-diagonals cancel in H_k (4303 vs 2566 for the 180 x 180 atom; the true top is
+// 2499): a narrower filter interval means fewer filter applications.  One block per point.
+__global__ void __launch_bounds__(256)
+mf_d2_bound(MfArgs a, const double *__restrict__ Hre, const double *__restrict__ Him) {
+    __shared__ double smax[2][8];
+    const long long p = blockIdx.x;
+    const PlanDev &P = a.P;
+    const int d0 = P.dims[0], d1 = P.dims[1], tid = threadIdx.x;
+    const size_t tot = (size_t)d0 * d0 + (size_t)d1 * d1;
+    const double *re = Hre + p * tot, *im = Him + p * tot;
+    double m0 = 0.0, m1 = 0.0;
+    for (int r = tid; r < d0 + d1; r += blockDim.x) {
+        const int k = r < d0 ? 0 : 1, dk = k ? d1 : d0, rr = k ? r - d0 : r;
+        const size_t base = (k ? (size_t)d0 * d0 : 0) + (size_t)rr * dk;
+        double sum = 0.0;
+        for (int c = 0; c < dk; ++c) sum += sqrt(re[base + c] * re[base + c] + im[base + c] * im[base + c]);
+        if (k) m1 = fmax(m1, sum); else m0 = fmax(m0, sum);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+        m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    }
+    if ((tid & 31) == 0) { smax[0][tid >> 5] = m0; smax[1][tid >> 5] = m1; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { m0 = fmax(m0, smax[0][w]); m1 = fmax(m1, smax[1][w]); }
+        double ub = m0 + m1;
+        const cplx *coef = a.coef + p * P.n_terms;
+        for (int q = 0; q < P.d2_nmulti; ++q) {
+            const int *tm = P.d2_meta + q * 7;
+            ub += sqrt(cabs2(coef[__ldg(P.d2_cidx + q)])) * __ldg(P.fac_rowsum + __ldg(tm + 4)) * __ldg(P.fac_rowsum + __ldg(tm + 5));
+        }
+        ub *= 1.0 + 1e-10;
+        if (ub < a.fpar[p * 4 + 1]) a.fpar[p * 4 + 1] = ub;
+    }
+}
+
 // max |Im X| over the block of every active point -> imax[2]  (decides whether the real-vector kernels apply)
 __global__ void __launch_bounds__(256)
 mf_d2_imag_max(MfArgs a, const cplx *__restrict__ X, double *__restrict__ imax) {
@@ -108,13 +148,19 @@ mf_d2_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const doubl
     double *sHim = sHre + (size_t)D2_RB * d0;
     cplx *sX = (cplx *)(sHim + (REALH ? 0 : (size_t)D2_RB * d0));
     cplx *sC = sX + (size_t)D2_RB * d1;
+    double *sXr = (double *)(sC + P.d2_nmulti + 1);          // REALX: real parts of the X rows, pitch d1e (even)
+    const int d1e = (d1 + 1) & ~1;
     const cplx *x = X + (p * a.b + j) * n;
     for (int q = tid; q < rb * d0; q += blockDim.x) {
         const int r = q / d0, c = q - r * d0;
         sHre[r * d0 + c] = H0re[(size_t)(R0 + r) * d0 + c];
         if (!REALH) sHim[r * d0 + c] = H0im[(size_t)(R0 + r) * d0 + c];
     }
-    for (int q = tid; q < rb * d1; q += blockDim.x) sX[q] = x[(size_t)R0 * d1 + q];
+    for (int q = tid; q < rb * d1; q += blockDim.x) {
+        const cplx v = x[(size_t)R0 * d1 + q];
+        sX[q] = v;
+        if (REALX) { const int r = q / d1; sXr[r * d1e + (q - r * d1)] = v.x; }
+    }
     for (int q = tid; q < P.d2_nmulti; q += blockDim.x) sC[q] = a.coef[p * P.n_terms + __ldg(P.d2_cidx + q)];
     __syncthreads();
     const int i1 = tid;
@@ -122,9 +168,38 @@ mf_d2_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const doubl
     cplx acc[D2_RB];
 #pragma unroll
     for (int r = 0; r < D2_RB; ++r) acc[r] = cmake(0.0, 0.0);
+    int bA = 0, bB = 0;
+    if (REALX && (d0 & 1) == 0) {
+        // real vectors: four independent global loads per step (the kernel is bound by the latency of this L2
+        // stream), H0 through 16-byte shared-memory broadcasts (two columns per load)
+        for (; bA + 4 <= d0; bA += 4) {
+            const double x0 = x[(size_t)bA * d1 + i1].x, x1 = x[(size_t)(bA + 1) * d1 + i1].x;
+            const double x2 = x[(size_t)(bA + 2) * d1 + i1].x, x3 = x[(size_t)(bA + 3) * d1 + i1].x;
+#pragma unroll
+            for (int r = 0; r < D2_RB; ++r) {
+                const double2 h01 = *(const double2 *)(sHre + r * d0 + bA);
+                const double2 h23 = *(const double2 *)(sHre + r * d0 + bA + 2);
+                double t = acc[r].x;
+                t = fma(h01.x, x0, t); t = fma(h01.y, x1, t); t = fma(h23.x, x2, t); t = fma(h23.y, x3, t);
+                acc[r].x = t;
+            }
+        }
+        for (; bB + 4 <= d1; bB += 4) {
+            const double h0 = H1re[(size_t)bB * d1 + i1], h1 = H1re[(size_t)(bB + 1) * d1 + i1];
+            const double h2 = H1re[(size_t)(bB + 2) * d1 + i1], h3 = H1re[(size_t)(bB + 3) * d1 + i1];
+#pragma unroll
+            for (int r = 0; r < D2_RB; ++r) {
+                const double2 v01 = *(const double2 *)(sXr + r * d1e + bB);
+                const double2 v23 = *(const double2 *)(sXr + r * d1e + bB + 2);
+                double t = acc[r].x;
+                t = fma(h0, v01.x, t); t = fma(h1, v01.y, t); t = fma(h2, v23.x, t); t = fma(h3, v23.y, t);
+                acc[r].x = t;
+            }
+        }
+    }
     // Y[R0 + r][i1] += sum_b H0[R0 + r][b] X[b][i1]   (X streams coalesced from L2, H0 broadcast from shared memory)
 #pragma unroll 2
-    for (int b = 0; b < d0; ++b) {
+    for (int b = bA; b < d0; ++b) {
         const cplx xb = x[(size_t)b * d1 + i1];
 #pragma unroll
         for (int r = 0; r < D2_RB; ++r) {
@@ -140,7 +215,7 @@ mf_d2_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const doubl
     }
     // Y[R0 + r][i1] += sum_b X[R0 + r][b] H1[i1][b];  H1 Hermitian: H1[i1][b] = conj(H1[b][i1]) (row b is contiguous)
 #pragma unroll 2
-    for (int b = 0; b < d1; ++b) {
+    for (int b = bB; b < d1; ++b) {
         const double hr = H1re[(size_t)b * d1 + i1];
         const double hi = REALH ? 0.0 : -H1im[(size_t)b * d1 + i1];
 #pragma unroll

@@ -1199,7 +1199,8 @@ static int run_matfree_core(scqed_plan *pl, const cplx *coef_all, long long n_pt
         d2imax = (double *)pl->d2h.p;
         d2re = (double *)((unsigned char *)pl->d2h.p + 256);
         d2im = d2re + (size_t)chunk * d2_tot;
-        d2_smem_real = (size_t)D2_RB * P.dims[0] * 8 + (size_t)D2_RB * P.dims[1] * 16 + (size_t)(P.d2_nmulti + 1) * 16;
+        d2_smem_real = (size_t)D2_RB * P.dims[0] * 8 + (size_t)D2_RB * P.dims[1] * 16 + (size_t)(P.d2_nmulti + 1) * 16 +
+                       (size_t)D2_RB * (P.dims[1] + 2) * 8 + 32;
         d2_smem_cplx = d2_smem_real + (size_t)D2_RB * P.dims[0] * 8;
         CK(cudaFuncSetAttribute(mf_d2_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_real));
         CK(cudaFuncSetAttribute(mf_d2_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_real));
@@ -1253,6 +1254,10 @@ static int run_matfree_core(scqed_plan *pl, const cplx *coef_all, long long n_pt
             CK(cudaMemsetAsync(d2imax, 0, 32, st));
             mf_d2_build<<<dim3((unsigned)((d2_tot + 255) / 256), (unsigned)np), 256, 0, st>>>(a, d2re, d2im, d2imax);
             LAUNCHED();
+            if (!getenv("SCQED_NO_D2_BOUND")) {
+                mf_d2_bound<<<(unsigned)np, 256, 0, st>>>(a, d2re, d2im);      // after mf_prepare: tightens fpar[1]
+                LAUNCHED();
+            }
             double h_imax[2] = {0.0, 0.0};
             CK(cudaMemcpyAsync(h_imax, d2imax, 16, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
