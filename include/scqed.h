@@ -115,8 +115,14 @@ typedef struct {
     int32_t res_qb;           /* scalar slot of the node's charge bias                       */
     int32_t raw_basis;        /* 1: leave eigenvectors in the plan's (rotated) basis; the caller runs
                                  scqed_matrix_elements on them and then scqed_back_transform      */
-    int32_t reserved[5];
+    int32_t real_vectors;     /* scqed_sweep_run_host only: the caller's `evecs` buffer is float64 [n_pts, k, n]; the
+                                 real parts are packed on the device and only they cross PCIe.  Valid when every
+                                 eigenvector is exactly real (real symmetric H: fluxonium, RF-SQUID ...); otherwise the
+                                 call returns SCQED_ECOMPLEX (1) and must be repeated with a complex buffer.        */
+    int32_t reserved[4];
 } scqed_sweep_opts;
+
+#define SCQED_ECOMPLEX 1   /* real_vectors requested but some eigenvector has a non-zero imaginary part */
 
 /* Create / destroy.  Uploads the tables to `device`. */
 int  scqed_plan_create(const scqed_plan_desc *desc, int device, scqed_plan **plan_out);

@@ -109,7 +109,7 @@ struct scqed_plan {
     // device copies of the tables
     DevBuf tables;
     // per-call workspaces (grown on demand, reused across calls)
-    DevBuf regs, coef, scal, work, in_params, out_evals, out_evecs, out_post, out_info, out_scal;
+    DevBuf regs, coef, scal, work, in_params, out_evals, out_evecs, out_post, out_info, out_scal, out_pack;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
 };
 
@@ -467,7 +467,7 @@ extern "C" void scqed_plan_destroy(scqed_plan *pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
     DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->s1work, &pl->s1vec, &pl->auxc, &pl->resvec, &pl->dcoef, &pl->d2h, &pl->mfwarm, &pl->in_params, &pl->out_evals,
-                      &pl->out_evecs, &pl->out_post, &pl->out_info, &pl->out_scal};
+                      &pl->out_evecs, &pl->out_post, &pl->out_info, &pl->out_scal, &pl->out_pack};
     for (DevBuf *b : bufs) b->release();
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
     if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
@@ -1569,6 +1569,15 @@ static int sweep_run_impl(scqed_plan *pl, const scqed_sweep_opts *o, const doubl
     return finish();
 }
 
+// real parts of a chunk of eigenvectors -> packed float64; flag[0] |= any non-zero imaginary part
+__global__ void __launch_bounds__(256)
+pack_real_kernel(const cplx *__restrict__ in, double *__restrict__ out, size_t count, int *__restrict__ flag) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (i < count) { const cplx v = in[i]; out[i] = v.x; bad = v.y != 0.0; }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
 extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, const double *params, int64_t n_pts,
                                     double *evals, double *evecs, double *scalars, double *post, int32_t *info) {
     if (!pl || !evals || !info || n_pts < 1) return fail(SCQED_EINVAL, "bad argument");
@@ -1628,6 +1637,15 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
     }
     double *d_ev = (double *)pl->out_evals.p, *d_sc = (double *)pl->out_scal.p;
     cplx *d_vec = (evecs && b_vec) ? (cplx *)pl->out_evecs.p : nullptr;
+    const bool pack = o->real_vectors && d_vec;
+    double *d_pack = nullptr;
+    int *d_flag = nullptr;
+    if (pack) {
+        if (pl->out_pack.ensure(b_vec / 2 + 256)) return fail(SCQED_ENOMEM, "packed eigenvector buffer");
+        d_flag = (int *)pl->out_pack.p;
+        d_pack = (double *)((unsigned char *)pl->out_pack.p + 256);
+        CK(cudaMemsetAsync(d_flag, 0, 4, st));
+    }
     double *d_post = b_post ? (double *)pl->out_post.p : nullptr;
     int32_t *d_info = (int32_t *)pl->out_info.p;
     const int ns = P.n_scalar;
@@ -1635,7 +1653,8 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
         CK(cudaStreamWaitEvent(cs, evt, 0));
         CK(cudaEventDestroy(evt));
         CK(cudaMemcpyAsync(evals + (size_t)c0 * k, d_ev + (size_t)c0 * k, (size_t)np * k * 8, cudaMemcpyDeviceToHost, cs));
-        if (d_vec) CK(cudaMemcpyAsync(evecs + (size_t)2 * c0 * k * n, d_vec + (size_t)c0 * k * n, (size_t)np * k * n * 16, cudaMemcpyDeviceToHost, cs));
+        if (pack) CK(cudaMemcpyAsync(evecs + (size_t)c0 * k * n, d_pack + (size_t)c0 * k * n, (size_t)np * k * n * 8, cudaMemcpyDeviceToHost, cs));
+        else if (d_vec) CK(cudaMemcpyAsync(evecs + (size_t)2 * c0 * k * n, d_vec + (size_t)c0 * k * n, (size_t)np * k * n * 16, cudaMemcpyDeviceToHost, cs));
         if (scalars && ns > 0) CK(cudaMemcpyAsync(scalars + (size_t)c0 * ns, d_sc + (size_t)c0 * ns, (size_t)np * ns * 8, cudaMemcpyDeviceToHost, cs));
         if (post && d_post) CK(cudaMemcpyAsync(post + (size_t)c0 * nstrips * k, d_post + (size_t)c0 * nstrips * k, (size_t)np * nstrips * k * 8, cudaMemcpyDeviceToHost, cs));
         CK(cudaMemcpyAsync(info + c0, d_info + c0, (size_t)np * 4, cudaMemcpyDeviceToHost, cs));
@@ -1652,6 +1671,11 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
                              d_vec ? (double *)(d_vec + (size_t)c0 * k * n) : nullptr, d_sc + (size_t)c0 * (ns > 0 ? ns : 1),
                              d_post ? d_post + (size_t)c0 * nstrips * k : nullptr, d_info + c0, st);
         if (rc) { cudaStreamSynchronize(cs); return rc; }
+        if (pack) {
+            const size_t cnt = (size_t)np * k * n;
+            pack_real_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d_vec + (size_t)c0 * k * n, d_pack + (size_t)c0 * k * n, cnt, d_flag);
+            LAUNCHED();
+        }
         cudaEvent_t evt;
         CK(cudaEventCreateWithFlags(&evt, cudaEventDisableTiming));
         CK(cudaEventRecord(evt, st));
@@ -1659,8 +1683,11 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
         prev_c0 = c0; prev_np = np; prev_evt = evt;
     }
     if (prev_c0 >= 0) { rc = copy_out(prev_c0, prev_np, prev_evt); if (rc) return rc; }
+    int h_flag = 0;
+    if (pack) CK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(cs));
+    if (pack && h_flag) { g_err = "real_vectors: some eigenvector has a non-zero imaginary part"; return SCQED_ECOMPLEX; }
     // a plan assumed real-symmetric produced a complex point: redo the sweep in complex mode (once)
     bool redo = false;
     for (long long q = 0; q < n_pts; ++q) if (info[q] == -2) { redo = true; break; }

@@ -532,7 +532,7 @@ class NumericalSystem:
         with _engine.Engine(plan, device=self.device) as eng:
             if want_h or resonator is not None:
                 res = eng.sweep(grid, k, want_vectors=get_vectors, resonator=resonator is not None,
-                                matrix_elements=bool(matel_specs))
+                                matrix_elements=bool(matel_specs), real_vectors="auto")
                 E, V, scal, Erwa, info = res.E, res.V, res.scalars, res.Erwa, res.info
                 col = 0
                 for method, op in zip(matel_methods, plan.aux_ops):      # :656-667,683-694 keep the real part

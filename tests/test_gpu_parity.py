@@ -422,6 +422,25 @@ def test_device_and_host_paths_agree(engine_mod):
     assert np.array_equal(host.V, V.cpu().numpy())
 
 
+def test_real_vector_output(engine_mod):
+    """opts.real_vectors: float64 eigenvectors for real symmetric H (same numbers as the complex buffer's real part),
+    SCQED_ECOMPLEX + automatic fallback when they are not real."""
+    g, plan = load_golden("c2_fluxonium_res")
+    k = int(g["k"])
+    with engine_mod.Engine(plan) as eng:
+        a = eng.sweep(g["params"], k, want_vectors=True, resonator=True)
+        b = eng.sweep(g["params"], k, want_vectors=True, resonator=True, real_vectors=True)
+    assert a.V.dtype == np.complex128 and b.V.dtype == np.float64
+    assert np.array_equal(a.V.real, b.V) and not np.any(a.V.imag)
+    assert np.array_equal(a.E, b.E) and np.array_equal(a.Erwa, b.Erwa)
+    g, plan = load_golden("c1_transmon_vec")           # complex Hermitian H: complex eigenvectors
+    with engine_mod.Engine(plan) as eng:
+        c = eng.sweep(g["params"], int(g["k"]), want_vectors=True, real_vectors="auto")
+        assert c.V.dtype == np.complex128
+        with pytest.raises(engine_mod.EngineError):
+            eng.sweep(g["params"], int(g["k"]), want_vectors=True, real_vectors=True)
+
+
 def test_dense_solver_on_small_problem_agrees(engine_mod):
     """Force the HBM dense path on a problem the fused path also solves."""
     g, plan = load_golden("c2_fluxonium")
