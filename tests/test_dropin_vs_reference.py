@@ -380,3 +380,31 @@ def test_operator_factors_match_reference():
     mine = ops.flux_basis(4)
     for a, b in zip(ref, mine):
         assert np.max(np.abs(np.abs(a) - np.abs(b))) < 1e-12
+
+
+def test_util_strip_helpers_match_reference():
+    """pycqed_b200.util against pyscqed.util on a golden Resonator result (util.py:178-240, 286-298, 393-402)."""
+    from tests.golden import make_golden as mg
+    from tests.conftest import load_golden
+    import pycqed_b200.util as mine
+    ps = mg.import_reference()
+    g, _ = load_golden("c2_fluxonium_res")
+    for p in (0, 17, 40):
+        Erwa = g["eval_getResonatorResponse"][p].T          # [level, strip] as getSweep(...)[:, :, p]
+        assert np.array_equal(mine.getResonatorShift(Erwa), ps.util.getResonatorShift(Erwa))
+        assert np.array_equal(mine.getCircuitLambShift(Erwa), ps.util.getCircuitLambShift(Erwa))
+        na, sa = ps.util.getACStarkShift(Erwa)
+        nb, sb = mine.getACStarkShift(Erwa)
+        assert np.array_equal(na, nb) and np.array_equal(sa, sb)
+    m = [np.linspace(0, 1, 5) + i for i in range(4)]
+    ra = ps.util.createSubspaceOperators(*m)
+    rb = mine.createSubspaceOperators(*m)
+    assert rb.shape == (5, 2, 2)
+    for a, b in zip(ra, rb):
+        assert np.max(np.abs(np.asarray(a) - b)) < 1e-6      # the reference stores complex64
+    sweep = np.empty((3, 2, 4), dtype=object)
+    sweep[:, 0, :] = 1.5
+    sweep[:, 1, :] = "ket"
+    Ea, Va = ps.util.getEigenValuesAndVectors(sweep)
+    Eb, Vb = mine.getEigenValuesAndVectors(sweep)
+    assert np.array_equal(Ea, Eb) and Eb.dtype == np.float64 and Vb.shape == Va.shape
