@@ -262,6 +262,185 @@ mf_d2_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const doubl
     }
 }
 
+// ---- TMA-pipelined variant for real H and real vectors (the production path of the 180 x 180 atom) --------------
+// The plain kernel above is bound by the latency of its L2 streams (X rows in the first mode product, H1 rows in
+// the second: long-scoreboard stalls at 18 % occupancy).  Here those streams go through the TMA: one thread issues
+// 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx) of D2_BK rows at a time into a D2_ST-stage shared-memory
+// ring; a "full" mbarrier per stage is completed by the copy engine, an "empty" mbarrier per stage by one arrival
+// per warp, so there is no block-wide barrier inside the mode products.  Same arithmetic, same results.
+#define D2_BK 4
+#define D2_ST 4
+
+__device__ __forceinline__ unsigned d2_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void d2_mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(d2_smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void d2_mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(d2_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void d2_tma_load(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    const unsigned b = d2_smem_addr(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d2_smem_addr(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void d2_mbar_wait(unsigned long long *bar, int parity) {
+    const unsigned b = d2_smem_addr(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "D2_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra D2_DONE_%=;\n"
+        "bra D2_WAIT_%=;\n"
+        "D2_DONE_%=:\n"
+        "}\n" ::"r"(b), "r"(parity) : "memory");
+}
+
+// One pass of the ring over `total` rows of `src` (row_bytes each): calls body(chunk rows pointer, b0, rows).
+// `it` is the running chunk counter shared by both mode products (stage = it % D2_ST, parity from it / D2_ST).
+template <typename Body>
+__device__ __forceinline__ void d2_ring(const unsigned char *src, int total, int row_bytes, unsigned char *stages,
+                                        size_t stage_bytes, unsigned long long *full, unsigned long long *empty,
+                                        int &it, int tid, Body body) {
+    const int nch = (total + D2_BK - 1) / D2_BK;
+    auto issue = [&](int c, int gi) {                      // chunk c of this pass, global chunk index gi
+        const int s = gi % D2_ST;
+        if (gi >= D2_ST) d2_mbar_wait(&empty[s], ((gi / D2_ST) - 1) & 1);      // all warps released the stage
+        const int b0 = c * D2_BK, rows = min(D2_BK, total - b0);
+        d2_tma_load(stages + s * stage_bytes, src + (size_t)b0 * row_bytes, (unsigned)(rows * row_bytes), &full[s]);
+    };
+    if (tid == 0) for (int c = 0; c < D2_ST - 1 && c < nch; ++c) issue(c, it + c);
+    for (int c = 0; c < nch; ++c) {
+        const int gi = it + c, s = gi % D2_ST;
+        if (tid == 0 && c + D2_ST - 1 < nch) issue(c + D2_ST - 1, gi + D2_ST - 1);
+        d2_mbar_wait(&full[s], (gi / D2_ST) & 1);
+        body(stages + s * stage_bytes, c * D2_BK, min(D2_BK, total - c * D2_BK));
+        __syncwarp();
+        if ((tid & 31) == 0) d2_mbar_arrive(&empty[s]);
+    }
+    it += nch;
+}
+
+// shared: ring of D2_ST stages (D2_BK * d1 * 16 B each), H0 rows [D2_RB][d0], X rows (real parts) [D2_RB][d1e],
+// coupling coefficients
+template <int MODE>
+__global__ void __launch_bounds__(256)
+mf_d2_tma_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const double *__restrict__ Hre) {
+    extern __shared__ __align__(128) unsigned char d2smem[];
+    __shared__ __align__(8) unsigned long long full[D2_ST], empty[D2_ST];
+    const long long p = blockIdx.z;
+    if (!a.active[p]) return;
+    const PlanDev &P = a.P;
+    const int d0 = P.dims[0], d1 = P.dims[1], n = a.n;
+    const int j = blockIdx.y, R0 = blockIdx.x * D2_RB, tid = threadIdx.x;
+    const int rb = min(D2_RB, d0 - R0);
+    const size_t tot = (size_t)d0 * d0 + (size_t)d1 * d1;
+    const double *H0re = Hre + p * tot, *H1re = H0re + (size_t)d0 * d0;
+    const int d1e = (d1 + 1) & ~1;
+    const size_t stage_bytes = ((size_t)D2_BK * d1 * 16 + 127) & ~(size_t)127;
+    double *sHre = (double *)(d2smem + D2_ST * stage_bytes);
+    double *sXr = sHre + (size_t)D2_RB * d0;
+    cplx *sC = (cplx *)(sXr + (size_t)D2_RB * d1e);
+    const cplx *x = X + (p * a.b + j) * n;
+    if (tid == 0) {
+        for (int s = 0; s < D2_ST; ++s) { d2_mbar_init(&full[s], 1); d2_mbar_init(&empty[s], (int)(blockDim.x >> 5)); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int q = tid; q < rb * d0; q += blockDim.x) { const int r = q / d0, c = q - r * d0; sHre[r * d0 + c] = H0re[(size_t)(R0 + r) * d0 + c]; }
+    for (int q = tid; q < rb * d1; q += blockDim.x) { const int r = q / d1; sXr[r * d1e + (q - r * d1)] = x[(size_t)R0 * d1 + q].x; }
+    for (int q = tid; q < P.d2_nmulti; q += blockDim.x) sC[q] = a.coef[p * P.n_terms + __ldg(P.d2_cidx + q)];
+    __syncthreads();
+    const int i1 = tid;
+    const bool on = i1 < d1;
+    double acc[D2_RB];
+#pragma unroll
+    for (int r = 0; r < D2_RB; ++r) acc[r] = 0.0;
+    int it = 0;
+    // Y[R0 + r][i1] += sum_b H0[R0 + r][b] X[b][i1]
+    d2_ring((const unsigned char *)x, d0, d1 * 16, d2smem, stage_bytes, full, empty, it, tid,
+            [&](const unsigned char *buf, int b0, int rows) {
+                if (!on) return;
+                const cplx *xs = (const cplx *)buf;
+                if (rows == D2_BK && (d0 & 1) == 0) {
+                    double xv[D2_BK];
+#pragma unroll
+                    for (int u = 0; u < D2_BK; ++u) xv[u] = xs[u * d1 + i1].x;
+#pragma unroll
+                    for (int r = 0; r < D2_RB; ++r) {
+                        double t = acc[r];
+#pragma unroll
+                        for (int u = 0; u < D2_BK; u += 2) {
+                            const double2 h = *(const double2 *)(sHre + r * d0 + b0 + u);
+                            t = fma(h.x, xv[u], t); t = fma(h.y, xv[u + 1], t);
+                        }
+                        acc[r] = t;
+                    }
+                } else {
+                    for (int u = 0; u < rows; ++u) {
+                        const double xv = xs[u * d1 + i1].x;
+#pragma unroll
+                        for (int r = 0; r < D2_RB; ++r) acc[r] = fma(sHre[r * d0 + b0 + u], xv, acc[r]);
+                    }
+                }
+            });
+    // Y[R0 + r][i1] += sum_b X[R0 + r][b] H1[b][i1]   (H1 real symmetric)
+    d2_ring((const unsigned char *)H1re, d1, d1 * 8, d2smem, stage_bytes, full, empty, it, tid,
+            [&](const unsigned char *buf, int b0, int rows) {
+                if (!on) return;
+                const double *hs = (const double *)buf;
+                if (rows == D2_BK) {
+                    double hv[D2_BK];
+#pragma unroll
+                    for (int u = 0; u < D2_BK; ++u) hv[u] = hs[u * d1 + i1];
+#pragma unroll
+                    for (int r = 0; r < D2_RB; ++r) {
+                        double t = acc[r];
+#pragma unroll
+                        for (int u = 0; u < D2_BK; u += 2) {
+                            const double2 v = *(const double2 *)(sXr + r * d1e + b0 + u);
+                            t = fma(hv[u], v.x, t); t = fma(hv[u + 1], v.y, t);
+                        }
+                        acc[r] = t;
+                    }
+                } else {
+                    for (int u = 0; u < rows; ++u) {
+                        const double hv = hs[u * d1 + i1];
+#pragma unroll
+                        for (int r = 0; r < D2_RB; ++r) acc[r] = fma(hv, sXr[r * d1e + b0 + u], acc[r]);
+                    }
+                }
+            });
+    if (!on) return;
+    ChebPar q;
+    double s = 0.0, t = 0.0;
+    if (MODE == 1) {
+        q = cheb_par(a.fpar + p * 4);
+        if (m == 1) s = q.sigma1 / q.e;
+        else {
+            double sigma = q.sigma1;
+            for (int u = 2; u < m; ++u) sigma = 1.0 / (2.0 / q.sigma1 - sigma);
+            const double sigma2 = 1.0 / (2.0 / q.sigma1 - sigma);
+            s = 2.0 * sigma2 / q.e;
+            t = sigma * sigma2;
+        }
+    }
+    cplx *o = out + (p * a.b + j) * n;
+#pragma unroll
+    for (int r = 0; r < D2_RB; ++r) {
+        if (r >= rb) break;
+        const int i = (R0 + r) * d1 + i1;
+        double h = acc[r];
+        if (P.d2_nmulti > 0) h += mf_apply_terms(P, P.d2_meta, 0, P.d2_nmulti, sC, x, i).x;
+        if (MODE == 0) o[i] = cmake(h, 0.0);
+        else {
+            const double yi = sXr[r * d1e + i1];
+            if (m == 1) o[i] = cmake(s * (h - q.c * yi), 0.0);
+            else o[i] = cmake(s * (h - q.c * yi) - t * o[i].x, 0.0);
+        }
+    }
+}
+
 // The whole degree-`deg` Chebyshev filter of one vector out of shared memory (n <= ~7000), two-node form with
 // REAL combined node Hamiltonians: H0, H1 and both n-vectors live on chip; y = H0 X + X H1^T + coupling costs
 // (d0 + d1) real MACs per element instead of four complex dense mode products through the ELL tables.

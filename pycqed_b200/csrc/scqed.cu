@@ -1210,6 +1210,20 @@ static int run_matfree_core(scqed_plan *pl, const cplx *coef_all, long long n_pt
         CK(cudaFuncSetAttribute(mf_d2_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_cplx));
     }
     bool d2_real = false, d2_cpl_real = false, d2_realx = false;
+    // TMA-pipelined real kernel: 1-D bulk copies need 16-byte aligned sources and sizes (rows of X and of H1)
+    size_t d2_smem_tma = 0;
+    bool d2_tma = false;
+    if (use_d2) {
+        const int d0_ = P.dims[0], d1_ = P.dims[1];
+        const size_t stage = (((size_t)D2_BK * d1_ * 16) + 127) & ~(size_t)127;
+        d2_smem_tma = D2_ST * stage + (size_t)D2_RB * d0_ * 8 + (size_t)D2_RB * ((d1_ + 1) & ~1) * 8 + (size_t)(P.d2_nmulti + 2) * 16 + 128;
+        d2_tma = (d1_ % 2 == 0) && (d0_ % 2 == 0) && (n % 1 == 0) && d2_smem_tma <= 200 * 1024 &&
+                 getenv("SCQED_D2_TMA") && atoi(getenv("SCQED_D2_TMA")) != 0;      // opt-in: measured 7 % slower than the plain kernel (35.6 vs 38.4 pts/s)
+        if (d2_tma) {
+            CK(cudaFuncSetAttribute(mf_d2_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_tma));
+            CK(cudaFuncSetAttribute(mf_d2_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_tma));
+        }
+    }
     const dim3 d2_grid_base((unsigned)((P.dims[0] + D2_RB - 1) / D2_RB), (unsigned)b, 1);
     const int d2_threads = P.n_nodes > 1 ? ((P.dims[1] + 31) / 32) * 32 : 32;
     // filter degree: 80 for the stencil filter (fewer Rayleigh-Ritz rounds per mat-vec: +4-9 % on the CSFQ sweeps),
@@ -1239,7 +1253,10 @@ static int run_matfree_core(scqed_plan *pl, const cplx *coef_all, long long n_pt
         }
         auto d2_launch = [&](int mode, const cplx *src, cplx *dst, int mstep) {
             dim3 g(d2_grid_base.x, d2_grid_base.y, (unsigned)np);
-            if (d2_real && d2_realx) {
+            if (d2_real && d2_realx && d2_tma) {
+                if (mode == 0) mf_d2_tma_kernel<0><<<g, d2_threads, d2_smem_tma, st>>>(a, src, dst, mstep, d2re);
+                else mf_d2_tma_kernel<1><<<g, d2_threads, d2_smem_tma, st>>>(a, src, dst, mstep, d2re);
+            } else if (d2_real && d2_realx) {
                 if (mode == 0) mf_d2_kernel<0, true, true><<<g, d2_threads, d2_smem_real, st>>>(a, src, dst, mstep, d2re, d2im);
                 else mf_d2_kernel<1, true, true><<<g, d2_threads, d2_smem_real, st>>>(a, src, dst, mstep, d2re, d2im);
             } else if (d2_real) {

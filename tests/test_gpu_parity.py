@@ -372,6 +372,12 @@ def test_two_node_dense_mode_products(engine_mod, monkeypatch):
     assert eig_rel_err(a.E, b.E) < E_RTOL
     for p in range(2):
         assert subspace_overlap(a.V[p].T, b.V[p].T, b.E[p]) >= 1 - 1e-7
+    # the TMA-pipelined variant of the real-vector kernel (opt-in) gives the same answers
+    monkeypatch.delenv("SCQED_NO_D2")
+    monkeypatch.setenv("SCQED_D2_TMA", "1")
+    with engine_mod.Engine(plan) as eng:
+        c = eng.sweep(pts, 6, want_vectors=True)
+    assert not c.info.any() and eig_rel_err(c.E, b.E) < E_RTOL
 
 
 @pytest.mark.parametrize("name", ["c1_transmon_vec", "c4_averin", "c6_cpb"])
