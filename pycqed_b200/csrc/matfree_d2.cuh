@@ -262,6 +262,144 @@ mf_d2_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const doubl
     }
 }
 
+// ---- FP64 tensor-core variant for real H and real vectors --------------------------------------------------------
+// Both mode products as DMMA.8x8x4 tiles (mma.sync.m8n8k4.f64; tcgen05 has no f64 kind).  A CTA owns D2_RB = 16
+// rows of Y (two 8-row tiles) and all d1 columns; warp w owns the 8-column tiles w, w + 8, w + 16, ...  The A operands
+// (H0 rows, then the X rows) come from shared memory, the B operands (X rows, then H1 rows) straight from L2 with the
+// next k-step prefetched into registers.  One DMMA carries 256 multiply-adds: 8x fewer issue slots than the DFMA
+// kernel and 12 accumulator registers per lane instead of 16-32, so four CTAs fit an SM.
+#define D2_NT 4      // column tiles per warp (8 warps x 4 x 8 = 256 columns max)
+
+__device__ __forceinline__ void d2_dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+mf_d2_dmma_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const double *__restrict__ Hre) {
+    extern __shared__ __align__(16) unsigned char d2smem[];
+    const long long p = blockIdx.z;
+    if (!a.active[p]) return;
+    const PlanDev &P = a.P;
+    const int d0 = P.dims[0], d1 = P.dims[1], n = a.n;
+    const int j = blockIdx.y, R0 = blockIdx.x * D2_RB, tid = threadIdx.x;
+    const int rb = min(D2_RB, d0 - R0);
+    const size_t tot = (size_t)d0 * d0 + (size_t)d1 * d1;
+    const double *H0re = Hre + p * tot, *H1re = H0re + (size_t)d0 * d0;
+    // pitches = 4 (mod 16) doubles: the 8 rows x 4 k of an A fragment cover the 16 64-bit banks exactly twice
+    const int d0p = d0 + ((20 - (d0 & 15)) & 15), d1p = d1 + ((20 - (d1 & 15)) & 15);
+    double *sH = (double *)d2smem;                            // [D2_RB][d0p]  H0 rows (zero beyond rb)
+    double *sXr = sH + (size_t)D2_RB * d0p;                   // [D2_RB][d1p]  real parts of the X rows
+    cplx *sC = (cplx *)(sXr + (size_t)D2_RB * d1p);
+    const cplx *x = X + (p * a.b + j) * n;
+    for (int q = tid; q < D2_RB * d0; q += blockDim.x) {
+        const int r = q / d0, c = q - r * d0;
+        sH[r * d0p + c] = r < rb ? H0re[(size_t)(R0 + r) * d0 + c] : 0.0;
+    }
+    for (int q = tid; q < D2_RB * d1; q += blockDim.x) {
+        const int r = q / d1, c = q - r * d1;
+        sXr[r * d1p + c] = r < rb ? x[(size_t)(R0 + r) * d1 + c].x : 0.0;
+    }
+    for (int q = tid; q < P.d2_nmulti; q += blockDim.x) sC[q] = a.coef[p * P.n_terms + __ldg(P.d2_cidx + q)];
+    __syncthreads();
+    const int warp = tid >> 5, l = tid & 31, ar = l >> 2, ak = l & 3;
+    const int ntiles = (d1 + 7) >> 3;
+    double c[2][D2_NT][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < D2_NT; ++nt) c[mt][nt][0] = c[mt][nt][1] = 0.0;
+    int col[D2_NT];
+#pragma unroll
+    for (int nt = 0; nt < D2_NT; ++nt) col[nt] = (warp + 8 * nt) < ntiles ? (warp + 8 * nt) * 8 + ar : -1;
+    // ---- Y[R0 + r][i1] += sum_b H0[R0 + r][b] X[b][i1] ----------------------------------------------------------------
+    {
+        double bn[D2_NT];
+#pragma unroll
+        for (int nt = 0; nt < D2_NT; ++nt) bn[nt] = (col[nt] >= 0 && col[nt] < d1 && ak < d0) ? x[(size_t)ak * d1 + col[nt]].x : 0.0;
+        for (int k0 = 0; k0 < d0; k0 += 4) {
+            double bc[D2_NT];
+#pragma unroll
+            for (int nt = 0; nt < D2_NT; ++nt) bc[nt] = bn[nt];
+            const int kn = k0 + 4 + ak;
+#pragma unroll
+            for (int nt = 0; nt < D2_NT; ++nt) bn[nt] = (col[nt] >= 0 && col[nt] < d1 && kn < d0) ? x[(size_t)kn * d1 + col[nt]].x : 0.0;
+            const int kk = k0 + ak;
+            const double a0 = kk < d0 ? sH[ar * d0p + kk] : 0.0;
+            const double a1 = kk < d0 ? sH[(8 + ar) * d0p + kk] : 0.0;
+#pragma unroll
+            for (int nt = 0; nt < D2_NT; ++nt) {
+                if (col[nt] >= 0) {
+                    d2_dmma(c[0][nt][0], c[0][nt][1], a0, bc[nt]);
+                    d2_dmma(c[1][nt][0], c[1][nt][1], a1, bc[nt]);
+                }
+            }
+        }
+    }
+    // ---- Y[R0 + r][i1] += sum_b X[R0 + r][b] H1[b][i1]   (H1 real symmetric) -------------------------------------------
+    {
+        double bn[D2_NT];
+#pragma unroll
+        for (int nt = 0; nt < D2_NT; ++nt) bn[nt] = (col[nt] >= 0 && col[nt] < d1 && ak < d1) ? H1re[(size_t)ak * d1 + col[nt]] : 0.0;
+        for (int k0 = 0; k0 < d1; k0 += 4) {
+            double bc[D2_NT];
+#pragma unroll
+            for (int nt = 0; nt < D2_NT; ++nt) bc[nt] = bn[nt];
+            const int kn = k0 + 4 + ak;
+#pragma unroll
+            for (int nt = 0; nt < D2_NT; ++nt) bn[nt] = (col[nt] >= 0 && col[nt] < d1 && kn < d1) ? H1re[(size_t)kn * d1 + col[nt]] : 0.0;
+            const int kk = k0 + ak;
+            const double a0 = kk < d1 ? sXr[ar * d1p + kk] : 0.0;
+            const double a1 = kk < d1 ? sXr[(8 + ar) * d1p + kk] : 0.0;
+#pragma unroll
+            for (int nt = 0; nt < D2_NT; ++nt) {
+                if (col[nt] >= 0) {
+                    d2_dmma(c[0][nt][0], c[0][nt][1], a0, bc[nt]);
+                    d2_dmma(c[1][nt][0], c[1][nt][1], a1, bc[nt]);
+                }
+            }
+        }
+    }
+    ChebPar q;
+    double s = 0.0, t = 0.0;
+    if (MODE == 1) {
+        q = cheb_par(a.fpar + p * 4);
+        if (m == 1) s = q.sigma1 / q.e;
+        else {
+            double sigma = q.sigma1;
+            for (int u = 2; u < m; ++u) sigma = 1.0 / (2.0 / q.sigma1 - sigma);
+            const double sigma2 = 1.0 / (2.0 / q.sigma1 - sigma);
+            s = 2.0 * sigma2 / q.e;
+            t = sigma * sigma2;
+        }
+    }
+    cplx *o = out + (p * a.b + j) * n;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int r = mt * 8 + ar;
+        if (r >= rb) continue;
+#pragma unroll
+        for (int nt = 0; nt < D2_NT; ++nt) {
+            if ((warp + 8 * nt) >= ntiles) continue;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int cc = (warp + 8 * nt) * 8 + 2 * ak + h2;
+                if (cc >= d1) continue;
+                const int i = (R0 + r) * d1 + cc;
+                double h = c[mt][nt][h2];
+                if (P.d2_nmulti > 0) h += mf_apply_terms(P, P.d2_meta, 0, P.d2_nmulti, sC, x, i).x;
+                if (MODE == 0) o[i] = cmake(h, 0.0);
+                else {
+                    const double yi = sXr[r * d1p + cc];
+                    if (m == 1) o[i] = cmake(s * (h - q.c * yi), 0.0);
+                    else o[i] = cmake(s * (h - q.c * yi) - t * o[i].x, 0.0);
+                }
+            }
+        }
+    }
+}
+
 // ---- TMA-pipelined variant for real H and real vectors (the production path of the 180 x 180 atom) --------------
 // The plain kernel above is bound by the latency of its L2 streams (X rows in the first mode product, H1 rows in
 // the second: long-scoreboard stalls at 18 % occupancy).  Here those streams go through the TMA: one thread issues

@@ -1211,8 +1211,16 @@ static int run_matfree_core(scqed_plan *pl, const cplx *coef_all, long long n_pt
     }
     bool d2_real = false, d2_cpl_real = false, d2_realx = false;
     // TMA-pipelined real kernel: 1-D bulk copies need 16-byte aligned sources and sizes (rows of X and of H1)
-    size_t d2_smem_tma = 0;
-    bool d2_tma = false;
+    size_t d2_smem_tma = 0, d2_smem_dmma = 0;
+    bool d2_tma = false, d2_dmma = false;
+    if (use_d2) {      // FP64 tensor-core kernel: the default for real H and real vectors
+        d2_smem_dmma = (size_t)D2_RB * (P.dims[0] + 16) * 8 + (size_t)D2_RB * (P.dims[1] + 16) * 8 + (size_t)(P.d2_nmulti + 2) * 16 + 64;
+        d2_dmma = P.dims[1] <= 8 * 8 * D2_NT && d2_smem_dmma <= 200 * 1024 && !getenv("SCQED_NO_D2_DMMA");
+        if (d2_dmma) {
+            CK(cudaFuncSetAttribute(mf_d2_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_dmma));
+            CK(cudaFuncSetAttribute(mf_d2_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_dmma));
+        }
+    }
     if (use_d2) {
         const int d0_ = P.dims[0], d1_ = P.dims[1];
         const size_t stage = (((size_t)D2_BK * d1_ * 16) + 127) & ~(size_t)127;
@@ -1253,7 +1261,10 @@ static int run_matfree_core(scqed_plan *pl, const cplx *coef_all, long long n_pt
         }
         auto d2_launch = [&](int mode, const cplx *src, cplx *dst, int mstep) {
             dim3 g(d2_grid_base.x, d2_grid_base.y, (unsigned)np);
-            if (d2_real && d2_realx && d2_tma) {
+            if (d2_real && d2_realx && d2_dmma) {
+                if (mode == 0) mf_d2_dmma_kernel<0><<<g, 256, d2_smem_dmma, st>>>(a, src, dst, mstep, d2re);
+                else mf_d2_dmma_kernel<1><<<g, 256, d2_smem_dmma, st>>>(a, src, dst, mstep, d2re);
+            } else if (d2_real && d2_realx && d2_tma) {
                 if (mode == 0) mf_d2_tma_kernel<0><<<g, d2_threads, d2_smem_tma, st>>>(a, src, dst, mstep, d2re);
                 else mf_d2_tma_kernel<1><<<g, d2_threads, d2_smem_tma, st>>>(a, src, dst, mstep, d2re);
             } else if (d2_real && d2_realx) {
