@@ -5,7 +5,8 @@
  * Python class API of pyscqed/numerical_system.py.  The entry points below are what a binding
  * of that path needs; each one names the reference function it replaces.  Conventions:
  *   - plain pointers and sizes only, no C++ or torch types;
- *   - every function returns 0 on success or a negative SCQED_E* code, and never throws;
+ *   - every function returns 0 on success or a negative SCQED_E* code (one positive code, SCQED_ECOMPLEX,
+ *     asks the caller to repeat a real_vectors request with a complex buffer), and never throws;
  *     scqed_last_error() returns a thread-local message for the last failure;
  *   - all *_dev pointers are device pointers owned by the caller (e.g. torch tensors),
  *     complex128 data is interleaved (re, im) doubles;
@@ -186,7 +187,8 @@ int64_t scqed_launch_count(void);
  * launching stream around the dominant kernel of a path (tag 1: small-path tridiagonalisation, real
  * symmetric; tag 2: same, complex Hermitian).  scqed_timing_read sums and clears the spans. */
 void scqed_timing_enable(int on);
-int scqed_timing_read(int tag, double *total_ms, int64_t *count);
+int scqed_timing_read(int tag, double *total_ms, int64_t *count);   /* tags: 1 / 2 real / complex tridiagonalisation,
+                                                                        3 dense assembly, 4 direct tridiagonal */
 
 /* FP64 peak probe: runs a register-resident DMMA (mma.sync m8n8k4 f64) loop on every SM and
  * returns TFLOP/s; the roofline denominator for the dense tridiagonalisation. */
