@@ -1050,7 +1050,10 @@ static int pick_dense_batch(int n, long long n_pts, int k, int sm_count) {
     size_t per = (size_t)n * n * 16 + blk_ws_bytes(n, k, 1, 64) + dense_ws_bytes(n, k, 1, 64);
     long long B = (long long)(budget / per);
     // enough matrices in flight to fill the SMs during the skinny tail of the reduction
-    long long want = n <= 512 ? 256 : (n <= 1536 ? 64 : (n <= 4096 ? 32 : 8));
+    // (the per-column kernels are launch / latency bound for small n: n = 256 runs 2.4 k matrices/s with 32 matrices
+    // per launch and 21.8 k/s with 2048)
+    long long want = n <= 512 ? 4096 : (n <= 1536 ? 512 : (n <= 4096 ? 64 : 8));
+    if (const char *e = getenv("SCQED_DENSE_BATCH")) { long long v = atoll(e); if (v >= 1) want = v; }
     if (B > want) B = want;
     if (B > n_pts) B = n_pts;
     if (B > 65535) B = 65535;
@@ -1441,7 +1444,8 @@ extern "C" int scqed_eigh_batched(int device, double *H_dev, int32_t n, int64_t 
         tmp.s1work.release(); tmp.s1vec.release();
     }
     if (!small) {
-        long long B = batch > 32 ? 32 : batch;
+        long long B = pick_dense_batch(n, batch, k, tmp.sm_count);
+        if (B < 1) return fail(SCQED_ENOMEM, "not enough device memory for one %d x %d matrix", n, n);
         int nseg = dense_nseg(n, tmp.sm_count, (int)B);
         const bool blocked = solver != 3;
         size_t wsb = blocked ? blk_ws_bytes(n, k, (int)B, nseg) : dense_ws_bytes(n, k, (int)B, nseg);
