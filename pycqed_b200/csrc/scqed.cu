@@ -825,7 +825,8 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
         if (thread_bisect) {
             const int ppw = 32 / k;
             const long long bw = (np + ppw - 1) / ppw;
-            s1_bisect_thread_kernel<<<(unsigned)((bw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, evals + (size_t)p0 * k);
+            // three-term (division-free) Sturm recurrence unless SCQED_STURM_RATIO is set
+            s1_bisect_thread_kernel<<<(unsigned)((bw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, evals + (size_t)p0 * k, getenv("SCQED_STURM_RATIO") ? 0 : 1);
         } else {
             const long long warps = np * k;
             s1_bisect_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(a, nullptr, evals + (size_t)p0 * k);

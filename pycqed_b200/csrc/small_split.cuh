@@ -321,7 +321,7 @@ s1_bisect_kernel(S1Args a, const int *__restrict__ skip, double *__restrict__ ev
 // hidden by the other warps.  The k eigenvalues of a point sit in adjacent lanes so that the loads
 // of d and e^2 are broadcasts.  Same count recurrence, tolerances and stopping rule as dstebz.
 __global__ void __launch_bounds__(128)
-s1_bisect_thread_kernel(S1Args a, const int *__restrict__ skip, double *__restrict__ evals) {
+s1_bisect_thread_kernel(S1Args a, const int *__restrict__ skip, double *__restrict__ evals, int prod) {
     const int k = a.k, n = a.n, l = threadIdx.x & 31;
     const int ppw = 32 / k;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -339,7 +339,7 @@ s1_bisect_thread_kernel(S1Args a, const int *__restrict__ skip, double *__restri
         if (width <= tol) break;
         const double x = lo + 0.5 * width;
         if (!(x > lo && x < hi)) break;                       // at resolution
-        if (sturm_count(d, e2, n, x, pivmin) >= j + 1) hi = x; else lo = x;
+        if ((prod ? sturm_count_prod(d, e2, n, x) : sturm_count(d, e2, n, x, pivmin)) >= j + 1) hi = x; else lo = x;
     }
     const double v = 0.5 * (lo + hi);
     a.W.lam[p * k + j] = v;
