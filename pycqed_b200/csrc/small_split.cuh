@@ -461,15 +461,44 @@ s1_backtr_kernel(S1Args a, const int *__restrict__ skip, long long G, cplx *__re
 #pragma unroll
             for (int q = 0; q < RQ; ++q) nfmac(dot[u], v[q], x[q][u]);      // v^H x
         }
+        if constexpr (sizeof(T) == sizeof(double) && S1_KV == 8) {
+            // transpose-reduce: 8 partial dots over 32 lanes in 4 + 2 + 1 + 1 + 1 exchanges (each stage halves the
+            // number of live values), then 8 broadcasts -- 17 shuffles instead of 40
+            double e4[4], e2[2], g;
+            const bool b16 = l & 16, b8 = l & 8, b4 = l & 4;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+            for (int u = 0; u < 4; ++u) {
+                const double send = b16 ? dot[u] : dot[u + 4];
+                const double keep = b16 ? dot[u + 4] : dot[u];
+                e4[u] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
 #pragma unroll
-            for (int u = 0; u < S1_KV; ++u) {
-                if constexpr (sizeof(T) == sizeof(double)) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
-                else {
-                    cplx *dc = (cplx *)&dot[u];
-                    dc->x += __shfl_xor_sync(0xffffffffu, dc->x, o);
-                    dc->y += __shfl_xor_sync(0xffffffffu, dc->y, o);
+            for (int u = 0; u < 2; ++u) {
+                const double send = b8 ? e4[u] : e4[u + 2];
+                const double keep = b8 ? e4[u + 2] : e4[u];
+                e2[u] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            {
+                const double send = b4 ? e2[0] : e2[1];
+                const double keep = b4 ? e2[1] : e2[0];
+                g = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            g += __shfl_xor_sync(0xffffffffu, g, 2);
+            g += __shfl_xor_sync(0xffffffffu, g, 1);
+            // lane with bits (16, 8, 4) = (u2, u1, u0) holds dot u = 4 u2 + 2 u1 + u0
+#pragma unroll
+            for (int u = 0; u < 8; ++u) dot[u] = __shfl_sync(0xffffffffu, g, ((u & 4) ? 16 : 0) | ((u & 2) ? 8 : 0) | ((u & 1) ? 4 : 0));
+        } else {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int u = 0; u < S1_KV; ++u) {
+                    if constexpr (sizeof(T) == sizeof(double)) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
+                    else {
+                        cplx *dc = (cplx *)&dot[u];
+                        dc->x += __shfl_xor_sync(0xffffffffu, dc->x, o);
+                        dc->y += __shfl_xor_sync(0xffffffffu, dc->y, o);
+                    }
                 }
             }
         }
