@@ -79,10 +79,6 @@ typedef struct {
     const int32_t *dense_re;        /* [n_dense]                                             */
     const int32_t *dense_im;        /* [n_dense]                                             */
     const double *dense_gmax;       /* [n_dense] max |G_g|                                   */
-    /* Nodes solved in a rotated basis (oscillator nodes whose impedance is swept, numerical_system.py:378-393:
-     * the plan's factors of node xform_node[i] are expressed in the eigenbasis of a + a^dagger).  Eigenvectors
-     * are rotated back on that tensor mode with the real orthogonal d x d matrix W_i (row-major,
-     * concatenated in xform_data) before they are returned. */
     /* Optional entry list for scqed_assemble_dense (pattern of H expanded once): entry e is position
      * ent_key[e] = i*n + j (sorted, distinct) and H[i][j] = sum over pairs q in [ent_ptr[e], ent_ptr[e+1]) of
      * c[ent_term[q]] * ent_val[q].  ent_dense != 0: the pattern covers >= 25 % of the matrix (one thread per
@@ -93,6 +89,10 @@ typedef struct {
     const int32_t *ent_ptr;         /* [n_entries + 1]                                       */
     const int32_t *ent_term;        /* [ent_ptr[n_entries]]                                  */
     const double *ent_val;          /* complex [ent_ptr[n_entries]]                          */
+    /* Nodes solved in a rotated basis (oscillator nodes whose impedance is swept, numerical_system.py:378-393:
+     * the plan's factors of node xform_node[i] are expressed in the eigenbasis of a + a^dagger).  Eigenvectors
+     * are rotated back on that tensor mode with the real orthogonal d x d matrix W_i (row-major,
+     * concatenated in xform_data) before they are returned. */
     int32_t n_xform;
     const int32_t *xform_node;      /* [n_xform]                                             */
     const double *xform_data;       /* concatenated W_i, d_i * d_i doubles each              */
@@ -125,7 +125,8 @@ typedef struct {
 
 #define SCQED_ECOMPLEX 1   /* real_vectors requested but some eigenvector has a non-zero imaginary part */
 
-/* Create / destroy.  Uploads the tables to `device`. */
+/* Create / destroy.  Uploads the tables to `device`.  No entry point of this library changes the caller's
+ * current CUDA device (it is saved and restored). */
 int  scqed_plan_create(const scqed_plan_desc *desc, int device, scqed_plan **plan_out);
 void scqed_plan_destroy(scqed_plan *plan);
 int  scqed_plan_hilbert_dim(const scqed_plan *plan);
@@ -155,8 +156,14 @@ int scqed_sweep_run(scqed_plan *plan, const scqed_sweep_opts *opts, const double
                     int64_t n_pts, double *evals_dev, double *evecs_dev, double *scalars_dev,
                     double *post_dev, int32_t *info_dev, void *stream);
 
-/* Same with HOST buffers: copies params in, results out (pinned staging inside the library).
- * This is the call the Python drop-in makes for one GPU shard. */
+/* Same with HOST buffers: copies params in, results out.  This is the call the Python drop-in makes for one
+ * GPU shard.  The sweep is cut into 2-3 chunks; the results of chunk c travel while chunk c+1 is solved.
+ * Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory; detected per buffer with
+ * cudaPointerGetAttributes) are written directly by the DMA engine.  PAGEABLE caller buffers go through a
+ * library-owned page-locked staging ring (two slots of <= 256 MB, allocated once per plan and kept): the GPU
+ * copies into a slot asynchronously and a host thread moves the slot into the caller's array (multi-threaded
+ * memcpy) while the next chunk is solved.  The caller's current CUDA device is left unchanged.  Thread-safe
+ * for different plans (one host thread per GPU is how a single process drives several GPUs). */
 int scqed_sweep_run_host(scqed_plan *plan, const scqed_sweep_opts *opts, const double *params,
                          int64_t n_pts, double *evals, double *evecs, double *scalars,
                          double *post, int32_t *info);

@@ -23,7 +23,7 @@ directly, same entry points as the reference).
 Parity pinning: the reference has NO tests or golden vectors for this path,
 so the oracle is pinned against outputs of the reference itself, run unmodified in the build
 container over ``oracle/shims`` -- see ``tests/golden/make_golden.py`` and
-``tests/test_oracle_vs_reference.py``.
+``tests/test_oracle_golden.py`` / ``tests/test_dropin_vs_reference.py``.
 """
 from __future__ import annotations
 
@@ -315,17 +315,26 @@ def cluster_indices(E, rtol=1e-7, atol=1e-9):
     return groups
 
 
-def subspace_overlap(Va, Vb, E, rtol=1e-7, atol=1e-9):
+def subspace_overlap(Va, Vb, E, rtol=1e-7, atol=1e-9, E_next=None):
     """min over degenerate clusters of the smallest singular value of Va_c^H Vb_c
     (== |<a|b>| for a non-degenerate level; invariant under phase and rotation inside a
-    degenerate subspace).  When only the lowest k < n levels are given, the cluster containing
-    level k-1 is skipped: its partner(s) may be level k, k+1, ... (the floating CSFQ has exact
-    doublets that the k-truncation cuts), in which case any vector of the eigenspace is correct."""
+    degenerate subspace).
+
+    The cluster containing level k-1 is compared like every other one UNLESS the k-truncation cuts it:
+    ``E_next`` (the reference's level k, i.e. the first one not returned) tells.  The floating CSFQ has
+    exact doublets; when the partner of level k-1 is level k any vector of that eigenspace is a correct
+    answer and only the residual can be checked.  Without ``E_next`` (k == n, nothing is cut) every
+    cluster is compared; for k < n ``E_next`` is required."""
     worst = 1.0
     k = Va.shape[1]
-    for g in cluster_indices(np.asarray(E), rtol, atol):
+    E = np.asarray(E, dtype=np.float64)
+    if k < Va.shape[0] and E_next is None:
+        raise ValueError("subspace_overlap: pass E_next (the reference's level k) when k < n")
+    for g in cluster_indices(E, rtol, atol):
         if g[-1] == k - 1 and k < Va.shape[0]:
-            continue
+            nxt = float(np.atleast_1d(E_next)[0])
+            if abs(nxt - E[k - 1]) <= atol + rtol * max(abs(nxt), abs(E[k - 1])):
+                continue                    # the truncation cuts a degenerate cluster
         S = np.linalg.svd(Va[:, g].conj().T @ Vb[:, g], compute_uv=False)
         worst = min(worst, float(S.min()))
     return worst

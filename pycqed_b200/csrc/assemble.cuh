@@ -43,7 +43,7 @@ __device__ __forceinline__ void digits(const PlanDev &P, int idx, int *d) {
 #define ASM_TC 128
 // grid.x = n_pts * row_tiles * col_tiles ; block = 128 threads, each owns one column of the tile
 // and walks ASM_TR rows, so a warp stores 512 contiguous bytes per row.
-__global__ void __launch_bounds__(ASM_TC)
+static __global__ void __launch_bounds__(ASM_TC)
 assemble_dense_kernel(PlanDev P, const cplx *__restrict__ coef_all, long long n_pts, int tidyup,
                       cplx *__restrict__ H) {
     extern __shared__ cplx s_coef[];
@@ -78,7 +78,7 @@ assemble_dense_kernel(PlanDev P, const cplx *__restrict__ coef_all, long long n_
 // sum_q c[term_q] * val_q -- every structural non-zero is written exactly once, 16 n^2 B/pt of HBM
 // writes and no per-element term walk.  grid = (point groups, entry blocks).
 #define ASM_PG 8      // points served by one block: the pattern tables are read once per ASM_PG points
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 assemble_entries_kernel(PlanDev P, const cplx *__restrict__ coef_all, long long n_pts, int tidyup, cplx *__restrict__ H) {
     extern __shared__ cplx s_coef[];                       // [ASM_PG][n_terms]
     const long long p0 = (long long)blockIdx.x * ASM_PG;
@@ -109,7 +109,7 @@ assemble_entries_kernel(PlanDev P, const cplx *__restrict__ coef_all, long long 
 // stores, element -> entry through a 4-byte map; structural zeros are written directly.  A block serves
 // ASM_PG consecutive points: the entry's (term, value) pairs are read once and applied to the ASM_PG
 // coefficient rows staged in shared memory, so the table traffic per stored element drops ASM_PG-fold.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 assemble_mapped_kernel(PlanDev P, const cplx *__restrict__ coef_all, long long n_pts, int tidyup, cplx *__restrict__ H) {
     extern __shared__ cplx s_coef[];                       // [ASM_PG][n_terms]
     const long long p0 = (long long)blockIdx.x * ASM_PG;

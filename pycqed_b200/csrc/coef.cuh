@@ -27,7 +27,7 @@ __device__ __forceinline__ double powi(double x, int n) {
     return neg ? 1.0 / r : r;
 }
 
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 coef_eval_kernel(PlanDev P, const double *__restrict__ params, long long n_pts,
                  double *__restrict__ regs, cplx *__restrict__ coef, double *__restrict__ scalars,
                  cplx *__restrict__ auxcoef, double *__restrict__ dcoef) {

@@ -1,0 +1,254 @@
+// dense.cu -- host side of S2: batches of dense Hermitian matrices through HBM (dense_blocked.cuh: blocked
+// tridiagonalisation with DMMA rank-2k updates; dense_eigh.cuh: the unblocked cross-check).
+#include "internal.h"
+#include "tridiag_eig.cuh"
+#include "dense_eigh.cuh"
+#include "dense_blocked.cuh"
+
+// S2 on a batch of B column-major matrices already resident in A.
+struct DenseWs {
+    cplx *vbuf, *wbuf, *part, *tau;
+    double *dd, *ee, *e2, *Z, *lu;
+    int nseg;
+};
+
+static size_t dense_ws_bytes(int n, int k, int B, int nseg) {
+    size_t per = (size_t)4 * n + (size_t)((n + 7) / 8);
+    size_t b = 0;
+    b += (size_t)B * n * 16 * 3;                 // vbuf, wbuf, tau
+    b += (size_t)B * nseg * n * 16;              // part
+    b += (size_t)B * n * 8 * 3;                  // dd, ee, e2
+    b += (size_t)B * k * n * 8;                  // Z
+    b += (size_t)B * k * per * 8;                // lu
+    return b + 4096;
+}
+
+static void dense_ws_carve(unsigned char *p, int n, int k, int B, int nseg, DenseWs *w) {
+    size_t per = (size_t)4 * n + (size_t)((n + 7) / 8);
+    auto take = [&](size_t bytes) { unsigned char *r = p; p += (bytes + 255) & ~(size_t)255; return r; };
+    w->vbuf = (cplx *)take((size_t)B * n * 16);
+    w->wbuf = (cplx *)take((size_t)B * n * 16);
+    w->tau = (cplx *)take((size_t)B * n * 16);
+    w->part = (cplx *)take((size_t)B * nseg * n * 16);
+    w->dd = (double *)take((size_t)B * n * 8);
+    w->ee = (double *)take((size_t)B * n * 8);
+    w->e2 = (double *)take((size_t)B * n * 8);
+    w->Z = (double *)take((size_t)B * k * n * 8);
+    w->lu = (double *)take((size_t)B * k * per * 8);
+    w->nseg = nseg;
+}
+
+static int dense_nseg(int n, int sm_count, int B) {
+    int rows = (n + D2_HEMV_ROWS - 1) / D2_HEMV_ROWS;
+    int want = (2 * sm_count + rows * B - 1) / (rows * B);
+    int floor_ = (n + 383) / 384;          // keeps the per-CTA column segment (80 B/col of smem) under 32 KB
+    if (want < floor_) want = floor_;
+    if (want < 1) want = 1;
+    if (want > 64) want = 64;
+    return want;
+}
+
+static int run_dense_batch(scqed_plan *pl, int sm_count, cplx *A, int n, int B, int k, int want_vec, int conj_out,
+                           const DenseWs &w, double *evals, cplx *evecs, int *info, cudaStream_t st) {
+    (void)pl;
+    for (int j = 0; j < n - 1; ++j) {
+        int m = n - j - 1;
+        d2_hh_gen<<<dim3(1, B), D2_THREADS, 0, st>>>(A, n, j, w.vbuf, w.dd, w.ee, w.tau);
+        int rows = (m + D2_HEMV_ROWS - 1) / D2_HEMV_ROWS;
+        int nseg = w.nseg;
+        if (nseg > m) nseg = m;
+        int seg = (m + nseg - 1) / nseg;
+        d2_hemv<<<dim3(rows, nseg, B), D2_HEMV_ROWS, (size_t)seg * 16, st>>>(A, n, j, w.vbuf, w.part, nseg);
+        d2_hh_w<<<dim3(1, B), D2_THREADS, 0, st>>>(n, j, w.vbuf, w.part, nseg, w.tau, w.wbuf);
+        int colb = (m + D2_R2_COLS - 1) / D2_R2_COLS;
+        d2_rank2<<<dim3(rows, colb, B), D2_HEMV_ROWS, 0, st>>>(A, n, j, w.vbuf, w.wbuf, w.tau, w.dd);
+        g_launches.fetch_add(4, std::memory_order_relaxed);
+    }
+    CK(cudaGetLastError());
+    tridiag_eig_kernel<<<B, 256, (size_t)k * 8, st>>>(w.dd, w.ee, n, k, want_vec, evals, w.Z, w.lu, k, w.e2, info);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    if (want_vec) {
+        CK(cudaFuncSetAttribute(d2_backtransform, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if ((size_t)n * 16 > 200 * 1024) return fail(SCQED_EUNSUPPORTED, "n=%d too large for the dense back-transformation", n);
+        d2_backtransform<<<dim3(k, B), D2_THREADS, (size_t)n * 16, st>>>(A, n, k, w.tau, w.Z, evecs, conj_out);
+        LAUNCHED();
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+// ---- S2b: blocked zlatrd + DMMA her2k -------------------------------------------------------------
+struct BlkWs {
+    BlkBufs K;
+    double *e2, *Z, *lu;
+    cplx *Ypart;
+};
+
+static size_t blk_ws_bytes(int n, int k, int B, int nseg) {
+    size_t nrb = (n + BLK_ROWS - 1) / BLK_ROWS, np = (n - 1 + BLK_NB - 1) / BLK_NB;
+    size_t per = (size_t)4 * n + (size_t)((n + 7) / 8);
+    size_t b = 0;
+    b += (size_t)B * n * BLK_NB * 16 * 3;          // Vp, Wp, G
+    b += (size_t)B * n * 16 * 2;                   // acol, tau
+    b += (size_t)B * nrb * 8;                      // normpart
+    b += (size_t)B * nseg * n * 16;                // part
+    b += (size_t)B * nrb * n * 16;                 // cpart
+    b += (size_t)B * nrb * BLK_NB * 16 * 2;        // s1part, s2part
+    b += (size_t)B * nrb * nseg * 8;               // vAvpart
+    b += (size_t)B * np * BLK_NB * BLK_NB * 16;    // Tbuf
+    b += (size_t)B * n * 8 * 3;                    // dd, ee, e2
+    b += (size_t)B * k * n * 8;                    // Z
+    b += (size_t)B * k * per * 8;                  // lu
+    b += (size_t)B * nrb * BLK_NB * k * 16;        // Ypart
+    return b + 24 * 256 + 4096;
+}
+
+static void blk_ws_carve(unsigned char *p, cplx *A, int n, int k, int B, int nseg, BlkWs *w) {
+    size_t nrb = (n + BLK_ROWS - 1) / BLK_ROWS, np = (n - 1 + BLK_NB - 1) / BLK_NB;
+    size_t per = (size_t)4 * n + (size_t)((n + 7) / 8);
+    auto take = [&](size_t bytes) { unsigned char *r = p; p += (bytes + 255) & ~(size_t)255; return r; };
+    BlkBufs &K = w->K;
+    K.A = A;
+    K.Vp = (cplx *)take((size_t)B * n * BLK_NB * 16);
+    K.Wp = (cplx *)take((size_t)B * n * BLK_NB * 16);
+    K.G = (cplx *)take((size_t)B * n * BLK_NB * 16);
+    K.acol = (cplx *)take((size_t)B * n * 16);
+    K.tau = (cplx *)take((size_t)B * n * 16);
+    K.normpart = (double *)take((size_t)B * nrb * 8);
+    K.part = (cplx *)take((size_t)B * nseg * n * 16);
+    K.cpart = (cplx *)take((size_t)B * nrb * n * 16);
+    K.s1part = (cplx *)take((size_t)B * nrb * BLK_NB * 16);
+    K.s2part = (cplx *)take((size_t)B * nrb * BLK_NB * 16);
+    K.vAvpart = (double *)take((size_t)B * nrb * nseg * 8);
+    K.Tbuf = (cplx *)take((size_t)B * np * BLK_NB * BLK_NB * 16);
+    K.dd = (double *)take((size_t)B * n * 8);
+    K.ee = (double *)take((size_t)B * n * 8);
+    w->e2 = (double *)take((size_t)B * n * 8);
+    w->Z = (double *)take((size_t)B * k * n * 8);
+    w->lu = (double *)take((size_t)B * k * per * 8);
+    w->Ypart = (cplx *)take((size_t)B * nrb * BLK_NB * k * 16);
+    K.n = n; K.nseg = nseg; K.nrb = (int)nrb; K.npanels = (int)np;
+}
+
+static int run_dense_blocked_batch(cplx *A, int n, int B, int k, int want_vec, int conj_out, BlkWs &w, double *evals,
+                                   cplx *evecs, int *info, cudaStream_t st) {
+    BlkBufs K = w.K;
+    K.A = A;
+    if (k > BLK_KMAX && want_vec) return fail(SCQED_EUNSUPPORTED, "blocked dense path supports k <= %d eigenvectors", BLK_KMAX);
+    const int seg_max = (n + K.nseg - 1) / K.nseg;
+    blk_w_nextcol<<<dim3(K.nrb, B), BLK_ROWS, 0, st>>>(K, -1, -1);
+    LAUNCHED();
+    for (int p = 0; p < K.npanels; ++p) {
+        const int j0 = p * BLK_NB;
+        const int nbp = (n - 1) - j0 < BLK_NB ? (n - 1) - j0 : BLK_NB;
+        for (int i = 0; i < nbp; ++i) {
+            blk_reflect_hemv<<<dim3(K.nrb, K.nseg, B), BLK_ROWS, (size_t)seg_max * 16 * 5, st>>>(K, j0 + i, i);
+            blk_w_nextcol<<<dim3(K.nrb, B), BLK_ROWS, 0, st>>>(K, j0 + i, i);
+        }
+        g_launches.fetch_add(2 * nbp, std::memory_order_relaxed);
+        const int j1 = j0 + nbp;
+        if (p + 1 < K.npanels && j1 < n) {
+            int tiles = (n - j1 + H2K_TILE - 1) / H2K_TILE;
+            blk_her2k_dmma<<<dim3(tiles, tiles, B), 256, 0, st>>>(K, j1, nbp);
+            LAUNCHED();
+        }
+    }
+    CK(cudaGetLastError());
+    tridiag_eig_kernel<<<B, 256, (size_t)k * 8, st>>>(K.dd, K.ee, n, k, want_vec, evals, w.Z, w.lu, k, w.e2, info);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    if (want_vec) {
+        blk_build_T<<<dim3(K.npanels, B), 32, 0, st>>>(K);
+        size_t total = (size_t)B * k * n;
+        blk_init_x<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w.Z, evecs, total);
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+        for (int p = K.npanels - 1; p >= 0; --p) {
+            blk_bt_dots<<<dim3(K.nrb, B), BLK_ROWS, 0, st>>>(K, p, k, evecs, w.Ypart);
+            blk_bt_apply<<<dim3(K.nrb, B), BLK_ROWS, (size_t)2 * BLK_NB * k * 16, st>>>(K, p, k, evecs, w.Ypart);
+        }
+        g_launches.fetch_add(2 * K.npanels, std::memory_order_relaxed);
+        if (conj_out) { blk_conj_x<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(evecs, total); LAUNCHED(); }
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+static int pick_dense_batch(int n, long long n_pts, int k, int sm_count) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
+    size_t budget = free_b / 2;
+    size_t per = (size_t)n * n * 16 + blk_ws_bytes(n, k, 1, 64) + dense_ws_bytes(n, k, 1, 64);
+    long long B = (long long)(budget / per);
+    // enough matrices in flight to fill the SMs during the skinny tail of the reduction
+    // (the per-column kernels are launch / latency bound for small n: n = 256 runs 2.4 k matrices/s with 32 matrices
+    // per launch and 21.8 k/s with 2048)
+    long long want = n <= 512 ? 4096 : (n <= 1536 ? 512 : (n <= 4096 ? 64 : 8));
+    if (const char *e = getenv("SCQED_DENSE_BATCH")) { long long v = atoll(e); if (v >= 1) want = v; }
+    if (B > want) B = want;
+    if (B > n_pts) B = n_pts;
+    if (B > 65535) B = 65535;
+    if (B < 1) B = 0;
+    (void)sm_count;
+    return (int)B;
+}
+
+
+// scqed_eigh_batched, dense part: `batch` caller matrices (row-major = column-major storage of conj(H): same
+// spectrum, conjugated eigenvectors) solved in batches sized from free memory.  `tmp` carries device
+// properties and the workspace buffer.
+int dense_eigh_resident(scqed_plan *tmp, cplx *H_dev, int n, long long batch, int k, int want_vec, double *evals,
+                        cplx *evecs, int *info, int solver, cudaStream_t st) {
+    long long B = pick_dense_batch(n, batch, k, tmp->sm_count);
+    if (B < 1) return fail(SCQED_ENOMEM, "not enough device memory for one %d x %d matrix", n, n);
+    int nseg = dense_nseg(n, tmp->sm_count, (int)B);
+    const bool blocked = solver != 3;
+    size_t wsb = blocked ? blk_ws_bytes(n, k, (int)B, nseg) : dense_ws_bytes(n, k, (int)B, nseg);
+    if (tmp->work.ensure(wsb)) return fail(SCQED_ENOMEM, "dense workspace");
+    DenseWs w;
+    BlkWs bw;
+    if (blocked) blk_ws_carve((unsigned char *)tmp->work.p, nullptr, n, k, (int)B, nseg, &bw);
+    else dense_ws_carve((unsigned char *)tmp->work.p, n, k, (int)B, nseg, &w);
+    int rc = 0;
+    for (long long b0 = 0; b0 < batch && !rc; b0 += B) {
+        int nb = (int)(batch - b0 < B ? batch - b0 : B);
+        cplx *Ab = H_dev + (size_t)b0 * n * n;
+        double *ev = evals + (size_t)b0 * k;
+        cplx *vec = evecs ? evecs + (size_t)b0 * k * n : nullptr;
+        rc = blocked ? run_dense_blocked_batch(Ab, n, nb, k, want_vec, 1, bw, ev, vec, info + b0, st)
+                     : run_dense_batch(tmp, tmp->sm_count, Ab, n, nb, k, want_vec, 1, w, ev, vec, info + b0, st);
+    }
+    return rc;
+}
+
+// scqed_sweep_run, S2: assemble B matrices at a time into HBM (K2) and reduce them.
+int dense_sweep(scqed_plan *pl, const cplx *coef, long long n_pts, int k, int want_vec, int tidyup, int solver,
+                double *evals, cplx *vecs, int *info, cudaStream_t st) {
+    const PlanDev &P = pl->P;
+    const int n = P.n;
+    const bool blocked = solver != 3;
+    int B = pick_dense_batch(n, n_pts, k, pl->sm_count);
+    if (B < 1) return fail(SCQED_ENOMEM, "not enough device memory for one %d x %d matrix", n, n);
+    int nseg = dense_nseg(n, pl->sm_count, B);
+    size_t a_bytes = ((size_t)B * n * n * 16 + 255) & ~(size_t)255;
+    size_t wsb = blocked ? blk_ws_bytes(n, k, B, nseg) : dense_ws_bytes(n, k, B, nseg);
+    if (pl->work.ensure(a_bytes + wsb)) return fail(SCQED_ENOMEM, "dense workspace (B=%d)", B);
+    cplx *A = (cplx *)pl->work.p;
+    DenseWs w;
+    BlkWs bw;
+    if (blocked) blk_ws_carve((unsigned char *)pl->work.p + a_bytes, A, n, k, B, nseg, &bw);
+    else dense_ws_carve((unsigned char *)pl->work.p + a_bytes, n, k, B, nseg, &w);
+    for (long long p0 = 0; p0 < n_pts; p0 += B) {
+        int nb = (int)(n_pts - p0 < B ? n_pts - p0 : B);
+        // The assembly writes row-major H.  Read column-major, that buffer is H^T = conj(H): same
+        // eigenvalues, conjugated eigenvectors -> conj_out = 1 restores them.
+        int rc = run_assemble(pl, coef + (size_t)p0 * P.n_terms, nb, tidyup, A, st);
+        if (rc) return rc;
+        double *ev = evals + (size_t)p0 * k;
+        cplx *vec = vecs ? vecs + (size_t)p0 * k * n : nullptr;
+        rc = blocked ? run_dense_blocked_batch(A, n, nb, k, want_vec, 1, bw, ev, vec, info + p0, st)
+                     : run_dense_batch(pl, pl->sm_count, A, n, nb, k, want_vec, 1, w, ev, vec, info + p0, st);
+        if (rc) return rc;
+    }
+    return 0;
+}

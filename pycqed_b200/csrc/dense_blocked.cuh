@@ -68,7 +68,7 @@ __device__ __forceinline__ void blk_reflector(cplx alpha, double xn, cplx &tj, d
 // an element A[r][c] (r > c) serves y_r += A[r][c] v_c in the owning thread and
 // y_c += conj(A[r][c]) v_r through a warp shuffle reduction, so the kernel moves 8 m^2 bytes per
 // column instead of 16 m^2.
-__global__ void __launch_bounds__(BLK_ROWS)
+static __global__ void __launch_bounds__(BLK_ROWS)
 blk_reflect_hemv(BlkBufs K, int c, int i) {
     extern __shared__ cplx s_dyn[];               // s_v[seg] | colacc[4][seg]
     __shared__ double red[32];
@@ -184,7 +184,7 @@ blk_reflect_hemv(BlkBufs K, int c, int i) {
 }
 
 // grid (NRB, B), block BLK_ROWS.  i = -1: only load column 0 (start of the reduction).
-__global__ void __launch_bounds__(BLK_ROWS)
+static __global__ void __launch_bounds__(BLK_ROWS)
 blk_w_nextcol(BlkBufs K, int c, int i) {
     __shared__ cplx s1[BLK_NB], s2[BLK_NB], vrow[BLK_NB + 1], wrow[BLK_NB + 1];
     __shared__ double red[32];
@@ -280,7 +280,7 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 #define H2K_TK 8
 #define H2K_LD 12          // row stride (doubles): 2*12 = 24 words -> rows 0..3 hit distinct 8-word groups
 // grid (tiles, tiles, B), 256 threads.  C[j1+.., j1+..] -= V W^H + W V^H over panel columns [0, nbp)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 blk_her2k_dmma(BlkBufs K, int j1, int nbp) {
     __shared__ double S[8][H2K_TILE][H2K_LD];   // 0..3: row side vr, vi, wr, wi ; 4..7: col side
     if (blockIdx.y > blockIdx.x) return;          // only the lower triangle is ever read again
@@ -362,7 +362,7 @@ blk_her2k_dmma(BlkBufs K, int j1, int nbp) {
 // ---- compact-WY back-transformation ---------------------------------------------------------------
 // T of every panel: T[0:i, i] = -tau_i T[0:i,0:i] G[0:i, i], T[i,i] = tau_i (zlarft, forward columnwise)
 // grid (npanels, B), block 32 (one warp).
-__global__ void __launch_bounds__(32)
+static __global__ void __launch_bounds__(32)
 blk_build_T(BlkBufs K) {
     __shared__ cplx T[BLK_NB][BLK_NB + 1];
     const int n = K.n, p = blockIdx.x, b = blockIdx.y, l = threadIdx.x;
@@ -388,7 +388,7 @@ blk_build_T(BlkBufs K) {
 
 // Y partial = V_p^H X over this block's rows.  grid (NRB, B), block 128. Ypart [B][NRB][NB][k]
 #define BLK_KMAX 64
-__global__ void __launch_bounds__(BLK_ROWS)
+static __global__ void __launch_bounds__(BLK_ROWS)
 blk_bt_dots(BlkBufs K, int p, int k, const cplx *__restrict__ X, cplx *__restrict__ Ypart) {
     __shared__ double sred[4][BLK_KMAX][2];
     const int n = K.n, b = blockIdx.y, rb = blockIdx.x, tid = threadIdx.x;
@@ -418,7 +418,7 @@ blk_bt_dots(BlkBufs K, int p, int k, const cplx *__restrict__ X, cplx *__restric
 }
 
 // X_rows -= V_p (T_p Y).  grid (NRB, B), block 128
-__global__ void __launch_bounds__(BLK_ROWS)
+static __global__ void __launch_bounds__(BLK_ROWS)
 blk_bt_apply(BlkBufs K, int p, int k, cplx *__restrict__ X, const cplx *__restrict__ Ypart) {
     extern __shared__ cplx sm[];          // Y [NB][k], TY [NB][k]
     const int n = K.n, b = blockIdx.y, rb = blockIdx.x, tid = threadIdx.x;
@@ -458,11 +458,11 @@ blk_bt_apply(BlkBufs K, int p, int k, cplx *__restrict__ X, const cplx *__restri
 }
 
 // X[b][jv][:] = Z (real) ; and the final optional conjugation
-__global__ void blk_init_x(const double *__restrict__ Z, cplx *__restrict__ X, size_t total) {
+static __global__ void blk_init_x(const double *__restrict__ Z, cplx *__restrict__ X, size_t total) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < total) X[i] = cmake(Z[i], 0.0);
 }
-__global__ void blk_conj_x(cplx *__restrict__ X, size_t total) {
+static __global__ void blk_conj_x(cplx *__restrict__ X, size_t total) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < total) X[i].y = -X[i].y;
 }

@@ -35,7 +35,7 @@ __device__ __forceinline__ double block_sum256(double v, double *red) {
 }
 
 // grid (1, B).  Generates reflector j; writes v to vbuf[b][0..m) (v[0] = 1) and into the column.
-__global__ void __launch_bounds__(D2_THREADS)
+static __global__ void __launch_bounds__(D2_THREADS)
 d2_hh_gen(cplx *A, int n, int j, cplx *vbuf, double *dd, double *ee, cplx *tau) {
     __shared__ double red[32];
     const int b = blockIdx.y;
@@ -77,7 +77,7 @@ d2_hh_gen(cplx *A, int n, int j, cplx *vbuf, double *dd, double *ee, cplx *tau) 
 
 // grid (row_blocks, nseg, B), block 128: part[b][seg][r] = sum_{c in seg} A22[r][c] v[c]
 #define D2_HEMV_ROWS 128
-__global__ void __launch_bounds__(D2_HEMV_ROWS)
+static __global__ void __launch_bounds__(D2_HEMV_ROWS)
 d2_hemv(const cplx *__restrict__ A, int n, int j, const cplx *__restrict__ vbuf, cplx *__restrict__ part, int nseg) {
     extern __shared__ cplx s_v[];
     const int b = blockIdx.z, m = n - j - 1;
@@ -101,7 +101,7 @@ d2_hemv(const cplx *__restrict__ A, int n, int j, const cplx *__restrict__ vbuf,
 }
 
 // grid (1, B): p = tau * sum_seg part ; w = p - 1/2 tau (p^H v) v
-__global__ void __launch_bounds__(D2_THREADS)
+static __global__ void __launch_bounds__(D2_THREADS)
 d2_hh_w(int n, int j, const cplx *vbuf, const cplx *part, int nseg, const cplx *tau, cplx *wbuf) {
     __shared__ double red[64];
     const int b = blockIdx.y, m = n - j - 1;
@@ -124,7 +124,7 @@ d2_hh_w(int n, int j, const cplx *vbuf, const cplx *part, int nseg, const cplx *
 
 // grid (row_blocks, col_blocks, B), block 128 rows x 16 columns per block
 #define D2_R2_COLS 16
-__global__ void __launch_bounds__(D2_HEMV_ROWS)
+static __global__ void __launch_bounds__(D2_HEMV_ROWS)
 d2_rank2(cplx *A, int n, int j, const cplx *__restrict__ vbuf, const cplx *__restrict__ wbuf,
          const cplx *__restrict__ tau, double *dd) {
     const int b = blockIdx.z, m = n - j - 1;
@@ -150,7 +150,7 @@ d2_rank2(cplx *A, int n, int j, const cplx *__restrict__ vbuf, const cplx *__res
 }
 
 // Stage 2: one CTA per matrix.  d/e [B][n]; lam [B][k]; Z real [B][k][n]; lu_ws [B][vb*per].
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 tridiag_eig_kernel(const double *dd, const double *ee, int n, int k, int want_vec, double *evals, double *Z,
                    double *lu_ws, int vb, double *e2buf, int *info) {
     __shared__ double red[96];
@@ -176,7 +176,7 @@ tridiag_eig_kernel(const double *dd, const double *ee, int n, int k, int want_ve
 
 // Stage 3: grid (k, B): x = H(0) ... H(n-2) z for one vector.  conj_out: write conj(x)
 // (used when the caller's matrix was row-major, i.e. the transposed = conjugated problem).
-__global__ void __launch_bounds__(D2_THREADS)
+static __global__ void __launch_bounds__(D2_THREADS)
 d2_backtransform(const cplx *__restrict__ A, int n, int k, const cplx *__restrict__ tau,
                  const double *__restrict__ Z, cplx *__restrict__ X, int conj_out) {
     extern __shared__ cplx s_x[];

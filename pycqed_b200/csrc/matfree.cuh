@@ -122,7 +122,7 @@ __device__ __forceinline__ cplx mf_apply(const PlanDev &P, const cplx *__restric
 
 // K7b: matrix elements of auxiliary operators between eigenvectors (Current / Voltage evaluables,
 // pyscqed/numerical_system.py:596-694; util.py:322-328): out[p][q] = <x_i| Op_q |x_j> (complex).  One warp per (point, pair).
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 aux_matel_kernel(PlanDev P, const cplx *__restrict__ auxcoef, const cplx *__restrict__ evecs, long long n_pts, int k,
                  cplx *__restrict__ out) {
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -172,7 +172,7 @@ __device__ __forceinline__ double mf_hash_uniform(unsigned long long s) {
 // ---- start block: unit vectors at the b smallest diagonal entries + small noise; Gershgorin-type
 // upper bound ub = sum_t |c_t| prod_k ||F_tk||_inf.   grid (n_pts), block MF_THREADS.
 // dscr: [n_pts][n] scratch for the diagonal.
-__global__ void __launch_bounds__(MF_THREADS)
+static __global__ void __launch_bounds__(MF_THREADS)
 mf_prepare(MfArgs a, cplx *X, double *dscr) {
     __shared__ double sval[MF_THREADS];
     __shared__ int sidx[MF_THREADS];
@@ -247,7 +247,7 @@ mf_prepare(MfArgs a, cplx *X, double *dscr) {
 }
 
 // ---- HX = H X.  grid (ceil(n/MF_THREADS), b, n_pts) --------------------------------------------------
-__global__ void __launch_bounds__(MF_THREADS)
+static __global__ void __launch_bounds__(MF_THREADS)
 mf_matvec(MfArgs a, const cplx *__restrict__ X, cplx *__restrict__ HX) {
     const long long p = blockIdx.z;
     if (!a.active[p]) return;
@@ -268,7 +268,7 @@ __device__ __forceinline__ ChebPar cheb_par(const double *fp) {
 }
 
 // ---- whole filter of one vector in shared memory.  grid (b, n_pts), dyn smem 2*n*16 -----------------
-__global__ void __launch_bounds__(512)
+static __global__ void __launch_bounds__(512)
 mf_cheb_smem(MfArgs a, const cplx *__restrict__ X, cplx *__restrict__ Y, int deg) {
     extern __shared__ cplx sbuf[];
     const long long p = blockIdx.y;
@@ -316,7 +316,7 @@ mf_cheb_smem(MfArgs a, const cplx *__restrict__ X, cplx *__restrict__ Y, int deg
 namespace cg = cooperative_groups;
 
 template <int CS>
-__global__ void __launch_bounds__(512, 1)
+static __global__ void __launch_bounds__(512, 1)
 mf_cheb_stencil(MfArgs a, const cplx *__restrict__ X, cplx *__restrict__ Y, int deg, int ns) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ cplx *peer[2][CS];
@@ -463,7 +463,7 @@ static inline size_t mf_stencil_smem(const PlanDev &P, int ns) {
 
 // ---- one Chebyshev step through global memory (large n).  grid (ceil(n/T), b, n_pts).
 // m == 1: out = s1 (H x - c x);  m >= 2: prev <- s (H cur - c cur) - t prev   (in place in prev)
-__global__ void __launch_bounds__(MF_THREADS)
+static __global__ void __launch_bounds__(MF_THREADS)
 mf_cheb_step(MfArgs a, const cplx *__restrict__ cur, cplx *prev, int m) {
     const long long p = blockIdx.z;
     if (!a.active[p]) return;
@@ -498,7 +498,7 @@ __device__ __forceinline__ double mf_block_sum(double v, double *red) {
 }
 
 // ---- CGS2 orthonormalisation of the block (in place).  grid (n_pts), block 512 -----------------------
-__global__ void __launch_bounds__(512)
+static __global__ void __launch_bounds__(512)
 mf_orth(MfArgs a, cplx *Y, int *info, const int *__restrict__ only) {
     __shared__ double red[32];
     __shared__ double sdot[MF_BMAX][2];
@@ -568,7 +568,7 @@ mf_orth(MfArgs a, cplx *Y, int *info, const int *__restrict__ only) {
 // (one CTA per point, 22 % of the n = 9261 solve).  A point whose scaled Gram matrix is numerically
 // singular (pivot^2 < 1e-10) is flagged in `redo` and orthonormalised by mf_orth afterwards.
 // One warp per point; lane = column.
-__global__ void __launch_bounds__(32)
+static __global__ void __launch_bounds__(32)
 mf_chol(MfArgs a, const cplx *__restrict__ M, cplx *__restrict__ Tout, int *__restrict__ redo, int first_round) {
     __shared__ cplx R[MF_BMAX][MF_BMAX + 1];
     __shared__ double sc[MF_BMAX];
@@ -627,7 +627,7 @@ mf_chol(MfArgs a, const cplx *__restrict__ M, cplx *__restrict__ Tout, int *__re
 
 // Y[:, j] <- sum_{q <= j} Y[:, q] T[q][j], in place; grid (ceil(n / 256), n_pts), one thread per row.
 template <int BB>
-__global__ void __launch_bounds__(MF_THREADS)
+static __global__ void __launch_bounds__(MF_THREADS)
 mf_right_apply(MfArgs a, cplx *__restrict__ Y, const cplx *__restrict__ Tm, const int *__restrict__ redo) {
     __shared__ cplx sT[BB * BB];
     const long long p = blockIdx.y;
@@ -653,7 +653,7 @@ mf_right_apply(MfArgs a, cplx *__restrict__ Y, const cplx *__restrict__ Tm, cons
 }
 
 // ---- G[a_][c] = <x_a, hx_c>.  grid (b, n_pts), block 256.  G row-major [n_pts][b][b] -----------------
-__global__ void __launch_bounds__(MF_THREADS)
+static __global__ void __launch_bounds__(MF_THREADS)
 mf_gram(MfArgs a, const cplx *__restrict__ X, const cplx *__restrict__ HX, cplx *__restrict__ G) {
     __shared__ double swarp[MF_THREADS / 32][MF_BMAX][2];
     const long long p = blockIdx.y;
@@ -686,7 +686,7 @@ mf_gram(MfArgs a, const cplx *__restrict__ X, const cplx *__restrict__ HX, cplx 
 }
 
 // symmetrise G in place (Hermitian part): grid (n_pts), block b*b threads (<= 1024)
-__global__ void mf_symmetrize(MfArgs a, cplx *G) {
+static __global__ void mf_symmetrize(MfArgs a, cplx *G) {
     const long long p = blockIdx.x;
     const int b = a.b, r = threadIdx.x / b, c = threadIdx.x % b;
     if (r >= b) return;
@@ -696,7 +696,7 @@ __global__ void mf_symmetrize(MfArgs a, cplx *G) {
 }
 
 // ---- Xn = X S, HXn = HX S; residual norms.  S[a_][j] = evec[j][a_].  grid (ceil(n/T), n_pts) --------
-__global__ void __launch_bounds__(MF_THREADS)
+static __global__ void __launch_bounds__(MF_THREADS)
 mf_rotate(MfArgs a, const cplx *__restrict__ X, const cplx *__restrict__ HX, const cplx *__restrict__ S,
           cplx *__restrict__ Xn, cplx *__restrict__ HXn) {
     __shared__ cplx sS[MF_BMAX * MF_BMAX];
@@ -744,7 +744,7 @@ mf_rotate(MfArgs a, const cplx *__restrict__ X, const cplx *__restrict__ HX, con
 }
 
 // ---- convergence + next filter window.  grid (ceil(n_pts/128)), block 128 ---------------------------
-__global__ void mf_converge(MfArgs a, double tol, int *info) {
+static __global__ void mf_converge(MfArgs a, double tol, int *info) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.n_pts || !a.active[p]) return;
     const int b = a.b, k = a.k;
@@ -765,7 +765,7 @@ __global__ void mf_converge(MfArgs a, double tol, int *info) {
 
 // ---- outputs: first k Ritz pairs.  grid (ceil(n*k/256), n_pts) -----------------------------------------
 // `oidx` (optional): position of local point p in the caller's arrays (coarse-to-fine ordering, see run_matfree)
-__global__ void mf_output(MfArgs a, const cplx *__restrict__ X, double *__restrict__ evals, cplx *__restrict__ evecs,
+static __global__ void mf_output(MfArgs a, const cplx *__restrict__ X, double *__restrict__ evals, cplx *__restrict__ evecs,
                           const int *__restrict__ oidx) {
     const long long p = blockIdx.y;
     const long long po = oidx ? oidx[p] : p;
@@ -778,7 +778,7 @@ __global__ void mf_output(MfArgs a, const cplx *__restrict__ X, double *__restri
 }
 
 // coarse-to-fine start: X[p] = Xsrc[src[p]] (the converged Ritz block of the nearest already-solved sweep point)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 mf_init_from(MfArgs a, cplx *__restrict__ X, const cplx *__restrict__ Xsrc, const int *__restrict__ src) {
     const long long p = blockIdx.y;
     const size_t tot = (size_t)a.b * a.n;
@@ -786,14 +786,14 @@ mf_init_from(MfArgs a, cplx *__restrict__ X, const cplx *__restrict__ Xsrc, cons
     if (i < tot) X[p * tot + i] = Xsrc[(size_t)src[p] * tot + i];
 }
 
-__global__ void mf_gather_coef(const cplx *__restrict__ in, cplx *__restrict__ out, const int *__restrict__ perm, long long n_pts, int n_terms) {
+static __global__ void mf_gather_coef(const cplx *__restrict__ in, cplx *__restrict__ out, const int *__restrict__ perm, long long n_pts, int n_terms) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pts * n_terms) return;
     const long long p = i / n_terms;
     out[i] = in[(long long)perm[p] * n_terms + (i - p * n_terms)];
 }
 
-__global__ void mf_scatter_info(const int *__restrict__ in, int *__restrict__ out, const int *__restrict__ perm, long long n_pts) {
+static __global__ void mf_scatter_info(const int *__restrict__ in, int *__restrict__ out, const int *__restrict__ perm, long long n_pts) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n_pts) out[perm[p]] = in[p];
 }

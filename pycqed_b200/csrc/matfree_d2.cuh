@@ -23,7 +23,7 @@ namespace scqed {
 #define D2_RB 16
 
 // H_k(p) for k = 0, 1: re / im planes [n_pts][d0*d0 + d1*d1]; max |Im| accumulated into imax[0].
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 mf_d2_build(MfArgs a, double *__restrict__ Hre, double *__restrict__ Him, double *__restrict__ imax) {
     const long long p = blockIdx.y;
     const PlanDev &P = a.P;
@@ -75,7 +75,7 @@ mf_d2_build(MfArgs a, double *__restrict__ Hre, double *__restrict__ Him, double
 // coupling terms |c| ||F_a||_inf ||F_b||_inf.  The term-by-term bound of mf_prepare counts charge^2 and flux^2
 // separately although their off-diagonals cancel in H_k (4303 vs 2566 for the 180 x 180 atom; the true top is
 // 2499): a narrower filter interval means fewer filter applications.  One block per point.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 mf_d2_bound(MfArgs a, const double *__restrict__ Hre, const double *__restrict__ Him) {
     __shared__ double smax[2][8];
     const long long p = blockIdx.x;
@@ -112,7 +112,7 @@ mf_d2_bound(MfArgs a, const double *__restrict__ Hre, const double *__restrict__
 }
 
 // max |Im X| over the block of every active point -> imax[2]  (decides whether the real-vector kernels apply)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 mf_d2_imag_max(MfArgs a, const cplx *__restrict__ X, double *__restrict__ imax) {
     const long long p = blockIdx.x;
     if (!a.active[p]) return;
@@ -130,7 +130,7 @@ mf_d2_imag_max(MfArgs a, const cplx *__restrict__ X, double *__restrict__ imax) 
 // REALX: H real AND the vectors real (exactly zero imaginary parts, checked by mf_d2_imag_max before every
 // use): the imaginary half of the arithmetic is skipped.
 template <int MODE, bool REALH, bool REALX>
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 mf_d2_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const double *__restrict__ Hre,
              const double *__restrict__ Him) {
     extern __shared__ __align__(16) unsigned char d2smem[];
@@ -276,7 +276,7 @@ __device__ __forceinline__ void d2_dmma(double &c0, double &c1, double a, double
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 mf_d2_dmma_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const double *__restrict__ Hre) {
     extern __shared__ __align__(16) unsigned char d2smem[];
     const long long p = blockIdx.z;
@@ -463,7 +463,7 @@ __device__ __forceinline__ void d2_ring(const unsigned char *src, int total, int
 // shared: ring of D2_ST stages (D2_BK * d1 * 16 B each), H0 rows [D2_RB][d0], X rows (real parts) [D2_RB][d1e],
 // coupling coefficients
 template <int MODE>
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 mf_d2_tma_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const double *__restrict__ Hre) {
     extern __shared__ __align__(128) unsigned char d2smem[];
     __shared__ __align__(8) unsigned long long full[D2_ST], empty[D2_ST];
@@ -584,7 +584,7 @@ mf_d2_tma_kernel(MfArgs a, const cplx *__restrict__ X, cplx *out, int m, const d
 // (d0 + d1) real MACs per element instead of four complex dense mode products through the ELL tables.
 // grid (b, n_pts), block 512.  REALX: the vector is exactly real (imaginary half skipped, half the footprint).
 template <bool REALX>
-__global__ void __launch_bounds__(512)
+static __global__ void __launch_bounds__(512)
 mf_cheb_smem_d2(MfArgs a, const cplx *__restrict__ X, cplx *__restrict__ Y, int deg, const double *__restrict__ Hre) {
     extern __shared__ __align__(16) unsigned char d2f[];
     typedef typename std::conditional<REALX, double, cplx>::type V;

@@ -12,7 +12,7 @@
 
 namespace scqed {
 
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 pauli_coef_kernel(const double *__restrict__ e01, const cplx *__restrict__ op, long long n_pts,
                   double *__restrict__ h) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -12,7 +12,7 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 probe_dmma_kernel(int iters, double *out) {
     double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
     double c[16];
@@ -28,7 +28,7 @@ probe_dmma_kernel(int iters, double *out) {
     if (s == 12345.678) out[0] = s;
 }
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 probe_dfma_kernel(int iters, double *out) {
     double x = 1.0 + threadIdx.x * 1e-9, y = 0.999999;
     double c[16];

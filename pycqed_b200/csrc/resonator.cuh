@@ -74,9 +74,9 @@ __device__ inline int tql_eigenvalues(double *d, double *e, int n, int st) {
 
 // Block-wide.  X: k eigenvectors [k][n]; lam: k eigenvalues; scratch: >= 8*k doubles.
 // out: [nstrips][k].
-__device__ void resonator_strips(const PlanDev &P, const ResonatorArgs &R, const double *scal,
+static __device__ void resonator_strips(const PlanDev &P, const ResonatorArgs &R, const double *scal,
                                  const double *lam, const cplx *X, int n, int k, double *scratch,
-                                 double *out, double *qlws = nullptr) {
+                                 double *out, double *qlws = nullptr, int *info_p = nullptr) {
     cplx *g = (cplx *)scratch;                   // [k]   matrix elements <i|Op|i+1>
     double *glist = scratch + 2 * k;             // [k]
     double *Erel = scratch + 3 * k;              // [k]
@@ -130,7 +130,7 @@ __device__ void resonator_strips(const PlanDev &P, const ResonatorArgs &R, const
                 int q = s - i;
                 e[i * T] = i < k - 1 ? glist[i] * sqrt((double)(q > 0 ? q : 0)) : 0.0;
             }
-            tql_eigenvalues(d, e, k, T);
+            if (tql_eigenvalues(d, e, k, T) && info_p) atomicOr(info_p, 4);      // QL did not converge: bad strip
             for (int i = 0; i < k; ++i) out[(size_t)s * k + i] = d[order[i] * T];
         }
     } else {
@@ -141,7 +141,7 @@ __device__ void resonator_strips(const PlanDev &P, const ResonatorArgs &R, const
                 int q = s - i;
                 e[i] = i < k - 1 ? glist[i] * sqrt((double)(q > 0 ? q : 0)) : 0.0;
             }
-            tql_eigenvalues(d, e, k, 1);
+            if (tql_eigenvalues(d, e, k, 1) && info_p) atomicOr(info_p, 4);      // QL did not converge: bad strip
             for (int i = 0; i < k; ++i) out[(size_t)s * k + i] = d[order[i]];
         }
     }

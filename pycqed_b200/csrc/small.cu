@@ -1,0 +1,273 @@
+// small.cu -- host side of S1: Hamiltonians that fit one SM's shared memory (small_eigh.cuh, small_split.cuh,
+// small_packed.cuh).  See internal.h for the entry points.
+#include "internal.h"
+#include "assemble.cuh"
+#include "tridiag_eig.cuh"
+#include "small_eigh.cuh"
+#include "small_split.cuh"
+#include "small_packed.cuh"
+
+static bool small_fits(const scqed_plan *pl, int n, int k, int want_vec, int n_terms, SmallLayout *Lout) {
+    SmallLayout L = small_smem_layout(n, k, want_vec, n_terms, pl->smem_optin);
+    if ((size_t)L.total + 1024 > pl->smem_optin) return false;
+    if (want_vec && L.vb < 1) return false;
+    if (Lout) *Lout = L;
+    return true;
+}
+
+bool small_fits(const scqed_plan *pl, int n, int k, int want_vec, int n_terms) {
+    return small_fits(pl, n, k, want_vec, n_terms, nullptr);
+}
+
+static int run_small(scqed_plan *pl, const PlanDev &P, const cplx *coef, const cplx *Hin, const double *scal,
+                     long long n_pts, int n, int k, int want_vec, int tidyup, const ResonatorArgs &res,
+                     double *evals, cplx *evecs, double *post, int *info, cudaStream_t st) {
+    SmallArgs a;
+    memset(&a, 0, sizeof(a));
+    if (!small_fits(pl, n, k, want_vec, P.n_terms, &a.L)) return fail(SCQED_EUNSUPPORTED, "n=%d k=%d does not fit the fused shared-memory path", n, k);
+    a.P = P; a.coef = coef; a.Hin = Hin; a.scalars = scal; a.n_pts = n_pts; a.n = n; a.k = k;
+    a.want_vec = want_vec; a.tidyup = tidyup; a.evals = evals; a.evecs = evecs; a.info = info;
+    a.res = res; a.post = post;
+    // per DEVICE, not per process: set on every launch (microseconds) so that several GPUs driven by one process work
+    CK(cudaFuncSetAttribute(small_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin - 1024));
+    long long grid = n_pts < pl->sm_count ? n_pts : pl->sm_count;
+    small_eigh_kernel<<<(unsigned)grid, SMALL_THREADS, a.L.total, st>>>(a);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- S1 as a phase pipeline (small_split.cuh) ------------------------------------------------------------
+// SCQED_S1_PACKED: 0 = full-storage kernel only (n <= 128), 1 = packed lower triangle for every n,
+// unset = auto: full storage for n <= 128 (faster per matrix: 6.6 vs 9.9 ms on the bench), packed above
+// (the only way 128 < n <= ~212 real symmetric stays on chip: 8x the HBM solver at n = 200)
+static int s1_packed_mode() {
+    const char *e = getenv("SCQED_S1_PACKED");
+    return e ? atoi(e) : 2;
+}
+
+// real_hint: -1 unknown, 1 known real, 0 known complex
+bool split_fits(const scqed_plan *pl, int n, int k, int n_terms, int real_hint) {
+    if (k > 32 || n < 2) return false;
+    if (n <= 32 * SMALL_RQ)
+        return S1Smem<cplx>::bytes(n, n_terms, 512) <= pl->smem_optin ||
+               (s1_packed_mode() && S1PSmem<cplx>::bytes(n, n_terms, 256) <= pl->smem_optin);
+    if (n > 224 || real_hint == 0 || !s1_packed_mode()) return false;
+    return S1PSmem<double>::bytes(n, n_terms, 512) <= pl->smem_optin;     // packed lower triangle, real symmetric only
+}
+
+template <typename T, int NQ>
+static int s1p_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t st, bool *launched) {
+    const int threads = NQ <= 4 ? 256 : 512;
+    const size_t smem = S1PSmem<T>::bytes(a.n, n_terms, threads);
+    *launched = false;
+    if (smem > pl->smem_optin) return 0;
+    CK(cudaFuncSetAttribute(s1p_tridiag_kernel<T, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s1p_tridiag_kernel<T, NQ>, threads, smem));
+    if (occ < 1) return 0;
+    long long grid = (long long)occ * pl->sm_count;
+    if (grid > a.n_pts) grid = a.n_pts;
+    TimingScope tscope_(st, sizeof(T) == sizeof(double) ? 1 : 2);
+    s1p_tridiag_kernel<T, NQ><<<(unsigned)grid, threads, smem, st>>>(a);
+    tscope_.end();
+    LAUNCHED();
+    CK(cudaGetLastError());
+    *launched = true;
+    return 0;
+}
+
+template <typename T>
+static int s1_launch_tridiag(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t st) {
+    const bool full_fits = a.n <= 32 * SMALL_RQ &&
+        S1Smem<T>::bytes(a.n, n_terms, sizeof(T) == sizeof(double) ? 256 : 512) <= pl->smem_optin;
+    if (s1_packed_mode() == 1 || (s1_packed_mode() == 2 && !full_fits)) {
+        bool launched = false;
+        int rc = 0;
+        if (a.n <= 128) rc = s1p_launch<T, 4>(pl, a, n_terms, st, &launched);
+        else if constexpr (sizeof(T) == sizeof(double)) rc = s1p_launch<T, 7>(pl, a, n_terms, st, &launched);
+        if (rc) return rc;
+        if (launched) return 0;
+        if (a.n > 32 * SMALL_RQ) return fail(SCQED_EUNSUPPORTED, "n=%d does not fit the shared-memory tridiagonalisation", a.n);
+    }
+    const int threads = sizeof(T) == sizeof(double) ? 256 : 512;
+    const size_t smem = S1Smem<T>::bytes(a.n, n_terms, threads);
+    CK(cudaFuncSetAttribute(s1_tridiag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s1_tridiag_kernel<T>, threads, smem));
+    if (occ < 1) return fail(SCQED_EUNSUPPORTED, "small tridiagonalisation kernel does not fit (n=%d)", a.n);
+    long long grid = (long long)occ * pl->sm_count;
+    if (grid > a.n_pts) grid = a.n_pts;
+    TimingScope tscope_(st, sizeof(T) == sizeof(double) ? 1 : 2);
+    s1_tridiag_kernel<T><<<(unsigned)grid, threads, smem, st>>>(a);
+    tscope_.end();
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// number of entries of info[] equal to `val` (device-side reduction, one atomic per block that saw one)
+static __global__ void __launch_bounds__(256)
+count_info_kernel(const int *__restrict__ info, long long n, int val, int *__restrict__ count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int hit = (i < n && info[i] == val) ? 1 : 0;
+    const int c = __syncthreads_count(hit);
+    if (threadIdx.x == 0 && c) atomicAdd(count, c);
+}
+
+static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, const cplx *Hin, const double *scal,
+                           long long n_pts, int n, int k, int want_vec, int tidyup, const ResonatorArgs &res,
+                           double *evals, cplx *evecs, double *post, int *info, cudaStream_t st) {
+    const bool need_vec = want_vec || res.enabled;
+    long long chunk = n_pts < 16384 ? n_pts : 16384;
+    // a plan whose realness is unknown is probed on a small first chunk
+    long long first = (pl->s1_real_mode < 0 && !Hin) ? (long long)2 * pl->sm_count : chunk;
+    if (first > chunk) first = chunk;
+    const long long G = chunk * k;
+    size_t bytes = 0;
+    auto need = [&](size_t b) { size_t r = bytes; bytes += (b + 255) & ~(size_t)255; return r; };
+    size_t o_dd = need((size_t)chunk * n * 8), o_ee = need((size_t)chunk * n * 8), o_e2 = need((size_t)chunk * n * 8);
+    size_t o_bnd = need((size_t)chunk * 4 * 8), o_tau = need((size_t)chunk * n * 16), o_lam = need((size_t)chunk * k * 8);
+    size_t o_flags = need((size_t)chunk * 4), o_cnt = need(256);
+    size_t o_V = 0, o_lu = 0, o_swp = 0, o_zw = 0;
+    if (need_vec) {
+        o_V = need((size_t)chunk * n * n * 16);
+        o_lu = need((size_t)4 * n * G * 8);
+        o_swp = need((size_t)n * G);
+        o_zw = need((size_t)n * G * 8);
+    }
+    if (pl->s1work.ensure(bytes)) return fail(SCQED_ENOMEM, "small-path workspace (%zu MB)", bytes >> 20);
+    unsigned char *base = (unsigned char *)pl->s1work.p;
+    cplx *vec_tmp = nullptr;
+    if (need_vec && !evecs) {
+        if (pl->s1vec.ensure((size_t)chunk * k * n * 16)) return fail(SCQED_ENOMEM, "small-path eigenvector staging");
+        vec_tmp = (cplx *)pl->s1vec.p;
+    }
+    S1Args a;
+    memset(&a, 0, sizeof(a));
+    a.P = P; a.n = n; a.k = k; a.tidyup = tidyup; a.want_vec = need_vec;
+    a.W.dd = (double *)(base + o_dd); a.W.ee = (double *)(base + o_ee); a.W.e2 = (double *)(base + o_e2);
+    a.W.bnd = (double *)(base + o_bnd); a.W.tau = (cplx *)(base + o_tau); a.W.lam = (double *)(base + o_lam);
+    a.W.flags = (int *)(base + o_flags);
+    int *d_cnt = (int *)(base + o_cnt);
+    bool assumed_real = false;          // some chunk ran on the strength of pl->s1_real_mode == 1 without a host check
+    if (need_vec) {
+        a.W.Vst = base + o_V; a.W.lu = (double *)(base + o_lu); a.W.swp = base + o_swp; a.W.zw = (double *)(base + o_zw);
+    }
+    for (long long p0 = 0; p0 < n_pts;) {
+        const long long np = (p0 == 0 ? first : chunk) < n_pts - p0 ? (p0 == 0 ? first : chunk) : n_pts - p0;
+        a.n_pts = np;
+        a.coef = coef ? coef + (size_t)p0 * P.n_terms : nullptr;
+        a.dcoef = (P.n_dense > 0 && !Hin && pl->dcoef.p) ? (const double *)pl->dcoef.p + (size_t)p0 * 2 * P.n_dense : nullptr;
+        a.Hin = Hin ? Hin + (size_t)p0 * n * n : nullptr;
+        a.info = info + p0;
+        const long long Gc = np * k;
+        CK(cudaMemsetAsync(a.info, 0, (size_t)np * 4, st));
+        bool real_mode = false;
+        const bool direct = P.dense_tridiag && a.dcoef && !Hin;     // H(p) is already tridiagonal: no Householder stage
+        if (direct) {
+            TimingScope tscope_(st, 4);
+            s1_direct_tridiag_kernel<<<(unsigned)((np * 32 + 127) / 128), 128, 0, st>>>(a);
+            tscope_.end();
+            LAUNCHED();
+            real_mode = true;
+        } else if (pl->s1_real_mode == 1 && !Hin) {
+            // known real-symmetric plan: no host round trip; a point that turns out complex is
+            // flagged info = -2 by the kernel and the host-level driver re-runs in complex mode
+            int rc = s1_launch_tridiag<double>(pl, a, P.n_terms > P.n_dense ? P.n_terms : P.n_dense, st);
+            if (rc) return rc;
+            real_mode = true;
+            assumed_real = true;
+        } else if (pl->s1_real_mode != 0) {
+            int rc = s1_launch_tridiag<double>(pl, a, P.n_terms > P.n_dense ? P.n_terms : P.n_dense, st);
+            if (rc) return rc;
+            int h_cnt = 0;
+            std::vector<int> hflags((size_t)np);
+            CK(cudaMemcpyAsync(hflags.data(), a.W.flags, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (long long q = 0; q < np; ++q) h_cnt += hflags[(size_t)q] != 0;
+            real_mode = (h_cnt == 0);
+            if (!Hin) pl->s1_real_mode = real_mode ? 1 : 0;
+            if (!real_mode) CK(cudaMemsetAsync(a.info, 0, (size_t)np * 4, st));
+        }
+        if (!real_mode && n > 32 * SMALL_RQ) return S1_NOT_REAL;       // caller falls back to the HBM solvers
+        if (!real_mode) {
+            int rc = s1_launch_tridiag<cplx>(pl, a, P.n_terms > P.n_dense ? P.n_terms : P.n_dense, st);
+            if (rc) return rc;
+        }
+        // enough (point, eigenvalue) pairs to fill the machine with one thread each: plain bisection
+        // (6.6x less arithmetic); small sweeps keep the 33-way warp multisection (short dependent chain)
+        const int bis_mode = getenv("SCQED_BISECT") ? atoi(getenv("SCQED_BISECT")) : 0;
+        const bool thread_bisect = bis_mode == 2 || (bis_mode == 0 && np * k >= 4096 && k <= 32);
+        if (thread_bisect) {
+            const int ppw = 32 / k;
+            const long long bw = (np + ppw - 1) / ppw;
+            // three-term (division-free) Sturm recurrence unless SCQED_STURM_RATIO is set
+            s1_bisect_thread_kernel<<<(unsigned)((bw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, evals + (size_t)p0 * k, getenv("SCQED_STURM_RATIO") ? 0 : 1);
+        } else {
+            const long long warps = np * k;
+            s1_bisect_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(a, nullptr, evals + (size_t)p0 * k);
+        }
+        LAUNCHED();
+        if (need_vec) {
+            const int ppw = 32 / k;
+            const long long iw = (np + ppw - 1) / ppw;
+            s1_invit_kernel<<<(unsigned)((iw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, Gc);
+            cplx *vout = evecs ? evecs + (size_t)p0 * k * n : vec_tmp;
+            if (direct) {
+                const long long tot = np * k * n;
+                s1_phase_backtr_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a, Gc, vout);
+            } else if (real_mode && n > 32 * SMALL_RQ) {
+                const long long bw = np * ((k + 7) / 8);
+                s1_backtr_kernel<double, 8, 7><<<(unsigned)((bw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, Gc, vout);
+            } else if (real_mode) {
+                const long long bw = np * ((k + 7) / 8);
+                s1_backtr_kernel<double, 8><<<(unsigned)((bw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, Gc, vout);
+            } else {
+                const long long bw = np * ((k + 3) / 4);
+                s1_backtr_kernel<cplx, 4><<<(unsigned)((bw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, Gc, vout);
+            }
+            g_launches.fetch_add(2, std::memory_order_relaxed);
+            if (res.enabled) {
+                s1_resonator_kernel<<<(unsigned)np, 128, 0, st>>>(a, res, nullptr, scal + (size_t)p0 * P.n_scalar, vout,
+                                                              post + (size_t)p0 * res.nstrips * k);
+                LAUNCHED();
+            }
+        }
+        CK(cudaGetLastError());
+        p0 += np;
+    }
+    if (assumed_real) {
+        // A plan known to be real symmetric on its first points may turn complex later in the grid (e.g. a 2-D sweep
+        // whose outer flux axis starts at 0): such points were flagged info = -2 and skipped by the real kernel.
+        // Count them on the device; if there are any, the plan is complex Hermitian: redo this call in complex mode.
+        int h_cnt = 0;
+        CK(cudaMemsetAsync(d_cnt, 0, 4, st));
+        count_info_kernel<<<(unsigned)((n_pts + 255) / 256), 256, 0, st>>>(info, n_pts, -2, d_cnt);
+        LAUNCHED();
+        CK(cudaMemcpyAsync(&h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_cnt > 0) {
+            pl->s1_real_mode = 0;
+            return run_small_split(pl, P, coef, Hin, scal, n_pts, n, k, want_vec, tidyup, res, evals, evecs, post, info, st);
+        }
+    }
+    return 0;
+}
+
+int run_small_any(scqed_plan *pl, const PlanDev &P, const cplx *coef, const cplx *Hin, const double *scal,
+                         long long n_pts, int n, int k, int want_vec, int tidyup, const ResonatorArgs &res,
+                         double *evals, cplx *evecs, double *post, int *info, cudaStream_t st, bool monolithic) {
+    if (!monolithic && split_fits(pl, n, k, P.n_terms > P.n_dense ? P.n_terms : P.n_dense, Hin ? -1 : pl->s1_real_mode))
+        return run_small_split(pl, P, coef, Hin, scal, n_pts, n, k, want_vec, tidyup, res, evals, evecs, post, info, st);
+    return run_small(pl, P, coef, Hin, scal, n_pts, n, k, want_vec, tidyup, res, evals, evecs, post, info, st);
+}
+
+
+int run_resonator_generic(const PlanDev &P, const ResonatorArgs &res, const double *scal, const double *evals,
+                          const cplx *vecs, long long n_pts, int n, int k, double *post, int *info, cudaStream_t st) {
+    resonator_generic_kernel<<<(unsigned)n_pts, 128, 0, st>>>(P, res, scal, evals, vecs, n, k, post, info);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}

@@ -300,7 +300,7 @@ __device__ void small_backtransform(const T *A, int n, const T *tau, cplx *X, in
     }
 }
 
-__global__ void __launch_bounds__(SMALL_THREADS, 1)
+static __global__ void __launch_bounds__(SMALL_THREADS, 1)
 small_eigh_kernel(SmallArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SmallLayout &L = a.L;

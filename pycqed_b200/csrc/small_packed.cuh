@@ -89,7 +89,7 @@ template <typename T> struct S1PSmem {
 
 // NQ = row tiles per lane (ceil(n / 32) <= NQ)
 template <typename T, int NQ>
-__global__ void __launch_bounds__(NQ <= 4 ? 256 : 512)
+static __global__ void __launch_bounds__(NQ <= 4 ? 256 : 512)
 s1p_tridiag_kernel(S1Args a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int n = a.n, tid = threadIdx.x, NT = blockDim.x;

@@ -64,7 +64,7 @@ template <typename T> struct S1Smem {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(sizeof(T) == sizeof(double) ? 256 : 512)
+static __global__ void __launch_bounds__(sizeof(T) == sizeof(double) ? 256 : 512)
 s1_tridiag_kernel(S1Args a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int n = a.n, tid = threadIdx.x, NT = blockDim.x;
@@ -176,7 +176,7 @@ s1_tridiag_kernel(S1Args a) {
 // similarity D = diag(ph), ph_0 = 1, ph_{i+1} = ph_i s_i / |s_i| turns H into the REAL symmetric tridiagonal
 // T = D^H H D with off-diagonals |s_i| (same spectrum; eigenvectors v = D z).  One warp per point: lanes
 // stride over i, Gershgorin bounds by shuffles, the phase prefix product serially per 32-chunk.
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 s1_direct_tridiag_kernel(S1Args a) {
     const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int l = threadIdx.x & 31, n = a.n;
@@ -261,7 +261,7 @@ s1_direct_tridiag_kernel(S1Args a) {
 }
 
 // v = D z: eigenvectors of the tridiagonal H from those of T.  One thread per (point, vector, i).
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 s1_phase_backtr_kernel(S1Args a, long long G, cplx *__restrict__ evecs) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int n = a.n, k = a.k;
@@ -275,7 +275,7 @@ s1_phase_backtr_kernel(S1Args a, long long G, cplx *__restrict__ evecs) {
 }
 
 // ---- phase B: one warp per (point, eigenvalue) -----------------------------------------------------------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 s1_bisect_kernel(S1Args a, const int *__restrict__ skip, double *__restrict__ evals) {
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int l = threadIdx.x & 31, n = a.n, k = a.k;
@@ -320,7 +320,7 @@ s1_bisect_kernel(S1Args a, const int *__restrict__ skip, double *__restrict__ ev
 // 32 x 11 for the 33-way multisection (6.6x fewer FP64 operations); the longer dependent chain is
 // hidden by the other warps.  The k eigenvalues of a point sit in adjacent lanes so that the loads
 // of d and e^2 are broadcasts.  Same count recurrence, tolerances and stopping rule as dstebz.
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 s1_bisect_thread_kernel(S1Args a, const int *__restrict__ skip, double *__restrict__ evals, int prod) {
     const int k = a.k, n = a.n, l = threadIdx.x & 31;
     const int ppw = 32 / k;
@@ -348,7 +348,7 @@ s1_bisect_thread_kernel(S1Args a, const int *__restrict__ skip, double *__restri
 }
 
 // ---- phase C: one thread per (point, vector); the k vectors of a point sit in one warp -------------------
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 s1_invit_kernel(S1Args a, const int *__restrict__ skip, long long G) {
     const int k = a.k, n = a.n, l = threadIdx.x & 31;
     const int ppw = 32 / k;                                     // points per warp
@@ -415,7 +415,7 @@ s1_invit_kernel(S1Args a, const int *__restrict__ skip, long long G) {
 
 // ---- phase D: x = Q z.  One warp per (point, group of KV vectors) ------------------------------------------
 template <typename T, int S1_KV, int RQ = SMALL_RQ>
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 s1_backtr_kernel(S1Args a, const int *__restrict__ skip, long long G, cplx *__restrict__ evecs) {
     const int n = a.n, k = a.k, l = threadIdx.x & 31;
     const int groups = (k + S1_KV - 1) / S1_KV;
@@ -524,29 +524,29 @@ s1_backtr_kernel(S1Args a, const int *__restrict__ skip, long long G, cplx *__re
 }
 
 // ---- phase E: resonator strips, one CTA per point -------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 s1_resonator_kernel(S1Args a, ResonatorArgs R, const int *__restrict__ skip, const double *__restrict__ scalars,
                     const cplx *__restrict__ evecs, double *__restrict__ post) {
     __shared__ double scratch[8 * SCQED_RES_KMAX];
     const long long p = blockIdx.x;
     if (skip && skip[p]) return;
     resonator_strips(a.P, R, scalars + p * a.P.n_scalar, a.W.lam + p * a.k, evecs + (size_t)p * a.k * a.n, a.n, a.k,
-                     scratch, post + (size_t)p * R.nstrips * a.k, nullptr);   // QL on private (L1-resident) arrays: a shared tile costs occupancy
+                     scratch, post + (size_t)p * R.nstrips * a.k, nullptr, a.info + p);   // QL on private (L1-resident) arrays: a shared tile costs occupancy
 }
 
 // The same post-op behind the HBM dense (S2) and matrix-free (S3) solvers: eigenpairs come from
 // global memory, nothing else is needed.
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 resonator_generic_kernel(PlanDev P, ResonatorArgs R, const double *__restrict__ scalars, const double *__restrict__ evals,
-                         const cplx *__restrict__ evecs, int n, int k, double *__restrict__ post) {
+                         const cplx *__restrict__ evecs, int n, int k, double *__restrict__ post, int *__restrict__ info) {
     __shared__ double scratch[8 * SCQED_RES_KMAX];
     const long long p = blockIdx.x;
     resonator_strips(P, R, scalars + p * P.n_scalar, evals + p * k, evecs + (size_t)p * k * n, n, k, scratch,
-                     post + (size_t)p * R.nstrips * k, nullptr);
+                     post + (size_t)p * R.nstrips * k, nullptr, info + p);
 }
 
 // complement of the flags (second, complex pass only handles the flagged points)
-__global__ void s1_invert_flags(const int *__restrict__ flags, int *__restrict__ skip, long long n, int *__restrict__ count) {
+static __global__ void s1_invert_flags(const int *__restrict__ flags, int *__restrict__ skip, long long n, int *__restrict__ count) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int f = flags[i];

@@ -82,7 +82,7 @@ __device__ __forceinline__ int sturm_count_prod(const double *__restrict__ d, co
 
 // Block-wide: Gershgorin interval and pivmin of T.  out[0]=gl, out[1]=gu, out[2]=pivmin,
 // out[3]=||T||_1-ish (max abs row sum).  `red` is scratch for 3*32 doubles.
-__device__ void tridiag_bounds(const double *d, const double *e, int n, double *out, double *red) {
+static __device__ void tridiag_bounds(const double *d, const double *e, int n, double *out, double *red) {
     double lo = 1e300, hi = -1e300, emax = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i < n - 1 ? fabs(e[i]) : 0.0);
@@ -115,7 +115,7 @@ __device__ void tridiag_bounds(const double *d, const double *e, int n, double *
 
 // Block-wide multisection for eigenvalue indices [0, k).  e2[i] = e[i]^2.  lam[k] out.
 // Returns (per thread) nonzero if some interval failed to converge.
-__device__ int tridiag_bisect(const double *d, const double *e2, int n, int k, const double *bounds,
+static __device__ int tridiag_bisect(const double *d, const double *e2, int n, int k, const double *bounds,
                               double *lam) {
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
     const double gl = bounds[0], gu = bounds[1], pivmin = bounds[2];
@@ -235,7 +235,7 @@ __device__ __forceinline__ double normalize_serial(int n, double *z, int zs) {
 
 // One warp: modified Gram-Schmidt of the vectors of each eigenvalue cluster.
 // Z: vector j element i at Z[j * zld + i * zs].
-__device__ void cluster_mgs_warp(int n, int k, const double *lam, double ortol, double *Z, int zld, int zs) {
+static __device__ void cluster_mgs_warp(int n, int k, const double *lam, double ortol, double *Z, int zld, int zs) {
     const int l = threadIdx.x & 31;
     int start = 0;
     for (int j = 0; j < k; ++j) {
@@ -263,7 +263,7 @@ __device__ void cluster_mgs_warp(int n, int k, const double *lam, double ortol, 
 // Block-wide inverse iteration for the k eigenvalues lam[] of T.  Vector j is written (real) to
 // Z[j*zld + i*zs].  lu_ws: workspace for `vb` simultaneous vectors, each 4n doubles + n bytes
 // (n bytes padded to 8).  Returns nonzero on a vector that failed to grow.
-__device__ int tridiag_inverse_iteration(const double *d, const double *e, int n, int k, const double *lam,
+static __device__ int tridiag_inverse_iteration(const double *d, const double *e, int n, int k, const double *lam,
                                          double tnorm, double *Z, int zld, int zs, double *lu_ws, int vb,
                                          unsigned long long seed) {
     const double eps3 = fmax(SCQED_EPS * tnorm, SCQED_SAFMIN * 1e16);

@@ -51,3 +51,39 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+def golden_vectors(g, a):
+    """Eigenvectors [n, k] of stored sample ``a`` as complex128.  The big fixtures keep them as complex64; rounding
+    changes the NORM at first order (the direction only at second order), so columns are re-normalised."""
+    V = np.asarray(g["V"][a])
+    if V.dtype != np.complex128:
+        V = V.astype(np.complex128)
+        V = V / np.linalg.norm(V, axis=0, keepdims=True)
+    return V
+
+
+_NEXT_CACHE = {}
+
+
+def e_next(g, plan, point, k):
+    """Level k (the first one the k-truncation drops) at fixture point ``point``: stored by the reference run
+    when the fixture was minted with ``k_extra`` (``E_next``), otherwise solved by the oracle.  It tells
+    ``subspace_overlap`` whether level k-1 sits in a degenerate cluster that the truncation cuts."""
+    if "E_next" in g:
+        return float(g["E_next"][point][0])
+    n = plan.hilbert_dim
+    if k >= n:
+        return None
+    key = (plan.meta.get("source"), int(point), int(k), tuple(np.asarray(g["params"][point]).tolist()))
+    if key not in _NEXT_CACHE:
+        from oracle.plan_oracle import PlanOracle, eval_program
+        orc = _NEXT_CACHE.setdefault(("oracle", id(plan)), PlanOracle(plan))
+        coef, _ = eval_program(plan.program, np.atleast_2d(g["params"][point]))
+        H = orc.hamiltonian(coef[0])
+        if n <= 2000:
+            E = orc.diag_dense(H, k + 1)
+        else:
+            E = orc.diag_sparse(H, k + 1, which="SA", tol=0)
+        _NEXT_CACHE[key] = float(np.sort(E)[k])
+    return _NEXT_CACHE[key]

@@ -322,11 +322,16 @@ def lower(h, sweeps, **kw):
 
 
 def freeze(name, h, sweeps, k=10, get_vectors=False, evaluations=(), sparse_opts=None, n_h_samples=3,
-           vec_points=(), lower_kw=None, extra_plans=None, store_h=True):
-    """Run the reference on ``sweeps`` and write <name>.npz + <name>.plan.json."""
+           vec_points=(), lower_kw=None, extra_plans=None, store_h=True, k_extra=0, vec_dtype=np.complex128):
+    """Run the reference on ``sweeps`` and write <name>.npz + <name>.plan.json.
+
+    ``k_extra``: the reference is asked for k + k_extra levels; ``E`` / ``V`` keep the lowest k and ``E_next`` the
+    following ones, so that a test can tell whether level k-1 belongs to a degenerate cluster cut by the truncation.
+    ``vec_dtype=np.complex64`` halves the stored eigenvectors of the big configurations (the overlap criterion
+    1 - |<a|b>| is quadratic in the stored rounding error: ~1e-14)."""
     lower_kw = lower_kw or {}
     t0 = time.time()
-    recs, dt = reference_sweep(h, sweeps, k, get_vectors, evaluations, sparse_opts)
+    recs, dt = reference_sweep(h, sweeps, k + k_extra, get_vectors, evaluations, sparse_opts)
     out = {}
     multi = isinstance(recs[0], dict)
     ham = [r["getHamiltonian"] for r in recs] if multi else recs
@@ -334,9 +339,13 @@ def freeze(name, h, sweeps, k=10, get_vectors=False, evaluations=(), sparse_opts
         E = np.array([np.asarray(r[0], dtype=np.float64) for r in ham])
         vec_points = list(vec_points) if len(vec_points) else [0]
         out["vec_points"] = np.asarray(vec_points, dtype=np.int64)
-        out["V"] = np.array([np.stack([v.data.to_array()[:, 0] for v in ham[i][1]], axis=1) for i in vec_points])
+        V = np.array([np.stack([v.data.to_array()[:, 0] for v in ham[i][1]], axis=1) for i in vec_points])
+        out["V"] = np.ascontiguousarray(V[:, :, :k]).astype(vec_dtype)
     else:
         E = np.array([np.asarray(r, dtype=np.float64) for r in ham])
+    if k_extra:
+        out["E_next"] = np.ascontiguousarray(E[:, k:])
+        E = np.ascontiguousarray(E[:, :k])
     out["E"] = E
     if multi:
         for key in recs[0]:
@@ -427,6 +436,19 @@ def make_c3():
     # (examples/csfq-example.py:535-553; agrees with dense to 1e-14)
     freeze("c3_csfqfloat_t10", build_csfq_floating(10), [S("alpha", 0.44, 0.9, 2), S("phiZ", 0.47, 0.5, 2)], k=10,
            sparse_opts={"sigma": -300, "mode": "normal", "maxiter": None, "tol": 0}, n_h_samples=1)
+
+
+_SA_EXACT = {"sigma": None, "mode": "normal", "maxiter": None, "tol": 0, "which": "SA"}
+
+
+def make_big():
+    """The two largest BASELINE configs through the reference's SPARSE path (util.diagSparseH, util.py:76-125) with
+    ``tol=0`` -- ARPACK to machine precision, the setting SURVEY.md section 8d names for n >= 9261 -- since the dense
+    path is out of reach (n = 32 400: 16.8 GB per matrix).  Eleven levels are requested, ten are the fixture."""
+    freeze("c3_csfq4jj_t50s", build_csfq_4jj(50), [S("d", 0.02, 0.1, 2), S("phiX", -0.35, 0.8, 2)], k=10, k_extra=1,
+           get_vectors=True, vec_points=[0, 3], sparse_opts=_SA_EXACT, store_h=False, vec_dtype=np.complex64)
+    freeze("c5_fluxatom_t180s", build_fluxonium_atom(180), [S("phi-", 0.13, 0.5, 2)], k=10, k_extra=1,
+           get_vectors=True, vec_points=[1], sparse_opts=_SA_EXACT, store_h=False, vec_dtype=np.complex64)
 
 
 def make_c4():
@@ -558,7 +580,7 @@ def make_c7():
     print("c7_fluxonium_C               n=%d pts=%d" % (int(out["n"]), len(grid)), flush=True)
 
 
-ALL = {"c6": make_c6, "c7": make_c7, "c2b": make_c2b, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c4": make_c4, "c5": make_c5}
+ALL = {"big": make_big, "c6": make_c6, "c7": make_c7, "c2b": make_c2b, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c4": make_c4, "c5": make_c5}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(ALL)

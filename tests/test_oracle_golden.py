@@ -9,10 +9,13 @@ import numpy as np
 import pytest
 
 from oracle.plan_oracle import PlanOracle, eig_rel_err, eval_program, rel_err, subspace_overlap
-from tests.conftest import golden_hamiltonian, golden_names, load_golden
+from tests.conftest import e_next, golden_vectors, golden_hamiltonian, golden_names, load_golden
 
 # the big cases only check a couple of points to keep the CPU suite in minutes
-MAX_POINTS = {81: 120, 41: 231, 101: 60, 200: 9, 441: 12, 961: 4, 1331: 15, 3025: 1, 3375: 1, 9261: 0}
+MAX_POINTS = {81: 120, 41: 231, 101: 60, 200: 9, 441: 12, 961: 4, 1331: 15, 3025: 1, 3375: 1, 9261: 1, 10201: 2, 32400: 1}
+# above this dimension the oracle follows the reference's SPARSE path (util.py:76-125, eigsh tol=0) like the fixture did
+SPARSE_FROM = 9000
+_SA = {"which": "SA", "tol": 0}
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -42,7 +45,7 @@ def test_eigenvalues_match_reference(name):
         pytest.skip("covered by the GPU / slow suites")
     idx = np.unique(np.linspace(0, len(g["E"]) - 1, min(cap, len(g["E"]))).astype(int))
     orc = PlanOracle(plan)
-    out = orc.sweep(g["params"][idx], k)
+    out = orc.sweep(g["params"][idx], k, sparse_opts=_SA if n >= SPARSE_FROM else None)
     # the gate of the whole project: 1e-9 relative (BASELINE.json); the oracle sits far inside it
     assert eig_rel_err(out["E"], g["E"][idx]) < 1e-10
     # transition energies E_i - E_0 (absolute, GHz)
@@ -59,9 +62,11 @@ def test_eigenvectors_match_reference(name):
     k = int(g["k"])
     orc = PlanOracle(plan)
     pts = g["vec_points"]
-    out = orc.sweep(g["params"][pts], k, get_vectors=True)
+    if plan.hilbert_dim >= SPARSE_FROM:
+        pts = pts[:1]
+    out = orc.sweep(g["params"][pts], k, get_vectors=True, sparse_opts=_SA if plan.hilbert_dim >= SPARSE_FROM else None)
     for j in range(len(pts)):
-        ov = subspace_overlap(out["V"][j], g["V"][j], g["E"][pts[j]])
+        ov = subspace_overlap(out["V"][j], golden_vectors(g, j), g["E"][pts[j]], E_next=e_next(g, plan, pts[j], k))
         assert ov >= 1 - 1e-8, (name, pts[j], ov)
 
 
@@ -166,3 +171,39 @@ def test_pauli_coefficients_match_reference(name):
     # the two-level model reproduces the gap (examples/local-basis-example.py:113-133)
     gap = 2 * np.sqrt(hx ** 2 + hy ** 2 + hz ** 2)
     assert np.max(np.abs(gap - (g["E"][:, 1] - g["E"][:, 0]))) < 1e-10 * scale
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_postsub_floats_match_coefficient_program(name):
+    """The floats the reference's ``_postsub`` leaves on the instance (numerical_system.py:395-437: ``Cinvnp``,
+    ``Linvnp``, ``Jvecnp``, ``Pexp_pnp``, frozen in the fixtures as postsub<j>_*) against the coefficient program
+    that replaces the substitution: the Q_i^2 / P_i^2 terms carry 1/2 Ec C^-1_ii and 1/2 El L^-1_ii, the cross terms
+    Ec C^-1_ij and El L^-1_ij (both orderings merged), and the displacement terms sum to -Ej sum_e J_e Re Pexp_e."""
+    g, plan = load_golden(name)
+    if "postsub0_Cinv" not in g:
+        pytest.skip("no _postsub samples stored")
+    pref = plan.meta["prefactors"]
+    coef, _ = eval_program(plan.program, g["params"])
+    checked = 0
+    for j, p in enumerate(g["h_points"]):
+        Cinv, Linv, J, Pexp = (g["postsub%d_%s" % (j, x)] for x in ("Cinv", "Linv", "J", "Pexp"))
+        disp_sum = 0.0
+        for t, fids in enumerate(plan.terms):
+            names = {ni: plan.factors[f][1] for ni, f in enumerate(fids) if f >= 0}
+            kinds = set(names.values())
+            c = coef[p, t]
+            if len(names) == 1 and kinds <= {"charge2", "flux2"}:
+                (ni, nm), = names.items()
+                ref = 0.5 * (pref["Ec"] * Cinv[ni, ni] if nm == "charge2" else pref["El"] * Linv[ni, ni])
+                assert abs(c - ref) <= 1e-13 * abs(ref), (name, t)
+                checked += 1
+            elif len(names) == 2 and kinds in ({"charge"}, {"flux"}):
+                a, b = sorted(names)
+                ref = pref["Ec"] * Cinv[a, b] if kinds == {"charge"} else pref["El"] * Linv[a, b]
+                assert abs(c - ref) <= 1e-13 * abs(ref), (name, t)
+                checked += 1
+            elif names and kinds <= {"disp", "disp_adj"}:
+                disp_sum += c
+        ref = -pref["Ej"] * np.sum(np.asarray(J).reshape(-1) * np.real(np.asarray(Pexp).reshape(-1)))
+        assert abs(disp_sum - ref) <= 1e-12 * max(1.0, np.sum(np.abs(J)) * pref["Ej"]), (name, p)
+    assert checked > 0
