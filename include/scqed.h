@@ -120,7 +120,10 @@ typedef struct {
                                  real parts are packed on the device and only they cross PCIe.  Valid when every
                                  eigenvector is exactly real (real symmetric H: fluxonium, RF-SQUID ...); otherwise the
                                  call returns SCQED_ECOMPLEX (1) and must be repeated with a complex buffer.        */
-    int32_t reserved[4];
+    int32_t evecs_on_device;  /* scqed_sweep_run_host only: `evecs` is a DEVICE pointer (complex [n_pts, k, n]); the eigenvectors
+                                 are written there and stay on the GPU (fetched lazily by the caller, or consumed by
+                                 scqed_matrix_elements); everything else is copied to the host buffers as usual         */
+    int32_t reserved[3];
 } scqed_sweep_opts;
 
 #define SCQED_ECOMPLEX 1   /* real_vectors requested but some eigenvector has a non-zero imaginary part */
@@ -186,6 +189,13 @@ int scqed_back_transform(scqed_plan *plan, double *evecs_dev, int64_t n_vectors,
  * (hx, hy, hz).  float64 throughout (the reference rounds to complex64). */
 int scqed_pauli_coefficients(int device, const double *e01_dev, const double *op_dev, int64_t n_pts,
                              double *h_dev, void *stream);
+
+/* Matrix elements of ONE fixed dense operator between the first m (<= 4) eigenvectors of every point: the
+ * fixed-operator branch of util.pauliCoefficients (util.py:320-342, `basis_op.matrix_element(V[a], V[b])` in a
+ * Python loop over sweep points).  op_dev complex [n, n] row-major; evecs_dev complex [n_pts, m, n];
+ * out_dev complex [n_pts, m, m] = <V_a| Op |V_b>. */
+int scqed_dense_matrix_elements(int device, const double *op_dev, const double *evecs_dev, int32_t n, int32_t m,
+                                int64_t n_pts, double *out_dev, void *stream);
 
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t scqed_launch_count(void);

@@ -496,6 +496,20 @@ extern "C" int scqed_pauli_coefficients(int device, const double *e01_dev, const
     return 0;
 }
 
+extern "C" int scqed_dense_matrix_elements(int device, const double *op_dev, const double *evecs_dev, int32_t n, int32_t m,
+                                           int64_t n_pts, double *out_dev, void *stream) {
+    if (!op_dev || !evecs_dev || !out_dev || n < 1 || n_pts < 1) return fail(SCQED_EINVAL, "bad argument");
+    if (m < 1 || m > DMEL_MMAX) return fail(SCQED_EUNSUPPORTED, "1 <= m <= %d vectors per point", DMEL_MMAX);
+    ON_DEVICE(device);
+    const size_t smem = ((size_t)m * n + (size_t)8 * m * m) * 16;
+    if (smem > 200 * 1024) return fail(SCQED_EUNSUPPORTED, "n=%d too large for the dense matrix-element kernel", n);
+    CK(cudaFuncSetAttribute(dense_matel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dense_matel_kernel<<<(unsigned)n_pts, 256, smem, (cudaStream_t)stream>>>((const cplx *)op_dev, (const cplx *)evecs_dev, n, m, n_pts, (cplx *)out_dev);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int scqed_eval_coefficients(scqed_plan *pl, const double *params_dev, int64_t n_pts, double *coef_dev,
                                        double *scalars_dev, void *stream) {
     if (!pl || !coef_dev || n_pts < 1) return fail(SCQED_EINVAL, "bad argument");
@@ -758,8 +772,10 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
     size_t b_vec = (o->want_vectors && (evecs || o->resonator)) ? (size_t)n_pts * k * n * 16 : 0;
     size_t b_sc = (size_t)n_pts * (P.n_scalar > 0 ? P.n_scalar : 1) * 8;
     size_t b_post = (size_t)n_pts * nstrips * k * 8;
+    const bool vec_dev = o->evecs_on_device && evecs && b_vec;      // eigenvectors stay in the caller's device buffer
+    if (vec_dev && o->real_vectors) return fail(SCQED_EINVAL, "real_vectors and evecs_on_device are mutually exclusive");
     if (pl->in_params.ensure(b_par) || pl->out_evals.ensure(b_ev) || pl->out_info.ensure((size_t)n_pts * 4) ||
-        pl->out_scal.ensure(b_sc) || (b_vec && evecs && pl->out_evecs.ensure(b_vec)) || (b_post && pl->out_post.ensure(b_post)))
+        pl->out_scal.ensure(b_sc) || (b_vec && evecs && !vec_dev && pl->out_evecs.ensure(b_vec)) || (b_post && pl->out_post.ensure(b_post)))
         return fail(SCQED_ENOMEM, "device staging buffers");
     if (!pl->copy_stream) CK(cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking));
     cudaStream_t cs = pl->copy_stream;
@@ -772,7 +788,7 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
     struct Seg { char *user; const char *dev; size_t per_pt; bool staged; };
     Seg segs[5] = {
         {(char *)evals, nullptr, (size_t)k * 8, false},
-        {(char *)evecs, nullptr, evecs && b_vec ? (size_t)k * n * (pack ? 8 : 16) : 0, false},
+        {(char *)evecs, nullptr, (evecs && b_vec && !vec_dev) ? (size_t)k * n * (pack ? 8 : 16) : 0, false},
         {(char *)scalars, nullptr, (scalars && ns > 0) ? (size_t)ns * 8 : 0, false},
         {(char *)post, nullptr, (post && b_post) ? (size_t)nstrips * k * 8 : 0, false},
         {(char *)info, nullptr, 4, false},
@@ -838,7 +854,7 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
     if (staged_per_pt && pl->hstage.ensure(2 * slot_bytes)) return fail(SCQED_ENOMEM, "pinned staging ring (%zu MB)", (2 * slot_bytes) >> 20);
 
     double *d_ev = (double *)pl->out_evals.p, *d_sc = (double *)pl->out_scal.p;
-    cplx *d_vec = (evecs && b_vec) ? (cplx *)pl->out_evecs.p : nullptr;
+    cplx *d_vec = (evecs && b_vec) ? (vec_dev ? (cplx *)evecs : (cplx *)pl->out_evecs.p) : nullptr;
     double *d_pack = nullptr;
     int *d_flag = nullptr;
     if (pack) {

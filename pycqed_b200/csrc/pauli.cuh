@@ -55,4 +55,53 @@ pauli_coef_kernel(const double *__restrict__ e01, const cplx *__restrict__ op, l
     h[3 * p + 2] = 0.5 * (hq00 - hq11);
 }
 
+// <V_a| A |V_b> of a FIXED dense operator A (n x n, row-major) between m vectors of every point:
+// out[p][a][b], one CTA per point.  The m vectors are staged in shared memory; warp w takes rows
+// i = w, w + nw, ...: lanes stride over the columns of row i (coalesced reads of A, which stays in L2 across
+// the points), y_b = sum_j A[i][j] V_b[j] for every b, then acc[a][b] += conj(V_a[i]) y_b.
+// util.pauliCoefficients' fixed-operator branch (util.py:320-342) loops this over points in Python.
+#define DMEL_MMAX 4
+static __global__ void __launch_bounds__(256)
+dense_matel_kernel(const cplx *__restrict__ A, const cplx *__restrict__ V, int n, int m, long long n_pts,
+                   cplx *__restrict__ out) {
+    extern __shared__ cplx dm_s[];
+    cplx *sv = dm_s;                                   // [m][n]
+    cplx *sacc = dm_s + (size_t)m * n;                 // [nw][m*m]
+    const long long p = blockIdx.x;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const cplx *Vp = V + (size_t)p * m * n;
+    for (int idx = threadIdx.x; idx < m * n; idx += blockDim.x) sv[idx] = Vp[idx];
+    __syncthreads();
+    cplx acc[DMEL_MMAX][DMEL_MMAX];
+#pragma unroll
+    for (int a = 0; a < DMEL_MMAX; ++a)
+#pragma unroll
+        for (int b = 0; b < DMEL_MMAX; ++b) acc[a][b] = cmake(0.0, 0.0);
+    for (int i = w; i < n; i += nw) {
+        cplx y[DMEL_MMAX];
+#pragma unroll
+        for (int b = 0; b < DMEL_MMAX; ++b) y[b] = cmake(0.0, 0.0);
+        for (int j = l; j < n; j += 32) {
+            const cplx aij = __ldg(A + (size_t)i * n + j);
+#pragma unroll
+            for (int b = 0; b < DMEL_MMAX; ++b) if (b < m) cfma(y[b], aij, sv[b * n + j]);
+        }
+#pragma unroll
+        for (int b = 0; b < DMEL_MMAX; ++b) y[b] = warp_sum(y[b]);
+#pragma unroll
+        for (int a = 0; a < DMEL_MMAX; ++a)
+#pragma unroll
+            for (int b = 0; b < DMEL_MMAX; ++b) if (a < m && b < m) cfmac(acc[a][b], sv[a * n + i], y[b]);
+    }
+    if (l == 0)
+        for (int a = 0; a < m; ++a)
+            for (int b = 0; b < m; ++b) sacc[(size_t)w * m * m + a * m + b] = acc[a][b];
+    __syncthreads();
+    if ((int)threadIdx.x < m * m) {
+        cplx s = cmake(0.0, 0.0);
+        for (int ww = 0; ww < nw; ++ww) s = cadd(s, sacc[(size_t)ww * m * m + threadIdx.x]);
+        out[(size_t)p * m * m + threadIdx.x] = s;
+    }
+}
+
 }  // namespace scqed

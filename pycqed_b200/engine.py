@@ -50,8 +50,8 @@ class _SweepOpts(C.Structure):
         ("k", C.c_int32), ("want_vectors", C.c_int32), ("solver", C.c_int32), ("tidyup", C.c_int32),
         ("resonator", C.c_int32), ("res_nmax", C.c_int32), ("res_op_factor", C.c_int32),
         ("res_gc", C.c_int32), ("res_frl", C.c_int32), ("res_qb", C.c_int32), ("raw_basis", C.c_int32),
-        ("real_vectors", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("real_vectors", C.c_int32), ("evecs_on_device", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -59,6 +59,7 @@ class _SweepOpts(C.Structure):
 EXPORTS = (
     "scqed_plan_create", "scqed_plan_destroy", "scqed_plan_hilbert_dim", "scqed_eval_coefficients",
     "scqed_assemble_dense", "scqed_eigh_batched", "scqed_sweep_run", "scqed_sweep_run_host", "scqed_matrix_elements", "scqed_pauli_coefficients", "scqed_back_transform",
+    "scqed_dense_matrix_elements",
     "scqed_launch_count", "scqed_timing_enable", "scqed_timing_read", "scqed_probe_fp64_tensor", "scqed_probe_fp64_fma", "scqed_last_error",
     "scqed_version",
 )
@@ -101,6 +102,8 @@ def load_library():
         lib.scqed_back_transform.restype = C.c_int
         lib.scqed_pauli_coefficients.argtypes = [i32, dp, dp, i64, dp, vp]
         lib.scqed_pauli_coefficients.restype = C.c_int
+        lib.scqed_dense_matrix_elements.argtypes = [i32, dp, dp, i32, i32, i64, dp, vp]
+        lib.scqed_dense_matrix_elements.restype = C.c_int
         lib.scqed_launch_count.argtypes = []
         lib.scqed_launch_count.restype = C.c_int64
         lib.scqed_timing_enable.argtypes = [C.c_int]
@@ -165,18 +168,60 @@ def _ptr(arr, ctype):
     return arr.ctypes.data_as(C.POINTER(ctype))
 
 
-def _stream_ptr():
+def _stream_ptr(device=None):
+    """cudaStream_t of torch's current stream ON ``device`` (not on whatever device happens to be current)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def pinned_empty(shape, dtype):
+    """A numpy array backed by page-locked host memory (torch's caching host allocator: the block is reused by
+    later sweeps once this array is garbage collected).  D2H copies into it are true asynchronous DMA."""
+    import torch
+    tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.complex128): torch.complex128,
+           np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
+    return torch.empty(tuple(int(x) for x in shape), dtype=tdt, pin_memory=True).numpy()
+
+
+def _check_out(name, arr, shape, dtypes):
+    """Caller-supplied result buffers are handed to the library by raw pointer: refuse anything that is not exactly
+    the array the library is going to write."""
+    if not isinstance(arr, np.ndarray):
+        raise EngineError("out[%r] must be a numpy array" % name)
+    if arr.dtype not in [np.dtype(d) for d in dtypes]:
+        raise EngineError("out[%r] has dtype %s, expected %s" % (name, arr.dtype, " or ".join(str(np.dtype(d)) for d in dtypes)))
+    if tuple(arr.shape) != tuple(shape):
+        raise EngineError("out[%r] has shape %r, expected %r" % (name, tuple(arr.shape), tuple(shape)))
+    if not arr.flags.c_contiguous or not arr.flags.writeable:
+        raise EngineError("out[%r] must be C-contiguous and writeable" % name)
+    return arr
 
 
 class SweepResult:
     """Results of one sweep on the host (numpy).  ``E`` [n_pts, k]; ``V`` [n_pts, k, n] or None;
-    ``scalars`` {name: [n_pts]}; ``Erwa`` [n_pts, nmax+1+k, k] or None; ``info`` [n_pts]."""
+    ``scalars`` {name: [n_pts]}; ``Erwa`` [n_pts, nmax+1+k, k] or None; ``info`` [n_pts].
+    ``V_dev``: when the sweep was asked to keep the eigenvectors on the device, the list of
+    ``(lo, hi, tensor[hi-lo, k, n])`` shards (one per GPU) and ``V`` is fetched lazily by :meth:`vectors`."""
 
-    def __init__(self, E, V, scalars, Erwa, info, matel=None):
+    def __init__(self, E, V, scalars, Erwa, info, matel=None, V_dev=None):
         self.E, self.V, self.scalars, self.Erwa, self.info = E, V, scalars, Erwa, info
         self.matel = matel          # complex [n_pts, n_pairs] (Current / Voltage matrix elements) or None
+        self.V_dev = V_dev
+
+    def vectors(self):
+        """Host eigenvectors [n_pts, k, n]; copies the device shards on first use."""
+        if self.V is None and self.V_dev:
+            n_pts = max(hi for _, hi, _ in self.V_dev)
+            t0 = self.V_dev[0][2]
+            V = pinned_empty((n_pts,) + tuple(t0.shape[1:]), np.complex128)
+            import torch
+            Vt = torch.from_numpy(V)
+            for lo, hi, t in self.V_dev:
+                Vt[lo:hi].copy_(t, non_blocking=True)
+            for _, _, t in self.V_dev:
+                torch.cuda.synchronize(t.device)
+            self.V = V
+        return self.V
 
 
 class Engine:
@@ -283,6 +328,9 @@ class Engine:
     def __exit__(self, *a):
         self.close()
 
+    def _st(self):
+        return _stream_ptr(self.device)
+
     # ------------------------------------------------------------------------------------------
     def _opts(self, k, want_vectors, solver, tidyup, resonator):
         o = _SweepOpts()
@@ -314,7 +362,7 @@ class Engine:
         n_pts = p.shape[0]
         coef = torch.empty((n_pts, len(self.plan.terms)), dtype=torch.complex128, device=self.device)
         scal = torch.empty((n_pts, max(self.plan.program.n_scalar, 1)), dtype=torch.float64, device=self.device)
-        _check(self.lib.scqed_eval_coefficients(self._handle, p.data_ptr(), n_pts, coef.data_ptr(), scal.data_ptr(), _stream_ptr()))
+        _check(self.lib.scqed_eval_coefficients(self._handle, p.data_ptr(), n_pts, coef.data_ptr(), scal.data_ptr(), self._st()))
         return coef, scal[:, :self.plan.program.n_scalar]
 
     def assemble_dense(self, params, tidyup=True):
@@ -323,7 +371,7 @@ class Engine:
         p = self._params_dev(params)
         n_pts = p.shape[0]
         H = torch.empty((n_pts, self.n, self.n), dtype=torch.complex128, device=self.device)
-        _check(self.lib.scqed_assemble_dense(self._handle, p.data_ptr(), n_pts, int(bool(tidyup)), H.data_ptr(), _stream_ptr()))
+        _check(self.lib.scqed_assemble_dense(self._handle, p.data_ptr(), n_pts, int(bool(tidyup)), H.data_ptr(), self._st()))
         return H
 
     def matrix_elements(self, params, V):
@@ -343,14 +391,14 @@ class Engine:
             raise EngineError("V must be a complex128 array / CUDA tensor [n_pts, k, n] of eigenvectors")
         V = V.contiguous()
         out = torch.empty((n_pts, self.n_pairs), dtype=torch.complex128, device=self.device)
-        _check(self.lib.scqed_matrix_elements(self._handle, p.data_ptr(), n_pts, int(V.shape[1]), V.data_ptr(), out.data_ptr(), _stream_ptr()))
+        _check(self.lib.scqed_matrix_elements(self._handle, p.data_ptr(), n_pts, int(V.shape[1]), V.data_ptr(), out.data_ptr(), self._st()))
         return out
 
     def back_transform(self, V):
         """Rotate eigenvectors [n_pts, k, n] (CUDA complex128, in place) from the plan's basis to the
         reference's Fock basis (only plans with swept-impedance oscillator nodes have one)."""
         if self.rotated:
-            _check(self.lib.scqed_back_transform(self._handle, V.data_ptr(), int(V.shape[0] * V.shape[1]), _stream_ptr()))
+            _check(self.lib.scqed_back_transform(self._handle, V.data_ptr(), int(V.shape[0] * V.shape[1]), self._st()))
         return V
 
     def sweep_device(self, params, k, want_vectors=False, resonator=False, solver=SOLVER_AUTO, tidyup=True,
@@ -371,66 +419,174 @@ class Engine:
         info = torch.empty((n_pts,), dtype=torch.int32, device=self.device)
         _check(self.lib.scqed_sweep_run(
             self._handle, C.byref(o), p.data_ptr(), n_pts, E.data_ptr(), V.data_ptr() if V is not None else None,
-            scal.data_ptr(), post.data_ptr() if post is not None else None, info.data_ptr(), _stream_ptr()))
+            scal.data_ptr(), post.data_ptr() if post is not None else None, info.data_ptr(), self._st()))
         return E, V, scal[:, :ns], post, info
 
     def sweep(self, params, k, want_vectors=False, resonator=False, solver=SOLVER_AUTO, tidyup=True,
-              out=None, matrix_elements=False, real_vectors=False) -> SweepResult:
-        """Host-buffer sweep (the call the drop-in ``paramSweep`` makes): params and results are
-        numpy / pinned host memory, the library does the H2D / D2H copies.  With
-        ``matrix_elements`` the eigenvectors stay on the device for ``scqed_matrix_elements`` and
-        everything is copied back afterwards.  ``real_vectors``: True / "auto" asks the library to ship only the
-        real parts of the eigenvectors (``V`` comes back float64 [n_pts, k, n]: a third less PCIe traffic for real
-        symmetric H); if some eigenvector is complex, "auto" repeats the call with a complex buffer and True raises."""
+              out=None, matrix_elements=False, real_vectors=False, vectors_on_device=False, row_offset=0) -> SweepResult:
+        """Host-buffer sweep (the call the drop-in ``paramSweep`` makes): params and results are numpy arrays, the
+        library does the H2D / D2H copies (``scqed_sweep_run_host``).
+
+        Result arrays the caller does not supply in ``out`` are allocated PAGE-LOCKED (:func:`pinned_empty`), so the
+        copies out of the GPU are asynchronous DMA overlapped with the next chunk's solve; pageable arrays supplied
+        in ``out`` work too (the library stages them through its own pinned ring).  ``out`` = {'E','V','Erwa',
+        'scalars','info'}: arrays of the FULL result; this call writes rows [row_offset, row_offset + n_pts) (how
+        several GPUs fill one result).
+
+        ``matrix_elements``: the eigenvectors stay on the device for ``scqed_matrix_elements`` and everything is
+        copied back afterwards.  ``real_vectors``: True / "auto" asks the library to ship only the real parts of the
+        eigenvectors (``V`` comes back float64 [n_pts, k, n]: a third less PCIe traffic for real symmetric H); if
+        some eigenvector is complex, "auto" repeats the call with a complex buffer and True raises.
+        ``vectors_on_device``: eigenvectors are NOT copied to the host; ``SweepResult.V_dev`` holds the device
+        tensor and ``SweepResult.vectors()`` fetches them on demand."""
+        import torch
         params = np.ascontiguousarray(params, dtype=np.float64)
         if params.ndim != 2 or params.shape[1] != self.plan.program.n_swept:
             raise EngineError("params must be [n_pts, %d]" % self.plan.program.n_swept)
         n_pts = params.shape[0]
-        if matrix_elements:
-            p = self._params_dev(params)
-            E, V, scal, post, info = self.sweep_device(p, k, want_vectors=True, resonator=resonator, solver=solver,
-                                                       tidyup=tidyup, raw_basis=True)
-            M = self.matrix_elements(p, V)            # operators and vectors both in the plan's basis
-            self.back_transform(V)
-            names = list(self.plan.program.scalar_names)
-            scal = scal.cpu().numpy()
-            return SweepResult(E.cpu().numpy(), V.cpu().numpy() if want_vectors else None,
-                               {nm: scal[:, i].copy() for i, nm in enumerate(names)},
-                               post.cpu().numpy() if post is not None else None, info.cpu().numpy(), M.cpu().numpy())
-        o = self._opts(k, want_vectors or resonator, solver, tidyup, resonator)
-        ns = self.plan.program.n_scalar
-        out = out or {}
-        E = out.get("E")
-        if E is None:
-            E = np.empty((n_pts, k), dtype=np.float64)
-        V = out.get("V") if want_vectors else None
-        real_req = bool(real_vectors) and want_vectors and not self.rotated
-        if want_vectors and V is not None:
-            real_req = real_req and V.dtype == np.float64
-        if want_vectors and V is None:
-            V = np.empty((n_pts, k, self.n), dtype=np.float64 if real_req else np.complex128)
-        o.real_vectors = int(real_req)
-        scal = np.empty((n_pts, max(ns, 1)), dtype=np.float64)
-        post = None
-        if resonator:
-            post = out.get("Erwa")
-            if post is None:
-                post = np.empty((n_pts, o.res_nmax + 1 + k, k), dtype=np.float64)
-        info = np.empty((n_pts,), dtype=np.int32)
-        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
-        rc = self.lib.scqed_sweep_run_host(self._handle, C.byref(o), vp(params), n_pts, vp(E), vp(V), vp(scal),
-                                           vp(post), vp(info))
-        if rc == 1 and real_req:                 # SCQED_ECOMPLEX: the eigenvectors are not real
-            if real_vectors != "auto":
-                raise EngineError("real_vectors=True but the eigenvectors are complex; use real_vectors='auto' or False")
-            o.real_vectors = 0
-            V = np.empty((n_pts, k, self.n), dtype=np.complex128)
-            rc = self.lib.scqed_sweep_run_host(self._handle, C.byref(o), vp(params), n_pts, vp(E), vp(V), vp(scal),
-                                               vp(post), vp(info))
-        _check(rc)
         names = list(self.plan.program.scalar_names)
+        with torch.cuda.device(self.device):
+            if matrix_elements:
+                p = self._params_dev(params)
+                E, V, scal, post, info = self.sweep_device(p, k, want_vectors=True, resonator=resonator, solver=solver,
+                                                           tidyup=tidyup, raw_basis=True)
+                M = self.matrix_elements(p, V)            # operators and vectors both in the plan's basis
+                self.back_transform(V)
+                scal = scal.cpu().numpy()
+                keep = want_vectors and vectors_on_device
+                return SweepResult(E.cpu().numpy(), V.cpu().numpy() if (want_vectors and not keep) else None,
+                                   {nm: scal[:, i].copy() for i, nm in enumerate(names)},
+                                   post.cpu().numpy() if post is not None else None, info.cpu().numpy(), M.cpu().numpy(),
+                                   V_dev=[(row_offset, row_offset + n_pts, V)] if keep else None)
+            o = self._opts(k, want_vectors or resonator, solver, tidyup, resonator)
+            ns = self.plan.program.n_scalar
+            out = out or {}
+            r0 = int(row_offset)
+
+            def rows(name, tail, dtypes):
+                """The [n_pts, ...] block of out[name] this call writes (validated), or a fresh pinned array."""
+                full = out.get(name)
+                if full is None:
+                    return pinned_empty((n_pts,) + tail, dtypes[0])
+                if full.ndim < 1 or full.shape[0] < r0 + n_pts:
+                    raise EngineError("out[%r] has %d rows, this call writes rows %d..%d" % (name, full.shape[0] if full.ndim else 0, r0, r0 + n_pts))
+                _check_out(name, full, (full.shape[0],) + tail, dtypes)
+                return full[r0:r0 + n_pts]
+
+            E = rows("E", (k,), [np.float64])
+            V = V_dev = None
+            to_dev = bool(vectors_on_device) and want_vectors
+            real_req = bool(real_vectors) and want_vectors and not self.rotated and not to_dev
+            if want_vectors and not to_dev:
+                if out.get("V") is not None:
+                    V = rows("V", (k, self.n), [np.complex128, np.float64])
+                    real_req = real_req and V.dtype == np.float64
+                    if V.dtype == np.float64 and not real_req:
+                        raise EngineError("out['V'] is float64 but real_vectors was not requested (or the plan has rotated nodes)")
+                else:
+                    V = pinned_empty((n_pts, k, self.n), np.float64 if real_req else np.complex128)
+            if to_dev:
+                V_dev = torch.empty((n_pts, k, self.n), dtype=torch.complex128, device=self.device)
+                o.evecs_on_device = 1
+            o.real_vectors = int(real_req)
+            scal = rows("scalars", (max(ns, 1),), [np.float64])
+            post = rows("Erwa", (o.res_nmax + 1 + k, k), [np.float64]) if resonator else None
+            info = rows("info", (), [np.int32])
+            vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+            vptr = C.c_void_p(V_dev.data_ptr()) if to_dev else vp(V)
+            rc = self.lib.scqed_sweep_run_host(self._handle, C.byref(o), vp(params), n_pts, vp(E), vptr, vp(scal),
+                                               vp(post), vp(info))
+            if rc == 1 and real_req:                 # SCQED_ECOMPLEX: the eigenvectors are not real
+                if real_vectors != "auto" or out.get("V") is not None:
+                    raise EngineError("real_vectors=True but the eigenvectors are complex; use real_vectors='auto' or False")
+                o.real_vectors = 0
+                V = pinned_empty((n_pts, k, self.n), np.complex128)
+                rc = self.lib.scqed_sweep_run_host(self._handle, C.byref(o), vp(params), n_pts, vp(E), vp(V), vp(scal),
+                                                   vp(post), vp(info))
+            _check(rc)
         scalars = {nm: scal[:, i].copy() for i, nm in enumerate(names)}
-        return SweepResult(E, V, scalars, post, info)
+        return SweepResult(E, V, scalars, post, info, V_dev=[(r0, r0 + n_pts, V_dev)] if to_dev else None)
+
+
+def visible_devices():
+    import torch
+    return list(range(torch.cuda.device_count())) if torch.cuda.is_available() else []
+
+
+class EnginePool:
+    """One plan on several GPUs of this box, driven from ONE process: the sweep driver of the reference
+    (numerical_system.py:885-928) shards the flattened grid into contiguous blocks, one host thread per GPU calls
+    ``scqed_sweep_run_host`` on its block (ctypes releases the GIL) and every block lands in its rows of the same
+    page-locked result arrays.  Sweep points are independent: no collective, no peer traffic."""
+
+    def __init__(self, plan, devices=None):
+        devs = visible_devices() if devices is None else [int(d) for d in devices]
+        if not devs:
+            raise EngineError("no CUDA device visible; the sweep engine has no CPU fallback")
+        self.plan = plan
+        self.devices = devs
+        self.engines = [Engine(plan, device=d) for d in devs]
+        self.n = self.engines[0].n
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+        self.engines = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sweep(self, params, k, want_vectors=False, resonator=False, min_points_per_gpu=256, **kw) -> SweepResult:
+        from .distributed import shard_bounds
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        n_pts = params.shape[0]
+        use = max(1, min(len(self.engines), n_pts // max(1, int(min_points_per_gpu))))
+        if use == 1 or kw.get("matrix_elements"):
+            return self.engines[0].sweep(params, k, want_vectors=want_vectors, resonator=resonator, **kw)
+        eng0 = self.engines[0]
+        to_dev = bool(kw.get("vectors_on_device")) and want_vectors
+        real_vectors = kw.pop("real_vectors", False)
+        ns = self.plan.program.n_scalar
+        out = {"E": pinned_empty((n_pts, k), np.float64), "scalars": pinned_empty((n_pts, max(ns, 1)), np.float64),
+               "info": pinned_empty((n_pts,), np.int32)}
+        if resonator:
+            out["Erwa"] = pinned_empty((n_pts, int(self.plan.post["resonator"]["nmax"]) + 1 + k, k), np.float64)
+
+        def run(real):
+            import threading
+            if want_vectors and not to_dev:
+                out["V"] = pinned_empty((n_pts, k, self.n), np.float64 if real else np.complex128)
+            res, errs = [None] * use, []
+
+            def work(i):
+                lo, hi = shard_bounds(n_pts, use, i)
+                if hi <= lo:
+                    return
+                try:
+                    res[i] = self.engines[i].sweep(params[lo:hi], k, want_vectors=want_vectors, resonator=resonator,
+                                                   out=out, row_offset=lo, real_vectors=bool(real), **kw)
+                except Exception as exc:            # re-raised on the calling thread
+                    errs.append(exc)
+            th = [threading.Thread(target=work, args=(i,)) for i in range(use)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            return res, errs
+
+        real_req = bool(real_vectors) and want_vectors and not eng0.rotated and not to_dev
+        res, errs = run(real_req)
+        if errs and real_req and real_vectors == "auto" and all("eigenvectors are complex" in str(e) for e in errs):
+            res, errs = run(False)
+        if errs:
+            raise errs[0]
+        names = list(self.plan.program.scalar_names)
+        scalars = {nm: out["scalars"][:, i].copy() for i, nm in enumerate(names)}
+        V_dev = [r.V_dev[0] for r in res if r is not None and r.V_dev] if to_dev else None
+        return SweepResult(out["E"], out.get("V"), scalars, out.get("Erwa"), out["info"], V_dev=V_dev)
 
 
 def pauli_coefficients(E0, E1, Op, device=None):
@@ -446,9 +602,27 @@ def pauli_coefficients(E0, E1, Op, device=None):
         raise EngineError("Op must hold one 2x2 operator per point (%d), got %d" % (n_pts, op.shape[0]))
     h = torch.empty((n_pts, 3), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        _check(lib.scqed_pauli_coefficients(dev.index, e01.data_ptr(), op.data_ptr(), n_pts, h.data_ptr(), _stream_ptr()))
+        _check(lib.scqed_pauli_coefficients(dev.index, e01.data_ptr(), op.data_ptr(), n_pts, h.data_ptr(), _stream_ptr(dev)))
     h = h.cpu().numpy()
     return h[:, 0].copy(), h[:, 1].copy(), h[:, 2].copy()
+
+
+def dense_matrix_elements(Op, W, device=None):
+    """``<W[p, a]| Op |W[p, b]>`` for one fixed dense operator ``Op`` [n, n] and ``W`` [n_pts, m, n] (m <= 4 vectors
+    per point): complex128 numpy array [n_pts, m, m] (``scqed_dense_matrix_elements``)."""
+    import torch
+    lib = load_library()
+    dev = _require_cuda(device)
+    A = torch.as_tensor(np.ascontiguousarray(np.asarray(Op, dtype=np.complex128)), device=dev)
+    Wd = W if isinstance(W, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(np.asarray(W, dtype=np.complex128)), device=dev)
+    Wd = Wd.to(device=dev, dtype=torch.complex128).contiguous()
+    if A.ndim != 2 or A.shape[0] != A.shape[1] or Wd.ndim != 3 or Wd.shape[2] != A.shape[0]:
+        raise EngineError("Op must be [n, n] and W [n_pts, m, n]")
+    n_pts, m, n = Wd.shape
+    out = torch.empty((n_pts, m, m), dtype=torch.complex128, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.scqed_dense_matrix_elements(dev.index, A.data_ptr(), Wd.data_ptr(), n, m, n_pts, out.data_ptr(), _stream_ptr(dev)))
+    return out.cpu().numpy()
 
 
 def eigh_batched(H, k, want_vectors=False, solver=SOLVER_AUTO):
@@ -466,5 +640,5 @@ def eigh_batched(H, k, want_vectors=False, solver=SOLVER_AUTO):
     info = torch.empty((B,), dtype=torch.int32, device=H.device)
     with torch.cuda.device(H.device):
         _check(lib.scqed_eigh_batched(H.device.index, H.data_ptr(), n, B, k, E.data_ptr(),
-                                      V.data_ptr() if V is not None else None, info.data_ptr(), int(solver), _stream_ptr()))
+                                      V.data_ptr() if V is not None else None, info.data_ptr(), int(solver), _stream_ptr(H.device)))
     return E, V, info

@@ -163,7 +163,7 @@ class _TermTable:
 
 
 def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scalars=None,
-                 resonator=None, matrix_elements=(), regen_mode="consistent") -> SweepPlan:
+                 resonator=None, matrix_elements=(), regen_mode="consistent", matrices=None) -> SweepPlan:
     """Build the plan.
 
     :param SS: the reference ``SymbolicSystem`` (after ``ndSweep`` if ``swept_names``)
@@ -176,6 +176,9 @@ def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scala
                        the impedance, i.e. H equals what ``setParameterValues`` + ``getHamiltonian`` give at each
                        point) or 'reference' (reproduce the reference's sweep loop, which leaves the charge /
                        flux operators at the pre-sweep impedance; see _expand_regen)
+    :param matrices: optional {'Cinv': ..., 'Linv': ...}: the symbolic inverse capacitance / inductance matrices when
+                     the caller already holds them (``SymbolicSystem.getInverse*Matrix`` re-derives a symbolic matrix
+                     inverse and re-registers the parameterisations on every call, symbolic_system.py:194-224,363-391)
     :param matrix_elements: [{'kind': 'Voltage', 'node': n, 'elements': [(i, j), ...]} |
                              {'kind': 'Current', 'edge': e, 'elements': [...]}] (numerical_system.py:596-694)
     """
@@ -226,8 +229,9 @@ def lower_system(SS, units, operator_data, swept_names=(), sweep_specs=(), scala
     Ej = units.getPrefactor("Ej")
     Ep = units.getPrefactor("Ep")
 
-    Cinv = SS.getInverseCapacitanceMatrix().applyfunc(R)
-    Linv = SS.getInverseInductanceMatrix().applyfunc(R)
+    matrices = matrices or {}
+    Cinv = (matrices["Cinv"] if matrices.get("Cinv") is not None else SS.getInverseCapacitanceMatrix()).applyfunc(R)
+    Linv = (matrices["Linv"] if matrices.get("Linv") is not None else SS.getInverseInductanceMatrix()).applyfunc(R)
     Jvec = SS.getJosephsonVector().applyfunc(R)
     Pvec = SS.getPhaseSlipVector().applyfunc(R)
     Qb = SS.getChargeBiasVector().applyfunc(R)

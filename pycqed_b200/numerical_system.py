@@ -26,12 +26,22 @@ Differences, all deliberate:
     reference's per-point records for code that indexed the old list.
   * eigenvectors are :class:`Ket` objects (``.full()``, ``.dims``, ``.norm()``, ``.dag_dot``);
     ``Ket.to_qobj()`` converts when QuTiP is installed.
-  * oscillator nodes whose impedance depends on a swept parameter (per-point operator
-    regeneration, :378-393) are refused with ``LoweringError`` for now.
+  * ``getSweep`` on a sweep with eigenvectors returns a lazy :class:`EVResult` that indexes like the
+    reference's ``(k, 2, N)`` object array (``EV[:, 0]`` energies, ``EV[:, 1]`` kets); ``np.asarray(EV)``
+    materialises the object array.  Eigenvectors stay on the GPU until something reads them.
+  * oscillator nodes whose impedance depends on a swept parameter (per-point operator regeneration,
+    :378-393) are lowered in the eigenbasis of a + a^dagger; ``regen_mode`` = 'reference' (default:
+    what the reference's sweep loop computes, charge / flux operators left at the pre-sweep impedance)
+    or 'consistent' (every operator follows the impedance).
+  * lowered plans and uploaded engines are cached per circuit configuration (SURVEY.md section 8 row f2);
+    ``device=None`` uses every visible GPU of the box (one host thread per GPU, points sharded in
+    contiguous blocks), ``device=i`` or a list restricts it.
 """
 from __future__ import annotations
 
 import time
+from collections import OrderedDict
+from dataclasses import replace as _dc_replace
 
 import numpy as np
 import sympy as sy
@@ -43,32 +53,110 @@ _qobj_atol = 1e-12
 
 
 class Ket:
-    """Eigenvector with the tensor ``dims`` the reference attaches (util.py:167)."""
+    """Eigenvector with the tensor ``dims`` the reference attaches (util.py:167).  Holds a view of the sweep's
+    eigenvector array; nothing is copied until ``full()`` is called."""
     __array_priority__ = 1000
+    __slots__ = ("_v", "dims")
 
     def __init__(self, data, dims):
-        self._v = np.asarray(data, dtype=np.complex128).reshape(-1)
+        self._v = data
         self.dims = dims
-        self.shape = (self._v.size, 1)
+
+    @property
+    def shape(self):
+        return (int(np.size(self._v)), 1)
+
+    def _vec(self):
+        return np.asarray(self._v, dtype=np.complex128).reshape(-1)
 
     def full(self):
-        return self._v.reshape(-1, 1)
+        return self._vec().reshape(-1, 1)
 
     def norm(self):
-        return float(np.linalg.norm(self._v))
+        return float(np.linalg.norm(self._vec()))
 
     def overlap(self, other):
-        return complex(np.vdot(self._v, other._v))
+        return complex(np.vdot(self._vec(), other._vec()))
 
     def to_qobj(self):
         import qutip as qt
-        return qt.Qobj(self._v.reshape(-1, 1), dims=self.dims)
+        return qt.Qobj(self.full(), dims=self.dims)
 
     def __truediv__(self, s):
-        return Ket(self._v / s, self.dims)
+        return Ket(self._vec() / s, self.dims)
 
     def __repr__(self):
         return "Ket(dims=%r, norm=%.6f)" % (self.dims, self.norm())
+
+
+class KetGrid:
+    """Lazy array of kets: ``grid[idx]`` indexes like the numpy object array the reference returns, a scalar index
+    gives a :class:`Ket`.  ``pt`` / ``lv`` hold, for every position, the sweep point and the level of the ket."""
+
+    def __init__(self, source, pt, lv, dims):
+        self._src = source            # callable -> eigenvector array [n_pts, k, n] (fetched from the GPU on first use)
+        self._pt, self._lv, self._dims = pt, lv, dims
+        self.shape = pt.shape
+        self.ndim = pt.ndim
+        self.dtype = np.dtype(object)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, idx):
+        pt, lv = self._pt[idx], self._lv[idx]
+        if np.ndim(pt) == 0:
+            return Ket(self._src()[int(pt), int(lv)], self._dims)
+        return KetGrid(self._src, pt, lv, self._dims)
+
+    def __iter__(self):
+        return (self[i] for i in range(self.shape[0]))
+
+    @property
+    def T(self):
+        return KetGrid(self._src, self._pt.T, self._lv.T, self._dims)
+
+    def vectors(self):
+        """The eigenvectors themselves, complex/float array of shape ``self.shape + (n,)`` (no per-ket objects)."""
+        return self._src()[self._pt, self._lv]
+
+    def __array__(self, dtype=None, copy=None):
+        V = self._src()
+        out = np.empty(self.shape, dtype=object)
+        flat = out.reshape(-1)
+        for a, (p, l) in enumerate(zip(self._pt.reshape(-1).tolist(), self._lv.reshape(-1).tolist())):
+            flat[a] = Ket(V[p, l], self._dims)
+        return out
+
+
+class EVResult:
+    """What ``getSweep`` returns for a sweep with eigenvectors: indexes like the reference's object array of shape
+    ``(k, 2, ...)`` (parameters.py:1063-1068): ``EV[:, 0]`` -> energies (float array), ``EV[:, 1]`` -> :class:`KetGrid`.
+    Any other indexing pattern goes through the materialised object array (``np.asarray(EV)``)."""
+
+    def __init__(self, E, kets):
+        self._E, self._kets = E, kets              # both of shape (k, ...)
+        self.shape = (E.shape[0], 2) + tuple(E.shape[1:])
+        self.ndim = len(self.shape)
+        self.dtype = np.dtype(object)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple) and len(idx) >= 2 and isinstance(idx[1], (int, np.integer)) and not any(i is Ellipsis for i in idx[:2]):
+            which = int(idx[1])
+            if which not in (0, 1, -1, -2):
+                raise IndexError("index %d is out of bounds for axis 1 with size 2" % which)
+            rest = (idx[0],) + tuple(idx[2:])
+            return (self._E if which in (0, -2) else self._kets)[rest]
+        return np.asarray(self)[idx]
+
+    def __array__(self, dtype=None, copy=None):
+        out = np.empty(self.shape, dtype=object)
+        out[:, 0] = self._E
+        out[:, 1] = np.asarray(self._kets)
+        return out
 
 
 class _Data:
@@ -84,8 +172,9 @@ class HamiltonianMatrix:
     ``Qobj`` members the reference's users touch (examples/*.py: ``.eigenenergies()``,
     ``.data.to_array()``, ``.dims``, ``.shape``)."""
 
-    def __init__(self, array, dims):
+    def __init__(self, array, dims, device=None):
         self._a = np.asarray(array, dtype=np.complex128)
+        self._device = device
         self.dims = [list(dims), list(dims)]
         self.shape = self._a.shape
         self.data = _Data(self._a)
@@ -99,8 +188,11 @@ class HamiltonianMatrix:
 
     def eigenenergies(self):
         import torch
-        H = torch.as_tensor(self._a[None].copy(), device="cuda")
+        dev = torch.device("cuda", self._device if self._device is not None else torch.cuda.current_device())
+        H = torch.as_tensor(self._a[None].copy(), device=dev)
         E, _, info = _engine.eigh_batched(H, self._a.shape[0], want_vectors=False)
+        if info.any():
+            raise RuntimeError("eigensolver did not converge")
         return E.cpu().numpy()[0]
 
     def to_qobj(self):
@@ -109,38 +201,62 @@ class HamiltonianMatrix:
 
 
 class SweepData:
-    """In-memory result of ``paramSweep`` (all points, all evaluables)."""
+    """In-memory result of ``paramSweep`` (all points, all evaluables).  Arrays: ``E`` [n_pts, k], ``Erwa``
+    [n_pts, nmax+1+k, k], ``scalars`` {name: [n_pts]}, ``matel`` {method: [n_pts, n_elements]}, ``info`` [n_pts];
+    ``V`` [n_pts, k, n] is fetched from the GPU(s) the first time it is read."""
 
-    def __init__(self, specs, evaluations, E, V, scalars, Erwa, info, dims, timings, matel=None):
+    def __init__(self, specs, evaluations, res, scalars, dims, timings, matel=None, scalar_map=None, none_methods=()):
         self.specs = specs                 # [{'name','start','end','N'}]
         self.evaluations = evaluations     # [method names in addEvaluation order]
-        self.E, self.V, self.scalars, self.Erwa, self.info = E, V, scalars, Erwa, info
+        self._res = res                    # engine.SweepResult or None (scalar-only sweeps)
+        self.E = res.E if res is not None else None
+        self.Erwa = res.Erwa if res is not None else None
+        self.info = res.info if res is not None else None
+        self.scalars = scalars
         self.matel = matel or {}           # {'getCurrentMatrixElement': [n_pts, n_elements] float64, ...}
+        self.scalar_map = scalar_map or {} # method -> scalar name, or {node / edge: scalar name} (all-nodes form)
+        self.none_methods = set(none_methods)
         self.dims = dims
         self.timings = timings
+
+    @property
+    def has_vectors(self):
+        return self._res is not None and (self._res.V is not None or bool(self._res.V_dev))
+
+    @property
+    def V(self):
+        return self._res.vectors() if self._res is not None else None
 
     def __len__(self):
         return len(self.E) if self.E is not None else len(next(iter(self.scalars.values())))
 
+    def ket_dims(self):
+        return [list(self.dims), [1] * len(self.dims)]
+
     def _kets(self, i):
-        out = np.empty(self.V.shape[1], dtype=object)
-        d = [list(self.dims), [1] * len(self.dims)]
-        for j in range(self.V.shape[1]):
-            out[j] = Ket(self.V[i, j], d)
+        V, d = self.V, self.ket_dims()
+        out = np.empty(V.shape[1], dtype=object)
+        for j in range(V.shape[1]):
+            out[j] = Ket(V[i, j], d)
         return out
 
     def record(self, i, key=None):
         """Per-point record in the reference's format (numerical_system.py:950-964,1021-1037)."""
         def one(name):
             if name == "getHamiltonian":
-                if self.V is not None:
+                if self.has_vectors:
                     return (tuple(self.E[i].tolist()), self._kets(i))
                 return self.E[i]
+            if name in self.none_methods:
+                return None
             if name == "getResonatorResponse":
                 return self.Erwa[i]
             if name in self.matel:
                 return self.matel[name][i]
-            return self.scalars[name][i]
+            m = self.scalar_map.get(name, name)
+            if isinstance(m, dict):                      # all nodes / edges: {node: value} (:696-724)
+                return {k_: self.scalars[nm][i] for k_, nm in m.items()}
+            return self.scalars[m][i]
         if len(self.evaluations) == 1 and key is None:
             return one(self.evaluations[0])
         if key is not None:
@@ -169,14 +285,20 @@ class NumericalSystem:
             unit = _units.Units("CQED1")
         self.SS = symbolic_system
         self.units = unit
+        #: GPUs used: None = every visible GPU of the box (sweep points sharded in contiguous blocks, one host thread
+        #: per GPU), an int = that device, a list = those devices
         self.device = device
         self.operator_data = {}
-        #: swept oscillator impedance: 'consistent' = H(p) is what setParameterValues + getHamiltonian give at p;
-        #: 'reference' = reproduce the reference's sweep loop, which keeps the charge / flux operators of the node
-        #: at the pre-sweep impedance (numerical_system.py:259-271 are not re-run by _postsub)
-        self.regen_mode = "consistent"
+        #: swept oscillator impedance: 'reference' (default, drop-in parity) = reproduce the reference's sweep loop, which
+        #: keeps the charge / flux operators of the node at the pre-sweep impedance (numerical_system.py:259-271 are not
+        #: re-run by _postsub); 'consistent' = H(p) is what setParameterValues + getHamiltonian give at every point p
+        self.regen_mode = "reference"
+        #: paramSweep leaves eigenvectors on the GPU and fetches them when first read ("auto": when they fit a quarter
+        #: of the free device memory; True / False force it)
+        self.lazy_vectors = "auto"
         self._circ_operators = None
-        self._single = None            # (plan, engine) for the current parameter values
+        self._cache = OrderedDict()    # plan / engine cache, see _lowered()
+        self._cache_max = 8
         self.setDiagConfig()
         self._init_sweep_data()
         self._set_parameter_units()
@@ -274,11 +396,78 @@ class NumericalSystem:
             self._circ_operators = out
         return self._circ_operators
 
+    # ---- plan / engine cache -----------------------------------------
+    def _devices(self):
+        if self.device is None:
+            devs = _engine.visible_devices()
+            if not devs:
+                raise _engine.EngineError("no CUDA device visible; the sweep engine has no CPU fallback")
+            return devs
+        if isinstance(self.device, (list, tuple)):
+            return [int(d) for d in self.device]
+        return [int(self.device)]
+
+    def _config_key(self, swept):
+        """Everything a lowered plan depends on apart from the request itself: operator configuration, the
+        parameterisations and the values of every parameter that is not swept."""
+        SS = self.SS
+        ops = tuple(sorted((repr(n), int(d["truncation"]), d["basis"]) for n, d in self.operator_data.items()))
+        vals = tuple(sorted((nm, v) for nm, v in SS.getParameterValuesDict().items() if nm not in swept))
+        par = tuple((nm, SS.getParametricExpression(nm)) for nm in sorted(SS.getParametricParametersList()))  # sympy expressions hash structurally (cached): no str()
+        return ops, vals, par
+
+    def _lowered(self, swept_names=(), sweep_specs=(), scalars=None, resonator=None, matrix_elements=(), regen_mode=None,
+                 aux_as_terms=None):
+        """(plan, EnginePool) for this request at the current circuit configuration.  ``lower_system`` (10-110 ms of
+        sympy) and the upload of the tables happen once per distinct request; a later call -- another ``paramSweep``
+        over a different grid of the same parameters, ``getHamiltonian`` again, a matrix-element evaluation -- reuses
+        both."""
+        regen_mode = regen_mode or self.regen_mode
+        swept = tuple(swept_names)
+        req = (swept, tuple(sorted(scalars)) if scalars else (), repr(sorted(resonator.items())) if resonator else None,
+               repr([sorted((k_, repr(v)) for k_, v in m.items()) for m in matrix_elements]), regen_mode, aux_as_terms)
+        # in 'reference' regen mode the pre-sweep value of a swept parameter enters the plan (stale impedance)
+        key = (req, self._config_key(() if regen_mode == "reference" else swept), tuple(self._devices()))
+        hit = self._cache.get(key)
+        if hit is None:
+            plan = lower_system(self.SS, self.units, self.operator_data, list(swept), list(sweep_specs), scalars=scalars,
+                                resonator=resonator, matrix_elements=list(matrix_elements), regen_mode=regen_mode,
+                                matrices={"Cinv": self.Cinv, "Linv": self.Linv})
+            if aux_as_terms is not None:
+                plan = plan.aux_as_terms(aux_as_terms)
+            hit = [plan, None]
+            self._cache[key] = hit
+            while len(self._cache) > self._cache_max:
+                _, (_, old) = self._cache.popitem(last=False)
+                if old is not None:
+                    old.close()
+        else:
+            self._cache.move_to_end(key)
+        plan = hit[0]
+        if sweep_specs:
+            plan = _dc_replace(plan, sweep_specs=[dict(name=s_["name"], start=float(s_["start"]), end=float(s_["end"]),
+                                                       N=int(s_["N"])) for s_ in sweep_specs])
+        if hit[1] is None:
+            hit[1] = _engine.EnginePool(hit[0], self._devices())
+        return plan, hit[1]
+
+    def close(self):
+        """Free the device tables of every cached engine."""
+        for _, pool in self._cache.values():
+            if pool is not None:
+                pool.close()
+        self._cache.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     # ---- parameters (numerical_system.py:817-854) -----------------------------------------------
     def _invalidate(self):
-        if self._single is not None:
-            self._single[1].close()
-        self._single = None
+        # plans are keyed on the configuration they were lowered for: nothing to flush, only the lazily built
+        # user-facing operator dictionary
         self._circ_operators = None
 
     def setParameterValue(self, name, value):
@@ -318,8 +507,7 @@ class NumericalSystem:
     def _scalar_exprs(self):
         out = {}
         Ec, El, Ej, Ep = (self.units.getPrefactor(x) for x in ("Ec", "El", "Ej", "Ep"))
-        Cinv = self.SS.getInverseCapacitanceMatrix()
-        Linv = self.SS.getInverseInductanceMatrix()
+        Cinv, Linv = self.Cinv, self.Linv          # cached at construction (each call re-derives a symbolic inverse)
         J = self.SS.getJosephsonVector()
         V = self.SS.getPhaseSlipVector()
         for i, node in enumerate(self.SS.nodes):
@@ -331,16 +519,14 @@ class NumericalSystem:
         return out
 
     def _single_plan(self):
-        if self._single is None:
-            plan = lower_system(self.SS, self.units, self.operator_data, scalars=self._scalar_exprs())
-            self._single = (plan, _engine.Engine(plan, device=self.device))
-        return self._single
+        plan, pool = self._lowered(scalars=self._scalar_exprs())
+        return plan, pool.engines[0]
 
     def getHamiltonian(self):
         """numerical_system.py:509-594, assembled on the device (K1 + K2)."""
         plan, eng = self._single_plan()
         H = eng.assemble_dense(np.zeros((1, 0)), tidyup=True).cpu().numpy()[0]
-        return HamiltonianMatrix(H, plan.dims)
+        return HamiltonianMatrix(H, plan.dims, device=getattr(getattr(eng, "device", None), "index", None))
 
     def _single_scalars(self):
         plan, eng = self._single_plan()
@@ -371,9 +557,8 @@ class NumericalSystem:
     def _aux_operator(self, spec):
         """Dense operator of one Current / Voltage spec at the current parameter values, assembled
         on the device by the same K1 + K2 kernels as H (its terms become the plan's term table)."""
-        plan = lower_system(self.SS, self.units, self.operator_data, matrix_elements=[dict(spec, elements=[])])
-        with _engine.Engine(plan.aux_as_terms(0), device=self.device) as eng:
-            M = eng.assemble_dense(np.zeros((1, 0)), tidyup=False).cpu().numpy()[0]
+        plan, pool = self._lowered(matrix_elements=[dict(spec, elements=[])], aux_as_terms=0)
+        M = pool.engines[0].assemble_dense(np.zeros((1, 0)), tidyup=False).cpu().numpy()[0]
         return HamiltonianMatrix(M, plan.dims)
 
     def getCurrentOperator(self, edge=None):
@@ -383,10 +568,17 @@ class NumericalSystem:
         return self._aux_operator({"kind": "Voltage", "node": node})
 
     def _aux_matrix_elements(self, spec, V):
-        plan = lower_system(self.SS, self.units, self.operator_data, matrix_elements=[spec])
-        vecs = np.stack([np.asarray(v.full() if hasattr(v, "full") else v, dtype=np.complex128).reshape(-1) for v in V])
-        with _engine.Engine(plan, device=self.device) as eng:
-            M = eng.matrix_elements(np.zeros((1, 0)), np.ascontiguousarray(vecs[None])).cpu().numpy()[0]
+        spec = dict(spec)
+        if spec.get("elements") is not None:
+            spec["elements"] = [tuple(int(x) for x in e) for e in spec["elements"]]
+        if isinstance(spec.get("edge"), list):
+            spec["edge"] = tuple(spec["edge"])
+        plan, pool = self._lowered(matrix_elements=[spec])
+        if isinstance(V, KetGrid):
+            vecs = np.asarray(V.vectors(), dtype=np.complex128)
+        else:
+            vecs = np.stack([np.asarray(v.full() if hasattr(v, "full") else v, dtype=np.complex128).reshape(-1) for v in V])
+        M = pool.engines[0].matrix_elements(np.zeros((1, 0)), np.ascontiguousarray(vecs[None])).cpu().numpy()[0]
         return np.ascontiguousarray(M.real)
 
     def getCurrentMatrixElement(self, E, V, edge=None, elements=None):
@@ -419,10 +611,9 @@ class NumericalSystem:
         if cpl_node is None:
             return None
         k = len(E)
-        plan = lower_system(self.SS, self.units, self.operator_data, resonator={"cpl_node": cpl_node, "nmax": nmax})
-        with _engine.Engine(plan, device=self.device) as eng:
-            res = eng.sweep(np.zeros((1, 0)), k, want_vectors=True, resonator=True)
-        return res.Erwa[0]
+        plan, pool = self._lowered(resonator={"cpl_node": cpl_node, "nmax": int(nmax)})
+        res = pool.engines[0].sweep(np.zeros((1, 0)), k, want_vectors=True, resonator=True)
+        return np.array(res.Erwa[0])
 
     # ---- diagonaliser (numerical_system.py:790-810; util.py:76-176) -----------------------------
     def setDiagConfig(self, eigvalues=5, get_vectors=False, sparse=False,
@@ -446,8 +637,11 @@ class NumericalSystem:
             a, dims = np.asarray(M.data.to_array(), dtype=np.complex128), list(M.dims[0])
         else:
             raise Exception("not a qutip Qobj instance.")              # util.py:96-97,147-148
-        H = torch.as_tensor(np.ascontiguousarray(a)[None].copy(), device="cuda")
+        dev = torch.device("cuda", self._devices()[0])
+        H = torch.as_tensor(np.ascontiguousarray(a)[None].copy(), device=dev)
         E, V, info = _engine.eigh_batched(H, int(eigvalues), want_vectors=bool(get_vectors))
+        if info.any():
+            raise RuntimeError("eigensolver did not converge")
         E = E.cpu().numpy()[0]
         if not get_vectors:
             return E
@@ -479,7 +673,7 @@ class NumericalSystem:
         data['name'] = evaluable
         self.evaluations.append(data)
 
-    def paramSweep(self, timesweep=True, keep_on_device=False):
+    def paramSweep(self, timesweep=True):
         init_time = time.time()
         if len(self.evaluations) == 0:
             self.evaluations = [dict(_EVAL_SPEC["Hamiltonian"], kwargs={}, name="Hamiltonian")]
@@ -491,7 +685,7 @@ class NumericalSystem:
 
         want_h = False
         resonator = None
-        scalars = {}
+        scalars, scalar_map, none_methods = {}, {}, []
         matel_specs, matel_methods = [], []
         all_scalars = None
         methods = []
@@ -507,49 +701,64 @@ class NumericalSystem:
                 want_h = True
             elif nm == "Resonator":
                 if kw.get("cpl_node") is None:
-                    raise NotImplementedError("Resonator evaluation without cpl_node returns None in the reference")
-                resonator = {"cpl_node": kw["cpl_node"], "nmax": kw.get("nmax", 100)}
+                    none_methods.append(entry['eval'])                           # the reference returns None (:737-741)
+                else:
+                    resonator = {"cpl_node": kw["cpl_node"], "nmax": int(kw.get("nmax", 100))}
             elif nm in ("ChargingEnergy", "FluxEnergy", "JosephsonEnergy"):
                 if all_scalars is None:
                     all_scalars = self._scalar_exprs()
                 key = kw.get("node") if nm != "JosephsonEnergy" else kw.get("edge")
-                if key is None:
-                    raise NotImplementedError("%s over all nodes/edges in a sweep: pass node=/edge=" % nm)
-                scalars[entry['eval']] = all_scalars["%s:%r" % (nm, key)]
+                keys = self.getNodeList() if nm != "JosephsonEnergy" else self.SS.edges
+                if key is None:                                                  # all nodes / edges: a dict per point (:696-724)
+                    scalar_map[entry['eval']] = {}
+                    for kk in keys:
+                        sname = "%s:%r" % (nm, kk)
+                        scalars[sname] = all_scalars[sname]
+                        scalar_map[entry['eval']][kk] = sname
+                else:
+                    if key not in keys:
+                        raise ValueError("%r is not in list" % (key,))
+                    sname = "%s:%r" % (nm, key)
+                    scalars[sname] = all_scalars[sname]
+                    scalar_map[entry['eval']] = sname
             elif nm in ("Current", "Voltage"):
                 spec = dict(kw, kind=nm)
                 spec.setdefault("elements", None)
+                if spec["elements"] is not None:
+                    spec["elements"] = [tuple(int(x) for x in e) for e in spec["elements"]]
                 matel_specs.append(spec)
                 matel_methods.append(entry['eval'])
             else:
                 raise NotImplementedError("evaluable '%s' is not implemented on the GPU path yet" % nm)
 
-        plan = lower_system(self.SS, self.units, self.operator_data, names, specs, scalars=scalars, resonator=resonator,
-                            matrix_elements=matel_specs, regen_mode=self.regen_mode)
+        plan, pool = self._lowered(names, specs, scalars=scalars, resonator=resonator, matrix_elements=matel_specs)
         grid = plan.sweep_grid()
         loop_time = time.time()
         matel = {}
-        with _engine.Engine(plan, device=self.device) as eng:
-            if want_h or resonator is not None:
-                res = eng.sweep(grid, k, want_vectors=get_vectors, resonator=resonator is not None,
-                                matrix_elements=bool(matel_specs), real_vectors="auto")
-                E, V, scal, Erwa, info = res.E, res.V, res.scalars, res.Erwa, res.info
-                col = 0
-                for method, op in zip(matel_methods, plan.aux_ops):      # :656-667,683-694 keep the real part
-                    ne = len(op["elements"])
-                    matel[method] = np.ascontiguousarray(res.matel[:, col:col + ne].real)
-                    col += ne
-            else:
-                _, sc = eng.coefficients(grid)
-                sc = sc.cpu().numpy()
-                scal = {nm: sc[:, i] for i, nm in enumerate(plan.program.scalar_names)}
-                E = V = Erwa = None
-                info = np.zeros(len(grid), dtype=np.int32)
+        res = None
+        if want_h or resonator is not None:
+            lazy = self.lazy_vectors
+            if lazy == "auto":
+                lazy = get_vectors and self._vectors_fit(len(grid), k, plan.hilbert_dim, len(pool.engines))
+            res = pool.sweep(grid, k, want_vectors=get_vectors, resonator=resonator is not None,
+                             matrix_elements=bool(matel_specs), real_vectors=False if lazy else "auto",
+                             vectors_on_device=bool(lazy and get_vectors))
+            scal, info = res.scalars, res.info
+            col = 0
+            for method, op in zip(matel_methods, plan.aux_ops):      # :656-667,683-694 keep the real part
+                ne = len(op["elements"])
+                matel[method] = np.ascontiguousarray(res.matel[:, col:col + ne].real)
+                col += ne
+        else:
+            _, sc = pool.engines[0].coefficients(grid)
+            sc = sc.cpu().numpy()
+            scal = {nm: sc[:, i] for i, nm in enumerate(plan.program.scalar_names)}
+            info = np.zeros(len(grid), dtype=np.int32)
         end_time = time.time()
         if info.any():
             raise RuntimeError("eigensolver did not converge at %d sweep point(s)" % int(np.count_nonzero(info)))
-        data = SweepData(specs, methods, E, V, scal, Erwa, info, plan.dims,
-                         {"init": loop_time - init_time, "loop": end_time - loop_time}, matel)
+        data = SweepData(specs, methods, res, scal, plan.dims,
+                         {"init": loop_time - init_time, "loop": end_time - loop_time}, matel, scalar_map, none_methods)
         self._init_sweep_data()                                   # :915
         if timesweep:
             print("Parameter Sweep Duration:")
@@ -557,6 +766,16 @@ class NumericalSystem:
             print("  Loop duration:\t%.3f s" % (end_time - loop_time))
             print("  Avg iteration:\t%.3g s" % ((end_time - loop_time) / len(grid)))
         return data
+
+    @staticmethod
+    def _vectors_fit(n_pts, k, n, n_gpus):
+        """Eigenvectors of one GPU's shard within a quarter of its free memory?"""
+        try:
+            import torch
+            free, _ = torch.cuda.mem_get_info()
+        except Exception:
+            return False
+        return (n_pts / max(1, n_gpus)) * k * n * 16 <= 0.25 * free
 
     def getSweep(self, data, ind_var, static_vars, evaluable="Hamiltonian"):
         if evaluable not in _EVAL_SPEC:
@@ -569,7 +788,8 @@ class NumericalSystem:
 
 def _sweep_result(SS, data, ind_var, static_vars, key):
     """``ParamCollection.getSweepResult`` (parameters.py:1002-1166) on in-memory arrays: identical
-    index selection and output layout (eigenvalue index first: ``np.array(records).T``)."""
+    index selection and output layout (eigenvalue index first: ``np.array(records).T``), built with array
+    indexing -- no per-point Python objects (eigenvectors come back as a lazy :class:`EVResult`)."""
     specs = data.specs
     if key not in data.evaluations:
         raise KeyError(key)
@@ -578,15 +798,38 @@ def _sweep_result(SS, data, ind_var, static_vars, key):
     axes = {s["name"]: np.linspace(s["start"], s["end"], int(s["N"])) for s in specs}
     shape = [Ns[n] for n in names]
 
-    def take(flat_idx):
-        recs = [data.record(int(i), key) for i in flat_idx]
-        if data.V is not None and key == "getHamiltonian":
-            arr = np.empty((len(recs), 2, data.E.shape[1]), dtype=object)
-            for a, (E, V) in enumerate(recs):
-                arr[a, 0, :] = E
-                arr[a, 1, :] = V
-            return arr
-        return np.array(recs)
+    def take(flat_idx, lead=None):
+        """records[flat_idx] stacked like np.array(records), optionally reshaped to ``lead`` + record shape,
+        then transposed (.T) as the reference does."""
+        flat = np.asarray(list(flat_idx) if isinstance(flat_idx, range) else flat_idx, dtype=np.int64)
+
+        def fin(a):
+            if lead is not None:
+                a = a.reshape(*lead, *a.shape[1:])
+            return a.T
+        if key == "getHamiltonian":
+            E = data.E[flat]
+            if not data.has_vectors:
+                return fin(E)
+            k = E.shape[1]
+            pt = np.broadcast_to(flat[:, None], (len(flat), k))
+            lv = np.broadcast_to(np.arange(k)[None, :], (len(flat), k))
+            # record = (E[k], V[k]) -> np.array(records) has shape (len, 2, k); .T puts the level first and the
+            # (E, V) selector second: the two halves are transposed separately with the selector axis left out
+            return EVResult(fin(E), KetGrid(lambda: data.V, fin(pt), fin(lv), data.ket_dims()))
+        if key in data.none_methods:
+            return fin(np.full(len(flat), None, dtype=object))
+        if key == "getResonatorResponse":
+            return fin(data.Erwa[flat])
+        if key in data.matel:
+            return fin(data.matel[key][flat])
+        m = data.scalar_map.get(key, key)
+        if isinstance(m, dict):
+            arr = np.empty(len(flat), dtype=object)
+            for a, i in enumerate(flat.tolist()):
+                arr[a] = {k_: data.scalars[nm][i] for k_, nm in m.items()}
+            return fin(arr)
+        return fin(data.scalars[m][flat])
 
     def nearest(static_vars):
         idx, vals = {}, {}
@@ -601,7 +844,7 @@ def _sweep_result(SS, data, ind_var, static_vars, key):
         if ind_var not in SS.getParameterNamesList():
             raise ValueError("Independent variable '%s' does not exist." % ind_var)
         if len(specs) == 1:
-            return axes[ind_var], take(range(len(data))).T, {}
+            return axes[ind_var], take(range(len(data))), {}
         sidx, svals = nearest(static_vars)
         multi = []
         for n in names:
@@ -610,7 +853,7 @@ def _sweep_result(SS, data, ind_var, static_vars, key):
             else:
                 multi.append(np.full(Ns[ind_var], sidx[n]))
         flat = np.ravel_multi_index(multi, shape)
-        return axes[ind_var], take(flat).T, svals
+        return axes[ind_var], take(flat), svals
     if type(ind_var) in (list, np.ndarray):
         for k_ in ind_var:
             if k_ not in SS.getParameterNamesList():
@@ -619,7 +862,5 @@ def _sweep_result(SS, data, ind_var, static_vars, key):
         sidx, svals = nearest(static_vars)
         grids = np.meshgrid(*[np.arange(Ns[n]) if n in ordered else np.array([sidx[n]]) for n in names], indexing="ij")
         flat = np.ravel_multi_index([g.reshape(-1) for g in grids], shape)
-        arr = take(flat)
-        out = arr.reshape(*[Ns[n] for n in ordered], *arr.shape[1:]).T
-        return [axes[n] for n in ordered], out, svals
+        return [axes[n] for n in ordered], take(flat, lead=[Ns[n] for n in ordered]), svals
     raise TypeError("Invalid independent variable specification. Found type '%s'" % repr(type(ind_var)))

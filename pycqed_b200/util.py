@@ -62,7 +62,7 @@ def pauliCoefficients(E, V, basis_op, device=None):
     array) or per-point 2x2 operators (list / array).  The 2x2 matrix elements of a fixed operator
     are formed on the device, and the per-point eigen-reduction runs as one kernel
     (``scqed_pauli_coefficients``) in float64 -- the reference loops in Python in complex64."""
-    if not (type(E) in (list, np.ndarray) and type(V) in (list, np.ndarray)):
+    if not (type(E) in (list, np.ndarray) and (type(V) in (list, np.ndarray) or hasattr(V, "vectors"))):
         raise Exception("incompatible input types for E (%s), V (%s) and basis_op (%s)." % (type(E), type(V), type(basis_op)))
     E = np.asarray(E)
     E0 = np.asarray(E[0], dtype=np.float64)
@@ -71,14 +71,12 @@ def pauliCoefficients(E, V, basis_op, device=None):
     if type(basis_op) in (list, np.ndarray) and np.asarray(basis_op).ndim == 3:
         Op = np.asarray(basis_op, dtype=np.complex128)
     elif hasattr(basis_op, "full") or (isinstance(basis_op, np.ndarray) and basis_op.ndim == 2):
-        import torch
-        dev = _engine._require_cuda(device)
-        A = torch.as_tensor(np.ascontiguousarray(np.asarray(basis_op.full() if hasattr(basis_op, "full") else basis_op,
-                                                            dtype=np.complex128)), device=dev)
-        W = np.stack([np.stack([_as_vector(V[a][i]) for a in (0, 1)]) for i in range(n_pts)])    # [N, 2, n]
-        W = torch.as_tensor(W, device=dev)
-        AW = torch.matmul(W, A.transpose(0, 1))                 # rows: (A w)^T
-        Op = torch.matmul(W.conj(), AW.transpose(1, 2)).cpu().numpy()   # Op[i, a, b] = <V_a| A |V_b>
+        A = np.asarray(basis_op.full() if hasattr(basis_op, "full") else basis_op, dtype=np.complex128)
+        if hasattr(V, "vectors") and hasattr(V, "shape"):           # lazy KetGrid from getSweep: no per-ket objects
+            W = np.asarray(V[:2].vectors(), dtype=np.complex128).transpose(1, 0, 2)     # [N, 2, n]
+        else:
+            W = np.stack([np.stack([_as_vector(V[a][i]) for a in (0, 1)]) for i in range(n_pts)])
+        Op = _engine.dense_matrix_elements(A, np.ascontiguousarray(W), device=device)   # Op[i, a, b] = <V_a| A |V_b>
     else:
         raise Exception("incompatible input types for E (%s), V (%s) and basis_op (%s)." % (type(E), type(V), type(basis_op)))
     if Op.shape != (n_pts, 2, 2):

@@ -373,7 +373,7 @@ def freeze(name, h, sweeps, k=10, get_vectors=False, evaluations=(), sparse_opts
                 out["postsub%d_Linv" % j] = np.asarray(h.Linvnp, dtype=np.float64)
                 out["postsub%d_J" % j] = np.asarray(h.Jvecnp, dtype=np.float64)
                 out["postsub%d_Pexp" % j] = np.asarray(h.Pexp_pnp, dtype=np.complex128)
-    out["n"] = np.int64(h.getHilbertSpaceSize())
+    out["n"] = np.int64(plan.hilbert_dim)      # (the reference's getHilbertSpaceSize ignores 'flux' nodes, :93-96)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     plan.meta["source"] = name
     plan.save(os.path.join(HERE, name + ".plan.json"))
@@ -449,6 +449,88 @@ def make_big():
            get_vectors=True, vec_points=[0, 3], sparse_opts=_SA_EXACT, store_h=False, vec_dtype=np.complex64)
     freeze("c5_fluxatom_t180s", build_fluxonium_atom(180), [S("phi-", 0.13, 0.5, 2)], k=10, k_extra=1,
            get_vectors=True, vec_points=[1], sparse_opts=_SA_EXACT, store_h=False, vec_dtype=np.complex64)
+
+
+def build_phaseslip(basis, trunc):
+    """a4: a phase-slip nanowire ("V" branch) shunted by L and C with a gate charge -- the dual of the Cooper-pair
+    box.  Exercises the Hp terms (numerical_system.py:558-591: exp(+-2 pi i q) pdisp / pdisp_adj) and, with
+    basis='flux', the flux basis of numerical_system.py:1159-1210 (P diagonal, Q dense, S = shift)."""
+    ps = import_reference()
+    with quiet():
+        g = ps.CircuitGraph()
+        g.addBranch(0, 1, "C")
+        g.addBranch(0, 1, "L")
+        g.addBranch(0, 1, "V")
+        g.addChargeBias(1, "g", "Cg")
+        h = ps.NumericalSystem(ps.SymbolicSystem(g))
+        h.configureOperator(1, trunc, basis)
+        h.setParameterValues("C", 20.0, "L", 800.0, "V", 30.0, "Cg", 1.0, "Qg", 0.3)
+    return h
+
+
+def make_a4():
+    """flux-basis node and phase-slip branch through the whole path."""
+    sw = [S("Qg", -0.45, 0.5, 9)]
+    freeze("c9_phaseslip_flux", build_phaseslip("flux", 10), sw, k=5, k_extra=1, get_vectors=True, vec_points=[0, 4, 7])
+    freeze("c9_phaseslip_osc", build_phaseslip("oscillator", 30), sw, k=5, k_extra=1, get_vectors=True, vec_points=[1, 6])
+    # two sweep axes, the second one through the phase-slip amplitude itself
+    freeze("c9_phaseslip_charge", build_phaseslip("charge", 10), [S("V", 5.0, 40.0, 3), S("Qg", -0.4, 0.4, 5)], k=5)
+
+
+def _dropin_twin(h):
+    """The drop-in class configured like reference system ``h`` (same symbolic system object)."""
+    from pycqed_b200.numerical_system import NumericalSystem
+    with quiet():
+        mine = NumericalSystem(h.SS, unit=h.units, device=0)
+        for node, data in h.operator_data.items():
+            mine.operator_data[node] = dict(data)
+    return mine
+
+
+def make_single():
+    """The single-point API -- getHamiltonian (numerical_system.py:509), diagonalize (:809), getResonatorResponse
+    (:736), get*Energies (:696-734) at the current parameter values -- i.e. plans WITHOUT a swept column, lowered with
+    the requests the drop-in class makes (``_single_plan``: all scalar evaluables; ``getResonatorResponse``)."""
+    for name, h, k, res in (("c8_single_fluxonium", build_fluxonium(101), 20, {"cpl_node": 1, "nmax": 100}),
+                            ("c8_single_csfq3jj", build_csfq_3jj(6), 8, None)):
+        out = {}
+        with quiet():
+            h.setDiagConfig(eigvalues=k, get_vectors=True)
+            H = h.getHamiltonian()
+            E, V = h.diagonalize(H)
+            out["E"] = np.asarray(E, dtype=np.float64)[None]
+            out["V"] = np.stack([v.data.to_array()[:, 0] for v in V], axis=1)[None]
+            out["vec_points"] = np.array([0])
+            r, c, v = _csr_triplets(H)
+            out["H0_row"], out["H0_col"], out["H0_val"] = r, c, v
+            out["h_points"] = np.array([0])
+            if res is not None:
+                out["eval_getResonatorResponse"] = np.asarray(h.getResonatorResponse(np.asarray(E), V, nmax=res["nmax"], cpl_node=res["cpl_node"]))[None]
+            ce, fe, je = h.getChargingEnergies(), h.getFluxEnergies(), h.getJosephsonEnergies()
+        mine = _dropin_twin(h)
+        scal = mine._scalar_exprs()
+        plan = lower(h, [], scalars=scal)
+        names = list(plan.program.scalar_names)
+        ref_scal = np.zeros(len(names))
+        for i, nm in enumerate(names):
+            kind, key = nm.split(":", 1)
+            key = eval(key)
+            ref_scal[i] = {"ChargingEnergy": ce, "FluxEnergy": fe, "JosephsonEnergy": je}.get(kind, {}).get(key, np.nan)
+        out["scalar_names"] = np.array(names)
+        out["scalar_values"] = ref_scal
+        out["params"] = np.zeros((1, 0))
+        out["swept_names"] = np.array([], dtype=str)
+        out["k"] = np.int64(k)
+        out["n"] = np.int64(h.getHilbertSpaceSize())
+        out["ref_seconds_per_point"] = np.float64(0.0)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        plan.meta["source"] = name
+        plan.save(os.path.join(HERE, name + ".plan.json"))
+        if res is not None:
+            p2 = lower(h, [], resonator=res)
+            p2.meta["source"] = name + "_res"
+            p2.save(os.path.join(HERE, name + "_res.plan.json"))
+        print("%-28s n=%d (single point)" % (name, int(out["n"])), flush=True)
 
 
 def make_c4():
@@ -580,7 +662,7 @@ def make_c7():
     print("c7_fluxonium_C               n=%d pts=%d" % (int(out["n"]), len(grid)), flush=True)
 
 
-ALL = {"big": make_big, "c6": make_c6, "c7": make_c7, "c2b": make_c2b, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c4": make_c4, "c5": make_c5}
+ALL = {"big": make_big, "a4": make_a4, "single": make_single, "c6": make_c6, "c7": make_c7, "c2b": make_c2b, "c1": make_c1, "c2": make_c2, "c3": make_c3, "c4": make_c4, "c5": make_c5}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(ALL)

@@ -57,6 +57,8 @@ class OracleEngine:
         c, _ = self.coefficients(params)
         return _FakeTensor(np.stack([self.orc.hamiltonian(row, tidy=tidyup).toarray() for row in c.numpy()]))
 
+    device = None
+
     def sweep(self, params, k, want_vectors=False, resonator=False, matrix_elements=False, **kw):
         from pycqed_b200.engine import SweepResult
         out = self.orc.sweep(params, k, get_vectors=want_vectors or matrix_elements, resonator=resonator)
@@ -70,10 +72,29 @@ class OracleEngine:
         return _FakeTensor(self.orc.matrix_elements(params, np.asarray(V).transpose(0, 2, 1)))
 
 
+class OraclePool:
+    """Test double for pycqed_b200.engine.EnginePool: one oracle-backed engine."""
+
+    def __init__(self, plan, devices=None):
+        self.plan = plan
+        self.engines = [OracleEngine(plan)]
+        self.n = plan.hilbert_dim
+
+    def close(self):
+        pass
+
+    def sweep(self, params, k, want_vectors=False, resonator=False, **kw):
+        kw.pop("real_vectors", None)
+        kw.pop("vectors_on_device", None)
+        return self.engines[0].sweep(params, k, want_vectors=want_vectors, resonator=resonator, **kw)
+
+
 @pytest.fixture()
 def patched(monkeypatch):
     import pycqed_b200.numerical_system as ns
     monkeypatch.setattr(ns._engine, "Engine", OracleEngine)
+    monkeypatch.setattr(ns._engine, "EnginePool", OraclePool)
+    monkeypatch.setattr(ns._engine, "visible_devices", lambda: [0])
     return ns
 
 
@@ -335,9 +356,10 @@ def test_swept_oscillator_impedance_matches_reference(patched):
 
 
 def test_swept_impedance_consistent_mode_matches_single_point_path(patched):
-    """Default regen_mode='consistent': at every sweep point H equals the reference's own single-point path
+    """regen_mode='consistent': at every sweep point H equals the reference's own single-point path
     (setParameterValues + getHamiltonian + diagonalize), which regenerates ALL operators of the node."""
     ref, mine, mg = _pair("build_fluxonium", patched, 20)
+    mine.regen_mode = "consistent"
     C0 = ref.getParameterValue("C")
     with mg.quiet():
         mine.newSweep()
@@ -408,3 +430,82 @@ def test_util_strip_helpers_match_reference():
     Ea, Va = ps.util.getEigenValuesAndVectors(sweep)
     Eb, Vb = mine.getEigenValuesAndVectors(sweep)
     assert np.array_equal(Ea, Eb) and Eb.dtype == np.float64 and Vb.shape == Va.shape
+
+
+def test_all_nodes_scalar_evaluables_and_resonator_without_node(patched):
+    """``addEvaluation('ChargingEnergy')`` without ``node=`` gives a dict per point (numerical_system.py:696-724);
+    ``Resonator`` without ``cpl_node`` gives None records (:737-741).  Same records / getSweep output as the reference."""
+    ref, mine, mg = _pair("build_csfq_3jj", patched, 3)
+    ev = [("Hamiltonian", {}), ("ChargingEnergy", {}), ("JosephsonEnergy", {}), ("FluxEnergy", {"node": 2}),
+          ("Resonator", {})]
+    a, b = _run_both(ref, mine, mg, [("phiZ", 0.4, 0.6, 3)], 4, True, ev)
+    recs_a = [mg.import_reference().util.pickleRead(f) for f in a]
+    for i, ra in enumerate(recs_a):
+        rb = b.record(i)
+        assert set(ra) == set(rb)
+        assert rb["getResonatorResponse"] is None and ra["getResonatorResponse"] is None
+        for meth in ("getChargingEnergies", "getJosephsonEnergies"):
+            assert set(ra[meth]) == set(rb[meth])
+            for kk in ra[meth]:
+                assert abs(ra[meth][kk] - rb[meth][kk]) <= 1e-13 * max(1.0, abs(ra[meth][kk]))
+        assert abs(ra["getFluxEnergies"] - rb["getFluxEnergies"]) <= 1e-13
+    for evn in ("ChargingEnergy", "JosephsonEnergy", "Resonator"):
+        _, Sa, _ = ref.getSweep(a, "phiZ", {}, evaluable=evn)
+        _, Sb, _ = mine.getSweep(b, "phiZ", {}, evaluable=evn)
+        assert Sa.shape == Sb.shape == (3,)
+        for x, y in zip(Sa, Sb):
+            if x is None:
+                assert y is None
+            else:
+                assert set(x) == set(y) and all(abs(x[q] - y[q]) <= 1e-13 * max(1.0, abs(x[q])) for q in x)
+
+
+def test_plan_cache_and_lazy_results(patched):
+    """Row f2: the second sweep of the same circuit re-uses the lowered plan and the uploaded engine (no sympy);
+    getSweep on 10^4 x 10 eigenvectors creates no per-ket objects."""
+    import time
+    ref, mine, mg = _pair("build_fluxonium", patched, 16)
+    calls = []
+    orig = patched.lower_system
+
+    def counting(*a, **kw):
+        calls.append(1)
+        return orig(*a, **kw)
+    patched.lower_system = counting
+    try:
+        with mg.quiet():
+            for N in (5, 7):
+                mine.newSweep()
+                mine.addSweep("phiZ", -0.5, 0.5, N)
+                mine.addEvaluation("Hamiltonian")
+                mine.addEvaluation("Resonator", cpl_node=1, nmax=6)
+                mine.setDiagConfig(eigvalues=4, get_vectors=True)
+                data = mine.paramSweep(timesweep=False)
+                assert len(data) == N
+            assert len(calls) == 1                      # the 7-point sweep re-used the plan of the 5-point one
+            assert data.timings["init"] < 0.05
+            H1 = mine.getHamiltonian()
+            H2 = mine.getHamiltonian()
+            assert len(calls) == 2 and np.array_equal(H1.full(), H2.full())
+            mine.setParameterValue("phiZ", 0.25)        # a different configuration: lowered again
+            mine.getHamiltonian()
+            assert len(calls) == 3
+    finally:
+        patched.lower_system = orig
+    x, EV, _ = mine.getSweep(data, "phiZ", {})
+    assert EV.shape == (4, 2, 7)
+    E, V = EV[:, 0], EV[:, 1]
+    assert E.shape == (4, 7) and E.dtype == np.float64 and V.shape == (4, 7)
+    assert abs(V[2, 3].norm() - 1.0) < 1e-12 and V[2, 3].dims == [[16], [1]]
+    full = np.asarray(EV)
+    assert full.shape == (4, 2, 7) and full[1, 0, 2] == E[1, 2] and isinstance(full[1, 1, 2], patched.Ket)
+    # timing of the retrieval on a bench-sized synthetic result
+    from pycqed_b200.engine import SweepResult
+    n_pts, k, n = 10000, 10, 101
+    res = SweepResult(np.zeros((n_pts, k)), np.zeros((n_pts, k, n)), {}, None, np.zeros(n_pts, dtype=np.int32))
+    big = patched.SweepData([{"name": "phiZ", "start": -1.0, "end": 1.0, "N": n_pts}], ["getHamiltonian"], res, {}, [n], {})
+    t0 = time.perf_counter()
+    x, EV, _ = mine.getSweep(big, "phiZ", {})
+    E, V = EV[:, 0], EV[:, 1]
+    dt = time.perf_counter() - t0
+    assert E.shape == (k, n_pts) and V.shape == (k, n_pts) and dt < 0.02, dt

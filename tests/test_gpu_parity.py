@@ -40,7 +40,7 @@ def _sample(n_total, cap):
 # K1: coefficient program
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["c1_transmon", "c2_fluxonium_res", "c3_csfq4jj_t10", "c3_csfqfloat_t5",
-                                  "c4_averin", "c5_fluxatom_t31"])
+                                  "c4_averin", "c5_fluxatom_t31", "c9_phaseslip_flux", "c9_phaseslip_charge"])
 def test_coefficient_program(engine_mod, name):
     g, plan = load_golden(name)
     coef_ref, scal_ref = eval_program(plan.program, g["params"])
@@ -58,7 +58,8 @@ def test_coefficient_program(engine_mod, name):
 # K2: dense assembly  (getHamiltonian parity)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["c1_transmon", "c2_fluxonium", "c3_csfq3jj_t10", "c3_csfq4jj_t10",
-                                  "c3_csfqfloat_t5", "c4_averin", "c5_fluxatom_t31"])
+                                  "c3_csfqfloat_t5", "c4_averin", "c5_fluxatom_t31", "c9_phaseslip_flux",
+                                  "c9_phaseslip_osc", "c9_phaseslip_charge"])
 def test_assemble_dense_matches_reference(engine_mod, name):
     g, plan = load_golden(name)
     n = int(g["n"])
@@ -213,6 +214,9 @@ SWEEP_CASES = [
     ("c3_csfq4jj_t10", 33, 0),
     ("c5_fluxatom_t31", 8, 0),
     ("c3_csfqfloat_t5", 15, 0),
+    # row a4: phase-slip branch (exp(+-2 pi i q) pdisp terms) in the flux, oscillator and charge bases
+    ("c9_phaseslip_flux", 9, 0), ("c9_phaseslip_osc", 9, 0), ("c9_phaseslip_charge", 15, 0),
+    ("c9_phaseslip_flux", 9, 2), ("c9_phaseslip_osc", 9, 4),
 ]
 
 
@@ -230,7 +234,8 @@ def test_sweep_eigenvalues_match_reference(engine_mod, name, cap, solver):
     assert np.max(np.abs(gaps - gaps_ref)) < E_RTOL * np.abs(g["E"]).max()
 
 
-@pytest.mark.parametrize("name", ["c1_transmon_vec", "c2_fluxonium_res", "c3_csfqfloat_t5"])
+@pytest.mark.parametrize("name", ["c1_transmon_vec", "c2_fluxonium_res", "c3_csfqfloat_t5", "c9_phaseslip_flux",
+                                  "c9_phaseslip_osc"])
 def test_sweep_eigenvectors_match_reference(engine_mod, name):
     g, plan = load_golden(name)
     k = int(g["k"])
