@@ -205,7 +205,13 @@ int64_t scqed_launch_count(void);
  * symmetric; tag 2: same, complex Hermitian).  scqed_timing_read sums and clears the spans. */
 void scqed_timing_enable(int on);
 int scqed_timing_read(int tag, double *total_ms, int64_t *count);   /* tags: 1 / 2 real / complex tridiagonalisation,
-                                                                        3 dense assembly, 4 direct tridiagonal */
+                                                                        3 dense assembly, 4 direct tridiagonal,
+                                                                        5 / 6 / 7 matrix-free filter (stencil /
+                                                                        shared-memory / global-memory form),
+                                                                        8 dense (HBM) tridiagonal reduction */
+/* Work counters for roofline reporting, cleared by the read.  which = 1: vector mat-vecs issued by the matrix-free
+ * filters (active points x block size x filter degree). */
+int scqed_counter_read(int which, int64_t *value);
 
 /* FP64 peak probe: runs a register-resident DMMA (mma.sync m8n8k4 f64) loop on every SM and
  * returns TFLOP/s; the roofline denominator for the dense tridiagonalisation. */

@@ -9,6 +9,7 @@
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_matvecs{0};
 std::atomic<int> g_timing{0};
 std::vector<TimedSpan> g_spans;
 std::mutex g_spans_mu;
@@ -401,6 +402,11 @@ extern "C" int scqed_timing_read(int tag, double *total_ms, int64_t *count) {
     { std::lock_guard<std::mutex> lk(g_spans_mu); g_spans.insert(g_spans.end(), keep.begin(), keep.end()); }
     *total_ms = tot; *count = cnt;
     return 0;
+}
+extern "C" int scqed_counter_read(int which, int64_t *value) {
+    if (!value) return fail(SCQED_EINVAL, "null argument");
+    if (which == 1) { *value = g_matvecs.exchange(0); return 0; }
+    return fail(SCQED_EINVAL, "unknown counter %d", which);
 }
 extern "C" const char *scqed_last_error(void) { return g_err.c_str(); }
 extern "C" const char *scqed_version(void) { return "scqed 0.1 (sm_100a)"; }
@@ -950,9 +956,10 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
         }
         return 0;
     };
-    // Enqueue order: compute(c), then the copies of chunk c-1, so that the copy never delays the next chunk's kernels.
-    long long prev_c0 = -1, prev_np = 0;
-    cudaEvent_t prev_evt = nullptr;
+    // The per-chunk solves stay asynchronous: the "a real plan turned complex" check of the shared-memory solver
+    // (one stream synchronisation per call on the device path) is done once, below, on the host copy of info.
+    struct DeferGuard { scqed_plan *p; bool old; DeferGuard(scqed_plan *q) : p(q), old(q->defer_real_check) { q->defer_real_check = true; }
+                        ~DeferGuard() { p->defer_real_check = old; } } defer_guard(pl);
     long long c0 = 0;
     for (size_t ci = 0; ci < sizes.size(); c0 += sizes[ci], ++ci) {
         const long long np = sizes[ci];
@@ -968,10 +975,11 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
         cudaEvent_t evt;
         if (events.add(&evt)) return bail(fail(SCQED_ECUDA, "cudaEventCreate failed"));
         CKH(cudaEventRecord(evt, st));
-        if (prev_c0 >= 0) { rc = copy_out(prev_c0, prev_np, prev_evt); if (rc) return rc; }
-        prev_c0 = c0; prev_np = np; prev_evt = evt;
+        // the copies of this chunk go to the copy stream at once (asynchronous: pinned destination or staging slot);
+        // they run while the next chunk is solved
+        rc = copy_out(c0, np, evt);
+        if (rc) return rc;
     }
-    if (prev_c0 >= 0) { rc = copy_out(prev_c0, prev_np, prev_evt); if (rc) return rc; }
     int h_flag = 0;
     if (pack) CKH(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
     CKH(cudaStreamSynchronize(st));
@@ -983,6 +991,16 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
     finish_mover();
 #undef CKH
     if (mover_failed) return fail(SCQED_ECUDA, "staging copy failed");
+    // a plan assumed real symmetric produced a complex point (info = -2): redo the sweep in complex mode, once
+    if (pl->s1_real_mode == 1) {
+        bool redo = false;
+        for (long long q = 0; q < n_pts; ++q) if (info[q] == -2) { redo = true; break; }
+        if (redo) {
+            pl->s1_real_mode = 0;
+            defer_guard.p->defer_real_check = defer_guard.old;
+            return scqed_sweep_run_host(pl, o, params, n_pts, evals, evecs, scalars, post, info);
+        }
+    }
     if (pack && h_flag) { g_err = "real_vectors: some eigenvector has a non-zero imaginary part"; return SCQED_ECOMPLEX; }
     return 0;
 }

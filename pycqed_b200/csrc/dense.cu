@@ -137,6 +137,7 @@ static int run_dense_blocked_batch(cplx *A, int n, int B, int k, int want_vec, i
     K.A = A;
     if (k > BLK_KMAX && want_vec) return fail(SCQED_EUNSUPPORTED, "blocked dense path supports k <= %d eigenvectors", BLK_KMAX);
     const int seg_max = (n + K.nseg - 1) / K.nseg;
+    TimingScope tscope_(st, 8);            // tag 8: the whole dense -> tridiagonal reduction of this batch
     blk_w_nextcol<<<dim3(K.nrb, B), BLK_ROWS, 0, st>>>(K, -1, -1);
     LAUNCHED();
     for (int p = 0; p < K.npanels; ++p) {
@@ -155,6 +156,7 @@ static int run_dense_blocked_batch(cplx *A, int n, int B, int k, int want_vec, i
         }
     }
     CK(cudaGetLastError());
+    tscope_.end();
     tridiag_eig_kernel<<<B, 256, (size_t)k * 8, st>>>(K.dd, K.ee, n, k, want_vec, evals, w.Z, w.lu, k, w.e2, info);
     LAUNCHED();
     CK(cudaGetLastError());

@@ -30,6 +30,7 @@ using namespace scqed;
 // ------------------------------------------------------------------------------------------------
 extern thread_local std::string g_err;
 extern std::atomic<long long> g_launches;
+extern std::atomic<long long> g_matvecs;      // vector mat-vecs issued by the matrix-free filters (scqed_counter_read(1))
 
 int fail(int code, const char *fmt, ...);
 
@@ -103,6 +104,7 @@ struct scqed_plan {
     int n_coef_scalar = 0;
     long long mf_work_per_row = 0;     // complex MACs per output element of the matrix-free mat-vec
     int s1_real_mode = -1;             // fused small path: -1 unknown, 0 complex Hermitian, 1 real symmetric
+    bool defer_real_check = false;     // scqed_sweep_run_host checks the "turned complex" flags itself, once, after its last chunk
     DevBuf s1work, s1vec, auxc, resvec, dcoef;
     std::vector<int> xform_node;
     std::vector<size_t> xform_off;     // byte offsets of W_i^T inside `tables`

@@ -281,6 +281,11 @@ static int run_matfree_core(scqed_plan *pl, const cplx *coef_all, long long n_pt
             if (h_active == 0) break;
             d2_realx = use_d2 && d2_real && d2_cpl_real && h_ximax == 0.0 && !getenv("SCQED_NO_D2_REALX");
             cplx *R;
+            // roofline accounting (bench.py): the whole filter of this outer iteration is one timed span; tag 5 = stencil
+            // filter, 6 = shared-memory filter (generic or two-node form), 7 = global-memory filter (generic step kernel or
+            // the two-node mode-product kernels); counter 1 += vector mat-vecs = active points x block size x degree
+            TimingScope fscope_(st, stencil_cs > 0 ? 5 : (smem_filter ? 6 : 7));
+            g_matvecs.fetch_add((long long)h_active * b * deg, std::memory_order_relaxed);
             if (stencil_cs > 0) {
                 const size_t smem = mf_stencil_smem(P, stencil_ns);
                 cudaLaunchConfig_t cfg;
@@ -330,6 +335,7 @@ static int run_matfree_core(scqed_plan *pl, const cplx *coef_all, long long n_pt
                 g_launches.fetch_add(deg, std::memory_order_relaxed);
                 R = cur;
             }
+            fscope_.end();
             // make the filtered block the "X" buffer for the Rayleigh-Ritz bookkeeping
             if (R != X) { cplx *t = X; X = R; Y = t; }
             rc = rayleigh_ritz(X);

@@ -6,6 +6,7 @@
 #include "small_eigh.cuh"
 #include "small_split.cuh"
 #include "small_packed.cuh"
+#include "small_rows.cuh"
 
 static bool small_fits(const scqed_plan *pl, int n, int k, int want_vec, int n_terms, SmallLayout *Lout) {
     SmallLayout L = small_smem_layout(n, k, want_vec, n_terms, pl->smem_optin);
@@ -77,8 +78,47 @@ static int s1p_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t
     return 0;
 }
 
+// SCQED_S1_ROWS=1: use the row-per-thread packed kernel (small_rows.cuh) for real symmetric matrices whenever it
+// fits.  Opt-in: measured SLOWER than the kernels it would replace (n = 101: 8.43 vs 6.61 ms per 10^4 points,
+// n = 200: 77.9 vs 64.9 ms) -- its shared-memory wavefront count came out the same (1.34e9 vs 1.13e9, ncu
+// profiles/r02_s1r_rows_ncu_summary.csv): on a packed triangle half of the lanes of the diagonal blocks are
+// predicated off and every warp re-loads the per-column broadcast operands.  Kept as a parity-tested alternate.
+static int s1_rows_mode() {
+    const char *e = getenv("SCQED_S1_ROWS");
+    return e ? atoi(e) : 0;
+}
+
+static int s1r_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t st, bool *launched) {
+    *launched = false;
+    if (a.n > 256 || a.n < 2) return 0;
+    const int threads = a.n <= 128 ? 128 : 256;
+    const size_t smem = S1RSmem::bytes(a.n, n_terms);
+    if (smem > pl->smem_optin) return 0;
+    CK(cudaFuncSetAttribute(s1r_tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s1r_tridiag_kernel, threads, smem));
+    if (occ < 1) return 0;
+    long long grid = (long long)occ * pl->sm_count;
+    if (grid > a.n_pts) grid = a.n_pts;
+    TimingScope tscope_(st, 1);
+    s1r_tridiag_kernel<<<(unsigned)grid, threads, smem, st>>>(a);
+    tscope_.end();
+    LAUNCHED();
+    CK(cudaGetLastError());
+    *launched = true;
+    return 0;
+}
+
 template <typename T>
 static int s1_launch_tridiag(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t st) {
+    if constexpr (sizeof(T) == sizeof(double)) {
+        if (s1_rows_mode()) {
+            bool launched = false;
+            int rc = s1r_launch(pl, a, n_terms, st, &launched);
+            if (rc) return rc;
+            if (launched) return 0;
+        }
+    }
     const bool full_fits = a.n <= 32 * SMALL_RQ &&
         S1Smem<T>::bytes(a.n, n_terms, sizeof(T) == sizeof(double) ? 256 : 512) <= pl->smem_optin;
     if (s1_packed_mode() == 1 || (s1_packed_mode() == 2 && !full_fits)) {
@@ -198,7 +238,7 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
         // enough (point, eigenvalue) pairs to fill the machine with one thread each: plain bisection
         // (6.6x less arithmetic); small sweeps keep the 33-way warp multisection (short dependent chain)
         const int bis_mode = getenv("SCQED_BISECT") ? atoi(getenv("SCQED_BISECT")) : 0;
-        const bool thread_bisect = bis_mode == 2 || (bis_mode == 0 && np * k >= 4096 && k <= 32);
+        const bool thread_bisect = bis_mode == 2 || (bis_mode == 0 && n_pts * k >= 4096 && k <= 32);      // by the size of the whole call: the result of a point must not depend on how the call is chunked
         if (thread_bisect) {
             const int ppw = 32 / k;
             const long long bw = (np + ppw - 1) / ppw;
@@ -237,7 +277,7 @@ static int run_small_split(scqed_plan *pl, const PlanDev &P, const cplx *coef, c
         CK(cudaGetLastError());
         p0 += np;
     }
-    if (assumed_real) {
+    if (assumed_real && !pl->defer_real_check) {
         // A plan known to be real symmetric on its first points may turn complex later in the grid (e.g. a 2-D sweep
         // whose outer flux axis starts at 0): such points were flagged info = -2 and skipped by the real kernel.
         // Count them on the device; if there are any, the plan is complex Hermitian: redo this call in complex mode.

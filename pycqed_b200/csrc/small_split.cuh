@@ -377,7 +377,9 @@ s1_invit_kernel(S1Args a, const int *__restrict__ skip, long long G) {
         if (act && (pass == 0 || clustered)) {
             trilu_factor(d, e, n, lj, eps3, W);
             if (pass == 0) {
-                unsigned long long s = ((unsigned long long)p + 1ULL) * 0x9E3779B97F4A7C15ULL + (unsigned long long)(j + 1) * 0xD1B54A32D192ED03ULL;
+                // the start vector depends on the level only, not on the position of the point inside the launch: a point's
+                // eigenvectors (signs included) must not change with the way a sweep is chunked or sharded
+                unsigned long long s = 0x9E3779B97F4A7C15ULL + (unsigned long long)(j + 1) * 0xD1B54A32D192ED03ULL;
                 for (int i = 0; i < n; ++i) z[(size_t)i * zs] = lcg_uniform(s);
                 trilu_solve(n, W, z, zs, eps3, false);
                 double gr = normalize_serial(n, z, zs);

@@ -35,12 +35,17 @@ def _all_gather_rows(local, n_total, world, device):
     return out.numpy()
 
 
-def sweep_sharded(make_engine, grid, k, want_vectors=False, resonator=False, gather_vectors=False, device=None):
-    """Run ``grid`` [n_pts, n_swept] across all ranks of the default process group.
+def sweep_sharded(make_engine, grid, k, want_vectors=False, resonator=False, gather_vectors=False, device=None,
+                  gather_strips=True, **sweep_kw):
+    """Run ``grid`` [n_pts, n_swept] across all ranks of the default process group (one process per GPU, launched
+    by torchrun; inside ONE process use :class:`pycqed_b200.engine.EnginePool` instead, which is what the drop-in
+    ``paramSweep`` does).
 
-    ``make_engine()`` returns this rank's engine (anything with ``.sweep(params, k, want_vectors=,
-    resonator=)``).  Every rank returns the full gathered result (eigenvalues, scalars, strips,
-    info); ``V`` is the local shard unless ``gather_vectors``.
+    ``make_engine()`` returns this rank's engine, or the engine itself may be passed (anything with
+    ``.sweep(params, k, want_vectors=, resonator=)``).  Every rank returns the full gathered eigenvalues, scalars
+    and info; the resonator strips are gathered too unless ``gather_strips=False`` (then ``Erwa`` is the local
+    shard, like ``V`` unless ``gather_vectors``).  ``sweep_kw`` goes to ``engine.sweep`` (``out=``,
+    ``real_vectors=``, ``vectors_on_device=`` ...).
     """
     import torch
     import torch.distributed as dist
@@ -48,11 +53,11 @@ def sweep_sharded(make_engine, grid, k, want_vectors=False, resonator=False, gat
     rank = dist.get_rank() if dist.is_initialized() else 0
     n_pts = len(grid)
     lo, hi = shard_bounds(n_pts, world, rank)
-    eng = make_engine()
-    local = eng.sweep(grid[lo:hi], k, want_vectors=want_vectors, resonator=resonator) if hi > lo else None
+    eng = make_engine() if callable(make_engine) else make_engine
+    local = eng.sweep(grid[lo:hi], k, want_vectors=want_vectors, resonator=resonator, **sweep_kw) if hi > lo else None
     if world == 1:
         return {"E": local.E, "V": local.V, "scalars": local.scalars, "Erwa": local.Erwa, "info": local.info,
-                "shard": (lo, hi)}
+                "shard": (lo, hi), "local": local}
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     n_loc = hi - lo
@@ -63,12 +68,14 @@ def sweep_sharded(make_engine, grid, k, want_vectors=False, resonator=False, gat
         return _all_gather_rows(a, n_pts, world, device)
 
     n = getattr(eng, "n", None)
-    out = {"shard": (lo, hi)}
+    out = {"shard": (lo, hi), "local": local}
     out["E"] = rows(local.E if local else None, (k,), np.float64)
     out["info"] = rows(local.info if local else None, (), np.int32)
     names = list(eng.plan.program.scalar_names)
     out["scalars"] = {nm: rows(local.scalars[nm] if local else None, (), np.float64) for nm in names}
-    if resonator:
+    if resonator and not gather_strips:
+        out["Erwa"] = local.Erwa if local else None
+    elif resonator:
         ns = eng.plan.post["resonator"]["nmax"] + 1 + k
         out["Erwa"] = rows(local.Erwa if local else None, (ns, k), np.float64)
     else:

@@ -60,7 +60,7 @@ EXPORTS = (
     "scqed_plan_create", "scqed_plan_destroy", "scqed_plan_hilbert_dim", "scqed_eval_coefficients",
     "scqed_assemble_dense", "scqed_eigh_batched", "scqed_sweep_run", "scqed_sweep_run_host", "scqed_matrix_elements", "scqed_pauli_coefficients", "scqed_back_transform",
     "scqed_dense_matrix_elements",
-    "scqed_launch_count", "scqed_timing_enable", "scqed_timing_read", "scqed_probe_fp64_tensor", "scqed_probe_fp64_fma", "scqed_last_error",
+    "scqed_launch_count", "scqed_timing_enable", "scqed_timing_read", "scqed_counter_read", "scqed_probe_fp64_tensor", "scqed_probe_fp64_fma", "scqed_last_error",
     "scqed_version",
 )
 
@@ -110,6 +110,8 @@ def load_library():
         lib.scqed_timing_enable.restype = None
         lib.scqed_timing_read.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         lib.scqed_timing_read.restype = C.c_int
+        lib.scqed_counter_read.argtypes = [C.c_int, C.POINTER(C.c_int64)]
+        lib.scqed_counter_read.restype = C.c_int
         lib.scqed_probe_fp64_tensor.argtypes = [C.c_int, C.POINTER(C.c_double)]
         lib.scqed_probe_fp64_tensor.restype = C.c_int
         lib.scqed_probe_fp64_fma.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -148,6 +150,13 @@ def timing_read(tag):
     ms, cnt = C.c_double(), C.c_int64()
     _check(load_library().scqed_timing_read(int(tag), C.byref(ms), C.byref(cnt)))
     return ms.value, cnt.value
+
+
+def counter_read(which):
+    """Work counter ``which`` since the last read (1: vector mat-vecs of the matrix-free filters)."""
+    v = C.c_int64()
+    _check(load_library().scqed_counter_read(int(which), C.byref(v)))
+    return int(v.value)
 
 
 def probe_fp64(device=0):

@@ -200,9 +200,15 @@ def test_numerical_system_param_sweep_on_gpu(engine_mod, monkeypatch, lazy):
     assert isinstance(rec["getHamiltonian"][0], tuple) and rec["getHamiltonian"][1].shape == (k,)
     # second sweep of the same circuit: plan and engine come from the cache
     h.addSweep("phiZ", -0.3, 0.3, 7)
-    h.setDiagConfig(eigvalues=5)
+    h.addEvaluation("Hamiltonian")
+    h.addEvaluation("Resonator", cpl_node=1)
     d2 = h.paramSweep(timesweep=False)
-    assert d2.timings["init"] < 0.01 and d2.E.shape == (7, 5)
+    assert d2.timings["init"] < 0.002 and d2.E.shape == (7, k) and d2.Erwa.shape == (7, 100 + 1 + k, k)
+    # a different request (no Resonator): lowered / uploaded once more, then cached as well
+    h.addSweep("phiZ", -0.3, 0.3, 7)
+    h.setDiagConfig(eigvalues=5)
+    d3 = h.paramSweep(timesweep=False)
+    assert d3.E.shape == (7, 5) and eig_rel_err(d3.E, d2.E[:, :5]) < 1e-12
     h.close()
 
 
@@ -271,7 +277,7 @@ def test_pageable_and_pinned_host_buffers_agree(engine_mod, monkeypatch):
         monkeypatch.setenv("SCQED_FORCE_STAGING", "1")
         c = eng.sweep(grid, k, want_vectors=True, resonator=True, real_vectors=True)
         monkeypatch.delenv("SCQED_FORCE_STAGING")
-        assert b.E is out["E"] and b.V is out["V"]
+        assert np.shares_memory(b.E, out["E"]) and np.shares_memory(b.V, out["V"])
         for r in (b, c):
             assert not r.info.any()
             assert np.array_equal(a.E, r.E) and np.array_equal(a.Erwa, r.Erwa)

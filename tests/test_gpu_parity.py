@@ -129,6 +129,34 @@ def test_small_path_full_and_packed_storage(engine_mod, monkeypatch, n, k, real,
         assert np.max(np.abs(H[b] @ X - X * E[b][None, :])) < 1e-11 * scale * n
 
 
+@pytest.mark.parametrize("n,k", [(2, 2), (3, 2), (33, 10), (64, 10), (101, 20), (128, 8), (129, 10), (200, 10)])
+def test_row_per_thread_packed_kernel(engine_mod, monkeypatch, n, k):
+    """SCQED_S1_ROWS=1: the row-per-thread packed-triangle tridiagonalisation (small_rows.cuh), an opt-in alternate
+    of the real-symmetric shared-memory path, on raw matrices and on a plan with the dense term table."""
+    import torch
+    monkeypatch.setenv("SCQED_S1_ROWS", "1")
+    rng = np.random.default_rng(7 + n)
+    H = _random_hermitian(rng, n, 5, real=True).astype(np.complex128)
+    E, V, info = engine_mod.eigh_batched(torch.as_tensor(H, device="cuda"), k, want_vectors=True, solver=1)
+    E, V, info = E.cpu().numpy(), V.cpu().numpy(), info.cpu().numpy()
+    assert not info.any()
+    for b in range(H.shape[0]):
+        w, v = np.linalg.eigh(H[b])
+        scale = np.abs(w).max()
+        assert np.max(np.abs(E[b] - w[:k])) < 1e-12 * scale * n
+        X = V[b].T
+        assert np.max(np.abs(X.conj().T @ X - np.eye(k))) < 1e-10
+        assert np.max(np.abs(H[b] @ X - X * E[b][None, :])) < 1e-11 * scale * n
+    if n == 101:
+        g, plan = load_golden("c2_fluxonium_res")
+        with engine_mod.Engine(plan) as eng:
+            res = eng.sweep(g["params"], int(g["k"]), want_vectors=True, resonator=True)
+        assert not res.info.any()
+        _check_levels(res.E, g["E"])
+        ref = g["eval_getResonatorResponse"]
+        assert np.max(np.abs(res.Erwa - ref)) < E_RTOL * np.max(np.abs(ref))
+
+
 @pytest.mark.parametrize("n,k", [(129, 10), (160, 12), (200, 10), (208, 6)])
 def test_real_symmetric_up_to_224_on_chip(engine_mod, n, k):
     """128 < n <= ~212: real symmetric matrices stay on the shared-memory path (packed storage); complex
