@@ -210,7 +210,8 @@ int scqed_timing_read(int tag, double *total_ms, int64_t *count);   /* tags: 1 /
                                                                         shared-memory / global-memory form),
                                                                         8 dense (HBM) tridiagonal reduction */
 /* Work counters for roofline reporting, cleared by the read.  which = 1: vector mat-vecs issued by the matrix-free
- * filters (active points x block size x filter degree). */
+ * filters (active points x block size x filter degree); which = 2: algorithmic flops of those mat-vecs (8 n x complex
+ * MACs per row of the term walk, or n (d0 + d1) real MACs of the combined two-node form). */
 int scqed_counter_read(int which, int64_t *value);
 
 /* FP64 peak probe: runs a register-resident DMMA (mma.sync m8n8k4 f64) loop on every SM and

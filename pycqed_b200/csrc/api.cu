@@ -2,6 +2,7 @@
 // functions each entry point replaces).  Host-side orchestration only; the solver families live in
 // small.cu / dense.cu / matfree.cu, kernels in the .cuh files next to this one.
 #include "internal.h"
+#include <immintrin.h>
 #include "coef.cuh"
 #include "assemble.cuh"
 #include "probe.cuh"
@@ -10,6 +11,7 @@
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_matvecs{0};
+std::atomic<long long> g_mf_flops{0};
 std::atomic<int> g_timing{0};
 std::vector<TimedSpan> g_spans;
 std::mutex g_spans_mu;
@@ -406,6 +408,7 @@ extern "C" int scqed_timing_read(int tag, double *total_ms, int64_t *count) {
 extern "C" int scqed_counter_read(int which, int64_t *value) {
     if (!value) return fail(SCQED_EINVAL, "null argument");
     if (which == 1) { *value = g_matvecs.exchange(0); return 0; }
+    if (which == 2) { *value = g_mf_flops.exchange(0); return 0; }
     return fail(SCQED_EINVAL, "unknown counter %d", which);
 }
 extern "C" const char *scqed_last_error(void) { return g_err.c_str(); }
@@ -729,23 +732,40 @@ static bool host_ptr_is_pinned(const void *ptr) {
     return at.type == cudaMemoryTypeHost;
 }
 
-// memcpy of a large block on a few threads (one core moves ~10 GB/s; results are 100s of MB per sweep)
+// Copy out of the page-locked staging ring into the caller's pageable array.  The destination is written once and not
+// read again by this library: non-temporal 32-byte stores skip the read-for-ownership of every destination line (a plain
+// memcpy moves 3 bytes of DRAM traffic per byte copied, this moves 2).
+__attribute__((target("avx"))) static void stream_copy_avx(char *dst, const char *src, size_t bytes) {
+    while (bytes && ((uintptr_t)dst & 31)) { *dst++ = *src++; --bytes; }
+    const size_t nv = bytes / 32;
+    for (size_t i = 0; i < nv; ++i)
+        _mm256_stream_si256((__m256i *)dst + i, _mm256_loadu_si256((const __m256i *)src + i));
+    _mm_sfence();
+    if (bytes - nv * 32) memcpy(dst + nv * 32, src + nv * 32, bytes - nv * 32);
+}
+static void stream_copy(char *dst, const char *src, size_t bytes) {
+    static const bool avx = __builtin_cpu_supports("avx");
+    if (avx && bytes >= 4096) stream_copy_avx(dst, src, bytes);
+    else memcpy(dst, src, bytes);
+}
+
+// a large block on up to 8 threads (one core moves ~5-10 GB/s; results are 100s of MB per sweep)
 static void parallel_memcpy(void *dst, const void *src, size_t bytes) {
-    const size_t min_part = (size_t)8 << 20;
+    const size_t min_part = (size_t)2 << 20;
     unsigned hw = std::thread::hardware_concurrency();
     int parts = (int)(bytes / min_part);
-    if (parts > 4) parts = 4;
-    if (hw > 0 && parts > (int)hw) parts = (int)hw;
-    if (parts <= 1) { memcpy(dst, src, bytes); return; }
+    if (parts > 8) parts = 8;
+    if (hw > 1 && parts > (int)hw / 2) parts = (int)hw / 2;
+    if (parts <= 1) { stream_copy((char *)dst, (const char *)src, bytes); return; }
     std::vector<std::thread> th;
     const size_t per = ((bytes / parts) + 4095) & ~(size_t)4095;
     for (int i = 1; i < parts; ++i) {
         const size_t off = (size_t)i * per;
         if (off >= bytes) break;
         const size_t len = bytes - off < per ? bytes - off : per;
-        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+        th.emplace_back([=] { stream_copy((char *)dst + off, (const char *)src + off, len); });
     }
-    memcpy(dst, src, per < bytes ? per : bytes);
+    stream_copy((char *)dst, (const char *)src, per < bytes ? per : bytes);
     for (auto &t : th) t.join();
 }
 
@@ -878,11 +898,12 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
     segs[4].dev = (const char *)d_info;
 
     // ---- the host-side mover of the staging ring ------------------------------------------------------------
-    struct Job { long long c0, np; int slot; cudaEvent_t copied; };
+    // A chunk's staged bytes travel in pieces of <= 32 MB: the DMA of piece i+1 overlaps the host copy of piece i.
+    struct Job { char *dst; const char *src; size_t bytes; cudaEvent_t copied; bool last_of_chunk; };
     std::mutex mu;
     std::condition_variable cv;
     std::vector<Job> jobs;
-    size_t jobs_done = 0;
+    size_t chunks_moved = 0;
     bool stop = false, mover_failed = false;
     std::thread mover;
     if (staged_per_pt) {
@@ -897,16 +918,11 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
                     job = jobs[j];
                 }
                 if (cudaEventSynchronize(job.copied) != cudaSuccess) { cudaGetLastError(); mover_failed = true; }
-                else {
-                    const char *src = (const char *)pl->hstage.p + (size_t)job.slot * slot_bytes;
-                    for (const Seg &sg : segs) {
-                        if (!sg.per_pt || !sg.staged) continue;
-                        parallel_memcpy(sg.user + (size_t)job.c0 * sg.per_pt, src, (size_t)job.np * sg.per_pt);
-                        src += (size_t)job.np * sg.per_pt;
-                    }
+                else parallel_memcpy(job.dst, job.src, job.bytes);
+                if (job.last_of_chunk) {
+                    { std::lock_guard<std::mutex> lk(mu); ++chunks_moved; }
+                    cv.notify_all();
                 }
-                { std::lock_guard<std::mutex> lk(mu); jobs_done = j + 1; }
-                cv.notify_all();
             }
         });
     }
@@ -926,34 +942,43 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
             return bail(fail(SCQED_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
     } while (0)
 
-    size_t n_jobs = 0;
+    size_t n_staged_chunks = 0;
+    const size_t piece = (size_t)32 << 20;
     auto copy_out = [&](long long c0, long long np, cudaEvent_t solved) -> int {
         CKH(cudaStreamWaitEvent(cs, solved, 0));
-        int slot = 0;
         char *dst_stage = nullptr;
         if (staged_per_pt) {
-            slot = (int)(n_jobs & 1);
-            if (n_jobs >= 2) {                       // the slot's previous content must have reached the caller
+            const int slot = (int)(n_staged_chunks & 1);
+            if (n_staged_chunks >= 2) {              // the slot's previous content must have reached the caller
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return jobs_done + 2 > n_jobs; });
+                cv.wait(lk, [&] { return chunks_moved + 2 > n_staged_chunks; });
             }
             dst_stage = (char *)pl->hstage.p + (size_t)slot * slot_bytes;
         }
-        for (const Seg &sg : segs) {
+        int last_staged = -1;
+        for (int q = 0; q < 5; ++q) if (segs[q].per_pt && segs[q].staged) last_staged = q;
+        for (int q = 0; q < 5; ++q) {
+            const Seg &sg = segs[q];
             if (!sg.per_pt) continue;
             const size_t bytes = (size_t)np * sg.per_pt;
-            char *dst = sg.staged ? dst_stage : sg.user + (size_t)c0 * sg.per_pt;
-            CKH(cudaMemcpyAsync(dst, sg.dev + (size_t)c0 * sg.per_pt, bytes, cudaMemcpyDeviceToHost, cs));
-            if (sg.staged) dst_stage += bytes;
+            const char *src = sg.dev + (size_t)c0 * sg.per_pt;
+            if (!sg.staged) {
+                CKH(cudaMemcpyAsync(sg.user + (size_t)c0 * sg.per_pt, src, bytes, cudaMemcpyDeviceToHost, cs));
+                continue;
+            }
+            for (size_t off = 0; off < bytes; off += piece) {
+                const size_t len = bytes - off < piece ? bytes - off : piece;
+                CKH(cudaMemcpyAsync(dst_stage + off, src + off, len, cudaMemcpyDeviceToHost, cs));
+                cudaEvent_t copied;
+                if (events.add(&copied)) return bail(fail(SCQED_ECUDA, "cudaEventCreate failed"));
+                CKH(cudaEventRecord(copied, cs));
+                { std::lock_guard<std::mutex> lk(mu);
+                  jobs.push_back({sg.user + (size_t)c0 * sg.per_pt + off, dst_stage + off, len, copied, q == last_staged && off + len >= bytes}); }
+                cv.notify_all();
+            }
+            dst_stage += bytes;
         }
-        if (staged_per_pt) {
-            cudaEvent_t copied;
-            if (events.add(&copied)) return bail(fail(SCQED_ECUDA, "cudaEventCreate failed"));
-            CKH(cudaEventRecord(copied, cs));
-            { std::lock_guard<std::mutex> lk(mu); jobs.push_back({c0, np, slot, copied}); }
-            cv.notify_all();
-            ++n_jobs;
-        }
+        if (staged_per_pt) ++n_staged_chunks;
         return 0;
     };
     // The per-chunk solves stay asynchronous: the "a real plan turned complex" check of the shared-memory solver
@@ -986,7 +1011,7 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
     CKH(cudaStreamSynchronize(cs));
     if (staged_per_pt) {
         std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return jobs_done >= n_jobs; });
+        cv.wait(lk, [&] { return chunks_moved >= n_staged_chunks; });
     }
     finish_mover();
 #undef CKH

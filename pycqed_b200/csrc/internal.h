@@ -30,6 +30,7 @@ using namespace scqed;
 // ------------------------------------------------------------------------------------------------
 extern thread_local std::string g_err;
 extern std::atomic<long long> g_launches;
+extern std::atomic<long long> g_mf_flops;     // algorithmic flops of those mat-vecs (scqed_counter_read(2))
 extern std::atomic<long long> g_matvecs;      // vector mat-vecs issued by the matrix-free filters (scqed_counter_read(1))
 
 int fail(int code, const char *fmt, ...);

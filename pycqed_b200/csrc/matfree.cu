@@ -286,6 +286,12 @@ static int run_matfree_core(scqed_plan *pl, const cplx *coef_all, long long n_pt
             // the two-node mode-product kernels); counter 1 += vector mat-vecs = active points x block size x degree
             TimingScope fscope_(st, stencil_cs > 0 ? 5 : (smem_filter ? 6 : 7));
             g_matvecs.fetch_add((long long)h_active * b * deg, std::memory_order_relaxed);
+            {   // algorithmic flops of one vector mat-vec in the form used: term walk / stencil = 8 n (complex MACs per row);
+                // two-node combined form = n (d0 + d1) real x complex MACs (4 flops), real x real (2 flops) for real vectors
+                const double per_vec = use_d2 ? (double)n * (P.dims[0] + (P.n_nodes > 1 ? P.dims[1] : 0)) * (d2_real && d2_realx ? 2.0 : (d2_real ? 4.0 : 8.0))
+                                              : 8.0 * (double)n * (double)pl->mf_work_per_row;
+                g_mf_flops.fetch_add((long long)(per_vec * (double)h_active * b * deg), std::memory_order_relaxed);
+            }
             if (stencil_cs > 0) {
                 const size_t smem = mf_stencil_smem(P, stencil_ns);
                 cudaLaunchConfig_t cfg;
