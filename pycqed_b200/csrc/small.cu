@@ -7,6 +7,8 @@
 #include "small_split.cuh"
 #include "small_packed.cuh"
 #include "small_rows.cuh"
+#include "small_reg.cuh"
+#include "small_blocked.cuh"
 
 static bool small_fits(const scqed_plan *pl, int n, int k, int want_vec, int n_terms, SmallLayout *Lout) {
     SmallLayout L = small_smem_layout(n, k, want_vec, n_terms, pl->smem_optin);
@@ -109,9 +111,83 @@ static int s1r_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t
     return 0;
 }
 
+// Blocked tridiagonalisation with DMMA trailing updates (small_blocked.cuh) for real symmetric matrices whose full
+// storage fits shared memory (n <= 128): SCQED_S1_BLK=1.
+static int s1b_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t st, bool *launched) {
+    *launched = false;
+    // opt-in: correct and parity-tested, but not faster than the unblocked kernel on the bench workload (n = 101: 7.2 ms
+    // with the O(m) sections on four warps, 9.1 ms on one warp, against 6.6 ms): every variant is bound by the dependent
+    // chain of a Householder step (~4000 clk per column and CTA at 2 CTAs per SM), not by the shared-memory traffic the
+    // blocked form removes (profiles/r02_s1b_blocked_ncu_summary.csv)
+    const char *e = getenv("SCQED_S1_BLK");
+    if (!e || atoi(e) == 0) return 0;
+    if (a.n < 3 || a.n > 128) return 0;
+    const size_t smem = S1BSmem::bytes(a.n, n_terms);
+    if (smem > pl->smem_optin) return 0;
+    CK(cudaFuncSetAttribute(s1b_tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s1b_tridiag_kernel, S1B_THREADS, smem));
+    if (occ < 1) return 0;
+    long long grid = (long long)occ * pl->sm_count;
+    if (grid > a.n_pts) grid = a.n_pts;
+    TimingScope tscope_(st, 1);
+    s1b_tridiag_kernel<<<(unsigned)grid, S1B_THREADS, smem, st>>>(a);
+    tscope_.end();
+    LAUNCHED();
+    CK(cudaGetLastError());
+    *launched = true;
+    return 0;
+}
+
+// Register-resident tridiagonalisation (small_reg.cuh), real symmetric matrices up to n = 128: SCQED_S1_REG=1.
+template <int TPR, int NPAIR, int MAXT, int MAXR>
+static int s1g_launch_t(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t st, bool *launched) {
+    constexpr int R = 32 / TPR, NC = 2 * TPR * NPAIR;
+    const int NW = (a.n + R - 1) / R;
+    const size_t smem = S1GSmem::bytes(a.n, n_terms, NC, NW);
+    if (smem > pl->smem_optin || NW * 32 > MAXT) return 0;
+    auto kern = s1g_tridiag_kernel<TPR, NPAIR, MAXT, MAXR>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, smem));
+    if (occ < 1) return 0;
+    long long grid = (long long)occ * pl->sm_count;
+    if (grid > a.n_pts) grid = a.n_pts;
+    TimingScope tscope_(st, 1);
+    kern<<<(unsigned)grid, NW * 32, smem, st>>>(a);
+    tscope_.end();
+    LAUNCHED();
+    CK(cudaGetLastError());
+    *launched = true;
+    return 0;
+}
+
+static int s1g_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t st, bool *launched) {
+    *launched = false;
+    const char *e = getenv("SCQED_S1_REG");          // opt-in: measured slower than the shared-memory kernels (17.2 vs 6.4 ms)
+    if (!e || atoi(e) == 0) return 0;
+    const int n = a.n;
+    if (n < 3 || n > 128) return 0;
+    if (n <= 32) return s1g_launch_t<2, 8, 64, 128>(pl, a, n_terms, st, launched);
+    if (n <= 48) return s1g_launch_t<2, 12, 96, 112>(pl, a, n_terms, st, launched);
+    if (n <= 64) return s1g_launch_t<2, 16, 128, 128>(pl, a, n_terms, st, launched);
+    if (n <= 80) return s1g_launch_t<2, 20, 160, 136>(pl, a, n_terms, st, launched);
+    if (n <= 104) return s1g_launch_t<2, 26, 224, 144>(pl, a, n_terms, st, launched);
+    return s1g_launch_t<4, 16, 512, 128>(pl, a, n_terms, st, launched);
+}
+
 template <typename T>
 static int s1_launch_tridiag(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t st) {
     if constexpr (sizeof(T) == sizeof(double)) {
+        {
+            bool launched = false;
+            int rc = s1g_launch(pl, a, n_terms, st, &launched);
+            if (rc) return rc;
+            if (launched) return 0;
+            rc = s1b_launch(pl, a, n_terms, st, &launched);
+            if (rc) return rc;
+            if (launched) return 0;
+        }
         if (s1_rows_mode()) {
             bool launched = false;
             int rc = s1r_launch(pl, a, n_terms, st, &launched);

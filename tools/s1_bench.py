@@ -17,7 +17,7 @@ plan = SweepPlan.load(os.path.join(os.path.dirname(__file__), "..", "tests", "go
 grid = torch.as_tensor(plan.sweep_grid(), device="cuda")
 res = "resonator" in plan.post
 out = {}
-for label, env in (("rows", {"SCQED_S1_ROWS": "1"}), ("full", {"SCQED_S1_ROWS": "0"})):
+for label, env in (("blk", {"SCQED_S1_BLK": "1"}), ("full", {"SCQED_S1_BLK": "0"})):
     os.environ.update(env)
     with engine.Engine(plan) as eng:
         for _ in range(3):
@@ -35,4 +35,4 @@ for label, env in (("rows", {"SCQED_S1_ROWS": "1"}), ("full", {"SCQED_S1_ROWS": 
         engine.timing_enable(False)
         out[label] = E.cpu().numpy()
         print("%-5s tridiag kernel %.3f ms/step   whole sweep %.3f ms/step   bad=%d" % (label, ms / 5, e0.elapsed_time(e1) / 5, int(info.sum())))
-print("max |dE| rows vs full: %.3e (scale %.3g)" % (np.abs(out["rows"] - out["full"]).max(), np.abs(out["full"]).max()))
+print("max |dE| blk vs full: %.3e (scale %.3g)" % (np.abs(out["blk"] - out["full"]).max(), np.abs(out["full"]).max()))
