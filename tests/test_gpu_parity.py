@@ -157,6 +157,37 @@ def test_row_per_thread_packed_kernel(engine_mod, monkeypatch, n, k):
         assert np.max(np.abs(res.Erwa - ref)) < E_RTOL * np.max(np.abs(ref))
 
 
+@pytest.mark.parametrize("env", ["SCQED_S1_BLK", "SCQED_S1_REG"])
+@pytest.mark.parametrize("n,k", [(3, 2), (8, 4), (9, 3), (33, 10), (64, 10), (65, 7), (101, 20), (104, 9), (128, 8)])
+def test_blocked_and_register_tridiagonalisation(engine_mod, monkeypatch, env, n, k):
+    """Opt-in alternates of the real-symmetric shared-memory tridiagonalisation: SCQED_S1_BLK=1 (small_blocked.cuh:
+    dlatrd panels of 8 columns, trailing update as DMMA 8x8x4 tiles) and SCQED_S1_REG=1 (small_reg.cuh: the matrix in
+    registers), on raw matrices against numpy and on the fluxonium plan against the reference's output."""
+    import torch
+    monkeypatch.setenv(env, "1")
+    rng = np.random.default_rng(17 + n)
+    H = _random_hermitian(rng, n, 6, real=True).astype(np.complex128)
+    H[1] = np.diag(np.diag(H[1]))                      # already diagonal: every reflector is the identity (tau = 0)
+    E, V, info = engine_mod.eigh_batched(torch.as_tensor(H, device="cuda"), k, want_vectors=True, solver=1)
+    E, V, info = E.cpu().numpy(), V.cpu().numpy(), info.cpu().numpy()
+    assert not info.any()
+    for b in range(H.shape[0]):
+        w, v = np.linalg.eigh(H[b])
+        scale = np.abs(w).max()
+        assert np.max(np.abs(E[b] - w[:k])) < 1e-12 * scale * n
+        X = V[b].T
+        assert np.max(np.abs(X.conj().T @ X - np.eye(k))) < 1e-10
+        assert np.max(np.abs(H[b] @ X - X * E[b][None, :])) < 1e-11 * scale * n
+    if n == 101:
+        g, plan = load_golden("c2_fluxonium_res")
+        with engine_mod.Engine(plan) as eng:
+            res = eng.sweep(g["params"], int(g["k"]), want_vectors=True, resonator=True)
+        assert not res.info.any()
+        _check_levels(res.E, g["E"])
+        ref = g["eval_getResonatorResponse"]
+        assert np.max(np.abs(res.Erwa - ref)) < E_RTOL * np.max(np.abs(ref))
+
+
 @pytest.mark.parametrize("n,k", [(129, 10), (160, 12), (200, 10), (208, 6)])
 def test_real_symmetric_up_to_224_on_chip(engine_mod, n, k):
     """128 < n <= ~212: real symmetric matrices stay on the shared-memory path (packed storage); complex
