@@ -29,10 +29,9 @@ def _all_gather_rows(local, n_total, world, device):
     pad = torch.zeros((per,) + tuple(t.shape[1:]), dtype=t.dtype)
     pad[: t.shape[0]] = t
     pad = pad.to(device)
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad)
-    out = torch.cat([p.cpu() for p in parts], dim=0)[:n_total]
-    return out.numpy()
+    full = torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=device)
+    dist.all_gather_into_tensor(full, pad)
+    return full[:n_total].cpu().numpy()
 
 
 def sweep_sharded(make_engine, grid, k, want_vectors=False, resonator=False, gather_vectors=False, device=None,
@@ -69,10 +68,20 @@ def sweep_sharded(make_engine, grid, k, want_vectors=False, resonator=False, gat
 
     n = getattr(eng, "n", None)
     out = {"shard": (lo, hi), "local": local}
-    out["E"] = rows(local.E if local else None, (k,), np.float64)
-    out["info"] = rows(local.info if local else None, (), np.int32)
+    # eigenvalues, scalar outputs and info travel as ONE [points, k + n_scalar + 1] block: one collective and one
+    # device -> host copy per sweep (info values are small integers, exact in float64)
     names = list(eng.plan.program.scalar_names)
-    out["scalars"] = {nm: rows(local.scalars[nm] if local else None, (), np.float64) for nm in names}
+    width = k + len(names) + 1
+    blk = np.zeros((n_loc, width), dtype=np.float64)
+    if local is not None and n_loc:
+        blk[:, :k] = local.E
+        for i, nm in enumerate(names):
+            blk[:, k + i] = local.scalars[nm]
+        blk[:, width - 1] = local.info
+    full = rows(blk, (width,), np.float64)
+    out["E"] = np.ascontiguousarray(full[:, :k])
+    out["scalars"] = {nm: np.ascontiguousarray(full[:, k + i]) for i, nm in enumerate(names)}
+    out["info"] = full[:, width - 1].astype(np.int32)
     if resonator and not gather_strips:
         out["Erwa"] = local.Erwa if local else None
     elif resonator:
