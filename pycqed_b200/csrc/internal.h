@@ -35,6 +35,17 @@ extern std::atomic<long long> g_matvecs;      // vector mat-vecs issued by the m
 
 int fail(int code, const char *fmt, ...);
 
+// Opt a kernel into the device's maximum dynamic shared memory (the opt-in limit minus the kernel's static shared
+// memory).  Always the same value for a given kernel and device: the attribute is per function, and host threads driving
+// different engines launch the same kernel with different footprints, so a per-launch value could undercut another thread.
+template <typename Kern>
+static inline cudaError_t set_max_dynamic_smem(Kern kern, size_t smem_optin) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin - (int)fa.sharedSizeBytes);
+}
+
 #define CK(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -106,7 +117,7 @@ struct scqed_plan {
     long long mf_work_per_row = 0;     // complex MACs per output element of the matrix-free mat-vec
     int s1_real_mode = -1;             // fused small path: -1 unknown, 0 complex Hermitian, 1 real symmetric
     bool defer_real_check = false;     // scqed_sweep_run_host checks the "turned complex" flags itself, once, after its last chunk
-    DevBuf s1work, s1vec, auxc, resvec, dcoef;
+    DevBuf s1work, s1vec, auxc, resvec, dcoef, s1ladder;
     std::vector<int> xform_node;
     std::vector<size_t> xform_off;     // byte offsets of W_i^T inside `tables`
     int pair_max_index = -1;

@@ -141,12 +141,12 @@ static int run_matfree_core(scqed_plan *pl, const cplx *coef_all, long long n_pt
         d2_smem_real = (size_t)D2_RB * P.dims[0] * 8 + (size_t)D2_RB * P.dims[1] * 16 + (size_t)(P.d2_nmulti + 1) * 16 +
                        (size_t)D2_RB * (P.dims[1] + 2) * 8 + 32;
         d2_smem_cplx = d2_smem_real + (size_t)D2_RB * P.dims[0] * 8;
-        CK(cudaFuncSetAttribute(mf_d2_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_real));
-        CK(cudaFuncSetAttribute(mf_d2_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_real));
-        CK(cudaFuncSetAttribute(mf_d2_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_real));
-        CK(cudaFuncSetAttribute(mf_d2_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_real));
-        CK(cudaFuncSetAttribute(mf_d2_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_cplx));
-        CK(cudaFuncSetAttribute(mf_d2_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_cplx));
+        CK(set_max_dynamic_smem(mf_d2_kernel<0, true, true>, pl->smem_optin));
+        CK(set_max_dynamic_smem(mf_d2_kernel<1, true, true>, pl->smem_optin));
+        CK(set_max_dynamic_smem(mf_d2_kernel<0, true, false>, pl->smem_optin));
+        CK(set_max_dynamic_smem(mf_d2_kernel<1, true, false>, pl->smem_optin));
+        CK(set_max_dynamic_smem(mf_d2_kernel<0, false, false>, pl->smem_optin));
+        CK(set_max_dynamic_smem(mf_d2_kernel<1, false, false>, pl->smem_optin));
     }
     bool d2_real = false, d2_cpl_real = false, d2_realx = false;
     // TMA-pipelined real kernel: 1-D bulk copies need 16-byte aligned sources and sizes (rows of X and of H1)
@@ -156,8 +156,8 @@ static int run_matfree_core(scqed_plan *pl, const cplx *coef_all, long long n_pt
         d2_smem_dmma = (size_t)D2_RB * (P.dims[0] + 16) * 8 + (size_t)D2_RB * (P.dims[1] + 16) * 8 + (size_t)(P.d2_nmulti + 2) * 16 + 64;
         d2_dmma = P.dims[1] <= 8 * 8 * D2_NT && d2_smem_dmma <= 200 * 1024 && !getenv("SCQED_NO_D2_DMMA");
         if (d2_dmma) {
-            CK(cudaFuncSetAttribute(mf_d2_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_dmma));
-            CK(cudaFuncSetAttribute(mf_d2_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_dmma));
+            CK(set_max_dynamic_smem(mf_d2_dmma_kernel<0>, pl->smem_optin));
+            CK(set_max_dynamic_smem(mf_d2_dmma_kernel<1>, pl->smem_optin));
         }
     }
     if (use_d2) {
@@ -167,8 +167,8 @@ static int run_matfree_core(scqed_plan *pl, const cplx *coef_all, long long n_pt
         d2_tma = (d1_ % 2 == 0) && (d0_ % 2 == 0) && (n % 1 == 0) && d2_smem_tma <= 200 * 1024 &&
                  getenv("SCQED_D2_TMA") && atoi(getenv("SCQED_D2_TMA")) != 0;      // opt-in: measured 7 % slower than the plain kernel (35.6 vs 38.4 pts/s)
         if (d2_tma) {
-            CK(cudaFuncSetAttribute(mf_d2_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_tma));
-            CK(cudaFuncSetAttribute(mf_d2_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_tma));
+            CK(set_max_dynamic_smem(mf_d2_tma_kernel<0>, pl->smem_optin));
+            CK(set_max_dynamic_smem(mf_d2_tma_kernel<1>, pl->smem_optin));
         }
     }
     const dim3 d2_grid_base((unsigned)((P.dims[0] + D2_RB - 1) / D2_RB), (unsigned)b, 1);
@@ -318,10 +318,10 @@ static int run_matfree_core(scqed_plan *pl, const cplx *coef_all, long long n_pt
                 const size_t sm_rx = (size_t)2 * n * 8 + hbytes + (P.d2_nmulti > 0 ? (size_t)n * 16 : 0) + 64;
                 const size_t sm_cx = (size_t)2 * n * 16 + hbytes + 64;
                 if (use_d2 && d2_real && d2_realx && sm_rx <= 220 * 1024) {
-                    CK(cudaFuncSetAttribute(mf_cheb_smem_d2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rx));
+                    CK(set_max_dynamic_smem(mf_cheb_smem_d2<true>, pl->smem_optin));
                     mf_cheb_smem_d2<true><<<dim3(b, (unsigned)np), 512, sm_rx, st>>>(a, X, Y, deg, d2re);
                 } else if (use_d2 && d2_real && sm_cx <= 220 * 1024) {
-                    CK(cudaFuncSetAttribute(mf_cheb_smem_d2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cx));
+                    CK(set_max_dynamic_smem(mf_cheb_smem_d2<false>, pl->smem_optin));
                     mf_cheb_smem_d2<false><<<dim3(b, (unsigned)np), 512, sm_cx, st>>>(a, X, Y, deg, d2re);
                 } else {
                     mf_cheb_smem<<<dim3(b, (unsigned)np), 512, (size_t)2 * n * 16, st>>>(a, X, Y, deg);

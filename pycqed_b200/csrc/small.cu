@@ -9,6 +9,7 @@
 #include "small_rows.cuh"
 #include "small_reg.cuh"
 #include "small_blocked.cuh"
+#include "small_ladder.cuh"
 
 static bool small_fits(const scqed_plan *pl, int n, int k, int want_vec, int n_terms, SmallLayout *Lout) {
     SmallLayout L = small_smem_layout(n, k, want_vec, n_terms, pl->smem_optin);
@@ -44,6 +45,9 @@ static int run_small(scqed_plan *pl, const PlanDev &P, const cplx *coef, const c
 // SCQED_S1_PACKED: 0 = full-storage kernel only (n <= 128), 1 = packed lower triangle for every n,
 // unset = auto: full storage for n <= 128 (faster per matrix: 6.6 vs 9.9 ms on the bench), packed above
 // (the only way 128 < n <= ~212 real symmetric stays on chip: 8x the HBM solver at n = 200)
+// Every launch below sets MaxDynamicSharedMemorySize to the device's opt-in maximum, never to the size of the launch at
+// hand: the attribute is per function and device, and several host threads (one per engine, EnginePool) launch the same
+// kernel with different footprints -- a per-launch value set by one thread could undercut another thread's launch.
 static int s1_packed_mode() {
     const char *e = getenv("SCQED_S1_PACKED");
     return e ? atoi(e) : 2;
@@ -65,7 +69,7 @@ static int s1p_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t
     const size_t smem = S1PSmem<T>::bytes(a.n, n_terms, threads);
     *launched = false;
     if (smem > pl->smem_optin) return 0;
-    CK(cudaFuncSetAttribute(s1p_tridiag_kernel<T, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(set_max_dynamic_smem(s1p_tridiag_kernel<T, NQ>, pl->smem_optin));
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s1p_tridiag_kernel<T, NQ>, threads, smem));
     if (occ < 1) return 0;
@@ -96,7 +100,7 @@ static int s1r_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t
     const int threads = a.n <= 128 ? 128 : 256;
     const size_t smem = S1RSmem::bytes(a.n, n_terms);
     if (smem > pl->smem_optin) return 0;
-    CK(cudaFuncSetAttribute(s1r_tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(set_max_dynamic_smem(s1r_tridiag_kernel, pl->smem_optin));
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s1r_tridiag_kernel, threads, smem));
     if (occ < 1) return 0;
@@ -124,17 +128,102 @@ static int s1b_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t
     if (a.n < 3 || a.n > 128) return 0;
     const size_t smem = S1BSmem::bytes(a.n, n_terms);
     if (smem > pl->smem_optin) return 0;
-    CK(cudaFuncSetAttribute(s1b_tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(set_max_dynamic_smem(s1b_tridiag_kernel, pl->smem_optin));
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s1b_tridiag_kernel, S1B_THREADS, smem));
     if (occ < 1) return 0;
     long long grid = (long long)occ * pl->sm_count;
     if (grid > a.n_pts) grid = a.n_pts;
     TimingScope tscope_(st, 1);
-    s1b_tridiag_kernel<<<(unsigned)grid, S1B_THREADS, smem, st>>>(a);
+    s1b_tridiag_kernel<<<(unsigned)grid, S1B_THREADS, smem, st>>>(a, 1 << 30, nullptr);
     tscope_.end();
     LAUNCHED();
     CK(cudaGetLastError());
+    *launched = true;
+    return 0;
+}
+
+// Occupancy ladder (small_ladder.cuh): the reduction of a real symmetric matrix in full storage is cut into stages of
+// decreasing dimension, each launched with as many CTAs per SM as its shared-memory footprint allows.
+// SCQED_S1_LADDER="n2,n3,..." fixes the stage dimensions, "0" disables the ladder.
+static int s1l_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t st, bool *launched) {
+    *launched = false;
+    const int n = a.n;
+    if (n < 40 || n > 32 * SMALL_RQ) return 0;
+    if (S1LSmem::bytes(n, n, n_terms) > pl->smem_optin) return 0;
+    std::vector<int> dims;                                   // dimensions of the stages after the first
+    if (const char *e = getenv("SCQED_S1_LADDER")) {
+        if (atoi(e) == 0) return 0;
+        for (const char *q = e; *q;) {
+            int v = atoi(q);
+            if (v >= 8 && v < (dims.empty() ? n : dims.back()) - 3) dims.push_back(v);
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+    } else {
+        // largest dimension at which 4 CTAs fit one SM (measured on the bench workload, n = 101: one hand-off at 72 gives
+        // 6.60 -> 6.18 ms, a second one at 48 gives nothing: the large-m columns carry most of the work)
+        const size_t cap = 227 * 1024;
+        int cur = n;
+        for (int occ_target : {4}) {
+            int best = 0;
+            for (int m = cur - 8; m >= 24; --m)
+                if ((S1LSmem::bytes(m, n, n_terms) + 1024) * occ_target <= cap) { best = m; break; }
+            if (best >= 24 && best <= cur - 12) { dims.push_back(best); cur = best; }
+        }
+    }
+    if (dims.empty()) return 0;
+    // hand-off buffers: stage i writes its trailing block for stage i + 1
+    size_t need = 0;
+    for (int m : dims) need += (size_t)a.n_pts * m * m * 8;
+    if (pl->s1ladder.ensure(need)) return fail(SCQED_ENOMEM, "ladder hand-off buffers (%zu MB)", need >> 20);
+    TimingScope tscope_(st, 1);
+    double *buf = (double *)pl->s1ladder.p;
+    const double *tin = nullptr;
+    int cur = n, off = 0;
+    const bool blocked_first = getenv("SCQED_S1_LADDER_BLK") && atoi(getenv("SCQED_S1_LADDER_BLK")) != 0 &&
+                               (n - dims[0]) % S1B_NB == 0 && S1BSmem::bytes(n, n_terms) <= pl->smem_optin;
+    for (size_t i = 0; i <= dims.size(); ++i) {
+        if (i == 0 && blocked_first) {
+            // first stage on the blocked kernel (read-only mat-vec pass + DMMA trailing update): the large-m columns
+            const size_t smem = S1BSmem::bytes(n, n_terms);
+            CK(set_max_dynamic_smem(s1b_tridiag_kernel, pl->smem_optin));
+            int occ = 1;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s1b_tridiag_kernel, S1B_THREADS, smem));
+            if (occ < 1) return fail(SCQED_EUNSUPPORTED, "blocked ladder stage does not fit (n=%d)", n);
+            long long grid = (long long)occ * pl->sm_count;
+            if (grid > a.n_pts) grid = a.n_pts;
+            s1b_tridiag_kernel<<<(unsigned)grid, S1B_THREADS, smem, st>>>(a, n - dims[0], buf);
+            LAUNCHED();
+            CK(cudaGetLastError());
+            tin = buf;
+            buf += (size_t)a.n_pts * dims[0] * dims[0];
+            off += cur - dims[0];
+            cur = dims[0];
+            continue;
+        }
+        S1LStage sg;
+        sg.n = cur; sg.off = off; sg.Tin = tin;
+        if (i < dims.size()) { sg.j_stop = cur - dims[i]; sg.Tout = buf; }
+        else { sg.j_stop = cur - 1; sg.Tout = nullptr; }
+        const size_t smem = S1LSmem::bytes(cur, n, n_terms);
+        CK(set_max_dynamic_smem(s1l_tridiag_kernel, pl->smem_optin));
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s1l_tridiag_kernel, 256, smem));
+        if (occ < 1) return fail(SCQED_EUNSUPPORTED, "ladder stage does not fit (n=%d)", cur);
+        long long grid = (long long)occ * pl->sm_count;
+        if (grid > a.n_pts) grid = a.n_pts;
+        s1l_tridiag_kernel<<<(unsigned)grid, 256, smem, st>>>(a, sg);
+        LAUNCHED();
+        CK(cudaGetLastError());
+        if (i < dims.size()) {
+            tin = buf;
+            buf += (size_t)a.n_pts * dims[i] * dims[i];
+            off += cur - dims[i];
+            cur = dims[i];
+        }
+    }
+    tscope_.end();
     *launched = true;
     return 0;
 }
@@ -147,7 +236,7 @@ static int s1g_launch_t(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream
     const size_t smem = S1GSmem::bytes(a.n, n_terms, NC, NW);
     if (smem > pl->smem_optin || NW * 32 > MAXT) return 0;
     auto kern = s1g_tridiag_kernel<TPR, NPAIR, MAXT, MAXR>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(set_max_dynamic_smem(kern, pl->smem_optin));
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, smem));
     if (occ < 1) return 0;
@@ -187,6 +276,11 @@ static int s1_launch_tridiag(scqed_plan *pl, const S1Args &a, int n_terms, cudaS
             rc = s1b_launch(pl, a, n_terms, st, &launched);
             if (rc) return rc;
             if (launched) return 0;
+            if (!s1_rows_mode() && s1_packed_mode() != 1) {
+                rc = s1l_launch(pl, a, n_terms, st, &launched);
+                if (rc) return rc;
+                if (launched) return 0;
+            }
         }
         if (s1_rows_mode()) {
             bool launched = false;
@@ -208,7 +302,7 @@ static int s1_launch_tridiag(scqed_plan *pl, const S1Args &a, int n_terms, cudaS
     }
     const int threads = sizeof(T) == sizeof(double) ? 256 : 512;
     const size_t smem = S1Smem<T>::bytes(a.n, n_terms, threads);
-    CK(cudaFuncSetAttribute(s1_tridiag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(set_max_dynamic_smem(s1_tridiag_kernel<T>, pl->smem_optin));
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s1_tridiag_kernel<T>, threads, smem));
     if (occ < 1) return fail(SCQED_EUNSUPPORTED, "small tridiagonalisation kernel does not fit (n=%d)", a.n);

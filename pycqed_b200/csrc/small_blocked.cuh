@@ -53,8 +53,10 @@ struct S1BSmem {
     }
 };
 
+// j_stop (a multiple of S1B_NB, or >= n for the complete reduction): stop after the panels below j_stop, write the exact
+// trailing block A[j_stop:, j_stop:] to Tout [n_pts][(n - j_stop)^2] (column-major) for a later stage (small_ladder.cuh).
 static __global__ void __launch_bounds__(S1B_THREADS)
-s1b_tridiag_kernel(S1Args a) {
+s1b_tridiag_kernel(S1Args a, int j_stop, double *Tout) {
     constexpr int NB = S1B_NB;
     extern __shared__ __align__(16) unsigned char smem[];
     const int n = a.n, tid = threadIdx.x;
@@ -82,7 +84,8 @@ s1b_tridiag_kernel(S1Args a) {
         if (tid == 0) { a.W.flags[p] = not_real; if (not_real) a.info[p] = -2; }
         if (not_real) continue;                              // info = -2: the caller re-runs in complex mode
 
-        for (int j0 = 0; j0 < n; j0 += NB) {
+        const bool complete = j_stop >= n;
+        for (int j0 = 0; j0 < n && j0 < j_stop; j0 += NB) {
             const int pn = min(NB, n - j0);
             for (int jj = 0; jj < pn; ++jj) {
                 const int j = j0 + jj;
@@ -248,21 +251,32 @@ s1b_tridiag_kernel(S1Args a) {
             }
         }
         __syncthreads();
-        if (tid == 0) { ev[n - 1] = 0.0; tauv[n - 1] = 0.0; }
+        if (complete && tid == 0) { ev[n - 1] = 0.0; tauv[n - 1] = 0.0; }
         __syncthreads();
-        tridiag_bounds(dv, ev, n, bounds, red);
-        for (int i = tid; i < n; i += S1B_THREADS) {
+        const int n_out = complete ? n : j_stop;
+        for (int i = tid; i < n_out; i += S1B_THREADS) {
             const double e = ev[i];
             a.W.dd[p * n + i] = dv[i];
             a.W.ee[p * n + i] = e;
             a.W.e2[p * n + i] = e * e;
             ((double *)a.W.tau)[p * n + i] = tauv[i];
         }
-        if (tid < 4) a.W.bnd[p * 4 + tid] = bounds[tid];
+        if (complete) {
+            tridiag_bounds(dv, ev, n, bounds, red);
+            if (tid < 4) a.W.bnd[p * 4 + tid] = bounds[tid];
+        } else {
+            const int m = n - j_stop;
+            double *Tp = Tout + (size_t)p * m * m;
+            for (int idx = tid; idx < m * m; idx += S1B_THREADS) {
+                const int c = idx / m, r = idx - c * m;
+                Tp[idx] = A[(j_stop + r) + (size_t)(j_stop + c) * lda];
+            }
+        }
         if (a.want_vec) {
             // reflector j: column j, rows j+1 .. n-1 (s1_backtr_kernel reads nothing else)
             double *dst = (double *)a.W.Vst + (size_t)p * n * n;
-            for (int j = wp; j < n - 1; j += S1B_THREADS / 32)
+            const int n_refl = complete ? n - 1 : j_stop;
+            for (int j = wp; j < n_refl; j += S1B_THREADS / 32)
                 for (int i = j + 1 + lane; i < n; i += 32) dst[(size_t)j * n + i] = A[i + (size_t)j * lda];
         }
         __syncthreads();

@@ -166,8 +166,11 @@ __device__ __forceinline__ void ser_next_reflector(T *col, int m, bool upd, cons
 // z/d-hetd2 'L' arithmetic, restructured so that one pass over the trailing block applies the
 // PENDING rank-2 update of step j-1 and accumulates A v_j of step j, and the O(m) work between
 // passes runs on four warps with named barriers: two block barriers per column instead of nine.
-template <typename T>
-__device__ void small_tridiag(T *A, int n, double *dv, double *ev, T *tau, T *vbuf, T *wbuf, T *part) {
+// j_stop < n - 1: PARTIAL reduction -- reflectors 0 .. j_stop-1 are formed and applied (d, e, tau of those columns are
+// set, the reflectors stay in their columns), then A[j_stop:, j_stop:] holds the exact trailing matrix whose reduction a
+// later stage continues as an independent (n - j_stop)-dimensional problem (small_ladder.cuh).
+template <typename T, bool PARTIAL = false>
+__device__ void small_tridiag(T *A, int n, double *dv, double *ev, T *tau, T *vbuf, T *wbuf, T *part, int j_stop = 1 << 30) {
     __shared__ double ser_sm[24];
     __shared__ cplx ser_t[2];
     const int tid = threadIdx.x, NT = blockDim.x;
@@ -252,10 +255,24 @@ __device__ void small_tridiag(T *A, int n, double *dv, double *ev, T *tau, T *vb
             const T w0 = ((T *)ser_t)[0];
             ser_barrier();                                       // ser_t is reused below
             // column j+1 with this step's update applied -> reflector j+1 (or the last diagonal)
-            ser_next_reflector<T>(A22, m, true, vcur, w0, wr, vprev /* becomes vcur */, dv, ev, tau, j + 1,
-                                  ser_sm, (T *)ser_t);
+            if (!PARTIAL || j + 1 != j_stop)
+                ser_next_reflector<T>(A22, m, true, vcur, w0, wr, vprev /* becomes vcur */, dv, ev, tau, j + 1,
+                                      ser_sm, (T *)ser_t);
         }
         __syncthreads();
+        if (PARTIAL && j + 1 == j_stop) {
+            // hand-off: the pending rank-2 update of this step goes into the whole trailing block, which then IS
+            // the remaining problem
+            for (int idx = tid; idx < m * m; idx += NT) {
+                const int c = idx / m, r = idx - c * m;
+                T x = A22[r + (size_t)c * n];
+                nfnmac(x, vcur[r], wcur[c]);
+                nfnmac(x, wcur[r], vcur[c]);
+                A22[r + (size_t)c * n] = x;
+            }
+            __syncthreads();
+            return;
+        }
         T *t = vcur; vcur = vprev; vprev = t;
         t = wcur; wcur = wprev; wprev = t;
     }
