@@ -73,14 +73,25 @@ static __device__ int s1g_assemble(const S1Args &a, long long p, double *A, doub
             const double *dg = a.P.dense_tab + (size_t)NF * nn;
             for (int j = wp; j < n; j += NW) {
                 const double *col = a.P.dense_tab + (size_t)j * n;
-                for (int i = j + lane; i < n; i += 32) {
-                    double re = 0.0;
-                    for (int g = 0; g < NF; ++g) re = fma(cf[g], __ldg(col + g * nn + i), re);
+                // two rows per lane and pass, the table loads of both issued back to back (the assembly was stalled on
+                // one L2 load at a time: ncu r02, 11 % of the first ladder stage)
+                for (int i = j + lane; i < n; i += 64) {
+                    const int i2 = i + 32;
+                    const bool two = i2 < n;
+                    double re = 0.0, re2 = 0.0;
+#pragma unroll 4
+                    for (int g = 0; g < NF; ++g) {
+                        const double t0 = __ldg(col + (size_t)g * nn + i);
+                        const double t1 = two ? __ldg(col + (size_t)g * nn + i2) : 0.0;
+                        re = fma(cf[g], t0, re);
+                        re2 = fma(cf[g], t1, re2);
+                    }
                     if (i == j)
                         for (int g = NF; g < NG; ++g) re = fma(cf[g], __ldg(dg + (size_t)(g - NF) * n + i), re);
-                    if (a.tidyup) re = fabs(re) < 1e-12 ? 0.0 : re;
+                    if (a.tidyup) { re = fabs(re) < 1e-12 ? 0.0 : re; re2 = fabs(re2) < 1e-12 ? 0.0 : re2; }
                     A[i + j * lda] = re;
                     A[j + i * lda] = re;
+                    if (two) { A[i2 + j * lda] = re2; A[j + i2 * lda] = re2; }
                 }
             }
         }
