@@ -842,6 +842,15 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
     // measured on the bench workload (10 000 points, 251 MB of results, 171 MB with packed real eigenvectors):
     // complex vectors 3 chunks x 0.6 (12.9 -> 11.9 ms end to end), packed real vectors 2 chunks 77 % / 23 % (11.2 ms)
     if (nchunks == 2) { if (o->real_vectors) geom = 0.3; else { nchunks = 3; geom = 0.6; } }
+    // Adaptive: when the copies are the long pole (measured on the previous call of this plan, see the end of this
+    // function) the first copy must start as early as possible and every copy needs a solve to hide behind: equal chunks
+    // of ~1250 points.  8 ranks of one box sharing the host: 170 MB per rank at 11.5 GB/s = 14.9 ms against 9.1 ms of solving.
+    const bool reprobe = pl->host_copy_bound && (++pl->host_calls % 16) == 0;      // now and then try the default again
+    if (pl->host_copy_bound && !reprobe && n_pts >= 2500) {
+        nchunks = n_pts / 1250;
+        if (nchunks > 8) nchunks = 8;
+        geom = 0.0;
+    }
     if (const char *envc = getenv("SCQED_HOST_CHUNKS")) { long long v = atoll(envc); if (v >= 1 && v <= 64) nchunks = v < n_pts ? v : n_pts; }
     // Chunk sizes.  Default: equal.  SCQED_HOST_GEOM=r (0 < r < 1): geometric, chunk i+1 = r * chunk i, so that the
     // copy of chunk i hides behind the (shorter) solve of chunk i+1 and only a small last copy is exposed.
@@ -985,6 +994,12 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
     // (one stream synchronisation per call on the device path) is done once, below, on the host copy of info.
     struct DeferGuard { scqed_plan *p; bool old; DeferGuard(scqed_plan *q) : p(q), old(q->defer_real_check) { q->defer_real_check = true; }
                         ~DeferGuard() { p->defer_real_check = old; } } defer_guard(pl);
+    // three timed events decide the chunking of the NEXT call: start, last chunk solved, last copy done
+    cudaEvent_t t_start = nullptr, t_solved = nullptr, t_copied = nullptr;
+    struct TimedEvents { cudaEvent_t *e[3]; ~TimedEvents() { for (auto p_ : e) if (*p_) cudaEventDestroy(*p_); } } timed_guard{{&t_start, &t_solved, &t_copied}};
+    if (cudaEventCreate(&t_start) != cudaSuccess || cudaEventCreate(&t_solved) != cudaSuccess || cudaEventCreate(&t_copied) != cudaSuccess)
+        return bail(fail(SCQED_ECUDA, "cudaEventCreate failed"));
+    CKH(cudaEventRecord(t_start, st));
     long long c0 = 0;
     for (size_t ci = 0; ci < sizes.size(); c0 += sizes[ci], ++ci) {
         const long long np = sizes[ci];
@@ -1006,9 +1021,19 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
         if (rc) return rc;
     }
     int h_flag = 0;
+    CKH(cudaEventRecord(t_solved, st));
+    CKH(cudaEventRecord(t_copied, cs));
     if (pack) CKH(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
     CKH(cudaStreamSynchronize(st));
     CKH(cudaStreamSynchronize(cs));
+    {
+        float ms_solve = 0.f, ms_all = 0.f;
+        if (cudaEventElapsedTime(&ms_solve, t_start, t_solved) == cudaSuccess && cudaEventElapsedTime(&ms_all, t_start, t_copied) == cudaSuccess) {
+            const float tail = ms_all - ms_solve;              // copies still running after the last solve
+            if (!pl->host_copy_bound && tail > 0.35f * ms_solve && tail > 1.0f) pl->host_copy_bound = 1;
+            else if (reprobe && tail < 0.25f * ms_solve) pl->host_copy_bound = 0;
+        } else cudaGetLastError();
+    }
     if (staged_per_pt) {
         std::unique_lock<std::mutex> lk(mu);
         cv.wait(lk, [&] { return chunks_moved >= n_staged_chunks; });

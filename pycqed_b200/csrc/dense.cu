@@ -44,6 +44,7 @@ static int dense_nseg(int n, int sm_count, int B) {
     int floor_ = (n + 383) / 384;          // keeps the per-CTA column segment (80 B/col of smem) under 32 KB
     if (want < floor_) want = floor_;
     if (want < 1) want = 1;
+    if (const char *e = getenv("SCQED_DENSE_NSEG")) { int v = atoi(e); if (v >= 1) want = v; }
     if (want > 64) want = 64;
     return want;
 }

@@ -254,10 +254,17 @@ def test_engine_pool_shards_like_one_engine(engine_mod):
         many = pool.sweep(grid, 10, want_vectors=True, resonator=True, real_vectors="auto")
         lazy = pool.sweep(grid, 10, want_vectors=True, resonator=True, vectors_on_device=True)
     assert not one.info.any() and not many.info.any()
-    assert np.array_equal(one.E, many.E) and np.array_equal(one.Erwa, many.Erwa)
-    assert many.V.dtype == np.float64 and np.array_equal(one.V.real, many.V)
+    # blocks of >= 410 points take the same kernels as the whole sweep (bit-identical results); smaller blocks (8 GPUs:
+    # 375 points each) use the warp multisection instead of the thread bisection: same tolerance, last-ulp differences
+    same_path = len(grid) // len(devs) * 10 >= 4096
+    scale = np.abs(one.E).max()
+
+    def close(a, b, tol):
+        return np.array_equal(a, b) if same_path else np.max(np.abs(a - b)) <= tol * max(1.0, np.abs(a).max())
+    assert close(one.E, many.E, 1e-13) and close(one.Erwa, many.Erwa, 1e-11), scale
+    assert many.V.dtype == np.float64 and close(one.V.real, many.V, 1e-9)
     assert lazy.V is None and len(lazy.V_dev) == len(devs)
-    assert np.array_equal(lazy.vectors(), one.V) and np.array_equal(lazy.Erwa, one.Erwa)
+    assert close(lazy.vectors(), one.V, 1e-9) and close(lazy.Erwa, one.Erwa, 1e-11)
     for nm in one.scalars:
         assert np.array_equal(one.scalars[nm], many.scalars[nm])
 
