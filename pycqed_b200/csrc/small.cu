@@ -10,6 +10,7 @@
 #include "small_reg.cuh"
 #include "small_blocked.cuh"
 #include "small_ladder.cuh"
+#include "small_tiled.cuh"
 
 static bool small_fits(const scqed_plan *pl, int n, int k, int want_vec, int n_terms, SmallLayout *Lout) {
     SmallLayout L = small_smem_layout(n, k, want_vec, n_terms, pl->smem_optin);
@@ -136,6 +137,38 @@ static int s1b_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t
     if (grid > a.n_pts) grid = a.n_pts;
     TimingScope tscope_(st, 1);
     s1b_tridiag_kernel<<<(unsigned)grid, S1B_THREADS, smem, st>>>(a, 1 << 30, nullptr);
+    tscope_.end();
+    LAUNCHED();
+    CK(cudaGetLastError());
+    *launched = true;
+    return 0;
+}
+
+// Tile-packed blocked tridiagonalisation (small_tiled.cuh): four CTAs per SM at n = 101.
+static int s1t_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t st, bool *launched) {
+    *launched = false;
+    // default for 80 <= n <= 128 (measured against the ladder / unblocked kernels, tools/s1_scaling.py, 4096 matrices:
+    // n = 88: 1.78 vs 1.89 ms, 101: 2.34 vs 2.69, 118: 3.82 vs 5.29, 128: 5.83 vs 6.21; below 80 the others win);
+    // SCQED_S1_TILED=1 forces it for every n >= 16, =0 disables it
+    const char *e = getenv("SCQED_S1_TILED");
+    const int mode = e ? atoi(e) : -1;
+    if (mode == 0 || (mode < 0 && (a.n < 80 || getenv("SCQED_S1_PACKED") || s1_rows_mode()))) return 0;   // explicit storage opt-ins win
+    if (a.n < 16 || a.n > 128 || !S1TSmem::scratch_fits(a.n, n_terms)) return 0;
+    const size_t smem = S1TSmem::bytes(a.n);
+    if (smem > pl->smem_optin) return 0;
+    const bool pser = !(getenv("SCQED_S1_TILED_PSER") && atoi(getenv("SCQED_S1_TILED_PSER")) == 0) && a.n <= S1T_THREADS;
+    auto kern = pser ? s1t_tridiag_kernel<true> : s1t_tridiag_kernel<false>;
+    CK(set_max_dynamic_smem(kern, pl->smem_optin));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, S1T_THREADS, smem));
+    if (occ < 1) return 0;
+    long long grid = (long long)occ * pl->sm_count;
+    if (grid > a.n_pts) grid = a.n_pts;
+    if (pl->s1slots.ensure(1024 * sizeof(int))) return fail(SCQED_ENOMEM, "per-SM slot counters");
+    CK(cudaMemsetAsync(pl->s1slots.p, 0, 1024 * sizeof(int), st));
+    TimingScope tscope_(st, 1);
+    const int rotate = getenv("SCQED_S1_TILED_ROTATE") ? atoi(getenv("SCQED_S1_TILED_ROTATE")) : 0;
+    kern<<<(unsigned)grid, S1T_THREADS, smem, st>>>(a, (int *)pl->s1slots.p, rotate);
     tscope_.end();
     LAUNCHED();
     CK(cudaGetLastError());
@@ -274,6 +307,9 @@ static int s1_launch_tridiag(scqed_plan *pl, const S1Args &a, int n_terms, cudaS
             if (rc) return rc;
             if (launched) return 0;
             rc = s1b_launch(pl, a, n_terms, st, &launched);
+            if (rc) return rc;
+            if (launched) return 0;
+            rc = s1t_launch(pl, a, n_terms, st, &launched);
             if (rc) return rc;
             if (launched) return 0;
             if (!s1_rows_mode() && s1_packed_mode() != 1) {

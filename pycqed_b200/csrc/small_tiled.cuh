@@ -1,0 +1,408 @@
+// small_tiled.cuh -- S1 phase A, real symmetric: blocked tridiagonalisation on a TILE-PACKED LOWER TRIANGLE.
+//
+// Measured (profiles/r02_s1_scaling.md): the shared-memory tridiagonalisation is bound by the dependent chain of a
+// Householder step times the number of matrices one SM can hold -- 2 at n = 101 in full storage (94 KB per CTA).  Here
+// only the lower triangle lives on chip, as 8 x 8 row-major tiles (R, C), R >= C (diagonal tiles complete): 91 tiles =
+// 46.6 KB at n = 101, and the whole CTA stays under 55 KB => FOUR CTAs per SM.  The layout is chosen for the three
+// accesses of the blocked (dlatrd) form:
+//   * trailing update A22 -= V W^T + W V^T once per panel of NB = 4 columns: a tile IS the C fragment of
+//     mma.sync.m8n8k4.f64 (lane (g, t) <-> T[g][2t], T[g][2t+1]): one LDS.128, two DMMA, one STS.128 per tile;
+//   * symmetric mat-vec y = A v per column from the stored half: work item R = "tile row R (T v_C, C <= R) + tile column
+//     R (T^T v_R', R' > R)".  Both parts feed the SAME eight rows 8R..8R+7, every item touches NT - T0 tiles (perfectly
+//     balanced over the warps), partial sums never leave the warp: two shuffles per item, no partial-sum arrays;
+//   * column j for the reflector: a strided walk over at most NT tiles (O(m), one warp).
+// The O(m) sections run on ONE warp (lane owns rows lane + 32 q): every reduction is a warp shuffle, ~700 instructions
+// per column instead of ~2000 on four warps -- at four CTAs per SM the issue slots, not the chain, are what is scarce.
+// Arithmetic: LAPACK dsytrd 'L' with nb = 4; outputs exactly like s1_tridiag_kernel<double>.
+#pragma once
+#include "common.cuh"
+#include "assemble.cuh"
+#include "tridiag_eig.cuh"
+#include "small_eigh.cuh"
+#include "small_split.cuh"
+#include "small_blocked.cuh"
+
+namespace scqed {
+
+#define S1T_NB 4
+#define S1T_THREADS 128
+
+struct S1TSmem {
+    __host__ __device__ static int nt(int n) { return (n + 7) >> 3; }
+    __host__ __device__ static int tile_doubles(int n) { return nt(n) * (nt(n) + 1) / 2 * 64; }
+    static size_t bytes(int n) {
+        const int ps = 8 * nt(n) + 4;
+        return (size_t)tile_doubles(n) * 8 + (size_t)2 * S1T_NB * ps * 8 + (size_t)ps * 8 + 2 * S1T_NB * 8 + 64;
+    }
+    // the coefficients of the assembly (and, after the reduction, d / e / bounds scratch) alias the panels
+    static bool scratch_fits(int n, int n_coef) {
+        const size_t panels = (size_t)2 * S1T_NB * (8 * nt(n) + 4) * 8;
+        return (size_t)n_coef * 16 <= panels && (size_t)(2 * n + 96 + 4 + 8) * 8 <= panels;
+    }
+};
+
+__device__ __forceinline__ int s1t_tile(int R, int C) { return ((R * (R + 1) >> 1) + C) << 6; }
+
+// element (i, j), i >= j, of the tile-packed lower triangle (diagonal tiles hold both triangles)
+__device__ __forceinline__ void s1t_store(double *tiles, int i, int j, double v) {
+    const int R = i >> 3, C = j >> 3;
+    double *t = tiles + s1t_tile(R, C);
+    t[(i & 7) * 8 + (j & 7)] = v;
+    if (R == C) t[(j & 7) * 8 + (i & 7)] = v;
+}
+
+// P: y = A_stale v from the stored half (item R = tile row R + tile column R, both feed rows 8R..8R+7), and the panel dot
+// products t1[k] = W[:,k].v, t2[k] = V[:,k].v for the corrections.
+__device__ __forceinline__ void s1t_pass(const double *tiles, const double *Vs, const double *Ws, double *Y, double *ts,
+                                         int n, int NT, int PS, int j, int jj, int wp, int lane, int rotate) {
+    constexpr int NB = S1T_NB;
+    const int g8 = lane >> 2, t4 = lane & 3, c8 = lane & 7, r4 = lane >> 3;
+
+                    const double *vj = Vs + jj * PS;
+                    const int T0 = (j + 1) >> 3;
+                    // rotate == 2: scheduler 0 (warps 0 and 4) is left to the serial warps of the co-resident CTAs; the six
+                    // other warps share the mat-vec items, warp 4 forms the panel dot products
+                    const int pw = rotate == 2 ? (wp & 3) - 1 + 3 * (wp >> 2) : wp;          // 1,2,3,5,6,7 -> 0..5
+                    const int npw = rotate == 2 ? 6 : S1T_THREADS / 32;
+                    const bool in_pass = rotate != 2 || (wp & 3) != 0;
+                    for (int R = T0 + pw; in_pass && R < NT; R += npw) {
+                        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+                        const double *trow = tiles + s1t_tile(R, T0) + g8 * 8 + 2 * t4;
+                        const double *vr = vj + 8 * T0 + 2 * t4;
+#pragma unroll 4
+                        for (int C = T0; C <= R; ++C, trow += 64, vr += 8) {
+                            const double2 x = *reinterpret_cast<const double2 *>(trow);
+                            const double2 vv = *reinterpret_cast<const double2 *>(vr);
+                            a0 = fma(x.x, vv.x, a0);
+                            a1 = fma(x.y, vv.y, a1);
+                        }
+                        // tile column R: lane (r4, c8) reads T[r4][c8] and T[r4 + 4][c8] of tile (R2, R)
+                        const double *tt = tiles + s1t_tile(R + 1, R) + 8 * r4 + c8;
+                        const double *vc = vj + 8 * (R + 1) + r4;
+#pragma unroll 4
+                        for (int R2 = R + 1; R2 < NT; ++R2) {
+                            const double x0 = tt[0], x1 = tt[32];
+                            b0 = fma(x0, vc[0], b0);
+                            b1 = fma(x1, vc[4], b1);
+                            tt += (R2 + 1) << 6;
+                            vc += 8;
+                        }
+                        double yr = a0 + a1, yc = b0 + b1;
+                        yr += __shfl_xor_sync(0xffffffffu, yr, 1);
+                        yr += __shfl_xor_sync(0xffffffffu, yr, 2);               // row 8R + g8 in every lane of the quad
+                        yc += __shfl_xor_sync(0xffffffffu, yc, 8);
+                        yc += __shfl_xor_sync(0xffffffffu, yc, 16);              // row 8R + c8 in the lanes with that c8
+                        yr = __shfl_sync(0xffffffffu, yr, 4 * c8);               // ... and the row part of the same row
+                        if (lane < 8) Y[8 * R + lane] = yr + yc;
+                    }
+                    for (int kt = 0; kt < jj; ++kt) {
+                        // panel column kt: warp 4 takes them all (rotate == 2), else warps 7, 6, 5 one each
+                        if (rotate == 2 ? wp != 4 : wp != S1T_THREADS / 32 - 1 - kt % (S1T_THREADS / 32)) continue;
+                        double t1 = 0.0, t2 = 0.0;
+                        for (int i = j + 1 + lane; i < n; i += 32) {
+                            const double vi = vj[i];
+                            t1 = fma(Ws[kt * PS + i], vi, t1);
+                            t2 = fma(Vs[kt * PS + i], vi, t2);
+                        }
+                        t1 = warp_sum(t1); t2 = warp_sum(t2);
+                        if (lane == 0) { ts[kt] = t1; ts[NB + kt] = t2; }
+                    }
+                }
+
+// PSER: the O(m) sections on ALL warps (thread r = row r, n <= S1T_THREADS) instead of one warp: shorter dependent chain
+// per column (one row per lane), four block barriers per column instead of two.
+template <bool PSER>
+static __global__ void __launch_bounds__(S1T_THREADS, 4)
+s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
+    constexpr int NB = S1T_NB;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int n = a.n, tid = threadIdx.x;
+    const int wp = tid >> 5, lane = tid & 31;
+    const int NT = S1TSmem::nt(n), PS = 8 * NT + 4, NTD = S1TSmem::tile_doubles(n);   // PS = 4 (mod 8): conflict-free fragments
+    double *tiles = (double *)smem;
+    double *Vs = tiles + NTD;
+    double *Ws = Vs + NB * PS;
+    double *Y = Ws + NB * PS;
+    double *ts = Y + PS;                                   // t1 = W^T v | t2 = V^T v
+    double *cf = Vs;                                       // assembly coefficients (before the first panel)
+    const int g8 = lane >> 2, t4 = lane & 3;             // row part / DMMA fragments: row g8, column pair 2 t4
+    const int c8 = lane & 7, r4 = lane >> 3;             // column part: column c8, rows r4 and r4 + 4 (conflict-free: 8 r4 + c8)
+    // The O(m) sections run on ONE warp per CTA.  Warp w of every CTA lives on scheduler w % 4: with warp 0 in all four
+    // co-resident CTAs the four serial sections would share one scheduler (and one FP64 unit) while three idle, so the
+    // serial warp is rotated with the position of the CTA inside its wave.
+    // The slot is the arrival order of the CTA on its SM (sm_slots: one zeroed counter per SM; CTAs are persistent).
+    __shared__ int s_sw;
+    if (tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_sw = rotate == 1 ? (atomicAdd(sm_slots + (smid & 1023), 1) & 3) : 0;
+    }
+    __syncthreads();
+    const int sw = s_sw;
+
+    for (long long p = blockIdx.x; p < a.n_pts; p += gridDim.x) {
+        // ---- assemble the lower triangle into the tiles ----
+        int not_real = 0;
+        for (int q = tid; q < NTD; q += S1T_THREADS) tiles[q] = 0.0;
+        if (a.Hin) {
+            __syncthreads();
+            const cplx *Hp = a.Hin + (size_t)p * n * n;
+            for (int idx = tid; idx < n * n; idx += S1T_THREADS) {
+                const int i = idx / n, j = idx - i * n;          // row-major source, coalesced
+                if (j <= i) {
+                    const cplx v = Hp[idx];
+                    not_real |= (v.y != 0.0);
+                    s1t_store(tiles, i, j, v.x);
+                }
+            }
+        } else if (a.dcoef) {
+            const int NG = a.P.n_dense;
+            for (int t = tid; t < 2 * NG; t += S1T_THREADS) cf[t] = a.dcoef[(size_t)p * 2 * NG + t];
+            __syncthreads();
+            const int NF = NG - a.P.n_dense_diag;
+            double imw = 0.0;
+            for (int g = 0; g < NF; ++g) imw += fabs(cf[NG + g]) * __ldg(a.P.dense_gmax + g);
+            const bool pt_real = a.tidyup ? imw < 1e-12 : imw == 0.0;
+            if (!pt_real) not_real = 1;
+            else {
+                const size_t nn = (size_t)n * n;
+                const double *dg = a.P.dense_tab + (size_t)NF * nn;
+                for (int j = wp; j < n; j += S1T_THREADS / 32) {
+                    const double *col = a.P.dense_tab + (size_t)j * n;
+                    for (int i = j + lane; i < n; i += 64) {
+                        const int i2 = i + 32;
+                        const bool two = i2 < n;
+                        double re = 0.0, re2 = 0.0;
+#pragma unroll 4
+                        for (int g = 0; g < NF; ++g) {
+                            const double t0 = __ldg(col + (size_t)g * nn + i);
+                            const double t1 = two ? __ldg(col + (size_t)g * nn + i2) : 0.0;
+                            re = fma(cf[g], t0, re);
+                            re2 = fma(cf[g], t1, re2);
+                        }
+                        if (i == j)
+                            for (int g = NF; g < NG; ++g) re = fma(cf[g], __ldg(dg + (size_t)(g - NF) * n + i), re);
+                        if (a.tidyup) { re = fabs(re) < 1e-12 ? 0.0 : re; re2 = fabs(re2) < 1e-12 ? 0.0 : re2; }
+                        s1t_store(tiles, i, j, re);
+                        if (two) s1t_store(tiles, i2, j, re2);
+                    }
+                }
+            }
+        } else {
+            cplx *s_coef = (cplx *)cf;
+            for (int t = tid; t < a.P.n_terms; t += S1T_THREADS) s_coef[t] = a.coef[p * a.P.n_terms + t];
+            __syncthreads();
+            for (int idx = tid; idx < n * n; idx += S1T_THREADS) {
+                const int j = idx / n, i = idx - j * n;
+                if (i < j) continue;
+                int id[SCQED_MAX_NODES], jd[SCQED_MAX_NODES];
+                digits(a.P, i, id);
+                digits(a.P, j, jd);
+                cplx v = cconj(h_element(a.P, s_coef, jd, id));
+                if (a.tidyup) v = tidy(v, 1e-12);
+                not_real |= (v.y != 0.0);
+                s1t_store(tiles, i, j, v.x);
+            }
+        }
+        not_real = __syncthreads_or(not_real);
+        if (tid == 0) { a.W.flags[p] = not_real; if (not_real) a.info[p] = -2; }
+        if (not_real) continue;                              // info = -2: the caller re-runs in complex mode
+        for (int q = tid; q < 2 * NB * PS + PS; q += S1T_THREADS) Vs[q] = 0.0;      // panels and Y (cf is dead now)
+        __syncthreads();
+
+        double *dd = a.W.dd + p * n, *ee = a.W.ee + p * n, *e2 = a.W.e2 + p * n, *tauo = (double *)a.W.tau + p * n;
+        __shared__ double s_red[2][8], s_scal[2];
+        for (int j0 = 0; j0 < n; j0 += NB) {
+            const int pn = min(NB, n - j0);
+            double v_r = 0.0, w_r = 0.0, wpiv = 0.0;          // PSER: this row's entries of the newest panel column
+            for (int jj = 0; jj < pn; ++jj) {
+                const int j = j0 + jj;
+                if constexpr (PSER) {
+                    const int r = tid;
+                    constexpr int NW = S1T_THREADS / 32;
+                    // ---- S1: column j made current (newest panel column from registers, older ones from the panels) ----
+                    double c = 0.0;
+                    if (r >= j && r < n) {
+                        c = tiles[s1t_tile(r >> 3, j >> 3) + (r & 7) * 8 + (j & 7)];
+                        for (int k = 0; k + 1 < jj; ++k)
+                            c = fma(-Vs[k * PS + r], Ws[k * PS + j], fma(-Ws[k * PS + r], Vs[k * PS + j], c));
+                        if (jj > 0) c = fma(-v_r, wpiv, c - w_r);                 // V[j][jj-1] = 1 (pivot row of column j-1)
+                    }
+                    if (r == j) dd[j] = c;
+                    if (j == n - 1) {
+                        if (tid == 0) { ee[j] = 0.0; e2[j] = 0.0; tauo[j] = 0.0; }
+                        break;
+                    }
+                    if (r == j + 1) s_scal[0] = c;
+                    double xn = (r >= j + 2 && r < n) ? c * c : 0.0;
+                    xn = warp_sum(xn);
+                    if (lane == 0) s_red[0][wp] = xn;
+                    __syncthreads();
+                    xn = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) xn += s_red[0][w];
+                    double tau, beta, sc;
+                    reflector_scalars(s_scal[0], xn, tau, beta, sc);
+                    v_r = (r == j + 1) ? 1.0 : ((r > j + 1 && r < n) ? c * sc : 0.0);
+                    if (r < PS) Vs[jj * PS + r] = v_r;
+                    if (r > j && r < n) tiles[s1t_tile(r >> 3, j >> 3) + (r & 7) * 8 + (j & 7)] = v_r;
+                    if (tid == 0) { ee[j] = beta; e2[j] = beta * beta; tauo[j] = tau; }
+                    __syncthreads();
+                    s1t_pass(tiles, Vs, Ws, Y, ts, n, NT, PS, j, jj, wp, lane, 0);
+                    __syncthreads();
+                    // ---- S3: corrections, w ----
+                    double pr = 0.0;
+                    if (r > j && r < n) {
+                        double y = Y[r];
+                        for (int k = 0; k < jj; ++k) y = fma(-Vs[k * PS + r], ts[k], fma(-Ws[k * PS + r], ts[NB + k], y));
+                        pr = tau * y;
+                    }
+                    if (r == j + 1) s_scal[1] = pr;
+                    double dt = warp_sum(pr * v_r);
+                    if (lane == 0) s_red[1][wp] = dt;
+                    __syncthreads();
+                    dt = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) dt += s_red[1][w];
+                    const double hc = -0.5 * tau * dt;
+                    w_r = (r > j && r < n) ? fma(hc, v_r, pr) : 0.0;
+                    wpiv = s_scal[1] + hc;                                        // w of the pivot row j + 1 (v = 1 there)
+                    if (r < PS) Ws[jj * PS + r] = w_r;
+                    continue;
+                }
+                double vq[4] = {0.0, 0.0, 0.0, 0.0}, tau = 0.0;
+                // ---- S1 / S2 (warp 0, lane owns rows lane + 32 q): column j made current, reflector j ----
+                if (wp == sw) {
+                    const int Cj = j >> 3, cj = j & 7;
+                    double c[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int r = lane + 32 * q;
+                        c[q] = (r >= j && r < n) ? tiles[s1t_tile(r >> 3, Cj) + (r & 7) * 8 + cj] : 0.0;
+                    }
+                    for (int k = 0; k < jj; ++k) {
+                        const double wjk = Ws[k * PS + j], vjk = Vs[k * PS + j];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int r = lane + 32 * q;
+                            if (r < PS) c[q] = fma(-Vs[k * PS + r], wjk, fma(-Ws[k * PS + r], vjk, c[q]));
+                        }
+                    }
+                    {
+                        const int qd = j >> 5;
+                        const double cd = qd == 0 ? c[0] : (qd == 1 ? c[1] : (qd == 2 ? c[2] : c[3]));
+                        if (lane == (j & 31)) dd[j] = cd;
+                    }
+                    if (j < n - 1) {
+                        double xn = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int r = lane + 32 * q;
+                            if (r >= j + 2 && r < n) xn = fma(c[q], c[q], xn);
+                        }
+                        xn = warp_sum(xn);
+                        const int qa = (j + 1) >> 5;
+                        const double ca = qa == 0 ? c[0] : (qa == 1 ? c[1] : (qa == 2 ? c[2] : c[3]));
+                        const double alpha = __shfl_sync(0xffffffffu, ca, (j + 1) & 31);
+                        double beta, sc;
+                        reflector_scalars(alpha, xn, tau, beta, sc);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int r = lane + 32 * q;
+                            vq[q] = (r == j + 1) ? 1.0 : ((r > j + 1 && r < n) ? c[q] * sc : 0.0);
+                            if (r < PS) Vs[jj * PS + r] = vq[q];
+                            if (r > j && r < n) tiles[s1t_tile(r >> 3, Cj) + (r & 7) * 8 + cj] = vq[q];     // kept for the back-transformation
+                        }
+                        if (lane == 0) { ee[j] = beta; e2[j] = beta * beta; tauo[j] = tau; }
+                    } else if (lane == 0) { ee[j] = 0.0; e2[j] = 0.0; tauo[j] = 0.0; }
+                }
+                if (j == n - 1) break;                                            // only the last diagonal was left
+                __syncthreads();
+                s1t_pass(tiles, Vs, Ws, Y, ts, n, NT, PS, j, jj, wp, lane, rotate);
+                __syncthreads();
+                // ---- S3 (warp 0): corrections, w ----
+                if (wp == sw) {
+                    double y[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int r = lane + 32 * q;
+                        y[q] = (r < PS) ? Y[r] : 0.0;
+                    }
+                    for (int k = 0; k < jj; ++k) {
+                        const double t1 = ts[k], t2 = ts[NB + k];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int r = lane + 32 * q;
+                            if (r < PS) y[q] = fma(-Vs[k * PS + r], t1, fma(-Ws[k * PS + r], t2, y[q]));
+                        }
+                    }
+                    double dt = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int r = lane + 32 * q;
+                        y[q] = (r > j && r < n) ? tau * y[q] : 0.0;               // p = tau y on the live rows
+                        dt = fma(y[q], vq[q], dt);
+                    }
+                    dt = warp_sum(dt);
+                    const double hc = -0.5 * tau * dt;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int r = lane + 32 * q;
+                        if (r < PS) Ws[jj * PS + r] = fma(hc, vq[q], y[q]);
+                    }
+                    __syncwarp();
+                }
+            }
+            // ---- trailing update on the FP64 tensor cores: A22 -= V W^T + W V^T on the stored tiles ----
+            const int b0 = j0 + NB;
+            if (pn == NB && b0 < n) {
+                __syncthreads();
+                const int B0 = b0 >> 3;                       // first tile row / column that holds trailing elements
+                const int K = NT - B0;
+                // tile rows in balanced pairs (r, K-1-r): r + 1 and K - r tiles; the A-operand fragments are per row
+                for (int it = wp; it < (K + 1) / 2; it += S1T_THREADS / 32) {
+                    for (int half = 0; half < 2; ++half) {
+                        const int r = half == 0 ? it : K - 1 - it;
+                        if (half == 1 && r == it) break;
+                        const int R = B0 + r;
+                        // rows / columns below b0 inside the first tile row / column are not part of the trailing block
+                        // (they hold reflectors of this panel): their operand fragments are zeroed
+                        const bool rok = 8 * R + g8 >= b0;
+                        const double va = rok ? -Vs[t4 * PS + 8 * R + g8] : 0.0, wa = rok ? -Ws[t4 * PS + 8 * R + g8] : 0.0;
+                        double2 *tp = reinterpret_cast<double2 *>(tiles + s1t_tile(R, B0) + g8 * 8 + 2 * t4);
+                        const double *vbp = Vs + t4 * PS + 8 * B0 + g8, *wbp = Ws + t4 * PS + 8 * B0 + g8;
+                        for (int C = B0; C <= R; ++C, tp += 32, vbp += 8, wbp += 8) {
+                            const bool cok = 8 * C + g8 >= b0;
+                            const double vb = cok ? *vbp : 0.0, wb = cok ? *wbp : 0.0;
+                            double2 d = *tp;
+                            s1b_dmma(d.x, d.y, va, wb);
+                            s1b_dmma(d.x, d.y, wa, vb);
+                            *tp = d;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+        // ---- Gershgorin bounds over the whole tridiagonal matrix (d, e come back from this CTA's own global writes) ----
+        {
+            double *dv = Vs, *ev = Vs + n, *red = Vs + 2 * n, *bounds = red + 96;
+            for (int i = tid; i < n; i += S1T_THREADS) { dv[i] = dd[i]; ev[i] = ee[i]; }
+            __syncthreads();
+            tridiag_bounds(dv, ev, n, bounds, red);
+            if (tid < 4) a.W.bnd[p * 4 + tid] = bounds[tid];
+        }
+        if (a.want_vec) {
+            // reflector j: column j, rows j+1 .. n-1 (s1_backtr_kernel reads nothing else)
+            double *dst = (double *)a.W.Vst + (size_t)p * n * n;
+            for (int j = wp; j < n - 1; j += S1T_THREADS / 32) {
+                const int Cj = j >> 3, cj = j & 7;
+                for (int i = j + 1 + lane; i < n; i += 32) dst[(size_t)j * n + i] = tiles[s1t_tile(i >> 3, Cj) + (i & 7) * 8 + cj];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace scqed

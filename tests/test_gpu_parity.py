@@ -157,14 +157,20 @@ def test_row_per_thread_packed_kernel(engine_mod, monkeypatch, n, k):
         assert np.max(np.abs(res.Erwa - ref)) < E_RTOL * np.max(np.abs(ref))
 
 
-@pytest.mark.parametrize("env", ["SCQED_S1_BLK", "SCQED_S1_REG"])
+@pytest.mark.parametrize("env", ["SCQED_S1_BLK", "SCQED_S1_REG", "SCQED_S1_TILED", "SCQED_S1_TILED_1WARP", "SCQED_S1_LADDER_ONLY"])
 @pytest.mark.parametrize("n,k", [(3, 2), (8, 4), (9, 3), (33, 10), (64, 10), (65, 7), (101, 20), (104, 9), (128, 8)])
 def test_blocked_and_register_tridiagonalisation(engine_mod, monkeypatch, env, n, k):
     """Opt-in alternates of the real-symmetric shared-memory tridiagonalisation: SCQED_S1_BLK=1 (small_blocked.cuh:
     dlatrd panels of 8 columns, trailing update as DMMA 8x8x4 tiles) and SCQED_S1_REG=1 (small_reg.cuh: the matrix in
-    registers), on raw matrices against numpy and on the fluxonium plan against the reference's output."""
+    registers) and SCQED_S1_TILED=1 (small_tiled.cuh: tile-packed lower triangle, four CTAs per SM), on raw matrices
+    against numpy and on the fluxonium plan against the reference's output."""
     import torch
     monkeypatch.setenv(env, "1")
+    if env == "SCQED_S1_TILED_1WARP":                      # tiled kernel with the O(m) sections on one warp
+        monkeypatch.setenv("SCQED_S1_TILED", "1")
+        monkeypatch.setenv("SCQED_S1_TILED_PSER", "0")
+    elif env != "SCQED_S1_TILED":
+        monkeypatch.setenv("SCQED_S1_TILED", "0")          # the tiled kernel is the default for 80 <= n <= 128
     rng = np.random.default_rng(17 + n)
     H = _random_hermitian(rng, n, 6, real=True).astype(np.complex128)
     H[1] = np.diag(np.diag(H[1]))                      # already diagonal: every reflector is the identity (tau = 0)

@@ -12,7 +12,18 @@ settings = sys.argv[1:] or ["0", "auto", "72,48", "72", "0"]
 ref = None
 with engine.Engine(plan) as eng:
     for s in settings:
-        if s == "auto":
+        os.environ["SCQED_S1_TILED"] = "0"
+        os.environ.pop("SCQED_S1_TILED_ROTATE", None)
+        os.environ.pop("SCQED_S1_TILED_PSER", None)
+        if s == "tiled-1warp":
+            os.environ["SCQED_S1_TILED_PSER"] = "0"
+        if s.startswith("tiled"):
+            os.environ["SCQED_S1_TILED"] = "1"
+            if s == "tiled-rot":
+                os.environ["SCQED_S1_TILED_ROTATE"] = "1"
+            if s == "tiled-ded":
+                os.environ["SCQED_S1_TILED_ROTATE"] = "2"
+        elif s == "auto":
             os.environ.pop("SCQED_S1_LADDER", None)
         else:
             os.environ["SCQED_S1_LADDER"] = s
