@@ -33,7 +33,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 METRIC = "diagonalised sweep points/sec (lowest-10 eigenpairs)"
 # `ncu --set full` capture the headline kernel's DRAM traffic is read from, and the points of that launch
-TRAFFIC_CSV, TRAFFIC_PTS = "r01_s1_tridiag_ncu_summary.csv", 9704.0
+TRAFFIC_CSV, TRAFFIC_PTS = "r02_s1t_tiled_ncu_summary.csv", 10000.0
 UNIT = "points/s"
 
 
@@ -560,13 +560,16 @@ def run_ours(args):
         real = k_real_n > 0 and k_cplx_n == 0
         kern_ms = (k_real_ms + k_cplx_ms) / args.steps
         flops_pt = (4.0 / 3.0 if real else 16.0 / 3.0) * n ** 3
-        kern = "s1_tridiag_kernel<%s> (assemble H in shared memory + Householder tridiagonalisation)" % ("double" if real else "complex")
+        kern = ("s1t_tridiag_kernel (assemble H as 8x8 tiles of the lower triangle in shared memory + blocked Householder "
+                "tridiagonalisation, trailing updates on DMMA)" if real and 80 <= n <= 128 else
+                "s1_tridiag_kernel<%s> (assemble H in shared memory + Householder tridiagonalisation)" % ("double" if real else "complex"))
         note = ("FP64-pipe roofline of the dominant kernel: %s flops/point (%s path) x %d points / the kernel's device time "
                 "(CUDA events on its stream, recorded by the library, averaged over warm-up + timed steps: %.3f ms of the %.3f ms step). "
                 "peak = FP64 DMMA/DFMA rate measured in this run by scqed_probe_fp64_* (DMMA %.1f, DFMA %.1f TFLOP/s; "
-                "MEASURED_PEAKS.json has no FP64 entry). The kernel is shared-memory-bandwidth / latency bound (n-1 dependent "
-                "Householder steps on a %dx%d matrix), not pipe bound; H never leaves shared memory; `traffic` (ncu dram bytes of "
-                "this kernel) is the n^2 x 8 B of Householder reflectors per point it writes for the back-transformation, i.e. the "
+                "MEASURED_PEAKS.json has no FP64 entry). The kernel is bound by the dependent chain of a Householder step times the "
+                "matrices resident per SM (n-1 dependent steps on a %dx%d matrix, 4 CTAs per SM; profiles/r02_s1_scaling.md), not by "
+                "the pipe; H never leaves shared memory; `traffic` (ncu dram bytes of this kernel, profiles/r02_s1t_tiled_ncu_summary.csv) "
+                "is the lower triangle of Householder reflectors per point it writes for the back-transformation, i.e. the "
                 "algorithmic output; results leaving the GPU: %.1f MB/step." % ("(4/3) n^3" if real else "(16/3) n^3", "real-symmetric" if real else "complex-Hermitian",
                                      n_pts, kern_ms, ms_per_step, dmma, dfma, n, n, d2h / 1e6))
     else:
@@ -580,9 +583,10 @@ def run_ours(args):
     traffic = None
     try:
         if k_real_n + k_cplx_n > 0 and args.workload == "c2_fluxonium_res_10k":
-            rows = dict((r.split(",")[0], r.split(",")) for r in open(os.path.join(ROOT, "profiles", TRAFFIC_CSV)) if r.count(",") >= 2)
-            mb = float(rows["dram__bytes_read.sum"][2]) + float(rows["dram__bytes_write.sum"][2])
-            traffic = mb * 1e6 / TRAFFIC_PTS * n_pts
+            rows = dict((r.split(",")[0], r.strip().split(",")) for r in open(os.path.join(ROOT, "profiles", TRAFFIC_CSV)) if r.count(",") >= 2)
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            by = sum(float(rows[m][2]) * unit[rows[m][1]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            traffic = by / TRAFFIC_PTS * n_pts
     except Exception:
         traffic = None
     roofline = {

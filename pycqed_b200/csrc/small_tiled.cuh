@@ -41,6 +41,26 @@ struct S1TSmem {
     }
 };
 
+// dlarfg scalars without IEEE sqrt / divisions (they were 6.5 % of the samples of this kernel): rsqrt + one Newton step for
+// the norm, MUFU reciprocal seed + two Newton steps for 1 / (alpha - beta); results within ~2 ulp, which is inside the
+// backward error of the reduction.
+__device__ __forceinline__ void s1t_reflector_scalars(double alpha, double xn, double &tau, double &beta, double &sc) {
+    if (xn == 0.0) { tau = 0.0; beta = alpha; sc = 0.0; return; }
+    const double s2 = fma(alpha, alpha, xn);
+    const double rs = rsqrt(s2);
+    double nrm = s2 * rs;
+    nrm = fma(0.5 * rs, fma(-nrm, nrm, s2), nrm);
+    beta = -copysign(nrm, alpha);
+    tau = fma(fabs(alpha), rs, 1.0);                     // (beta - alpha) / beta = 1 + |alpha| / norm
+    const double d = alpha - beta;
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    sc = fma(y, e, y);
+}
+
 __device__ __forceinline__ int s1t_tile(int R, int C) { return ((R * (R + 1) >> 1) + C) << 6; }
 
 // element (i, j), i >= j, of the tile-packed lower triangle (diagonal tiles hold both triangles)
@@ -127,10 +147,11 @@ s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
     double *cf = Vs;                                       // assembly coefficients (before the first panel)
     const int g8 = lane >> 2, t4 = lane & 3;             // row part / DMMA fragments: row g8, column pair 2 t4
     const int c8 = lane & 7, r4 = lane >> 3;             // column part: column c8, rows r4 and r4 + 4 (conflict-free: 8 r4 + c8)
-    // The O(m) sections run on ONE warp per CTA.  Warp w of every CTA lives on scheduler w % 4: with warp 0 in all four
-    // co-resident CTAs the four serial sections would share one scheduler (and one FP64 unit) while three idle, so the
-    // serial warp is rotated with the position of the CTA inside its wave.
-    // The slot is the arrival order of the CTA on its SM (sm_slots: one zeroed counter per SM; CTAs are persistent).
+    // !PSER: the O(m) sections run on ONE warp per CTA.  Warp w of every CTA lives on scheduler w % 4, so with warp 0 in
+    // all four co-resident CTAs the serial sections share one scheduler.  Spreading them (rotate = 1: serial warp = arrival
+    // order of the CTA on its SM) or keeping scheduler 0 free of mat-vec work (rotate = 2) both measured SLOWER (6.2-6.5 vs
+    // 5.95 ms at 256 threads): the serial warps are latency bound and interleave well on one scheduler, the mat-vec warps
+    // are what needs the other three.  Kept as experiment switches (SCQED_S1_TILED_ROTATE).
     __shared__ int s_sw;
     if (tid == 0) {
         unsigned smid;
@@ -169,22 +190,26 @@ s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
                 const double *dg = a.P.dense_tab + (size_t)NF * nn;
                 for (int j = wp; j < n; j += S1T_THREADS / 32) {
                     const double *col = a.P.dense_tab + (size_t)j * n;
-                    for (int i = j + lane; i < n; i += 64) {
-                        const int i2 = i + 32;
-                        const bool two = i2 < n;
-                        double re = 0.0, re2 = 0.0;
-#pragma unroll 4
+                    for (int i = j + lane; i < n; i += 128) {       // four rows per lane, their table loads back to back
+                        double re[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
                         for (int g = 0; g < NF; ++g) {
-                            const double t0 = __ldg(col + (size_t)g * nn + i);
-                            const double t1 = two ? __ldg(col + (size_t)g * nn + i2) : 0.0;
-                            re = fma(cf[g], t0, re);
-                            re2 = fma(cf[g], t1, re2);
+                            const double cg = cf[g];
+                            double t[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) t[u] = i + 32 * u < n ? __ldg(col + (size_t)g * nn + i + 32 * u) : 0.0;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) re[u] = fma(cg, t[u], re[u]);
                         }
                         if (i == j)
-                            for (int g = NF; g < NG; ++g) re = fma(cf[g], __ldg(dg + (size_t)(g - NF) * n + i), re);
-                        if (a.tidyup) { re = fabs(re) < 1e-12 ? 0.0 : re; re2 = fabs(re2) < 1e-12 ? 0.0 : re2; }
-                        s1t_store(tiles, i, j, re);
-                        if (two) s1t_store(tiles, i2, j, re2);
+                            for (int g = NF; g < NG; ++g) re[0] = fma(cf[g], __ldg(dg + (size_t)(g - NF) * n + i), re[0]);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (i + 32 * u >= n) break;
+                            double v = re[u];
+                            if (a.tidyup) v = fabs(v) < 1e-12 ? 0.0 : v;
+                            s1t_store(tiles, i + 32 * u, j, v);
+                        }
                     }
                 }
             }
@@ -242,7 +267,7 @@ s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
 #pragma unroll
                     for (int w = 0; w < NW; ++w) xn += s_red[0][w];
                     double tau, beta, sc;
-                    reflector_scalars(s_scal[0], xn, tau, beta, sc);
+                    s1t_reflector_scalars(s_scal[0], xn, tau, beta, sc);
                     v_r = (r == j + 1) ? 1.0 : ((r > j + 1 && r < n) ? c * sc : 0.0);
                     if (r < PS) Vs[jj * PS + r] = v_r;
                     if (r > j && r < n) tiles[s1t_tile(r >> 3, j >> 3) + (r & 7) * 8 + (j & 7)] = v_r;
