@@ -843,12 +843,13 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
     // complex vectors 3 chunks x 0.6 (12.9 -> 11.9 ms end to end), packed real vectors 2 chunks 77 % / 23 % (11.2 ms)
     if (nchunks == 2) { if (o->real_vectors) geom = 0.3; else { nchunks = 3; geom = 0.6; } }
     // Adaptive: when the copies are the long pole (measured on the previous call of this plan, see the end of this
-    // function) the first copy must start as early as possible and every copy needs a solve to hide behind: equal chunks
-    // of ~1250 points.  8 ranks of one box sharing the host: 170 MB per rank at 11.5 GB/s = 14.9 ms against 9.1 ms of solving.
+    // function) the first copy must start as early as possible and every copy needs a solve to hide behind: four equal
+    // chunks.  Measured with 2 / 4 / 8 chunks of a 10 000-point sweep: solve 8.7 / 10.2 / 12.7 ms -- chunks are not free,
+    // so the switch needs copies that outlast the solve by 45 % of its time (4 or more GPUs sharing this host).  8 ranks of one box sharing the host: 170 MB per rank at 11.5 GB/s = 14.9 ms against 9.1 ms of solving.
+    if (pl->host_copy_pts != n_pts) { pl->host_copy_pts = n_pts; pl->host_copy_bound = 0; }     // measured per sweep size
     const bool reprobe = pl->host_copy_bound && (++pl->host_calls % 16) == 0;      // now and then try the default again
-    if (pl->host_copy_bound && !reprobe && n_pts >= 2500) {
-        nchunks = n_pts / 1250;
-        if (nchunks > 8) nchunks = 8;
+    if (pl->host_copy_bound && !reprobe && n_pts >= 5000) {
+        nchunks = 4;            // every extra chunk costs ~0.5 ms of kernel tails (8 launches per chunk): 8 chunks were not better
         geom = 0.0;
     }
     if (const char *envc = getenv("SCQED_HOST_CHUNKS")) { long long v = atoll(envc); if (v >= 1 && v <= 64) nchunks = v < n_pts ? v : n_pts; }
@@ -1030,8 +1031,11 @@ extern "C" int scqed_sweep_run_host(scqed_plan *pl, const scqed_sweep_opts *o, c
         float ms_solve = 0.f, ms_all = 0.f;
         if (cudaEventElapsedTime(&ms_solve, t_start, t_solved) == cudaSuccess && cudaEventElapsedTime(&ms_all, t_start, t_copied) == cudaSuccess) {
             const float tail = ms_all - ms_solve;              // copies still running after the last solve
-            if (!pl->host_copy_bound && tail > 0.35f * ms_solve && tail > 1.0f) pl->host_copy_bound = 1;
-            else if (reprobe && tail < 0.25f * ms_solve) pl->host_copy_bound = 0;
+            if (getenv("SCQED_HOST_DEBUG"))
+                fprintf(stderr, "[scqed host] dev %d pts %lld chunks %zu level %d%s solve %.2f ms all %.2f ms\n", pl->device, (long long)n_pts,
+                        sizes.size(), pl->host_copy_bound, reprobe ? " (reprobe)" : "", ms_solve, ms_all);
+            if (!pl->host_copy_bound && tail > 0.45f * ms_solve && tail > 1.0f) pl->host_copy_bound = 1;
+            else if (reprobe && tail < 0.30f * ms_solve) pl->host_copy_bound = 0;
         } else cudaGetLastError();
     }
     if (staged_per_pt) {

@@ -116,7 +116,7 @@ struct scqed_plan {
     int n_coef_scalar = 0;
     long long mf_work_per_row = 0;     // complex MACs per output element of the matrix-free mat-vec
     int s1_real_mode = -1;             // fused small path: -1 unknown, 0 complex Hermitian, 1 real symmetric
-    long long host_calls = 0;
+    long long host_calls = 0, host_copy_pts = -1;
     int host_copy_bound = 0;           // scqed_sweep_run_host: the previous call spent longer draining its device -> host copies than
                                        // solving (several GPUs sharing the host's PCIe / memory bandwidth): cut into more chunks
     bool defer_real_check = false;     // scqed_sweep_run_host checks the "turned complex" flags itself, once, after its last chunk
