@@ -61,7 +61,10 @@ bool split_fits(const scqed_plan *pl, int n, int k, int n_terms, int real_hint) 
         return S1Smem<cplx>::bytes(n, n_terms, 512) <= pl->smem_optin ||
                (s1_packed_mode() && S1PSmem<cplx>::bytes(n, n_terms, 256) <= pl->smem_optin);
     if (n > 224 || real_hint == 0 || !s1_packed_mode()) return false;
-    return S1PSmem<double>::bytes(n, n_terms, 512) <= pl->smem_optin;     // packed lower triangle, real symmetric only
+    // real symmetric only: tile-packed (small_tiled.cuh, up to n = 224) or column-packed lower triangle
+    const bool tiled_off = getenv("SCQED_S1_TILED") && atoi(getenv("SCQED_S1_TILED")) == 0;
+    if (!tiled_off && S1TSmem::scratch_fits(n, n_terms) && S1TSmem::bytes(n) + 1024 <= pl->smem_optin) return true;
+    return S1PSmem<double>::bytes(n, n_terms, 512) <= pl->smem_optin;
 }
 
 template <typename T, int NQ>
@@ -148,19 +151,25 @@ static int s1b_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t
 static int s1t_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t st, bool *launched) {
     *launched = false;
     // default for 80 <= n <= 128 (measured against the ladder / unblocked kernels, tools/s1_scaling.py, 4096 matrices:
-    // n = 88: 1.78 vs 1.89 ms, 101: 2.34 vs 2.69, 118: 3.82 vs 5.29, 128: 5.83 vs 6.21; below 80 the others win);
+    // n = 88: 1.78 vs 1.89 ms, 101: 2.34 vs 2.69, 118: 3.82 vs 5.29, 128: 5.83 vs 6.21; below 80 the others win) and for
+    // 128 < n <= 224 with 256 threads and one CTA per SM (fluxonium at truncation 200, 10^4 points: 64.9 -> 39.3 ms);
     // SCQED_S1_TILED=1 forces it for every n >= 16, =0 disables it
     const char *e = getenv("SCQED_S1_TILED");
     const int mode = e ? atoi(e) : -1;
     if (mode == 0 || (mode < 0 && (a.n < 80 || getenv("SCQED_S1_PACKED") || s1_rows_mode()))) return 0;   // explicit storage opt-ins win
-    if (a.n < 16 || a.n > 128 || !S1TSmem::scratch_fits(a.n, n_terms)) return 0;
+    if (a.n < 16 || a.n > 224 || !S1TSmem::scratch_fits(a.n, n_terms)) return 0;
+    if (a.n > 128 && getenv("SCQED_S1_TILED_BIG") && atoi(getenv("SCQED_S1_TILED_BIG")) == 0) return 0;   // A/B switch: packed kernel instead
     const size_t smem = S1TSmem::bytes(a.n);
-    if (smem > pl->smem_optin) return 0;
-    const bool pser = !(getenv("SCQED_S1_TILED_PSER") && atoi(getenv("SCQED_S1_TILED_PSER")) == 0) && a.n <= S1T_THREADS;
-    auto kern = pser ? s1t_tridiag_kernel<true> : s1t_tridiag_kernel<false>;
+    if (smem + 1024 > pl->smem_optin) return 0;
+    const bool big = a.n > 128;                            // one row per thread in the O(m) sections: 256 threads
+    const int threads = big ? 256 : S1T_THREADS;
+    const bool pser = !(getenv("SCQED_S1_TILED_PSER") && atoi(getenv("SCQED_S1_TILED_PSER")) == 0);
+    if (big && !pser) return 0;                            // the one-warp O(m) sections cover 128 rows
+    void (*kern)(S1Args, int *, int) = big ? (pser ? s1t_tridiag_kernel<true, 256> : s1t_tridiag_kernel<false, 256>)
+                                           : (pser ? s1t_tridiag_kernel<true, S1T_THREADS> : s1t_tridiag_kernel<false, S1T_THREADS>);
     CK(set_max_dynamic_smem(kern, pl->smem_optin));
     int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, S1T_THREADS, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     if (occ < 1) return 0;
     long long grid = (long long)occ * pl->sm_count;
     if (grid > a.n_pts) grid = a.n_pts;
@@ -168,7 +177,7 @@ static int s1t_launch(scqed_plan *pl, const S1Args &a, int n_terms, cudaStream_t
     CK(cudaMemsetAsync(pl->s1slots.p, 0, 1024 * sizeof(int), st));
     TimingScope tscope_(st, 1);
     const int rotate = getenv("SCQED_S1_TILED_ROTATE") ? atoi(getenv("SCQED_S1_TILED_ROTATE")) : 0;
-    kern<<<(unsigned)grid, S1T_THREADS, smem, st>>>(a, (int *)pl->s1slots.p, rotate);
+    kern<<<(unsigned)grid, threads, smem, st>>>(a, (int *)pl->s1slots.p, rotate);
     tscope_.end();
     LAUNCHED();
     CK(cudaGetLastError());

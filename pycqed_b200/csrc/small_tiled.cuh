@@ -73,6 +73,7 @@ __device__ __forceinline__ void s1t_store(double *tiles, int i, int j, double v)
 
 // P: y = A_stale v from the stored half (item R = tile row R + tile column R, both feed rows 8R..8R+7), and the panel dot
 // products t1[k] = W[:,k].v, t2[k] = V[:,k].v for the corrections.
+template <int NTHR>
 __device__ __forceinline__ void s1t_pass(const double *tiles, const double *Vs, const double *Ws, double *Y, double *ts,
                                          int n, int NT, int PS, int j, int jj, int wp, int lane, int rotate) {
     constexpr int NB = S1T_NB;
@@ -83,7 +84,7 @@ __device__ __forceinline__ void s1t_pass(const double *tiles, const double *Vs, 
                     // rotate == 2: scheduler 0 (warps 0 and 4) is left to the serial warps of the co-resident CTAs; the six
                     // other warps share the mat-vec items, warp 4 forms the panel dot products
                     const int pw = rotate == 2 ? (wp & 3) - 1 + 3 * (wp >> 2) : wp;          // 1,2,3,5,6,7 -> 0..5
-                    const int npw = rotate == 2 ? 6 : S1T_THREADS / 32;
+                    const int npw = rotate == 2 ? 6 : NTHR / 32;
                     const bool in_pass = rotate != 2 || (wp & 3) != 0;
                     for (int R = T0 + pw; in_pass && R < NT; R += npw) {
                         double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
@@ -117,7 +118,7 @@ __device__ __forceinline__ void s1t_pass(const double *tiles, const double *Vs, 
                     }
                     for (int kt = 0; kt < jj; ++kt) {
                         // panel column kt: warp 4 takes them all (rotate == 2), else warps 7, 6, 5 one each
-                        if (rotate == 2 ? wp != 4 : wp != S1T_THREADS / 32 - 1 - kt % (S1T_THREADS / 32)) continue;
+                        if (rotate == 2 ? wp != 4 : wp != NTHR / 32 - 1 - kt % (NTHR / 32)) continue;
                         double t1 = 0.0, t2 = 0.0;
                         for (int i = j + 1 + lane; i < n; i += 32) {
                             const double vi = vj[i];
@@ -129,10 +130,10 @@ __device__ __forceinline__ void s1t_pass(const double *tiles, const double *Vs, 
                     }
                 }
 
-// PSER: the O(m) sections on ALL warps (thread r = row r, n <= S1T_THREADS) instead of one warp: shorter dependent chain
+// PSER: the O(m) sections on ALL warps (thread r = row r, n <= NTHR) instead of one warp: shorter dependent chain
 // per column (one row per lane), four block barriers per column instead of two.
-template <bool PSER>
-static __global__ void __launch_bounds__(S1T_THREADS, 4)
+template <bool PSER, int NTHR>
+static __global__ void __launch_bounds__(NTHR, NTHR <= 128 ? 4 : 1)
 s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
     constexpr int NB = S1T_NB;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -164,11 +165,11 @@ s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
     for (long long p = blockIdx.x; p < a.n_pts; p += gridDim.x) {
         // ---- assemble the lower triangle into the tiles ----
         int not_real = 0;
-        for (int q = tid; q < NTD; q += S1T_THREADS) tiles[q] = 0.0;
+        for (int q = tid; q < NTD; q += NTHR) tiles[q] = 0.0;
         if (a.Hin) {
             __syncthreads();
             const cplx *Hp = a.Hin + (size_t)p * n * n;
-            for (int idx = tid; idx < n * n; idx += S1T_THREADS) {
+            for (int idx = tid; idx < n * n; idx += NTHR) {
                 const int i = idx / n, j = idx - i * n;          // row-major source, coalesced
                 if (j <= i) {
                     const cplx v = Hp[idx];
@@ -178,7 +179,7 @@ s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
             }
         } else if (a.dcoef) {
             const int NG = a.P.n_dense;
-            for (int t = tid; t < 2 * NG; t += S1T_THREADS) cf[t] = a.dcoef[(size_t)p * 2 * NG + t];
+            for (int t = tid; t < 2 * NG; t += NTHR) cf[t] = a.dcoef[(size_t)p * 2 * NG + t];
             __syncthreads();
             const int NF = NG - a.P.n_dense_diag;
             double imw = 0.0;
@@ -188,7 +189,7 @@ s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
             else {
                 const size_t nn = (size_t)n * n;
                 const double *dg = a.P.dense_tab + (size_t)NF * nn;
-                for (int j = wp; j < n; j += S1T_THREADS / 32) {
+                for (int j = wp; j < n; j += NTHR / 32) {
                     const double *col = a.P.dense_tab + (size_t)j * n;
                     for (int i = j + lane; i < n; i += 128) {       // four rows per lane, their table loads back to back
                         double re[4] = {0.0, 0.0, 0.0, 0.0};
@@ -215,9 +216,9 @@ s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
             }
         } else {
             cplx *s_coef = (cplx *)cf;
-            for (int t = tid; t < a.P.n_terms; t += S1T_THREADS) s_coef[t] = a.coef[p * a.P.n_terms + t];
+            for (int t = tid; t < a.P.n_terms; t += NTHR) s_coef[t] = a.coef[p * a.P.n_terms + t];
             __syncthreads();
-            for (int idx = tid; idx < n * n; idx += S1T_THREADS) {
+            for (int idx = tid; idx < n * n; idx += NTHR) {
                 const int j = idx / n, i = idx - j * n;
                 if (i < j) continue;
                 int id[SCQED_MAX_NODES], jd[SCQED_MAX_NODES];
@@ -232,7 +233,7 @@ s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
         not_real = __syncthreads_or(not_real);
         if (tid == 0) { a.W.flags[p] = not_real; if (not_real) a.info[p] = -2; }
         if (not_real) continue;                              // info = -2: the caller re-runs in complex mode
-        for (int q = tid; q < 2 * NB * PS + PS; q += S1T_THREADS) Vs[q] = 0.0;      // panels and Y (cf is dead now)
+        for (int q = tid; q < 2 * NB * PS + PS; q += NTHR) Vs[q] = 0.0;      // panels and Y (cf is dead now)
         __syncthreads();
 
         double *dd = a.W.dd + p * n, *ee = a.W.ee + p * n, *e2 = a.W.e2 + p * n, *tauo = (double *)a.W.tau + p * n;
@@ -244,7 +245,7 @@ s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
                 const int j = j0 + jj;
                 if constexpr (PSER) {
                     const int r = tid;
-                    constexpr int NW = S1T_THREADS / 32;
+                    constexpr int NW = NTHR / 32;
                     // ---- S1: column j made current (newest panel column from registers, older ones from the panels) ----
                     double c = 0.0;
                     if (r >= j && r < n) {
@@ -273,7 +274,7 @@ s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
                     if (r > j && r < n) tiles[s1t_tile(r >> 3, j >> 3) + (r & 7) * 8 + (j & 7)] = v_r;
                     if (tid == 0) { ee[j] = beta; e2[j] = beta * beta; tauo[j] = tau; }
                     __syncthreads();
-                    s1t_pass(tiles, Vs, Ws, Y, ts, n, NT, PS, j, jj, wp, lane, 0);
+                    s1t_pass<NTHR>(tiles, Vs, Ws, Y, ts, n, NT, PS, j, jj, wp, lane, 0);
                     __syncthreads();
                     // ---- S3: corrections, w ----
                     double pr = 0.0;
@@ -343,7 +344,7 @@ s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
                 }
                 if (j == n - 1) break;                                            // only the last diagonal was left
                 __syncthreads();
-                s1t_pass(tiles, Vs, Ws, Y, ts, n, NT, PS, j, jj, wp, lane, rotate);
+                s1t_pass<NTHR>(tiles, Vs, Ws, Y, ts, n, NT, PS, j, jj, wp, lane, rotate);
                 __syncthreads();
                 // ---- S3 (warp 0): corrections, w ----
                 if (wp == sw) {
@@ -385,7 +386,7 @@ s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
                 const int B0 = b0 >> 3;                       // first tile row / column that holds trailing elements
                 const int K = NT - B0;
                 // tile rows in balanced pairs (r, K-1-r): r + 1 and K - r tiles; the A-operand fragments are per row
-                for (int it = wp; it < (K + 1) / 2; it += S1T_THREADS / 32) {
+                for (int it = wp; it < (K + 1) / 2; it += NTHR / 32) {
                     for (int half = 0; half < 2; ++half) {
                         const int r = half == 0 ? it : K - 1 - it;
                         if (half == 1 && r == it) break;
@@ -413,7 +414,7 @@ s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
         // ---- Gershgorin bounds over the whole tridiagonal matrix (d, e come back from this CTA's own global writes) ----
         {
             double *dv = Vs, *ev = Vs + n, *red = Vs + 2 * n, *bounds = red + 96;
-            for (int i = tid; i < n; i += S1T_THREADS) { dv[i] = dd[i]; ev[i] = ee[i]; }
+            for (int i = tid; i < n; i += NTHR) { dv[i] = dd[i]; ev[i] = ee[i]; }
             __syncthreads();
             tridiag_bounds(dv, ev, n, bounds, red);
             if (tid < 4) a.W.bnd[p * 4 + tid] = bounds[tid];
@@ -421,7 +422,7 @@ s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
         if (a.want_vec) {
             // reflector j: column j, rows j+1 .. n-1 (s1_backtr_kernel reads nothing else)
             double *dst = (double *)a.W.Vst + (size_t)p * n * n;
-            for (int j = wp; j < n - 1; j += S1T_THREADS / 32) {
+            for (int j = wp; j < n - 1; j += NTHR / 32) {
                 const int Cj = j >> 3, cj = j & 7;
                 for (int i = j + 1 + lane; i < n; i += 32) dst[(size_t)j * n + i] = tiles[s1t_tile(i >> 3, Cj) + (i & 7) * 8 + cj];
             }

@@ -158,13 +158,16 @@ def test_row_per_thread_packed_kernel(engine_mod, monkeypatch, n, k):
 
 
 @pytest.mark.parametrize("env", ["SCQED_S1_BLK", "SCQED_S1_REG", "SCQED_S1_TILED", "SCQED_S1_TILED_1WARP", "SCQED_S1_LADDER_ONLY"])
-@pytest.mark.parametrize("n,k", [(3, 2), (8, 4), (9, 3), (33, 10), (64, 10), (65, 7), (101, 20), (104, 9), (128, 8)])
+@pytest.mark.parametrize("n,k", [(3, 2), (8, 4), (9, 3), (33, 10), (64, 10), (65, 7), (101, 20), (104, 9), (128, 8), (129, 10),
+                                 (177, 7), (200, 12), (224, 5)])
 def test_blocked_and_register_tridiagonalisation(engine_mod, monkeypatch, env, n, k):
     """Opt-in alternates of the real-symmetric shared-memory tridiagonalisation: SCQED_S1_BLK=1 (small_blocked.cuh:
     dlatrd panels of 8 columns, trailing update as DMMA 8x8x4 tiles) and SCQED_S1_REG=1 (small_reg.cuh: the matrix in
     registers) and SCQED_S1_TILED=1 (small_tiled.cuh: tile-packed lower triangle, four CTAs per SM), on raw matrices
     against numpy and on the fluxonium plan against the reference's output."""
     import torch
+    if n > 128 and env != "SCQED_S1_TILED":
+        pytest.skip("only the tile-packed kernel (256 threads, one row per thread) goes beyond n = 128")
     monkeypatch.setenv(env, "1")
     if env == "SCQED_S1_TILED_1WARP":                      # tiled kernel with the O(m) sections on one warp
         monkeypatch.setenv("SCQED_S1_TILED", "1")
