@@ -378,7 +378,7 @@ extern "C" int scqed_plan_create(const scqed_plan_desc *d, int device, scqed_pla
 extern "C" void scqed_plan_destroy(scqed_plan *pl) {
     if (!pl) return;
     DeviceGuard dev_guard_(pl->device);
-    DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->s1work, &pl->s1vec, &pl->auxc, &pl->resvec, &pl->dcoef, &pl->s1ladder, &pl->s1slots, &pl->d2h, &pl->mfwarm, &pl->in_params, &pl->out_evals,
+    DevBuf *bufs[] = {&pl->tables, &pl->regs, &pl->coef, &pl->scal, &pl->work, &pl->s1work, &pl->s1vec, &pl->auxc, &pl->resvec, &pl->dcoef, &pl->s1ladder, &pl->s1slots, &pl->dtg, &pl->d2h, &pl->mfwarm, &pl->in_params, &pl->out_evals,
                       &pl->out_evecs, &pl->out_post, &pl->out_info, &pl->out_scal, &pl->out_pack};
     for (DevBuf *b : bufs) b->release();
     pl->hstage.release();
@@ -604,7 +604,7 @@ extern "C" int scqed_eigh_batched(int device, double *H_dev, int32_t n, int64_t 
     if (!small) {
         rc = dense_eigh_resident(&tmp, (cplx *)H_dev, n, batch, k, want_vec, evals_dev, (cplx *)evecs_dev, info_dev, solver, st);
         if (!rc) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) rc = fail(SCQED_ECUDA, "dense eigh: %s", cudaGetErrorString(e)); }
-        tmp.work.release();
+        tmp.work.release(); tmp.dtg.release();
     }
     return rc;
 }

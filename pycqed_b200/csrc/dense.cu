@@ -4,6 +4,7 @@
 #include "tridiag_eig.cuh"
 #include "dense_eigh.cuh"
 #include "dense_blocked.cuh"
+#include "dense_tiled.cuh"
 
 // S2 on a batch of B column-major matrices already resident in A.
 struct DenseWs {
@@ -177,6 +178,66 @@ static int run_dense_blocked_batch(cplx *A, int n, int B, int k, int want_vec, i
     return 0;
 }
 
+// S2t (dense_tiled.cuh): real symmetric matrices, 224 < n <= 2048, one persistent CTA per matrix on the tile-packed lower
+// triangle.  *done = false (and nothing written) when the batch is not real symmetric or does not fit: the caller then
+// takes the complex blocked solver.  SCQED_DENSE_TILED=0 disables the path.
+static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, int k, int want_vec, BlkWs &w, double *evals,
+                                 cplx *evecs, int *info, cudaStream_t st, bool *done) {
+    *done = false;
+    if (const char *e = getenv("SCQED_DENSE_TILED")) if (atoi(e) == 0) return 0;
+    // one CTA per matrix needs a batch to fill the machine, and beyond n ~ 1500 a single CTA cannot pull its matrix through
+    // L2 fast enough (measured, matrices/s, this path vs the blocked complex solver: n = 256: 68 k vs 22 k, 400: 15 k vs 2.7 k,
+    // 600: 5.5 k vs 1.6 k, 1000: 1.1 k vs 0.7 k, 1500 (148 matrices): 291 vs 137, 2000 (148): 66 vs 97)
+    const bool forced = getenv("SCQED_DENSE_TILED") != nullptr;
+    if (n <= 224 || n > 2048 || k > 32) return 0;
+    if (!forced && (n > 1536 || B < 48)) return 0;
+    const size_t sm_tri = DtgGeom::tridiag_smem(n), sm_bt = DtgGeom::backtr_smem(n, k);
+    if (sm_tri + 2048 > pl->smem_optin || (want_vec && sm_bt + 4096 > pl->smem_optin)) return 0;
+    const size_t td = DtgGeom::tile_doubles(n);
+    if (pl->dtg.ensure((size_t)B * td * 8 + 256)) return fail(SCQED_ENOMEM, "tile-packed matrices (%zu MB)", ((size_t)B * td * 8) >> 20);
+    int *d_flag = (int *)pl->dtg.p;
+    double *tiles = (double *)((unsigned char *)pl->dtg.p + 256);
+    CK(cudaMemsetAsync(d_flag, 0, 4, st));
+    const long long warps = (long long)B * (long long)(DtgGeom::nt(n)) * (DtgGeom::nt(n) + 1) / 2;
+    dtg_pack_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(A, n, B, tiles, d_flag);
+    LAUNCHED();
+    int h_flag = 0;
+    CK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_flag) return 0;                                    // some imaginary part: complex solver
+    BlkBufs &K = w.K;
+    double *tau = (double *)K.tau;
+    CK(set_max_dynamic_smem(dtg_tridiag_kernel, pl->smem_optin));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dtg_tridiag_kernel, DTG_THREADS, sm_tri));
+    if (occ < 1) return 0;
+    long long grid = (long long)occ * pl->sm_count;
+    if (grid > B) grid = B;
+    {
+        TimingScope tscope_(st, 8);
+        dtg_tridiag_kernel<<<(unsigned)grid, DTG_THREADS, sm_tri, st>>>(tiles, n, B, K.dd, K.ee, tau);
+        tscope_.end();
+    }
+    LAUNCHED();
+    CK(cudaGetLastError());
+    tridiag_eig_kernel<<<B, 256, (size_t)k * 8, st>>>(K.dd, K.ee, n, k, want_vec, evals, w.Z, w.lu, k, w.e2, info);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    if (want_vec) {
+        if (k <= 12) {
+            CK(set_max_dynamic_smem(dtg_backtr_kernel<12>, pl->smem_optin));
+            dtg_backtr_kernel<12><<<B, DTG_THREADS, sm_bt, st>>>(tiles, n, k, tau, w.Z, evecs);
+        } else {
+            CK(set_max_dynamic_smem(dtg_backtr_kernel<32>, pl->smem_optin));
+            dtg_backtr_kernel<32><<<B, DTG_THREADS, sm_bt, st>>>(tiles, n, k, tau, w.Z, evecs);
+        }
+        LAUNCHED();
+        CK(cudaGetLastError());
+    }
+    *done = true;
+    return 0;
+}
+
 static int pick_dense_batch(int n, long long n_pts, int k, int sm_count) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
@@ -218,6 +279,9 @@ int dense_eigh_resident(scqed_plan *tmp, cplx *H_dev, int n, long long batch, in
         cplx *Ab = H_dev + (size_t)b0 * n * n;
         double *ev = evals + (size_t)b0 * k;
         cplx *vec = evecs ? evecs + (size_t)b0 * k * n : nullptr;
+        bool done = false;
+        if (blocked && solver != 2) rc = run_dense_tiled_batch(tmp, Ab, n, nb, k, want_vec, bw, ev, vec, info + b0, st, &done);
+        if (rc || done) continue;
         rc = blocked ? run_dense_blocked_batch(Ab, n, nb, k, want_vec, 1, bw, ev, vec, info + b0, st)
                      : run_dense_batch(tmp, tmp->sm_count, Ab, n, nb, k, want_vec, 1, w, ev, vec, info + b0, st);
     }
@@ -249,6 +313,9 @@ int dense_sweep(scqed_plan *pl, const cplx *coef, long long n_pts, int k, int wa
         if (rc) return rc;
         double *ev = evals + (size_t)p0 * k;
         cplx *vec = vecs ? vecs + (size_t)p0 * k * n : nullptr;
+        bool done = false;
+        if (blocked && solver != 2) { rc = run_dense_tiled_batch(pl, A, n, nb, k, want_vec, bw, ev, vec, info + p0, st, &done); if (rc) return rc; }
+        if (done) continue;
         rc = blocked ? run_dense_blocked_batch(A, n, nb, k, want_vec, 1, bw, ev, vec, info + p0, st)
                      : run_dense_batch(pl, pl->sm_count, A, n, nb, k, want_vec, 1, w, ev, vec, info + p0, st);
         if (rc) return rc;

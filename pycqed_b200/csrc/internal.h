@@ -120,7 +120,7 @@ struct scqed_plan {
     int host_copy_bound = 0;           // scqed_sweep_run_host: the previous call spent longer draining its device -> host copies than
                                        // solving (several GPUs sharing the host's PCIe / memory bandwidth): cut into more chunks
     bool defer_real_check = false;     // scqed_sweep_run_host checks the "turned complex" flags itself, once, after its last chunk
-    DevBuf s1work, s1vec, auxc, resvec, dcoef, s1ladder, s1slots;
+    DevBuf s1work, s1vec, auxc, resvec, dcoef, s1ladder, s1slots, dtg;
     std::vector<int> xform_node;
     std::vector<size_t> xform_off;     // byte offsets of W_i^T inside `tables`
     int pair_max_index = -1;

@@ -21,10 +21,10 @@
 #include "small_eigh.cuh"
 #include "small_split.cuh"
 #include "small_blocked.cuh"
+#include "tiled_common.cuh"
 
 namespace scqed {
 
-#define S1T_NB 4
 #define S1T_THREADS 128
 
 struct S1TSmem {
@@ -41,28 +41,6 @@ struct S1TSmem {
     }
 };
 
-// dlarfg scalars without IEEE sqrt / divisions (they were 6.5 % of the samples of this kernel): rsqrt + one Newton step for
-// the norm, MUFU reciprocal seed + two Newton steps for 1 / (alpha - beta); results within ~2 ulp, which is inside the
-// backward error of the reduction.
-__device__ __forceinline__ void s1t_reflector_scalars(double alpha, double xn, double &tau, double &beta, double &sc) {
-    if (xn == 0.0) { tau = 0.0; beta = alpha; sc = 0.0; return; }
-    const double s2 = fma(alpha, alpha, xn);
-    const double rs = rsqrt(s2);
-    double nrm = s2 * rs;
-    nrm = fma(0.5 * rs, fma(-nrm, nrm, s2), nrm);
-    beta = -copysign(nrm, alpha);
-    tau = fma(fabs(alpha), rs, 1.0);                     // (beta - alpha) / beta = 1 + |alpha| / norm
-    const double d = alpha - beta;
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    double e = fma(-d, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-d, y, 1.0);
-    sc = fma(y, e, y);
-}
-
-__device__ __forceinline__ int s1t_tile(int R, int C) { return ((R * (R + 1) >> 1) + C) << 6; }
-
 // element (i, j), i >= j, of the tile-packed lower triangle (diagonal tiles hold both triangles)
 __device__ __forceinline__ void s1t_store(double *tiles, int i, int j, double v) {
     const int R = i >> 3, C = j >> 3;
@@ -70,65 +48,6 @@ __device__ __forceinline__ void s1t_store(double *tiles, int i, int j, double v)
     t[(i & 7) * 8 + (j & 7)] = v;
     if (R == C) t[(j & 7) * 8 + (i & 7)] = v;
 }
-
-// P: y = A_stale v from the stored half (item R = tile row R + tile column R, both feed rows 8R..8R+7), and the panel dot
-// products t1[k] = W[:,k].v, t2[k] = V[:,k].v for the corrections.
-template <int NTHR>
-__device__ __forceinline__ void s1t_pass(const double *tiles, const double *Vs, const double *Ws, double *Y, double *ts,
-                                         int n, int NT, int PS, int j, int jj, int wp, int lane, int rotate) {
-    constexpr int NB = S1T_NB;
-    const int g8 = lane >> 2, t4 = lane & 3, c8 = lane & 7, r4 = lane >> 3;
-
-                    const double *vj = Vs + jj * PS;
-                    const int T0 = (j + 1) >> 3;
-                    // rotate == 2: scheduler 0 (warps 0 and 4) is left to the serial warps of the co-resident CTAs; the six
-                    // other warps share the mat-vec items, warp 4 forms the panel dot products
-                    const int pw = rotate == 2 ? (wp & 3) - 1 + 3 * (wp >> 2) : wp;          // 1,2,3,5,6,7 -> 0..5
-                    const int npw = rotate == 2 ? 6 : NTHR / 32;
-                    const bool in_pass = rotate != 2 || (wp & 3) != 0;
-                    for (int R = T0 + pw; in_pass && R < NT; R += npw) {
-                        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-                        const double *trow = tiles + s1t_tile(R, T0) + g8 * 8 + 2 * t4;
-                        const double *vr = vj + 8 * T0 + 2 * t4;
-#pragma unroll 4
-                        for (int C = T0; C <= R; ++C, trow += 64, vr += 8) {
-                            const double2 x = *reinterpret_cast<const double2 *>(trow);
-                            const double2 vv = *reinterpret_cast<const double2 *>(vr);
-                            a0 = fma(x.x, vv.x, a0);
-                            a1 = fma(x.y, vv.y, a1);
-                        }
-                        // tile column R: lane (r4, c8) reads T[r4][c8] and T[r4 + 4][c8] of tile (R2, R)
-                        const double *tt = tiles + s1t_tile(R + 1, R) + 8 * r4 + c8;
-                        const double *vc = vj + 8 * (R + 1) + r4;
-#pragma unroll 4
-                        for (int R2 = R + 1; R2 < NT; ++R2) {
-                            const double x0 = tt[0], x1 = tt[32];
-                            b0 = fma(x0, vc[0], b0);
-                            b1 = fma(x1, vc[4], b1);
-                            tt += (R2 + 1) << 6;
-                            vc += 8;
-                        }
-                        double yr = a0 + a1, yc = b0 + b1;
-                        yr += __shfl_xor_sync(0xffffffffu, yr, 1);
-                        yr += __shfl_xor_sync(0xffffffffu, yr, 2);               // row 8R + g8 in every lane of the quad
-                        yc += __shfl_xor_sync(0xffffffffu, yc, 8);
-                        yc += __shfl_xor_sync(0xffffffffu, yc, 16);              // row 8R + c8 in the lanes with that c8
-                        yr = __shfl_sync(0xffffffffu, yr, 4 * c8);               // ... and the row part of the same row
-                        if (lane < 8) Y[8 * R + lane] = yr + yc;
-                    }
-                    for (int kt = 0; kt < jj; ++kt) {
-                        // panel column kt: warp 4 takes them all (rotate == 2), else warps 7, 6, 5 one each
-                        if (rotate == 2 ? wp != 4 : wp != NTHR / 32 - 1 - kt % (NTHR / 32)) continue;
-                        double t1 = 0.0, t2 = 0.0;
-                        for (int i = j + 1 + lane; i < n; i += 32) {
-                            const double vi = vj[i];
-                            t1 = fma(Ws[kt * PS + i], vi, t1);
-                            t2 = fma(Vs[kt * PS + i], vi, t2);
-                        }
-                        t1 = warp_sum(t1); t2 = warp_sum(t2);
-                        if (lane == 0) { ts[kt] = t1; ts[NB + kt] = t2; }
-                    }
-                }
 
 // PSER: the O(m) sections on ALL warps (thread r = row r, n <= NTHR) instead of one warp: shorter dependent chain
 // per column (one row per lane), four block barriers per column instead of two.
@@ -383,30 +302,7 @@ s1t_tridiag_kernel(S1Args a, int *sm_slots, int rotate) {
             const int b0 = j0 + NB;
             if (pn == NB && b0 < n) {
                 __syncthreads();
-                const int B0 = b0 >> 3;                       // first tile row / column that holds trailing elements
-                const int K = NT - B0;
-                // tile rows in balanced pairs (r, K-1-r): r + 1 and K - r tiles; the A-operand fragments are per row
-                for (int it = wp; it < (K + 1) / 2; it += NTHR / 32) {
-                    for (int half = 0; half < 2; ++half) {
-                        const int r = half == 0 ? it : K - 1 - it;
-                        if (half == 1 && r == it) break;
-                        const int R = B0 + r;
-                        // rows / columns below b0 inside the first tile row / column are not part of the trailing block
-                        // (they hold reflectors of this panel): their operand fragments are zeroed
-                        const bool rok = 8 * R + g8 >= b0;
-                        const double va = rok ? -Vs[t4 * PS + 8 * R + g8] : 0.0, wa = rok ? -Ws[t4 * PS + 8 * R + g8] : 0.0;
-                        double2 *tp = reinterpret_cast<double2 *>(tiles + s1t_tile(R, B0) + g8 * 8 + 2 * t4);
-                        const double *vbp = Vs + t4 * PS + 8 * B0 + g8, *wbp = Ws + t4 * PS + 8 * B0 + g8;
-                        for (int C = B0; C <= R; ++C, tp += 32, vbp += 8, wbp += 8) {
-                            const bool cok = 8 * C + g8 >= b0;
-                            const double vb = cok ? *vbp : 0.0, wb = cok ? *wbp : 0.0;
-                            double2 d = *tp;
-                            s1b_dmma(d.x, d.y, va, wb);
-                            s1b_dmma(d.x, d.y, wa, vb);
-                            *tp = d;
-                        }
-                    }
-                }
+                s1t_update<NTHR>(tiles, Vs, Ws, NT, PS, b0, wp, lane);
                 __syncthreads();
             }
         }

@@ -242,6 +242,42 @@ def test_eigh_degenerate_and_clustered(engine_mod, solver, n):
         assert np.max(np.abs(P @ X[:, grp] - X[:, grp])) < 1e-8
 
 
+@pytest.mark.parametrize("n,k,batch", [(225, 10, 3), (257, 12, 5), (400, 8, 2), (517, 10, 64), (1000, 10, 2), (1030, 20, 1)])
+def test_eigh_dense_tiled_real_symmetric(engine_mod, monkeypatch, n, k, batch):
+    """S2t (dense_tiled.cuh): real symmetric matrices beyond the shared-memory path, one persistent CTA per matrix on the
+    tile-packed lower triangle in global memory, against numpy.  SCQED_DENSE_TILED=1 forces the path for the small
+    batches of this test; a matrix with exact doublets and a 1e-11 cluster rides along; a complex batch must fall back
+    to the blocked complex solver and still be right."""
+    import torch
+    monkeypatch.setenv("SCQED_DENSE_TILED", "1")
+    rng = np.random.default_rng(4321 + n)
+    H = _random_hermitian(rng, n, batch, real=True).astype(np.complex128)
+    lam = np.sort(rng.uniform(0, 50, n))
+    lam[:8] = [-10.0, -10.0, -7.5, -7.5, -7.5, -3.0, -3.0 + 1e-11, -1.0]
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    H[0] = (Q * lam[None, :]) @ Q.T
+    H[0] = (H[0] + H[0].T) / 2
+    E, V, info = engine_mod.eigh_batched(torch.as_tensor(H, device="cuda"), k, want_vectors=True)
+    E, V, info = E.cpu().numpy(), V.cpu().numpy(), info.cpu().numpy()
+    assert not info.any()
+    for b in range(batch):
+        w, v = np.linalg.eigh(H[b].real)
+        scale = np.abs(w).max()
+        assert np.max(np.abs(E[b] - w[:k])) < 1e-12 * scale * n
+        X = V[b].T
+        assert np.max(np.abs(X.imag)) == 0.0
+        assert np.max(np.abs(X.conj().T @ X - np.eye(k))) < 1e-9
+        assert np.max(np.abs(H[b] @ X - X * E[b][None, :])) < 1e-11 * scale * n
+        if b > 0:
+            assert subspace_overlap(X, v[:, :k], w[:k], E_next=w[k]) >= OVERLAP
+    Hc = _random_hermitian(rng, n, 2).astype(np.complex128)                  # complex: not this path
+    Ec, Vc, ic = engine_mod.eigh_batched(torch.as_tensor(Hc, device="cuda"), k, want_vectors=True)
+    assert not ic.cpu().numpy().any()
+    for b in range(2):
+        w = np.linalg.eigvalsh(Hc[b])
+        assert np.max(np.abs(Ec.cpu().numpy()[b] - w[:k])) < 1e-12 * np.abs(w).max() * n
+
+
 def test_eigh_real_symmetric_fast_path(engine_mod):
     """Real symmetric input takes the compacted real path of the small solver."""
     import torch
