@@ -2,6 +2,7 @@
 // functions each entry point replaces).  Host-side orchestration only; the solver families live in
 // small.cu / dense.cu / matfree.cu, kernels in the .cuh files next to this one.
 #include "internal.h"
+#include <mutex>
 #include <immintrin.h>
 #include "coef.cuh"
 #include "assemble.cuh"
@@ -575,13 +576,34 @@ extern "C" int scqed_eigh_batched(int device, double *H_dev, int32_t n, int64_t 
     if (!H_dev || !evals_dev || !info_dev || n < 1 || batch < 1 || k < 1 || k > n) return fail(SCQED_EINVAL, "bad argument");
     ON_DEVICE(device);
     cudaStream_t st = (cudaStream_t)stream;
-    scqed_plan tmp;   // only carries device properties + workspaces
-    tmp.device = device;
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    tmp.sm_count = prop.multiProcessorCount;
-    tmp.smem_optin = prop.sharedMemPerBlockOptin;
-    memset(&tmp.P, 0, sizeof(tmp.P));
+    // A per-device context carries the device properties and the workspaces from call to call (cudaMalloc / cudaFree of the
+    // GB-sized dense workspaces cost 10-500 ms per call, several times the solve itself for mid-size batches).  Calls on
+    // one device are serialised by its mutex; the buffers are kept while they hold <= 16 GB, else released at the end.
+    if (device < 0 || device >= 64) return fail(SCQED_EINVAL, "device %d", device);
+    static std::mutex eigh_mu[64];
+    static scqed_plan *eigh_ctx[64];
+    std::lock_guard<std::mutex> eigh_lock(eigh_mu[device]);
+    if (!eigh_ctx[device]) {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        scqed_plan *c = new scqed_plan();
+        c->device = device;
+        c->sm_count = prop.multiProcessorCount;
+        c->smem_optin = prop.sharedMemPerBlockOptin;
+        memset(&c->P, 0, sizeof(c->P));
+        eigh_ctx[device] = c;
+    }
+    scqed_plan &tmp = *eigh_ctx[device];
+    tmp.s1_real_mode = -1;                         // per-call state: the realness of THIS batch is probed afresh
+    struct Trim {
+        scqed_plan &t;
+        ~Trim() {
+            DevBuf *b[] = {&t.s1work, &t.s1vec, &t.s1ladder, &t.s1slots, &t.dcoef, &t.work, &t.dtg};
+            size_t tot = 0;
+            for (DevBuf *x : b) tot += x->cap;
+            if (tot > ((size_t)16 << 30)) for (DevBuf *x : b) x->release();
+        }
+    } trim_{tmp};
     int want_vec = evecs_dev != nullptr;
     ResonatorArgs res;
     memset(&res, 0, sizeof(res));
@@ -599,12 +621,10 @@ extern "C" int scqed_eigh_batched(int device, double *H_dev, int32_t n, int64_t 
             else small = false;
         }
         if (small && !rc) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) rc = fail(SCQED_ECUDA, "small eigh: %s", cudaGetErrorString(e)); }
-        tmp.s1work.release(); tmp.s1vec.release(); tmp.s1ladder.release(); tmp.s1slots.release(); tmp.dcoef.release();
     }
     if (!small) {
         rc = dense_eigh_resident(&tmp, (cplx *)H_dev, n, batch, k, want_vec, evals_dev, (cplx *)evecs_dev, info_dev, solver, st);
         if (!rc) { cudaError_t e = cudaStreamSynchronize(st); if (e != cudaSuccess) rc = fail(SCQED_ECUDA, "dense eigh: %s", cudaGetErrorString(e)); }
-        tmp.work.release(); tmp.dtg.release();
     }
     return rc;
 }

@@ -178,28 +178,75 @@ static int run_dense_blocked_batch(cplx *A, int n, int B, int k, int want_vec, i
     return 0;
 }
 
-// S2t (dense_tiled.cuh): real symmetric matrices, 224 < n <= 2048, one persistent CTA per matrix on the tile-packed lower
-// triangle.  *done = false (and nothing written) when the batch is not real symmetric or does not fit: the caller then
-// takes the complex blocked solver.  SCQED_DENSE_TILED=0 disables the path.
+// S2t (dense_tiled.cuh): real symmetric matrices beyond the shared-memory path, one persistent CTA per matrix on the
+// tile-packed lower triangle in global memory.  Two kernels: dtg_tridiag_kernel (row-major tiles, register loads; the fastest
+// below n ~ 400 where a step is latency bound) and the streamed dtc_tridiag_kernel (column-major tiles through a bulk-copy
+// ring, every tile read once per column).  *done = false (and nothing written) when the batch is not real symmetric or does
+// not fit: the caller then takes the complex blocked solver.  SCQED_DENSE_TILED = 0 disables the path, 1 forces the
+// register kernel, 2 the streamed one; SCQED_DTC_NB / SCQED_DTC_NST override the panel width / ring depth.
+template <int NB, int YS>
+static int launch_dtc(scqed_plan *pl, double *tiles, int n, int B, double *dd, double *ee, double *tau, int nst, cudaStream_t st) {
+    // nst = ring size in units of 16 KB
+    const size_t sm = DtcGeom::fixed(n, NB, YS) + (size_t)nst * 16384;
+    CK((set_max_dynamic_smem(dtc_tridiag_kernel<NB, YS>, pl->smem_optin)));
+    long long grid = pl->sm_count;
+    if (grid > B) grid = B;
+    dtc_tridiag_kernel<NB, YS><<<(unsigned)grid, DTC_THREADS, sm, st>>>(tiles, n, B, dd, ee, tau, nst * 16384);
+    return 0;
+}
+
 static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, int k, int want_vec, BlkWs &w, double *evals,
                                  cplx *evecs, int *info, cudaStream_t st, bool *done) {
     *done = false;
-    if (const char *e = getenv("SCQED_DENSE_TILED")) if (atoi(e) == 0) return 0;
-    // one CTA per matrix needs a batch to fill the machine, and beyond n ~ 1500 a single CTA cannot pull its matrix through
-    // L2 fast enough (measured, matrices/s, this path vs the blocked complex solver: n = 256: 68 k vs 22 k, 400: 15 k vs 2.7 k,
-    // 600: 5.5 k vs 1.6 k, 1000: 1.1 k vs 0.7 k, 1500 (148 matrices): 291 vs 137, 2000 (148): 66 vs 97)
-    const bool forced = getenv("SCQED_DENSE_TILED") != nullptr;
-    if (n <= 224 || n > 2048 || k > 32) return 0;
-    if (!forced && (n > 1536 || B < 48)) return 0;
-    const size_t sm_tri = DtgGeom::tridiag_smem(n), sm_bt = DtgGeom::backtr_smem(n, k);
-    if (sm_tri + 2048 > pl->smem_optin || (want_vec && sm_bt + 4096 > pl->smem_optin)) return 0;
+    int mode = -1;
+    if (const char *e = getenv("SCQED_DENSE_TILED")) mode = atoi(e);
+    if (mode == 0) return 0;
+    const bool forced = mode > 0;
+    if (n <= 224 || n > 4096 || k > 32) return 0;
+    // one CTA per matrix needs a batch to fill the machine (measured against the blocked complex solver in DESIGN.md)
+    if (!forced && B < 48) return 0;
+    bool streamed = mode == 2 || (mode < 0 && n >= 560);        // measured crossover (tools/s2t_ab.sh): n ~ 550
+    const size_t cap = pl->smem_optin > 4096 ? pl->smem_optin - 2048 : 0;
+    int nb = 0, ys = 0, nst = 0;
+    if (streamed) {
+        // Panel width NB and ring size (nst units of 16 KB).  Measured at n = 1000 (ms per 296 matrices): NB = 8 with the 48 KB
+        // ring that is left: 114-127 (latency bound: 3.7 TB/s); NB = 4 with 96 KB: 108-120 (5.2 TB/s, 33 % more traffic).  So:
+        // the widest panel that leaves >= 64 KB in flight, else the widest that leaves 48 KB; the four-slot row accumulators
+        // (no shuffles) before the one-slot ones.
+        static const int cand[6][2] = {{8, 4}, {4, 4}, {8, 1}, {4, 1}, {2, 4}, {2, 1}};
+        int fnb = 0, fys = 0, fst = 0;
+        if (const char *e = getenv("SCQED_DTC_NB")) { int v = atoi(e); if (v == 8 || v == 4 || v == 2) fnb = v; }
+        if (const char *e = getenv("SCQED_DTC_YS")) { int v = atoi(e); if (v == 4 || v == 1) fys = v; }
+        if (const char *e = getenv("SCQED_DTC_NST")) { int v = atoi(e); if (v >= 2 && v <= 8) fst = v; }
+        for (int minst = 4; minst >= 3 && !nb; --minst)
+            for (int c = 0; c < 6 && !nb; ++c) {
+                if ((fnb && cand[c][0] != fnb) || (fys && cand[c][1] != fys)) continue;
+                for (int s = fst ? fst : 6; s >= (fst ? fst : minst); --s)
+                    if (DtcGeom::fixed(n, cand[c][0], cand[c][1]) + (size_t)s * 16384 <= cap) { nb = cand[c][0]; ys = cand[c][1]; nst = s; break; }
+            }
+        if (!nb) {
+            if (mode == 2) return 0;
+            streamed = false;
+        }
+    }
+    if (!streamed && (n > 2048 || DtgGeom::tridiag_smem(n) + 2048 > pl->smem_optin)) return 0;
+    // back-transformation: groups of kg vectors per CTA
+    int kg = k;
+    if (want_vec) {
+        const size_t per = (size_t)n * 8;
+        const size_t fit = cap > 1024 ? (cap - 1024) / per : 0;
+        if (fit < 1) return 0;
+        if ((size_t)kg > fit) kg = (int)fit;
+    }
+    const size_t sm_bt = DtgGeom::backtr_smem(n, kg);
     const size_t td = DtgGeom::tile_doubles(n);
     if (pl->dtg.ensure((size_t)B * td * 8 + 256)) return fail(SCQED_ENOMEM, "tile-packed matrices (%zu MB)", ((size_t)B * td * 8) >> 20);
     int *d_flag = (int *)pl->dtg.p;
     double *tiles = (double *)((unsigned char *)pl->dtg.p + 256);
     CK(cudaMemsetAsync(d_flag, 0, 4, st));
     const long long warps = (long long)B * (long long)(DtgGeom::nt(n)) * (DtgGeom::nt(n) + 1) / 2;
-    dtg_pack_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(A, n, B, tiles, d_flag);
+    if (streamed) dtg_pack_kernel<true><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(A, n, B, tiles, d_flag);
+    else dtg_pack_kernel<false><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(A, n, B, tiles, d_flag);
     LAUNCHED();
     int h_flag = 0;
     CK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
@@ -207,15 +254,26 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
     if (h_flag) return 0;                                    // some imaginary part: complex solver
     BlkBufs &K = w.K;
     double *tau = (double *)K.tau;
-    CK(set_max_dynamic_smem(dtg_tridiag_kernel, pl->smem_optin));
-    int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dtg_tridiag_kernel, DTG_THREADS, sm_tri));
-    if (occ < 1) return 0;
-    long long grid = (long long)occ * pl->sm_count;
-    if (grid > B) grid = B;
     {
         TimingScope tscope_(st, 8);
-        dtg_tridiag_kernel<<<(unsigned)grid, DTG_THREADS, sm_tri, st>>>(tiles, n, B, K.dd, K.ee, tau);
+        if (streamed) {
+            int rc = nb == 8 ? (ys == 4 ? launch_dtc<8, 4>(pl, tiles, n, B, K.dd, K.ee, tau, nst, st)
+                                        : launch_dtc<8, 1>(pl, tiles, n, B, K.dd, K.ee, tau, nst, st))
+                   : nb == 4 ? (ys == 4 ? launch_dtc<4, 4>(pl, tiles, n, B, K.dd, K.ee, tau, nst, st)
+                                        : launch_dtc<4, 1>(pl, tiles, n, B, K.dd, K.ee, tau, nst, st))
+                             : (ys == 4 ? launch_dtc<2, 4>(pl, tiles, n, B, K.dd, K.ee, tau, nst, st)
+                                        : launch_dtc<2, 1>(pl, tiles, n, B, K.dd, K.ee, tau, nst, st));
+            if (rc) return rc;
+        } else {
+            const size_t sm_tri = DtgGeom::tridiag_smem(n);
+            CK(set_max_dynamic_smem(dtg_tridiag_kernel, pl->smem_optin));
+            int occ = 1;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dtg_tridiag_kernel, DTG_THREADS, sm_tri));
+            if (occ < 1) return 0;
+            long long grid = (long long)occ * pl->sm_count;
+            if (grid > B) grid = B;
+            dtg_tridiag_kernel<<<(unsigned)grid, DTG_THREADS, sm_tri, st>>>(tiles, n, B, K.dd, K.ee, tau);
+        }
         tscope_.end();
     }
     LAUNCHED();
@@ -224,13 +282,15 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
     LAUNCHED();
     CK(cudaGetLastError());
     if (want_vec) {
-        if (k <= 12) {
-            CK(set_max_dynamic_smem(dtg_backtr_kernel<12>, pl->smem_optin));
-            dtg_backtr_kernel<12><<<B, DTG_THREADS, sm_bt, st>>>(tiles, n, k, tau, w.Z, evecs);
-        } else {
-            CK(set_max_dynamic_smem(dtg_backtr_kernel<32>, pl->smem_optin));
-            dtg_backtr_kernel<32><<<B, DTG_THREADS, sm_bt, st>>>(tiles, n, k, tau, w.Z, evecs);
-        }
+        const dim3 grid((unsigned)B, (unsigned)((k + kg - 1) / kg));
+#define DTG_BT(KM, CMV)                                                                                   \
+        do {                                                                                              \
+            CK(set_max_dynamic_smem(dtg_backtr_kernel<KM, CMV>, pl->smem_optin));                         \
+            dtg_backtr_kernel<KM, CMV><<<grid, DTG_THREADS, sm_bt, st>>>(tiles, n, k, kg, tau, w.Z, evecs); \
+        } while (0)
+        if (kg <= 12) { if (streamed) DTG_BT(12, true); else DTG_BT(12, false); }
+        else { if (streamed) DTG_BT(32, true); else DTG_BT(32, false); }
+#undef DTG_BT
         LAUNCHED();
         CK(cudaGetLastError());
     }
@@ -247,13 +307,13 @@ static int pick_dense_batch(int n, long long n_pts, int k, int sm_count) {
     // enough matrices in flight to fill the SMs during the skinny tail of the reduction
     // (the per-column kernels are launch / latency bound for small n: n = 256 runs 2.4 k matrices/s with 32 matrices
     // per launch and 21.8 k/s with 2048)
-    long long want = n <= 512 ? 4096 : (n <= 1536 ? 512 : (n <= 4096 ? 64 : 8));
+    // (one persistent CTA per matrix on the tile-packed path: whole waves of sm_count matrices)
+    long long want = n <= 512 ? 28LL * sm_count : (n <= 1536 ? 4LL * sm_count : (n <= 4096 ? sm_count : 8));
     if (const char *e = getenv("SCQED_DENSE_BATCH")) { long long v = atoll(e); if (v >= 1) want = v; }
     if (B > want) B = want;
     if (B > n_pts) B = n_pts;
     if (B > 65535) B = 65535;
     if (B < 1) B = 0;
-    (void)sm_count;
     return (int)B;
 }
 

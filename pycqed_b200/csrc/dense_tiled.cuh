@@ -31,6 +31,15 @@ struct DtgGeom {
     static size_t backtr_smem(int n, int k) { return ((size_t)k * n + 64) * 8; }
 };
 
+// Tile order in global memory.  CM = false: row-major over tiles (tiled_common.cuh, what dtg_tridiag_kernel walks); CM = true:
+// COLUMN-major over tiles -- tile column C holds (C, C), (C + 1, C), ... (NT - 1, C) back to back, so the trailing block of
+// every Householder step (tile columns >= T0) is ONE contiguous suffix of the array: the streamed kernel below reads it
+// with linear bulk copies.
+template <bool CM>
+__device__ __forceinline__ int dtg_off(int R, int C, int NT) {
+    return CM ? ((C * NT - ((C * (C - 1)) >> 1) + R - C) << 6) : s1t_tile(R, C);
+}
+
 __device__ __forceinline__ double dtg_block_sum(double v, double *red) {
     v = warp_sum(v);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -45,6 +54,7 @@ __device__ __forceinline__ double dtg_block_sum(double v, double *red) {
 
 // A [B][n*n] complex row-major Hermitian -> tiles [B][tile_doubles] (real parts of the lower triangle, zero padded);
 // flags[0] |= 1 when some imaginary part is not zero (the caller then takes the complex solver).  One warp per tile.
+template <bool CM>
 static __global__ void __launch_bounds__(256)
 dtg_pack_kernel(const cplx *__restrict__ A, int n, long long B, double *__restrict__ tiles, int *__restrict__ flags) {
     const int NT = DtgGeom::nt(n);
@@ -67,7 +77,7 @@ dtg_pack_kernel(const cplx *__restrict__ A, int n, long long B, double *__restri
         if (j < n) { const cplx v = j <= i ? Ab[(size_t)i * n + j] : Ab[(size_t)j * n + i]; out.x = v.x; bad |= v.y != 0.0; }
         if (j + 1 < n) { const cplx v = j + 1 <= i ? Ab[(size_t)i * n + j + 1] : Ab[(size_t)(j + 1) * n + i]; out.y = v.x; bad |= v.y != 0.0; }
     }
-    *reinterpret_cast<double2 *>(tiles + (size_t)b * DtgGeom::tile_doubles(n) + (size_t)idx * 64 + g * 8 + 2 * t) = out;
+    *reinterpret_cast<double2 *>(tiles + (size_t)b * DtgGeom::tile_doubles(n) + (size_t)dtg_off<CM>(R, C, NT) + g * 8 + 2 * t) = out;
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flags, 1);
 }
 
@@ -150,25 +160,28 @@ dtg_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
     }
 }
 
-// x = H(0) H(1) ... H(n-2) z for the k tridiagonal eigenvectors of one matrix (Z [B][k][n] real): one CTA per matrix,
-// the vectors in shared memory, reflector j read straight from column j of the tiles.  X complex [B][k][n].
-template <int KMAX>
+// x = H(0) H(1) ... H(n-2) z for the k tridiagonal eigenvectors of one matrix (Z [B][k][n] real): one CTA per (matrix,
+// group of kg vectors), the vectors in shared memory, reflector j read straight from column j of the tiles.  X complex [B][k][n].
+template <int KMAX, bool CM>
 static __global__ void __launch_bounds__(DTG_THREADS)
-dtg_backtr_kernel(const double *__restrict__ tiles_all, int n, int k, const double *__restrict__ tau_all,
+dtg_backtr_kernel(const double *__restrict__ tiles_all, int n, int k, int kg, const double *__restrict__ tau_all,
                   const double *__restrict__ Z, cplx *__restrict__ X) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double red[DTG_THREADS / 32][KMAX];
     double *xs = (double *)smem;                             // [k][n]
     const int tid = threadIdx.x, wp = tid >> 5, lane = tid & 31;
     const long long b = blockIdx.x;
+    // blockIdx.y: group of kg consecutive vectors (all k when they fit the shared memory at once)
+    const int k0 = blockIdx.y * kg, ktot = k;
+    k = min(kg, ktot - k0);
     const double *tiles = tiles_all + (size_t)b * DtgGeom::tile_doubles(n);
     const double *tau = tau_all + (size_t)b * n;
-    for (int q = tid; q < k * n; q += DTG_THREADS) xs[q] = Z[(size_t)b * k * n + q];
+    for (int q = tid; q < k * n; q += DTG_THREADS) xs[q] = Z[((size_t)b * ktot + k0) * n + q];
     __syncthreads();
     for (int j = n - 2; j >= 0; --j) {
         const double tj = tau[j];
         if (tj == 0.0) continue;
-        const int Cj = j >> 3, cj = j & 7;
+        const int Cj = j >> 3, cj = j & 7, NT = DtgGeom::nt(n);
         double dot[KMAX];
 #pragma unroll
         for (int u = 0; u < KMAX; ++u) dot[u] = 0.0;
@@ -177,7 +190,7 @@ dtg_backtr_kernel(const double *__restrict__ tiles_all, int n, int k, const doub
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int r = j + 1 + tid + q * DTG_THREADS;
-            vr[q] = r < n ? (r == j + 1 ? 1.0 : tiles[s1t_tile(r >> 3, Cj) + (r & 7) * 8 + cj]) : 0.0;
+            vr[q] = r < n ? (r == j + 1 ? 1.0 : tiles[dtg_off<CM>(r >> 3, Cj, NT) + (r & 7) * 8 + cj]) : 0.0;
             if (r < n) {
 #pragma unroll
                 for (int u = 0; u < KMAX; ++u) if (u < k) dot[u] = fma(vr[q], xs[u * n + r], dot[u]);
@@ -209,8 +222,383 @@ dtg_backtr_kernel(const double *__restrict__ tiles_all, int n, int k, const doub
         }
         __syncthreads();
     }
-    cplx *out = X + (size_t)b * k * n;
+    cplx *out = X + ((size_t)b * ktot + k0) * n;
     for (int q = tid; q < k * n; q += DTG_THREADS) out[q] = cmake(xs[q], 0.0);
+}
+
+// ======================================================================================================================
+// S2t, streamed (dtc_*): the same reduction for the sizes where the matrix is read from HBM / L2 every column
+// (n >~ 600).  dtg_tridiag_kernel reads every stored tile TWICE per column (item R = tile row R + tile column R) through
+// register loads of which the compiler keeps two or three in flight per warp: ~10 GB/s per SM.  Here
+//   * the tiles are stored column-major (dtg_off<true>): the trailing block is one contiguous suffix, which a PRODUCER warp
+//     streams through a shared-memory ring with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx) of DTC_PIECE tiles =
+//     16 KB each, whatever tile columns they span, nst copies in flight per SM;
+//   * every tile is read ONCE per column: the consumer warp R mod 8 takes tile (R, C) out of the ring (one LDS.128 per
+//     lane) and forms both y_R += T v_C (row part: four partial sums per row, one per lane of the quad, accumulated in
+//     place in Yd4[32 R + lane]: no shuffles, rows owned by one warp) and y_C += T^T v_R (column part: two accumulators per
+//     lane carried over the warp's tiles of the column, reduced over the lanes once per column and handed to a FOLDER warp
+//     that adds the 8 warps' parts in warp order into Yt[8 C ..]): deterministic, no atomics, no per-warp copies of y;
+//   * the rank-2*NB trailing update streams the same suffix through the same ring, DMMA on the fragment read from shared
+//     memory, result stored straight to global memory; NB = 8 while the panels fit, else 4 or 2;
+//   * the producer runs ahead into the next pass while the O(m) sections of a column execute.
+// HBM traffic per column: 4 m^2 B (mat-vec) + 8 m^2 / NB B (update read + write) => (4/3 + 8 / (3 NB)) n^3 B per matrix.
+#define DTC_CW 16                                   // consumer warps (two tiles each per full piece; 8 warps x 4 tiles measured 4 % slower)
+#define DTC_THREADS (32 * (DTC_CW + 2))             // + the producer warp + the folder warp
+#define DTC_PIECE 32                                // tiles per bulk copy (at most; a piece never spans two tile columns)
+#define DTC_NBAR 16                                 // pieces in flight (barrier pairs)
+
+struct DtcGeom {
+    static size_t fixed(int n, int nb, int ys) {
+        const size_t PS = DtgGeom::ps(n);
+        return (size_t)2 * DTC_CW * 64 + ((size_t)2 * nb * PS + (ys + 1) * PS + 2 * 8 + 8) * 8;
+    }
+};
+
+__device__ __forceinline__ unsigned dtc_saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dtc_mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dtc_saddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void dtc_mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void dtc_bulk_load(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void dtc_mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "DTC_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DTC_DONE_%=;\n"
+        "bra DTC_WAIT_%=;\n"
+        "DTC_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+struct DtcSh {
+    double *ring, *tpart, *Vs, *Ws, *Yd4, *Yt, *ts;
+    int *szs;                                     // producer: bytes held by the pieces in flight (by barrier index)
+    unsigned full, empty, tfull, tempty;          // shared-memory addresses of the barrier arrays (8 B per barrier)
+    int ringb;                                    // ring size in bytes
+};
+
+// Per-thread pipeline position, carried over the passes of the whole kernel.  The ring is a BYTE ring: a piece takes
+// exactly its size (the short pieces of the last tile columns of a pass do not occupy a 16 KB stage each, so that many of
+// them are in flight), placed at the running offset, or at 0 when it would not fit before the end of the ring -- the same
+// rule on both sides.  g = index of the next piece (barrier g mod 16, phase (g / 16) & 1).
+struct DtcPos {
+    unsigned g;                                    // consumers: next piece to take; producer: next piece to issue
+    int off;                                       // ring offset (bytes) of that piece
+    unsigned tc;                                   // tile columns handed over so far (slot = tc & 1, phase from tc >> 1)
+    // producer only
+    unsigned tail;                                 // oldest piece not yet released
+    int infl;                                      // bytes held by pieces tail .. g - 1 (skipped ring ends included)
+    int pre, pC, pR0;                              // the current pass was issued ahead up to (pC, pR0)
+};
+
+template <int YS>
+__device__ __forceinline__ void dtc_row_part(const DtcSh &S, const double2 x, const double2 vc, int R, int lane) {
+    if (YS == 4) {
+        double *yd = S.Yd4 + 32 * R + lane;
+        *yd += fma(x.x, vc.x, x.y * vc.y);
+    } else {
+        double d = fma(x.x, vc.x, x.y * vc.y);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        if ((lane & 3) == 0) S.Yd4[8 * R + (lane >> 2)] += d;
+    }
+}
+
+// One pass over the tile columns >= T0, pieces = runs of at most DTC_PIECE tiles of one tile column.  MODE 0: y = A v
+// (v = panel column jj of Vs) and, at the tail, the panel dot products ts[k] = W_k.v, ts[8 + k] = V_k.v (k < jj).
+// MODE 1: A -= V W^T + W V^T on the elements with row, column >= b0.
+// YS = 4: row-part partial sums per lane of the quad (no shuffles); YS = 1: reduced over the quad before the accumulation
+// (a quarter of the shared memory: the large sizes).
+template <int NB, int YS, int MODE>
+__device__ __forceinline__ void dtc_stream(double *tiles, const DtcSh &S, int n, int NT, int PS, int T0, int j, int jj,
+                                           int b0, int nextT0, DtcPos &P, int wp, int lane) {
+    if (wp == DTC_CW) {
+        // ---- producer: a piece is issued as soon as the ring has room for it and a barrier pair is free (pieces are
+        // released in order).  After the last piece of this pass it runs AHEAD into the next pass (`nextT0` >= 0: the tiles
+        // are not modified in between) as far as that is possible without waiting for a piece of the next pass itself, so
+        // that the O(m) sections between two passes overlap the latency of the first copies. ----
+        if (lane == 0) {
+            const unsigned ring = dtc_saddr(S.ring);
+            // returns false when (ahead) the piece would have to wait for a piece of the pass being issued ahead
+            auto issue = [&](int &C, int &R0, bool ahead, unsigned first) -> bool {
+                while (C < NT) {
+                    const int cnt = min(DTC_PIECE, NT - R0), sz = cnt * 512;
+                    int off = P.off, skip = 0;
+                    if (off + sz > S.ringb) { skip = S.ringb - off; off = 0; }
+                    const int need = sz + skip;
+                    while (P.infl + need > S.ringb || P.g - P.tail >= (unsigned)DTC_NBAR) {
+                        if (ahead && P.tail >= first) return false;
+                        dtc_mbar_wait(S.empty + 8 * (P.tail & (DTC_NBAR - 1)), (P.tail >> 4) & 1u);
+                        P.infl -= S.szs[P.tail & (DTC_NBAR - 1)];
+                        ++P.tail;
+                    }
+                    S.szs[P.g & (DTC_NBAR - 1)] = need;
+                    dtc_bulk_load(ring + (unsigned)off, tiles + dtg_off<true>(R0, C, NT), (unsigned)sz, S.full + 8 * (P.g & (DTC_NBAR - 1)));
+                    P.infl += need;
+                    P.off = off + sz;
+                    ++P.g;
+                    R0 += DTC_PIECE;
+                    if (R0 >= NT) { ++C; R0 = C; }
+                }
+                return true;
+            };
+            int C = P.pre ? P.pC : T0, R0 = P.pre ? P.pR0 : T0;
+            issue(C, R0, false, 0u);
+            P.pre = 0;
+            if (nextT0 >= 0 && nextT0 < NT) {
+                P.pC = nextT0; P.pR0 = nextT0; P.pre = 1;
+                issue(P.pC, P.pR0, true, P.g);
+            }
+        }
+        __syncwarp();
+    } else if (wp == DTC_CW + 1) {
+        // ---- folder: column parts of the consumer warps, added in warp order ----
+        if (MODE == 0) {
+            for (int C = T0; C < NT; ++C) {
+                const unsigned slot = P.tc & 1u, use = P.tc >> 1;
+                dtc_mbar_wait(S.tfull + 8 * slot, use & 1u);
+                if (lane < 8) {
+                    const double *tp = S.tpart + (size_t)slot * DTC_CW * 8 + lane;
+                    double a[DTC_CW];
+#pragma unroll
+                    for (int w = 0; w < DTC_CW; ++w) a[w] = tp[w * 8];
+                    double sum = 0.0;
+#pragma unroll
+                    for (int w = 0; w < DTC_CW; ++w) sum += a[w];
+                    S.Yt[8 * C + lane] = sum;
+                }
+                __syncwarp();
+                if (lane == 0) dtc_mbar_arrive(S.tempty + 8 * slot);
+                ++P.tc;
+            }
+        }
+    } else {
+        const int g8 = lane >> 2, t4 = lane & 3;
+        const double *vj = S.Vs + jj * PS;
+        const int lofs = g8 * 8 + 2 * t4;
+        for (int C = T0; C < NT; ++C) {
+            double2 vc = make_double2(0.0, 0.0);
+            double vb[NB > 4 ? 2 : 1], wb[NB > 4 ? 2 : 1];
+            double tc0 = 0.0, tc1 = 0.0;
+            if (MODE == 0) vc = *reinterpret_cast<const double2 *>(vj + 8 * C + 2 * t4);
+            else {
+                const bool cok = 8 * C + g8 >= b0;
+#pragma unroll
+                for (int h = 0; h < (NB > 4 ? 2 : 1); ++h) {
+                    const bool kok = t4 + 4 * h < NB;
+                    vb[h] = cok && kok ? S.Vs[(t4 + 4 * h) * PS + 8 * C + g8] : 0.0;
+                    wb[h] = cok && kok ? S.Ws[(t4 + 4 * h) * PS + 8 * C + g8] : 0.0;
+                }
+            }
+            for (int R0 = C; R0 < NT; R0 += DTC_PIECE) {
+                const int cnt = min(DTC_PIECE, NT - R0), sz = cnt * 512;
+                if (P.off + sz > S.ringb) P.off = 0;
+                const unsigned bi = P.g & (DTC_NBAR - 1);
+                dtc_mbar_wait(S.full + 8 * bi, (P.g >> 4) & 1u);
+                const double *tb = S.ring + (P.off >> 3) + lofs;
+#pragma unroll
+                for (int u = 0; u < DTC_PIECE / DTC_CW; ++u) {
+                    const int q = ((wp - R0) & (DTC_CW - 1)) + u * DTC_CW;             // rows with R mod DTC_CW == wp
+                    if (q < cnt) {
+                        const int R = R0 + q;
+                        if (MODE == 0) {
+                            const double2 x = *reinterpret_cast<const double2 *>(tb + q * 64);
+                            const double vr = R > C ? vj[8 * R + g8] : 0.0;          // the diagonal tile is complete
+                            dtc_row_part<YS>(S, x, vc, R, lane);
+                            tc0 = fma(x.x, vr, tc0);
+                            tc1 = fma(x.y, vr, tc1);
+                        } else {
+                            const bool rok = 8 * R + g8 >= b0;
+                            double2 d = *reinterpret_cast<const double2 *>(tb + q * 64);
+#pragma unroll
+                            for (int h = 0; h < (NB > 4 ? 2 : 1); ++h) {
+                                const bool kok = t4 + 4 * h < NB;
+                                const double va = rok && kok ? -S.Vs[(t4 + 4 * h) * PS + 8 * R + g8] : 0.0;
+                                const double wa = rok && kok ? -S.Ws[(t4 + 4 * h) * PS + 8 * R + g8] : 0.0;
+                                tc_dmma(d.x, d.y, va, wb[h]);
+                                tc_dmma(d.x, d.y, wa, vb[h]);
+                            }
+                            *reinterpret_cast<double2 *>(tiles + dtg_off<true>(R, C, NT) + lofs) = d;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) dtc_mbar_arrive(S.empty + 8 * bi);
+                P.off += sz;
+                ++P.g;
+            }
+            if (MODE == 0) {
+                // column part of this warp: sum over the rows g8, lanes 0..3 hold columns 2 t4, 2 t4 + 1 (nothing to reduce
+                // when the warp had no tile below the diagonal in this column)
+                const int Rf = C + ((wp - C) & (DTC_CW - 1));
+                if (Rf < NT && (Rf > C || Rf + DTC_CW < NT)) {
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) {
+                        tc0 += __shfl_xor_sync(0xffffffffu, tc0, o);
+                        tc1 += __shfl_xor_sync(0xffffffffu, tc1, o);
+                    }
+                }
+                const unsigned slot = P.tc & 1u, use = P.tc >> 1;
+                if (use >= 1u) dtc_mbar_wait(S.tempty + 8 * slot, (use - 1u) & 1u);
+                if (lane < 4) *reinterpret_cast<double2 *>(S.tpart + ((size_t)slot * DTC_CW + wp) * 8 + 2 * lane) = make_double2(tc0, tc1);
+                __syncwarp();
+                if (lane == 0) dtc_mbar_arrive(S.tfull + 8 * slot);
+                ++P.tc;
+            }
+        }
+        if (MODE == 0) {
+            // panel dot products for the corrections of this column (warp kt: column kt of the panel)
+            if (wp < jj) {
+                double t1 = 0.0, t2 = 0.0;
+                for (int i = j + 1 + lane; i < n; i += 32) {
+                    const double vi = vj[i];
+                    t1 = fma(S.Ws[wp * PS + i], vi, t1);
+                    t2 = fma(S.Vs[wp * PS + i], vi, t2);
+                }
+                t1 = warp_sum(t1); t2 = warp_sum(t2);
+                if (lane == 0) { S.ts[wp] = t1; S.ts[8 + wp] = t2; }
+            }
+        } else {
+            // the next pass reads these tiles through the async proxy
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+    }
+}
+
+__device__ __forceinline__ double dtc_block_sum(double v, double *red) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < DTC_THREADS / 32; ++q) s += red[q];
+    return s;
+}
+
+// One persistent CTA per matrix (column-major tiles).  Outputs d, e, tau [B][n]; reflectors stay in the tiles.
+template <int NB, int YS>
+static __global__ void __maxnreg__(96)                 // 576 threads, one CTA per SM (__launch_bounds__(576) makes ptxas aim at 56 registers and spill)
+dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *__restrict__ dd_all, double *__restrict__ ee_all,
+                   double *__restrict__ tau_all, int ringb) {
+    constexpr int NTHR = DTC_THREADS;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ double red[NTHR / 32];
+    __shared__ double s_scal[2];
+    __shared__ __align__(8) unsigned long long bars[2 * DTC_NBAR + 4];
+    __shared__ int szs[DTC_NBAR];
+    const int tid = threadIdx.x, wp = tid >> 5, lane = tid & 31;
+    const int NT = DtgGeom::nt(n), PS = DtgGeom::ps(n);
+    DtcSh S;
+    S.ringb = ringb;
+    S.ring = (double *)smem;
+    S.tpart = S.ring + (size_t)(ringb >> 3);
+    S.Vs = S.tpart + (size_t)2 * DTC_CW * 8;
+    S.Ws = S.Vs + NB * PS;
+    S.Yd4 = S.Ws + NB * PS;
+    S.Yt = S.Yd4 + YS * PS;
+    S.ts = S.Yt + PS;
+    S.szs = szs;
+    S.full = dtc_saddr(bars);
+    S.empty = S.full + 8 * DTC_NBAR;
+    S.tfull = S.empty + 8 * DTC_NBAR;
+    S.tempty = S.tfull + 16;
+    double *Vs = S.Vs, *Ws = S.Ws;
+    if (tid == 0) {
+        for (int s = 0; s < DTC_NBAR; ++s) { dtc_mbar_init(&bars[s], 1); dtc_mbar_init(&bars[DTC_NBAR + s], DTC_CW); }
+        for (int s = 0; s < 2; ++s) { dtc_mbar_init(&bars[2 * DTC_NBAR + s], DTC_CW); dtc_mbar_init(&bars[2 * DTC_NBAR + 2 + s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    DtcPos P;
+    P.g = 0u; P.off = 0; P.tc = 0u; P.tail = 0u; P.infl = 0; P.pre = 0; P.pC = 0; P.pR0 = 0;
+    for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+        double *tiles = tiles_all + (size_t)b * DtgGeom::tile_doubles(n);
+        double *dd = dd_all + (size_t)b * n, *ee = ee_all + (size_t)b * n, *tauo = tau_all + (size_t)b * n;
+        for (int q = tid; q < 2 * NB * PS + (YS + 1) * PS; q += NTHR) Vs[q] = 0.0;
+        __syncthreads();
+        for (int j0 = 0; j0 < n; j0 += NB) {
+            const int pn = min(NB, n - j0);
+            bool last = false;
+            for (int jj = 0; jj < pn; ++jj) {
+                const int j = j0 + jj, Cj = j >> 3, cj = j & 7;
+                double *vj = Vs + jj * PS;
+                // ---- column j made current (stale column + the corrections of this panel) ----
+                double xn = 0.0;
+                for (int r = j + tid; r < n; r += NTHR) {
+                    double cv = tiles[dtg_off<true>(r >> 3, Cj, NT) + (r & 7) * 8 + cj];
+                    for (int k = 0; k < jj; ++k)
+                        cv = fma(-Vs[k * PS + r], Ws[k * PS + j], fma(-Ws[k * PS + r], Vs[k * PS + j], cv));
+                    vj[r] = cv;
+                    if (r == j) dd[j] = cv;
+                    if (r == j + 1) s_scal[0] = cv;
+                    if (r >= j + 2) xn = fma(cv, cv, xn);
+                }
+                if (j == n - 1) {
+                    if (tid == 0) { ee[j] = 0.0; tauo[j] = 0.0; }
+                    last = true;
+                    break;
+                }
+                {
+                    // row-part accumulators of the live rows (the column parts are assigned, not accumulated)
+                    double2 *z = reinterpret_cast<double2 *>(S.Yd4 + 8 * YS * ((j + 1) >> 3));
+                    const int nz = YS * (PS - 8 * ((j + 1) >> 3)) / 2;
+                    for (int q = tid; q < nz; q += NTHR) z[q] = make_double2(0.0, 0.0);
+                }
+                xn = dtc_block_sum(xn, red);
+                double tau, beta, sc;
+                s1t_reflector_scalars(s_scal[0], xn, tau, beta, sc);
+                for (int r = j + tid; r < n; r += NTHR) {
+                    const double v = r == j ? 0.0 : (r == j + 1 ? 1.0 : vj[r] * sc);
+                    vj[r] = v;
+                    if (r > j) tiles[dtg_off<true>(r >> 3, Cj, NT) + (r & 7) * 8 + cj] = v;       // kept for the back-transformation
+                }
+                if (tid == 0) { ee[j] = beta; tauo[j] = tau; }
+                __syncthreads();
+                // what the producer may run ahead into: the next column's mat-vec, or the trailing update after the last
+                // column of a full panel (same tiles, unchanged until then)
+                int nextT0 = -1;
+                if (jj + 1 < pn) { if (j + 1 < n - 1) nextT0 = (j + 2) >> 3; }
+                else if (pn == NB && j0 + NB < n) nextT0 = (j0 + NB) >> 3;
+                dtc_stream<NB, YS, 0>(tiles, S, n, NT, PS, (j + 1) >> 3, j, jj, 0, nextT0, P, wp, lane);
+                __syncthreads();
+                // ---- corrections, w ----
+                double dt = 0.0;
+                for (int r = j + 1 + tid; r < n; r += NTHR) {
+                    double y;
+                    if (YS == 4) {
+                        const double2 ya = *reinterpret_cast<const double2 *>(S.Yd4 + 4 * r), yb = *reinterpret_cast<const double2 *>(S.Yd4 + 4 * r + 2);
+                        y = ((ya.x + ya.y) + (yb.x + yb.y)) + S.Yt[r];
+                    } else y = S.Yd4[r] + S.Yt[r];
+                    for (int k = 0; k < jj; ++k) y = fma(-Vs[k * PS + r], S.ts[k], fma(-Ws[k * PS + r], S.ts[8 + k], y));
+                    const double pr = tau * y;
+                    S.Yd4[YS * r] = pr;
+                    dt = fma(pr, vj[r], dt);
+                }
+                dt = dtc_block_sum(dt, red);
+                const double hc = -0.5 * tau * dt;
+                for (int r = tid; r < PS; r += NTHR) Ws[jj * PS + r] = (r > j && r < n) ? fma(hc, vj[r], S.Yd4[YS * r]) : 0.0;
+                __syncthreads();
+            }
+            const int b0 = j0 + NB;
+            if (!last && pn == NB && b0 < n) {
+                dtc_stream<NB, YS, 1>(tiles, S, n, NT, PS, b0 >> 3, 0, 0, b0, -1, P, wp, lane);
+                __syncthreads();
+                for (int q = tid; q < 2 * NB * PS; q += NTHR) Vs[q] = 0.0;
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+    }
 }
 
 }  // namespace scqed
