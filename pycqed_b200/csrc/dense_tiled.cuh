@@ -250,7 +250,7 @@ dtg_backtr_kernel(const double *__restrict__ tiles_all, int n, int k, int kg, co
 struct DtcGeom {
     static size_t fixed(int n, int nb, int ys) {
         const size_t PS = DtgGeom::ps(n);
-        return (size_t)2 * DTC_CW * 64 + ((size_t)2 * nb * PS + (ys + 1) * PS + 2 * 8 + 8) * 8;
+        return (size_t)2 * DTC_CW * 64 + ((size_t)2 * nb * PS + (ys + 2) * PS + 2 * 8 + 8) * 8;
     }
 };
 
@@ -279,7 +279,7 @@ __device__ __forceinline__ void dtc_mbar_wait(unsigned bar, unsigned parity) {
 }
 
 struct DtcSh {
-    double *ring, *tpart, *Vs, *Ws, *Yd4, *Yt, *ts;
+    double *ring, *tpart, *Vs, *Ws, *Yd4, *Yt, *Vn, *ts;
     int *szs;                                     // producer: bytes held by the pieces in flight (by barrier index)
     unsigned full, empty, tfull, tempty;          // shared-memory addresses of the barrier arrays (8 B per barrier)
     int ringb;                                    // ring size in bytes
@@ -313,13 +313,15 @@ __device__ __forceinline__ void dtc_row_part(const DtcSh &S, const double2 x, co
 }
 
 // One pass over the tile columns >= T0, pieces = runs of at most DTC_PIECE tiles of one tile column.  MODE 0: y = A v
-// (v = panel column jj of Vs) and, at the tail, the panel dot products ts[k] = W_k.v, ts[8 + k] = V_k.v (k < jj).
-// MODE 1: A -= V W^T + W V^T on the elements with row, column >= b0.
+// (v = vj) and, at the tail, the panel dot products ts[k] = W_k.v, ts[8 + k] = V_k.v (k < jj).
+// MODE 2 (first column of a panel): the pending rank-2*NB update of the previous panel, A -= V W^T + W V^T on the elements
+// with row, column >= b0 (only those are stored back: the reflectors next to them may be newer in global memory than in a
+// piece that was copied ahead), FUSED with y = A v on the updated tile -- the update costs no pass of its own.
 // YS = 4: row-part partial sums per lane of the quad (no shuffles); YS = 1: reduced over the quad before the accumulation
 // (a quarter of the shared memory: the large sizes).
 template <int NB, int YS, int MODE>
-__device__ __forceinline__ void dtc_stream(double *tiles, const DtcSh &S, int n, int NT, int PS, int T0, int j, int jj,
-                                           int b0, int nextT0, DtcPos &P, int wp, int lane) {
+__device__ __forceinline__ void dtc_stream(double *tiles, const DtcSh &S, const double *vj, int n, int NT, int PS, int T0, int j,
+                                           int jj, int b0, int nextT0, DtcPos &P, int wp, int lane) {
     if (wp == DTC_CW) {
         // ---- producer: a piece is issued as soon as the ring has room for it and a barrier pair is free (pieces are
         // released in order).  After the last piece of this pass it runs AHEAD into the next pass (`nextT0` >= 0: the tiles
@@ -361,7 +363,7 @@ __device__ __forceinline__ void dtc_stream(double *tiles, const DtcSh &S, int n,
         __syncwarp();
     } else if (wp == DTC_CW + 1) {
         // ---- folder: column parts of the consumer warps, added in warp order ----
-        if (MODE == 0) {
+        {
             for (int C = T0; C < NT; ++C) {
                 const unsigned slot = P.tc & 1u, use = P.tc >> 1;
                 dtc_mbar_wait(S.tfull + 8 * slot, use & 1u);
@@ -382,14 +384,12 @@ __device__ __forceinline__ void dtc_stream(double *tiles, const DtcSh &S, int n,
         }
     } else {
         const int g8 = lane >> 2, t4 = lane & 3;
-        const double *vj = S.Vs + jj * PS;
         const int lofs = g8 * 8 + 2 * t4;
         for (int C = T0; C < NT; ++C) {
-            double2 vc = make_double2(0.0, 0.0);
             double vb[NB > 4 ? 2 : 1], wb[NB > 4 ? 2 : 1];
             double tc0 = 0.0, tc1 = 0.0;
-            if (MODE == 0) vc = *reinterpret_cast<const double2 *>(vj + 8 * C + 2 * t4);
-            else {
+            const double2 vc = *reinterpret_cast<const double2 *>(vj + 8 * C + 2 * t4);
+            if (MODE == 2) {
                 const bool cok = 8 * C + g8 >= b0;
 #pragma unroll
                 for (int h = 0; h < (NB > 4 ? 2 : 1); ++h) {
@@ -409,25 +409,28 @@ __device__ __forceinline__ void dtc_stream(double *tiles, const DtcSh &S, int n,
                     const int q = ((wp - R0) & (DTC_CW - 1)) + u * DTC_CW;             // rows with R mod DTC_CW == wp
                     if (q < cnt) {
                         const int R = R0 + q;
-                        if (MODE == 0) {
-                            const double2 x = *reinterpret_cast<const double2 *>(tb + q * 64);
-                            const double vr = R > C ? vj[8 * R + g8] : 0.0;          // the diagonal tile is complete
-                            dtc_row_part<YS>(S, x, vc, R, lane);
-                            tc0 = fma(x.x, vr, tc0);
-                            tc1 = fma(x.y, vr, tc1);
-                        } else {
+                        double2 x = *reinterpret_cast<const double2 *>(tb + q * 64);
+                        if (MODE == 2) {
                             const bool rok = 8 * R + g8 >= b0;
-                            double2 d = *reinterpret_cast<const double2 *>(tb + q * 64);
 #pragma unroll
                             for (int h = 0; h < (NB > 4 ? 2 : 1); ++h) {
                                 const bool kok = t4 + 4 * h < NB;
                                 const double va = rok && kok ? -S.Vs[(t4 + 4 * h) * PS + 8 * R + g8] : 0.0;
                                 const double wa = rok && kok ? -S.Ws[(t4 + 4 * h) * PS + 8 * R + g8] : 0.0;
-                                tc_dmma(d.x, d.y, va, wb[h]);
-                                tc_dmma(d.x, d.y, wa, vb[h]);
+                                tc_dmma(x.x, x.y, va, wb[h]);
+                                tc_dmma(x.x, x.y, wa, vb[h]);
                             }
-                            *reinterpret_cast<double2 *>(tiles + dtg_off<true>(R, C, NT) + lofs) = d;
+                            double *dst = tiles + dtg_off<true>(R, C, NT) + lofs;
+                            if (rok) {
+                                const int c0 = 8 * C + 2 * t4;
+                                if (c0 >= b0) *reinterpret_cast<double2 *>(dst) = x;
+                                else if (c0 + 1 >= b0) dst[1] = x.y;
+                            }
                         }
+                        const double vr = R > C ? vj[8 * R + g8] : 0.0;          // the diagonal tile is complete
+                        dtc_row_part<YS>(S, x, vc, R, lane);
+                        tc0 = fma(x.x, vr, tc0);
+                        tc1 = fma(x.y, vr, tc1);
                     }
                 }
                 __syncwarp();
@@ -435,7 +438,7 @@ __device__ __forceinline__ void dtc_stream(double *tiles, const DtcSh &S, int n,
                 P.off += sz;
                 ++P.g;
             }
-            if (MODE == 0) {
+            {
                 // column part of this warp: sum over the rows g8, lanes 0..3 hold columns 2 t4, 2 t4 + 1 (nothing to reduce
                 // when the warp had no tile below the diagonal in this column)
                 const int Rf = C + ((wp - C) & (DTC_CW - 1));
@@ -454,7 +457,11 @@ __device__ __forceinline__ void dtc_stream(double *tiles, const DtcSh &S, int n,
                 ++P.tc;
             }
         }
-        if (MODE == 0) {
+        if (MODE == 2) {
+            // a later pass reads these tiles through the async proxy
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        {
             // panel dot products for the corrections of this column (warp kt: column kt of the panel)
             if (wp < jj) {
                 double t1 = 0.0, t2 = 0.0;
@@ -466,9 +473,6 @@ __device__ __forceinline__ void dtc_stream(double *tiles, const DtcSh &S, int n,
                 t1 = warp_sum(t1); t2 = warp_sum(t2);
                 if (lane == 0) { S.ts[wp] = t1; S.ts[8 + wp] = t2; }
             }
-        } else {
-            // the next pass reads these tiles through the async proxy
-            asm volatile("fence.proxy.async;" ::: "memory");
         }
     }
 }
@@ -506,7 +510,8 @@ dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
     S.Ws = S.Vs + NB * PS;
     S.Yd4 = S.Ws + NB * PS;
     S.Yt = S.Yd4 + YS * PS;
-    S.ts = S.Yt + PS;
+    S.Vn = S.Yt + PS;
+    S.ts = S.Vn + PS;
     S.szs = szs;
     S.full = dtc_saddr(bars);
     S.empty = S.full + 8 * DTC_NBAR;
@@ -524,19 +529,24 @@ dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
     for (long long b = blockIdx.x; b < B; b += gridDim.x) {
         double *tiles = tiles_all + (size_t)b * DtgGeom::tile_doubles(n);
         double *dd = dd_all + (size_t)b * n, *ee = ee_all + (size_t)b * n, *tauo = tau_all + (size_t)b * n;
-        for (int q = tid; q < 2 * NB * PS + (YS + 1) * PS; q += NTHR) Vs[q] = 0.0;
+        for (int q = tid; q < 2 * NB * PS + (YS + 2) * PS; q += NTHR) Vs[q] = 0.0;
         __syncthreads();
         for (int j0 = 0; j0 < n; j0 += NB) {
             const int pn = min(NB, n - j0);
-            bool last = false;
             for (int jj = 0; jj < pn; ++jj) {
                 const int j = j0 + jj, Cj = j >> 3, cj = j & 7;
-                double *vj = Vs + jj * PS;
-                // ---- column j made current (stale column + the corrections of this panel) ----
+                // First column of a panel after the first: the panel arrays still hold the PREVIOUS panel, whose rank-2*NB
+                // update is pending; the column is made current from all NB of its columns, its reflector goes to Vn, and the
+                // update is applied to the rest of the trailing block inside this column's mat-vec pass (MODE 2).
+                const bool fused = jj == 0 && j0 > 0;
+                const int nc = fused ? NB : jj;
+                double *vj = fused ? S.Vn : Vs + jj * PS;
+                // ---- column j made current (stale column + the corrections of the panel) ----
                 double xn = 0.0;
+                if (fused) for (int r = tid; r < j; r += NTHR) vj[r] = 0.0;
                 for (int r = j + tid; r < n; r += NTHR) {
                     double cv = tiles[dtg_off<true>(r >> 3, Cj, NT) + (r & 7) * 8 + cj];
-                    for (int k = 0; k < jj; ++k)
+                    for (int k = 0; k < nc; ++k)
                         cv = fma(-Vs[k * PS + r], Ws[k * PS + j], fma(-Ws[k * PS + r], Vs[k * PS + j], cv));
                     vj[r] = cv;
                     if (r == j) dd[j] = cv;
@@ -545,7 +555,6 @@ dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
                 }
                 if (j == n - 1) {
                     if (tid == 0) { ee[j] = 0.0; tauo[j] = 0.0; }
-                    last = true;
                     break;
                 }
                 {
@@ -564,13 +573,18 @@ dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
                 }
                 if (tid == 0) { ee[j] = beta; tauo[j] = tau; }
                 __syncthreads();
-                // what the producer may run ahead into: the next column's mat-vec, or the trailing update after the last
-                // column of a full panel (same tiles, unchanged until then)
-                int nextT0 = -1;
-                if (jj + 1 < pn) { if (j + 1 < n - 1) nextT0 = (j + 2) >> 3; }
-                else if (pn == NB && j0 + NB < n) nextT0 = (j0 + NB) >> 3;
-                dtc_stream<NB, YS, 0>(tiles, S, n, NT, PS, (j + 1) >> 3, j, jj, 0, nextT0, P, wp, lane);
-                __syncthreads();
+                if (fused) {
+                    // (the producer does not run ahead out of this pass: it rewrites the tiles)
+                    dtc_stream<NB, YS, 2>(tiles, S, vj, n, NT, PS, (j + 1) >> 3, j, 0, j + 1, -1, P, wp, lane);
+                    __syncthreads();
+                    for (int q = tid; q < 2 * NB * PS; q += NTHR) Vs[q] = 0.0;
+                    __syncthreads();
+                } else {
+                    // the producer may run ahead into the next column's pass (plain or fused: same tiles, unchanged until then)
+                    const int nextT0 = j + 1 < n - 1 ? (j + 2) >> 3 : -1;
+                    dtc_stream<NB, YS, 0>(tiles, S, vj, n, NT, PS, (j + 1) >> 3, j, jj, 0, nextT0, P, wp, lane);
+                    __syncthreads();
+                }
                 // ---- corrections, w ----
                 double dt = 0.0;
                 for (int r = j + 1 + tid; r < n; r += NTHR) {
@@ -586,14 +600,10 @@ dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
                 }
                 dt = dtc_block_sum(dt, red);
                 const double hc = -0.5 * tau * dt;
-                for (int r = tid; r < PS; r += NTHR) Ws[jj * PS + r] = (r > j && r < n) ? fma(hc, vj[r], S.Yd4[YS * r]) : 0.0;
-                __syncthreads();
-            }
-            const int b0 = j0 + NB;
-            if (!last && pn == NB && b0 < n) {
-                dtc_stream<NB, YS, 1>(tiles, S, n, NT, PS, b0 >> 3, 0, 0, b0, -1, P, wp, lane);
-                __syncthreads();
-                for (int q = tid; q < 2 * NB * PS; q += NTHR) Vs[q] = 0.0;
+                for (int r = tid; r < PS; r += NTHR) {
+                    Ws[jj * PS + r] = (r > j && r < n) ? fma(hc, vj[r], S.Yd4[YS * r]) : 0.0;
+                    if (fused) Vs[r] = vj[r];                                  // the reflector becomes column 0 of the new panel
+                }
                 __syncthreads();
             }
         }
