@@ -1,5 +1,7 @@
-// dense_tiled.cuh -- S2t: REAL SYMMETRIC dense matrices beyond the shared-memory path (224 < n <= 2048), ONE PERSISTENT CTA
-// PER MATRIX on the tile-packed lower triangle in global memory (L2 resident for the later panels).
+// dense_tiled.cuh -- S2t: REAL SYMMETRIC dense matrices beyond the shared-memory path (224 < n <= ~3100), ONE PERSISTENT CTA
+// PER MATRIX on the tile-packed lower triangle in global memory.  Two tridiagonalisation kernels: dtg_tridiag_kernel (first
+// half of this file: row-major tiles, register loads, the fastest below n ~ 550) and the streamed dtc_tridiag_kernel (second
+// half: column-major tiles through a bulk-copy ring, every tile read once per column, update fused into a mat-vec pass).
 //
 // Why: the blocked HBM solver (dense_blocked.cuh) is complex-only and re-reads the trailing matrix with two launches per
 // column; for the real symmetric matrices that dominate the dense mid-size cases (single oscillator node: fluxonium at
@@ -231,17 +233,18 @@ dtg_backtr_kernel(const double *__restrict__ tiles_all, int n, int k, int kg, co
 // (n >~ 600).  dtg_tridiag_kernel reads every stored tile TWICE per column (item R = tile row R + tile column R) through
 // register loads of which the compiler keeps two or three in flight per warp: ~10 GB/s per SM.  Here
 //   * the tiles are stored column-major (dtg_off<true>): the trailing block is one contiguous suffix, which a PRODUCER warp
-//     streams through a shared-memory ring with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx) of DTC_PIECE tiles =
-//     16 KB each, whatever tile columns they span, nst copies in flight per SM;
-//   * every tile is read ONCE per column: the consumer warp R mod 8 takes tile (R, C) out of the ring (one LDS.128 per
+//     streams through a shared-memory BYTE ring with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx): pieces of at
+//     most DTC_PIECE tiles = 16 KB of one tile column, up to 16 pieces / 48-96 KB in flight per SM;
+//   * every tile is read ONCE per column: the consumer warp R mod 16 takes tile (R, C) out of the ring (one LDS.128 per
 //     lane) and forms both y_R += T v_C (row part: four partial sums per row, one per lane of the quad, accumulated in
 //     place in Yd4[32 R + lane]: no shuffles, rows owned by one warp) and y_C += T^T v_R (column part: two accumulators per
 //     lane carried over the warp's tiles of the column, reduced over the lanes once per column and handed to a FOLDER warp
-//     that adds the 8 warps' parts in warp order into Yt[8 C ..]): deterministic, no atomics, no per-warp copies of y;
-//   * the rank-2*NB trailing update streams the same suffix through the same ring, DMMA on the fragment read from shared
-//     memory, result stored straight to global memory; NB = 8 while the panels fit, else 4 or 2;
+//     that adds the 16 warps' parts in warp order into Yt[8 C ..]): deterministic, no atomics, no per-warp copies of y;
+//   * the rank-2*NB trailing update of a panel has no pass of its own: it is applied inside the first mat-vec pass of the
+//     NEXT panel (MODE 2: DMMA on the fragment read from the ring, live elements stored straight to global memory, the
+//     updated fragment then feeds the mat-vec); NB = 8 / 4 / 2 by what the panels leave for the ring;
 //   * the producer runs ahead into the next pass while the O(m) sections of a column execute.
-// HBM traffic per column: 4 m^2 B (mat-vec) + 8 m^2 / NB B (update read + write) => (4/3 + 8 / (3 NB)) n^3 B per matrix.
+// HBM traffic per column: 4 m^2 B read + 4 m^2 / NB B written => (4/3) (1 + 1 / NB) n^3 B per matrix.
 #define DTC_CW 16                                   // consumer warps (two tiles each per full piece; 8 warps x 4 tiles measured 4 % slower)
 #define DTC_THREADS (32 * (DTC_CW + 2))             // + the producer warp + the folder warp
 #define DTC_PIECE 32                                // tiles per bulk copy (at most; a piece never spans two tile columns)
