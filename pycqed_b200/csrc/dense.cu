@@ -202,7 +202,7 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
     if (const char *e = getenv("SCQED_DENSE_TILED")) mode = atoi(e);
     if (mode == 0) return 0;
     const bool forced = mode > 0;
-    if (n <= 224 || n > 4096 || k > 32) return 0;
+    if (n <= 224 || n > 3400 || k > 32) return 0;
     // one CTA per matrix needs a batch to fill the machine (measured against the blocked complex solver in DESIGN.md)
     if (!forced && B < 48) return 0;
     bool streamed = mode == 2 || (mode < 0 && n >= 560);        // measured crossover (tools/s2t_ab.sh): n ~ 550
@@ -218,7 +218,7 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
         if (const char *e = getenv("SCQED_DTC_NB")) { int v = atoi(e); if (v == 8 || v == 4 || v == 2) fnb = v; }
         if (const char *e = getenv("SCQED_DTC_YS")) { int v = atoi(e); if (v == 4 || v == 1) fys = v; }
         if (const char *e = getenv("SCQED_DTC_NST")) { int v = atoi(e); if (v >= 2 && v <= 8) fst = v; }
-        for (int minst = 4; minst >= 3 && !nb; --minst)
+        for (int minst = 4; minst >= 2 && !nb; --minst)            // 32 KB: the last resort (n ~ 3100 ... 3400)
             for (int c = 0; c < 6 && !nb; ++c) {
                 if ((fnb && cand[c][0] != fnb) || (fys && cand[c][1] != fys)) continue;
                 for (int s = fst ? fst : 6; s >= (fst ? fst : minst); --s)

@@ -1,4 +1,4 @@
-// dense_tiled.cuh -- S2t: REAL SYMMETRIC dense matrices beyond the shared-memory path (224 < n <= ~3100), ONE PERSISTENT CTA
+// dense_tiled.cuh -- S2t: REAL SYMMETRIC dense matrices beyond the shared-memory path (224 < n <= 3400), ONE PERSISTENT CTA
 // PER MATRIX on the tile-packed lower triangle in global memory.  Two tridiagonalisation kernels: dtg_tridiag_kernel (first
 // half of this file: row-major tiles, register loads, the fastest below n ~ 550) and the streamed dtc_tridiag_kernel (second
 // half: column-major tiles through a bulk-copy ring, every tile read once per column, update fused into a mat-vec pass).
