@@ -230,15 +230,8 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
         }
     }
     if (!streamed && (n > 2048 || DtgGeom::tridiag_smem(n) + 2048 > pl->smem_optin)) return 0;
-    // back-transformation: groups of kg vectors per CTA
-    int kg = k;
-    if (want_vec) {
-        const size_t per = (size_t)n * 8;
-        const size_t fit = cap > 1024 ? (cap - 1024) / per : 0;
-        if (fit < 1) return 0;
-        if ((size_t)kg > fit) kg = (int)fit;
-    }
-    const size_t sm_bt = DtgGeom::backtr_smem(n, kg);
+    const size_t sm_bt = DtgGeom::backtr_smem(n);
+    if (want_vec && sm_bt + 1024 > cap) return 0;
     const size_t td = DtgGeom::tile_doubles(n);
     if (pl->dtg.ensure((size_t)B * td * 8 + 256)) return fail(SCQED_ENOMEM, "tile-packed matrices (%zu MB)", ((size_t)B * td * 8) >> 20);
     int *d_flag = (int *)pl->dtg.p;
@@ -278,19 +271,22 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
     }
     LAUNCHED();
     CK(cudaGetLastError());
-    tridiag_eig_kernel<<<B, 256, (size_t)k * 8, st>>>(K.dd, K.ee, n, k, want_vec, evals, w.Z, w.lu, k, w.e2, info);
-    LAUNCHED();
-    CK(cudaGetLastError());
+    const double *zw = nullptr;
+    long long G = 0;
+    {
+        int rc = s1_tridiag_eig_batch(pl, K.dd, K.ee, n, k, B, want_vec, evals, &zw, &G, info, st);
+        if (rc) return rc;
+    }
     if (want_vec) {
-        const dim3 grid((unsigned)B, (unsigned)((k + kg - 1) / kg));
-#define DTG_BT(KM, CMV)                                                                                   \
-        do {                                                                                              \
-            CK(set_max_dynamic_smem(dtg_backtr_kernel<KM, CMV>, pl->smem_optin));                         \
-            dtg_backtr_kernel<KM, CMV><<<grid, DTG_THREADS, sm_bt, st>>>(tiles, n, k, kg, tau, w.Z, evecs); \
-        } while (0)
-        if (kg <= 12) { if (streamed) DTG_BT(12, true); else DTG_BT(12, false); }
-        else { if (streamed) DTG_BT(32, true); else DTG_BT(32, false); }
-#undef DTG_BT
+        const long long pairs = (long long)B * k;
+        const unsigned grid = (unsigned)((pairs + DTG_BT_WARPS - 1) / DTG_BT_WARPS);
+        if (streamed) {
+            CK(set_max_dynamic_smem(dtg_backtr_kernel<true>, pl->smem_optin));
+            dtg_backtr_kernel<true><<<grid, 32 * DTG_BT_WARPS, sm_bt, st>>>(tiles, n, k, B, tau, zw, G, evecs);
+        } else {
+            CK(set_max_dynamic_smem(dtg_backtr_kernel<false>, pl->smem_optin));
+            dtg_backtr_kernel<false><<<grid, 32 * DTG_BT_WARPS, sm_bt, st>>>(tiles, n, k, B, tau, zw, G, evecs);
+        }
         LAUNCHED();
         CK(cudaGetLastError());
     }

@@ -30,7 +30,7 @@ struct DtgGeom {
     __host__ __device__ static size_t tile_doubles(int n) { return (size_t)nt(n) * (nt(n) + 1) / 2 * 64; }
     __host__ __device__ static int ps(int n) { return 8 * nt(n) + 4; }
     static size_t tridiag_smem(int n) { return ((size_t)2 * S1T_NB * ps(n) + ps(n) + 2 * S1T_NB + 8) * 8; }
-    static size_t backtr_smem(int n, int k) { return ((size_t)k * n + 64) * 8; }
+    static size_t backtr_smem(int n) { return (size_t)8 * n * 8; }            // DTG_BT_WARPS vectors
 };
 
 // Tile order in global memory.  CM = false: row-major over tiles (tiled_common.cuh, what dtg_tridiag_kernel walks); CM = true:
@@ -162,70 +162,51 @@ dtg_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
     }
 }
 
-// x = H(0) H(1) ... H(n-2) z for the k tridiagonal eigenvectors of one matrix (Z [B][k][n] real): one CTA per (matrix,
-// group of kg vectors), the vectors in shared memory, reflector j read straight from column j of the tiles.  X complex [B][k][n].
-template <int KMAX, bool CM>
-static __global__ void __launch_bounds__(DTG_THREADS)
-dtg_backtr_kernel(const double *__restrict__ tiles_all, int n, int k, int kg, const double *__restrict__ tau_all,
-                  const double *__restrict__ Z, cplx *__restrict__ X) {
+// x = H(0) H(1) ... H(n-2) z for the tridiagonal eigenvectors (Z interleaved: element i of vector `pair` at Z[i * G + pair],
+// as s1_tridiag_eig_batch leaves them): ONE WARP per (matrix, vector), the vector in
+// shared memory with a fixed row -> lane mapping (row r belongs to lane r mod 32: no hazards between lanes, no barriers of
+// any kind), reflector j read straight from column j of the tiles (the warps of one matrix share those lines through L1 /
+// L2).  Per column: one warp reduction instead of the block-wide reduction of k dot products (2 block barriers + 10 warp
+// reductions per thread) of the first version, which cost as much as the tridiagonalisation itself at n = 256
+// (15.0 ms vs 15.5 ms per 2072 matrices).  X complex [B][k][n].
+#define DTG_BT_WARPS 8
+template <bool CM>
+static __global__ void __launch_bounds__(32 * DTG_BT_WARPS)
+dtg_backtr_kernel(const double *__restrict__ tiles_all, int n, int k, long long B, const double *__restrict__ tau_all,
+                  const double *__restrict__ Z, long long G, cplx *__restrict__ X) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ double red[DTG_THREADS / 32][KMAX];
-    double *xs = (double *)smem;                             // [k][n]
-    const int tid = threadIdx.x, wp = tid >> 5, lane = tid & 31;
-    const long long b = blockIdx.x;
-    // blockIdx.y: group of kg consecutive vectors (all k when they fit the shared memory at once)
-    const int k0 = blockIdx.y * kg, ktot = k;
-    k = min(kg, ktot - k0);
+    const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long pair = (long long)blockIdx.x * DTG_BT_WARPS + wp;
+    if (pair >= B * k) return;
+    const long long b = pair / k;
+    const int NT = DtgGeom::nt(n);
+    double *x = (double *)smem + (size_t)wp * n;
     const double *tiles = tiles_all + (size_t)b * DtgGeom::tile_doubles(n);
     const double *tau = tau_all + (size_t)b * n;
-    for (int q = tid; q < k * n; q += DTG_THREADS) xs[q] = Z[((size_t)b * ktot + k0) * n + q];
-    __syncthreads();
+    for (int i = lane; i < n; i += 32) x[i] = Z[(size_t)i * G + pair];
     for (int j = n - 2; j >= 0; --j) {
         const double tj = tau[j];
         if (tj == 0.0) continue;
-        const int Cj = j >> 3, cj = j & 7, NT = DtgGeom::nt(n);
-        double dot[KMAX];
-#pragma unroll
-        for (int u = 0; u < KMAX; ++u) dot[u] = 0.0;
-        // this thread's rows of the reflector stay in registers between the dot products and the update (n <= 2048: <= 8)
-        double vr[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int r = j + 1 + tid + q * DTG_THREADS;
-            vr[q] = r < n ? (r == j + 1 ? 1.0 : tiles[dtg_off<CM>(r >> 3, Cj, NT) + (r & 7) * 8 + cj]) : 0.0;
-            if (r < n) {
-#pragma unroll
-                for (int u = 0; u < KMAX; ++u) if (u < k) dot[u] = fma(vr[q], xs[u * n + r], dot[u]);
-            }
+        const int Cj = j >> 3, cj = j & 7;
+        // rows r > j with r mod 32 == lane
+        const int r0 = ((j + 1 - lane + 31) & ~31) + lane;
+        double dot = 0.0;
+        if (CM) {
+            // column-major tiles: element (r, j) at (colstart(Cj) - Cj) * 64 + 8 r + cj
+            const double *col = tiles + (size_t)dtg_off<true>(Cj, Cj, NT) - (size_t)Cj * 64 + cj;
+            for (int r = r0; r < n; r += 32) dot = fma(r == j + 1 ? 1.0 : col[8 * r], x[r], dot);
+            dot = -tj * warp_sum(dot);
+            for (int r = r0; r < n; r += 32) x[r] = fma(dot, r == j + 1 ? 1.0 : col[8 * r], x[r]);
+        } else {
+            for (int r = r0; r < n; r += 32)
+                dot = fma(r == j + 1 ? 1.0 : tiles[dtg_off<false>(r >> 3, Cj, NT) + (r & 7) * 8 + cj], x[r], dot);
+            dot = -tj * warp_sum(dot);
+            for (int r = r0; r < n; r += 32)
+                x[r] = fma(dot, r == j + 1 ? 1.0 : tiles[dtg_off<false>(r >> 3, Cj, NT) + (r & 7) * 8 + cj], x[r]);
         }
-#pragma unroll
-        for (int u = 0; u < KMAX; ++u) if (u < k) dot[u] = warp_sum(dot[u]);
-        if (lane == 0) {
-#pragma unroll
-            for (int u = 0; u < KMAX; ++u) if (u < k) red[wp][u] = dot[u];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < KMAX; ++u) {
-            if (u < k) {
-                double s = 0.0;
-#pragma unroll
-                for (int w = 0; w < DTG_THREADS / 32; ++w) s += red[w][u];
-                dot[u] = -tj * s;
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int r = j + 1 + tid + q * DTG_THREADS;
-            if (r < n) {
-#pragma unroll
-                for (int u = 0; u < KMAX; ++u) if (u < k) xs[u * n + r] = fma(dot[u], vr[q], xs[u * n + r]);
-            }
-        }
-        __syncthreads();
     }
-    cplx *out = X + ((size_t)b * ktot + k0) * n;
-    for (int q = tid; q < k * n; q += DTG_THREADS) out[q] = cmake(xs[q], 0.0);
+    cplx *out = X + (size_t)pair * n;
+    for (int i = lane; i < n; i += 32) out[i] = cmake(x[i], 0.0);
 }
 
 // ======================================================================================================================

@@ -167,6 +167,8 @@ int run_small_any(scqed_plan *pl, const PlanDev &P, const cplx *coef, const cplx
 int run_resonator_generic(const PlanDev &P, const ResonatorArgs &res, const double *scal, const double *evals,
                           const cplx *vecs, long long n_pts, int n, int k, double *post, int *info, cudaStream_t st);
 // dense.cu (S2: batches of dense matrices through HBM)
+int s1_tridiag_eig_batch(scqed_plan *pl, double *dd, double *ee, int n, int k, long long B, int want_vec, double *evals,
+                         const double **zw_out, long long *G_out, int *info, cudaStream_t st);
 int dense_eigh_resident(scqed_plan *tmp, cplx *H_dev, int n, long long batch, int k, int want_vec, double *evals,
                         cplx *evecs, int *info, int solver, cudaStream_t st);
 int dense_sweep(scqed_plan *pl, const cplx *coef, long long n_pts, int k, int want_vec, int tidyup, int solver,

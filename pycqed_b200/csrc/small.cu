@@ -526,3 +526,83 @@ int run_resonator_generic(const PlanDev &P, const ResonatorArgs &res, const doub
     CK(cudaGetLastError());
     return 0;
 }
+
+// ---- tridiagonal eigenpairs for the dense tile-packed solver (S2t, dense.cu) -----------------------------------------
+// B real symmetric tridiagonal matrices (dd, ee [B][n], already on the device) through the sweep-sized kernels of the S1
+// pipeline: one thread per (matrix, eigenvalue) Sturm bisection (or the warp multisection for small batches) and one
+// thread per (matrix, vector) inverse iteration on workspaces interleaved over the threads.  tridiag_eig_kernel (one CTA
+// per matrix: ten busy threads of 256 in the inverse iteration) took 5-6 ms per launch whatever the batch; these take
+// the length of one dependent chain.  Eigenvectors come back INTERLEAVED: element i of vector (b, j) at zw[i * G + b * k + j].
+static __global__ void __launch_bounds__(128)
+s1_bounds_kernel(S1Args a) {
+    const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int l = threadIdx.x & 31, n = a.n;
+    if (p >= a.n_pts) return;
+    const double *d = a.W.dd + p * n, *e = a.W.ee + p * n;
+    double lo = 1e300, hi = -1e300, emax = 0.0;
+    for (int i = l; i < n; i += 32) {
+        const double ei = i < n - 1 ? e[i] : 0.0;
+        const double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + fabs(ei);
+        lo = fmin(lo, d[i] - r);
+        hi = fmax(hi, d[i] + r);
+        emax = fmax(emax, ei * ei);
+        a.W.e2[p * n + i] = ei * ei;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    }
+    if (l == 0) {                           // same conventions as tridiag_bounds
+        const double tn = fmax(fabs(lo), fabs(hi));
+        const double pad = 2.0 * tn * SCQED_EPS * n + 2.0 * SCQED_SAFMIN;
+        a.W.bnd[p * 4 + 0] = lo - pad;
+        a.W.bnd[p * 4 + 1] = hi + pad;
+        a.W.bnd[p * 4 + 2] = fmax(SCQED_SAFMIN * fmax(1.0, emax), SCQED_SAFMIN);
+        a.W.bnd[p * 4 + 3] = tn;
+    }
+}
+
+int s1_tridiag_eig_batch(scqed_plan *pl, double *dd, double *ee, int n, int k, long long B, int want_vec, double *evals,
+                         const double **zw_out, long long *G_out, int *info, cudaStream_t st) {
+    if (k > 32) return fail(SCQED_EUNSUPPORTED, "tridiagonal batch solver: k <= 32");
+    const long long G = B * k;
+    size_t bytes = 0;
+    auto need = [&](size_t b) { size_t r = bytes; bytes += (b + 255) & ~(size_t)255; return r; };
+    const size_t o_e2 = need((size_t)B * n * 8), o_bnd = need((size_t)B * 4 * 8), o_lam = need((size_t)B * k * 8);
+    size_t o_lu = 0, o_swp = 0, o_zw = 0;
+    if (want_vec) {
+        o_lu = need((size_t)4 * n * G * 8);
+        o_swp = need((size_t)n * G);
+        o_zw = need((size_t)n * G * 8);
+    }
+    if (pl->s1work.ensure(bytes)) return fail(SCQED_ENOMEM, "tridiagonal batch workspace (%zu MB)", bytes >> 20);
+    unsigned char *base = (unsigned char *)pl->s1work.p;
+    S1Args a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.k = k; a.n_pts = B; a.want_vec = want_vec; a.info = info;
+    a.W.dd = dd; a.W.ee = ee; a.W.e2 = (double *)(base + o_e2); a.W.bnd = (double *)(base + o_bnd);
+    a.W.lam = (double *)(base + o_lam);
+    if (want_vec) { a.W.lu = (double *)(base + o_lu); a.W.swp = base + o_swp; a.W.zw = (double *)(base + o_zw); }
+    CK(cudaMemsetAsync(info, 0, (size_t)B * 4, st));
+    s1_bounds_kernel<<<(unsigned)((B * 32 + 127) / 128), 128, 0, st>>>(a);
+    LAUNCHED();
+    const int ppw = 32 / k;
+    if (B * k >= 4096) {
+        const long long bw = (B + ppw - 1) / ppw;
+        s1_bisect_thread_kernel<<<(unsigned)((bw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, evals, 1);
+    } else {
+        s1_bisect_kernel<<<(unsigned)((G * 32 + 255) / 256), 256, 0, st>>>(a, nullptr, evals);
+    }
+    LAUNCHED();
+    if (want_vec) {
+        const long long iw = (B + ppw - 1) / ppw;
+        s1_invit_kernel<<<(unsigned)((iw * 32 + 127) / 128), 128, 0, st>>>(a, nullptr, G);
+        LAUNCHED();
+    }
+    CK(cudaGetLastError());
+    if (zw_out) *zw_out = a.W.zw;
+    if (G_out) *G_out = G;
+    return 0;
+}
