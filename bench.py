@@ -415,6 +415,29 @@ def dense_eigh_block(dev, hbm_peak):
                                "unit": "GB/s", "frac": alg / (rms * 1e-3) / 1e9 / hbm_peak,
                                "note": "algorithmic bytes (4/3)(1 + 1/NB) n^3 B per matrix, NB = %d / the reduction's event span" % nb}
         out.append(blk)
+    # the same path behind the sweep API: fluxonium plan (c2_fluxonium_t200) at node truncation 640, dense real symmetric
+    # H(phiZ) assembled by K2 into HBM and reduced by S2t; end to end through Engine.sweep (host arrays in and out)
+    try:
+        from pycqed_b200.plan import SweepPlan
+        d = json.load(open(os.path.join(ROOT, "tests", "golden", "c2_fluxonium_t200.plan.json")))
+        d["nodes"][0]["trunc"] = 640
+        plan = SweepPlan.from_dict(d)
+        full = plan.sweep_grid()
+        grid = np.ascontiguousarray(full[np.linspace(0, len(full) - 1, 592).round().astype(int)])
+        with engine.Engine(plan, device=dev) as eng:
+            ts = []
+            for rep in range(3):
+                t0 = time.perf_counter(); res = eng.sweep(grid, 10, want_vectors=True); ts.append(time.perf_counter() - t0)
+        t = min(ts[1:])
+        from oracle.plan_oracle import PlanOracle
+        t0 = time.perf_counter(); ref = PlanOracle(plan).sweep(grid[:4], 10, get_vectors=True); cpu_s = (time.perf_counter() - t0) / 4
+        out.append({"workload": "c2 fluxonium at truncation 640 (dense real symmetric n=640), 592-point phiZ sweep, k=10 + vectors",
+                    "n": 640, "points": 592, "e2e_pts_s": 592 / t, "ms": t * 1e3,
+                    "cpu": {"value": 1.0 / cpu_s, "unit": "points/s", "kind": "oracle port, 4 points"},
+                    "max_rel_dE": float(np.abs(res.E[:4] - ref["E"]).max() / np.abs(ref["E"]).max()),
+                    "nonconverged": int(np.count_nonzero(res.info))})
+    except Exception as exc:
+        out.append({"workload": "c2 fluxonium at truncation 640", "error": "%s: %s" % (type(exc).__name__, str(exc)[:300])})
     return out
 
 def run_ours(args):

@@ -5,6 +5,7 @@ Tolerances are the project's gates (BASELINE.json): eigenvalues 1e-9 relative, e
 subspace overlap >= 1 - 1e-8, derived quantities (transition energies, resonator strips,
 dispersive shift) to the same tolerance relative to the energy scale they are computed from.
 """
+import os
 import numpy as np
 import pytest
 
@@ -617,6 +618,33 @@ def test_full_size_properties_c2(engine_mod):
         r2 = eng.sweep(grid[idx], 10, want_vectors=True)
     assert np.max(np.abs(r2.E - E[idx])) < 1e-9 * np.abs(E).max()
     _oracle_check(plan, grid, idx, r2.E, r2.V, 10)
+
+
+@pytest.mark.parametrize("trunc,npts", [(300, 96), (640, 64)])
+def test_dense_real_symmetric_sweep_beyond_shared_memory(engine_mod, trunc, npts):
+    """A PLAN whose dense real symmetric H does not fit the shared-memory path (fluxonium in the oscillator basis at
+    truncation 300 / 640: the plan of c2_fluxonium_t200 with a larger node truncation -- factor matrices are generated
+    from the node description) through scqed_sweep_run: K2 assembly to HBM -> S2t (dense_tiled.cuh: register kernel at
+    n = 300, streamed kernel at n = 640) -> eigenvectors, against the ORACLE (CSR assembly + scipy eigh,
+    util.py:127-176) on sampled points; phi -> -phi symmetry over the whole sample."""
+    import copy, json
+    from pycqed_b200.plan import SweepPlan
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "c2_fluxonium_t200.plan.json")))
+    d = copy.deepcopy(d)
+    d["nodes"][0]["trunc"] = trunc
+    plan = SweepPlan.from_json(d) if hasattr(SweepPlan, "from_json") else SweepPlan.from_dict(d)
+    assert plan.hilbert_dim == trunc
+    full = plan.sweep_grid()
+    sel = np.linspace(0, len(full) - 1, npts).round().astype(int)
+    grid = np.ascontiguousarray(full[sel])
+    k = 10
+    with engine_mod.Engine(plan) as eng:
+        res = eng.sweep(grid, k, want_vectors=True)
+    assert not res.info.any()
+    assert np.all(np.diff(res.E, axis=1) >= -1e-9)
+    assert np.max(np.abs(res.E - res.E[::-1])) < 1e-9 * np.abs(res.E).max()      # symmetric sample of a symmetric grid
+    idx = _sample(npts, 6)
+    _oracle_check(plan, grid, idx, res.E[idx], res.V[idx], k)
 
 
 def _mirror_index(plan, flip):
