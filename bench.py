@@ -424,7 +424,7 @@ def dense_eigh_block(dev, hbm_peak):
         plan = SweepPlan.from_dict(d)
         full = plan.sweep_grid()
         grid = np.ascontiguousarray(full[np.linspace(0, len(full) - 1, 592).round().astype(int)])
-        with engine.Engine(plan, device=dev) as eng:
+        with engine.Engine(plan, device=dev.index) as eng:
             ts = []
             for rep in range(3):
                 t0 = time.perf_counter(); res = eng.sweep(grid, 10, want_vectors=True); ts.append(time.perf_counter() - t0)

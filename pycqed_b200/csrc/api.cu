@@ -729,7 +729,9 @@ static int sweep_run_impl(scqed_plan *pl, const scqed_sweep_opts *o, const doubl
         return rc ? rc : finish();
     }
     // ---- S2: batches of B matrices through HBM (dense.cu) ----------------------------------------
-    rc = dense_sweep(pl, (const cplx *)pl->coef.p, n_pts, k, o->want_vectors, o->tidyup, solver, evals_dev, vecs, info_dev, st);
+    // (o->solver == 0: the tile-packed real symmetric path S2t may take the batch; an explicit solver = 2 / 3 keeps the
+    // complex blocked / unblocked kernels, e.g. for the cross-checks of the test suite)
+    rc = dense_sweep(pl, (const cplx *)pl->coef.p, n_pts, k, o->want_vectors, o->tidyup, solver, o->solver == 0, evals_dev, vecs, info_dev, st);
     if (rc) return rc;
     return finish();
 }

@@ -345,7 +345,7 @@ int dense_eigh_resident(scqed_plan *tmp, cplx *H_dev, int n, long long batch, in
 }
 
 // scqed_sweep_run, S2: assemble B matrices at a time into HBM (K2) and reduce them.
-int dense_sweep(scqed_plan *pl, const cplx *coef, long long n_pts, int k, int want_vec, int tidyup, int solver,
+int dense_sweep(scqed_plan *pl, const cplx *coef, long long n_pts, int k, int want_vec, int tidyup, int solver, bool allow_tiled,
                 double *evals, cplx *vecs, int *info, cudaStream_t st) {
     const PlanDev &P = pl->P;
     const int n = P.n;
@@ -370,7 +370,7 @@ int dense_sweep(scqed_plan *pl, const cplx *coef, long long n_pts, int k, int wa
         double *ev = evals + (size_t)p0 * k;
         cplx *vec = vecs ? vecs + (size_t)p0 * k * n : nullptr;
         bool done = false;
-        if (blocked && solver != 2) { rc = run_dense_tiled_batch(pl, A, n, nb, k, want_vec, bw, ev, vec, info + p0, st, &done); if (rc) return rc; }
+        if (blocked && allow_tiled) { rc = run_dense_tiled_batch(pl, A, n, nb, k, want_vec, bw, ev, vec, info + p0, st, &done); if (rc) return rc; }
         if (done) continue;
         rc = blocked ? run_dense_blocked_batch(A, n, nb, k, want_vec, 1, bw, ev, vec, info + p0, st)
                      : run_dense_batch(pl, pl->sm_count, A, n, nb, k, want_vec, 1, w, ev, vec, info + p0, st);

@@ -171,7 +171,7 @@ int s1_tridiag_eig_batch(scqed_plan *pl, double *dd, double *ee, int n, int k, l
                          const double **zw_out, long long *G_out, int *info, cudaStream_t st);
 int dense_eigh_resident(scqed_plan *tmp, cplx *H_dev, int n, long long batch, int k, int want_vec, double *evals,
                         cplx *evecs, int *info, int solver, cudaStream_t st);
-int dense_sweep(scqed_plan *pl, const cplx *coef, long long n_pts, int k, int want_vec, int tidyup, int solver,
+int dense_sweep(scqed_plan *pl, const cplx *coef, long long n_pts, int k, int want_vec, int tidyup, int solver, bool allow_tiled,
                 double *evals, cplx *vecs, int *info, cudaStream_t st);
 // matfree.cu (S3: Chebyshev-filtered subspace iteration on the Kronecker mat-vec)
 int run_matfree(scqed_plan *pl, const cplx *coef_all, long long n_pts, int k, int want_vec, double *evals,

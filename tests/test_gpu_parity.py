@@ -639,7 +639,11 @@ def test_dense_real_symmetric_sweep_beyond_shared_memory(engine_mod, trunc, npts
     grid = np.ascontiguousarray(full[sel])
     k = 10
     with engine_mod.Engine(plan) as eng:
+        l0 = engine_mod.launch_count()
         res = eng.sweep(grid, k, want_vectors=True)
+        launches = engine_mod.launch_count() - l0
+    # the tile-packed path is a handful of launches per chunk; the complex blocked solver needs two per column
+    assert launches < 200, "the sweep did not take the tile-packed real symmetric path (%d launches)" % launches
     assert not res.info.any()
     assert np.all(np.diff(res.E, axis=1) >= -1e-9)
     assert np.max(np.abs(res.E - res.E[::-1])) < 1e-9 * np.abs(res.E).max()      # symmetric sample of a symmetric grid
