@@ -184,14 +184,14 @@ static int run_dense_blocked_batch(cplx *A, int n, int B, int k, int want_vec, i
 // ring, every tile read once per column).  *done = false (and nothing written) when the batch is not real symmetric or does
 // not fit: the caller then takes the complex blocked solver.  SCQED_DENSE_TILED = 0 disables the path, 1 forces the
 // register kernel, 2 the streamed one; SCQED_DTC_NB / SCQED_DTC_NST override the panel width / ring depth.
-template <int NB, int YS>
-static int launch_dtc(scqed_plan *pl, double *tiles, int n, int B, double *dd, double *ee, double *tau, int nst, cudaStream_t st) {
-    // nst = ring size in units of 16 KB
-    const size_t sm = DtcGeom::fixed(n, NB, YS) + (size_t)nst * 16384;
-    CK((set_max_dynamic_smem(dtc_tridiag_kernel<NB, YS>, pl->smem_optin)));
-    long long grid = pl->sm_count;
+template <int NB, int YS, int CW>
+static int launch_dtc(scqed_plan *pl, double *tiles, int n, int B, double *dd, double *ee, double *tau, int ringb, int per_sm,
+                      cudaStream_t st) {
+    const size_t sm = DtcGeom::fixed(n, NB, YS) + (size_t)ringb;
+    CK((set_max_dynamic_smem(dtc_tridiag_kernel<NB, YS, CW>, pl->smem_optin)));
+    long long grid = (long long)per_sm * pl->sm_count;
     if (grid > B) grid = B;
-    dtc_tridiag_kernel<NB, YS><<<(unsigned)grid, DTC_THREADS, sm, st>>>(tiles, n, B, dd, ee, tau, nst * 16384);
+    dtc_tridiag_kernel<NB, YS, CW><<<(unsigned)grid, DTC_NTHREADS(CW), sm, st>>>(tiles, n, B, dd, ee, tau, ringb);
     return 0;
 }
 
@@ -207,7 +207,8 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
     if (!forced && B < 48) return 0;
     bool streamed = mode == 2 || (mode < 0 && n >= 560);        // measured crossover (tools/s2t_ab.sh): n ~ 550
     const size_t cap = pl->smem_optin > 4096 ? pl->smem_optin - 2048 : 0;
-    int nb = 0, ys = 0, nst = 0;
+    int nb = 0, ys = 0, nst = 0, ringb = 0;
+    bool two = false;
     if (streamed) {
         // Panel width NB and ring size (nst units of 16 KB).  Measured at n = 1000 (ms per 296 matrices): NB = 8 with the 48 KB
         // ring that is left: 114-127 (latency bound: 3.7 TB/s); NB = 4 with 96 KB: 108-120 (5.2 TB/s, 33 % more traffic).  So:
@@ -227,6 +228,21 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
         if (!nb) {
             if (mode == 2) return 0;
             streamed = false;
+        }
+        ringb = nst * 16384;
+        // Opt-in (SCQED_DTC_TWO=1): two matrices per SM (two CTAs of 8 consumer warps, NB = 4, a ring of >= 32 KB each within
+        // half of the SM's shared memory).  Measured SLOWER than one CTA of 16 consumer warps with the whole shared memory
+        // (n = 600: 68 vs 58 ms per 592 matrices, 700: 122 vs 84, 300 / 400: equal): a second resident matrix does not
+        // overlap anything the first one waits for -- the passes are bound by bytes in flight per SM, not by their
+        // dependent sections.  Kept as a tested variant.
+        if (streamed && B > pl->sm_count && getenv("SCQED_DTC_TWO") && atoi(getenv("SCQED_DTC_TWO")) == 1 && !fnb && !fys && !fst) {
+            const size_t half = (size_t)113 * 1024;
+            const size_t fx = DtcGeom::fixed(n, 4, 4);
+            if (fx + 32768 <= half) {
+                two = true; nb = 4; ys = 4;
+                ringb = (int)(((half - fx) / 512) * 512);
+                if (ringb > 98304) ringb = 98304;
+            }
         }
     }
     if (!streamed && (n > 2048 || DtgGeom::tridiag_smem(n) + 2048 > pl->smem_optin)) return 0;
@@ -250,12 +266,13 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
     {
         TimingScope tscope_(st, 8);
         if (streamed) {
-            int rc = nb == 8 ? (ys == 4 ? launch_dtc<8, 4>(pl, tiles, n, B, K.dd, K.ee, tau, nst, st)
-                                        : launch_dtc<8, 1>(pl, tiles, n, B, K.dd, K.ee, tau, nst, st))
-                   : nb == 4 ? (ys == 4 ? launch_dtc<4, 4>(pl, tiles, n, B, K.dd, K.ee, tau, nst, st)
-                                        : launch_dtc<4, 1>(pl, tiles, n, B, K.dd, K.ee, tau, nst, st))
-                             : (ys == 4 ? launch_dtc<2, 4>(pl, tiles, n, B, K.dd, K.ee, tau, nst, st)
-                                        : launch_dtc<2, 1>(pl, tiles, n, B, K.dd, K.ee, tau, nst, st));
+            int rc = two ? launch_dtc<4, 4, 8>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 2, st)
+                   : nb == 8 ? (ys == 4 ? launch_dtc<8, 4, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, st)
+                                        : launch_dtc<8, 1, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, st))
+                   : nb == 4 ? (ys == 4 ? launch_dtc<4, 4, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, st)
+                                        : launch_dtc<4, 1, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, st))
+                             : (ys == 4 ? launch_dtc<2, 4, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, st)
+                                        : launch_dtc<2, 1, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, st));
             if (rc) return rc;
         } else {
             const size_t sm_tri = DtgGeom::tridiag_smem(n);

@@ -226,15 +226,16 @@ dtg_backtr_kernel(const double *__restrict__ tiles_all, int n, int k, long long 
 //     updated fragment then feeds the mat-vec); NB = 8 / 4 / 2 by what the panels leave for the ring;
 //   * the producer runs ahead into the next pass while the O(m) sections of a column execute.
 // HBM traffic per column: 4 m^2 B read + 4 m^2 / NB B written => (4/3) (1 + 1 / NB) n^3 B per matrix.
-#define DTC_CW 16                                   // consumer warps (two tiles each per full piece; 8 warps x 4 tiles measured 4 % slower)
-#define DTC_THREADS (32 * (DTC_CW + 2))             // + the producer warp + the folder warp
+#define DTC_CWMAX 16                                // consumer warps: CW = 16 (one CTA of 18 warps per SM) or CW = 8 (10 warps, two
+                                                    // CTAs per SM when two matrices fit the shared memory: the mid sizes)
+#define DTC_NTHREADS(CW) (32 * ((CW) + 2))          // + the producer warp + the folder warp
 #define DTC_PIECE 32                                // tiles per bulk copy (at most; a piece never spans two tile columns)
 #define DTC_NBAR 16                                 // pieces in flight (barrier pairs)
 
 struct DtcGeom {
     static size_t fixed(int n, int nb, int ys) {
         const size_t PS = DtgGeom::ps(n);
-        return (size_t)2 * DTC_CW * 64 + ((size_t)2 * nb * PS + (ys + 2) * PS + 2 * 8 + 8) * 8;
+        return (size_t)2 * DTC_CWMAX * 64 + ((size_t)2 * nb * PS + (ys + 2) * PS + 2 * 8 + 8) * 8;
     }
 };
 
@@ -303,10 +304,10 @@ __device__ __forceinline__ void dtc_row_part(const DtcSh &S, const double2 x, co
 // piece that was copied ahead), FUSED with y = A v on the updated tile -- the update costs no pass of its own.
 // YS = 4: row-part partial sums per lane of the quad (no shuffles); YS = 1: reduced over the quad before the accumulation
 // (a quarter of the shared memory: the large sizes).
-template <int NB, int YS, int MODE>
+template <int NB, int YS, int MODE, int CW>
 __device__ __forceinline__ void dtc_stream(double *tiles, const DtcSh &S, const double *vj, int n, int NT, int PS, int T0, int j,
                                            int jj, int b0, int nextT0, DtcPos &P, int wp, int lane) {
-    if (wp == DTC_CW) {
+    if (wp == CW) {
         // ---- producer: a piece is issued as soon as the ring has room for it and a barrier pair is free (pieces are
         // released in order).  After the last piece of this pass it runs AHEAD into the next pass (`nextT0` >= 0: the tiles
         // are not modified in between) as far as that is possible without waiting for a piece of the next pass itself, so
@@ -345,20 +346,20 @@ __device__ __forceinline__ void dtc_stream(double *tiles, const DtcSh &S, const 
             }
         }
         __syncwarp();
-    } else if (wp == DTC_CW + 1) {
+    } else if (wp == CW + 1) {
         // ---- folder: column parts of the consumer warps, added in warp order ----
         {
             for (int C = T0; C < NT; ++C) {
                 const unsigned slot = P.tc & 1u, use = P.tc >> 1;
                 dtc_mbar_wait(S.tfull + 8 * slot, use & 1u);
                 if (lane < 8) {
-                    const double *tp = S.tpart + (size_t)slot * DTC_CW * 8 + lane;
-                    double a[DTC_CW];
+                    const double *tp = S.tpart + (size_t)slot * CW * 8 + lane;
+                    double a[CW];
 #pragma unroll
-                    for (int w = 0; w < DTC_CW; ++w) a[w] = tp[w * 8];
+                    for (int w = 0; w < CW; ++w) a[w] = tp[w * 8];
                     double sum = 0.0;
 #pragma unroll
-                    for (int w = 0; w < DTC_CW; ++w) sum += a[w];
+                    for (int w = 0; w < CW; ++w) sum += a[w];
                     S.Yt[8 * C + lane] = sum;
                 }
                 __syncwarp();
@@ -389,8 +390,8 @@ __device__ __forceinline__ void dtc_stream(double *tiles, const DtcSh &S, const 
                 dtc_mbar_wait(S.full + 8 * bi, (P.g >> 4) & 1u);
                 const double *tb = S.ring + (P.off >> 3) + lofs;
 #pragma unroll
-                for (int u = 0; u < DTC_PIECE / DTC_CW; ++u) {
-                    const int q = ((wp - R0) & (DTC_CW - 1)) + u * DTC_CW;             // rows with R mod DTC_CW == wp
+                for (int u = 0; u < DTC_PIECE / CW; ++u) {
+                    const int q = ((wp - R0) & (CW - 1)) + u * CW;             // rows with R mod CW == wp
                     if (q < cnt) {
                         const int R = R0 + q;
                         double2 x = *reinterpret_cast<const double2 *>(tb + q * 64);
@@ -425,8 +426,8 @@ __device__ __forceinline__ void dtc_stream(double *tiles, const DtcSh &S, const 
             {
                 // column part of this warp: sum over the rows g8, lanes 0..3 hold columns 2 t4, 2 t4 + 1 (nothing to reduce
                 // when the warp had no tile below the diagonal in this column)
-                const int Rf = C + ((wp - C) & (DTC_CW - 1));
-                if (Rf < NT && (Rf > C || Rf + DTC_CW < NT)) {
+                const int Rf = C + ((wp - C) & (CW - 1));
+                if (Rf < NT && (Rf > C || Rf + CW < NT)) {
 #pragma unroll
                     for (int o = 4; o < 32; o <<= 1) {
                         tc0 += __shfl_xor_sync(0xffffffffu, tc0, o);
@@ -435,7 +436,7 @@ __device__ __forceinline__ void dtc_stream(double *tiles, const DtcSh &S, const 
                 }
                 const unsigned slot = P.tc & 1u, use = P.tc >> 1;
                 if (use >= 1u) dtc_mbar_wait(S.tempty + 8 * slot, (use - 1u) & 1u);
-                if (lane < 4) *reinterpret_cast<double2 *>(S.tpart + ((size_t)slot * DTC_CW + wp) * 8 + 2 * lane) = make_double2(tc0, tc1);
+                if (lane < 4) *reinterpret_cast<double2 *>(S.tpart + ((size_t)slot * CW + wp) * 8 + 2 * lane) = make_double2(tc0, tc1);
                 __syncwarp();
                 if (lane == 0) dtc_mbar_arrive(S.tfull + 8 * slot);
                 ++P.tc;
@@ -461,6 +462,7 @@ __device__ __forceinline__ void dtc_stream(double *tiles, const DtcSh &S, const 
     }
 }
 
+template <int NW>
 __device__ __forceinline__ double dtc_block_sum(double v, double *red) {
     v = warp_sum(v);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -469,16 +471,16 @@ __device__ __forceinline__ double dtc_block_sum(double v, double *red) {
     __syncthreads();
     double s = 0.0;
 #pragma unroll
-    for (int q = 0; q < DTC_THREADS / 32; ++q) s += red[q];
+    for (int q = 0; q < NW; ++q) s += red[q];
     return s;
 }
 
 // One persistent CTA per matrix (column-major tiles).  Outputs d, e, tau [B][n]; reflectors stay in the tiles.
-template <int NB, int YS>
+template <int NB, int YS, int CW>
 static __global__ void __maxnreg__(96)                 // 576 threads, one CTA per SM (__launch_bounds__(576) makes ptxas aim at 56 registers and spill)
 dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *__restrict__ dd_all, double *__restrict__ ee_all,
                    double *__restrict__ tau_all, int ringb) {
-    constexpr int NTHR = DTC_THREADS;
+    constexpr int NTHR = DTC_NTHREADS(CW);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double red[NTHR / 32];
     __shared__ double s_scal[2];
@@ -490,7 +492,7 @@ dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
     S.ringb = ringb;
     S.ring = (double *)smem;
     S.tpart = S.ring + (size_t)(ringb >> 3);
-    S.Vs = S.tpart + (size_t)2 * DTC_CW * 8;
+    S.Vs = S.tpart + (size_t)2 * DTC_CWMAX * 8;
     S.Ws = S.Vs + NB * PS;
     S.Yd4 = S.Ws + NB * PS;
     S.Yt = S.Yd4 + YS * PS;
@@ -503,8 +505,8 @@ dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
     S.tempty = S.tfull + 16;
     double *Vs = S.Vs, *Ws = S.Ws;
     if (tid == 0) {
-        for (int s = 0; s < DTC_NBAR; ++s) { dtc_mbar_init(&bars[s], 1); dtc_mbar_init(&bars[DTC_NBAR + s], DTC_CW); }
-        for (int s = 0; s < 2; ++s) { dtc_mbar_init(&bars[2 * DTC_NBAR + s], DTC_CW); dtc_mbar_init(&bars[2 * DTC_NBAR + 2 + s], 1); }
+        for (int s = 0; s < DTC_NBAR; ++s) { dtc_mbar_init(&bars[s], 1); dtc_mbar_init(&bars[DTC_NBAR + s], CW); }
+        for (int s = 0; s < 2; ++s) { dtc_mbar_init(&bars[2 * DTC_NBAR + s], CW); dtc_mbar_init(&bars[2 * DTC_NBAR + 2 + s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -547,7 +549,7 @@ dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
                     const int nz = YS * (PS - 8 * ((j + 1) >> 3)) / 2;
                     for (int q = tid; q < nz; q += NTHR) z[q] = make_double2(0.0, 0.0);
                 }
-                xn = dtc_block_sum(xn, red);
+                xn = dtc_block_sum<NTHR / 32>(xn, red);
                 double tau, beta, sc;
                 s1t_reflector_scalars(s_scal[0], xn, tau, beta, sc);
                 for (int r = j + tid; r < n; r += NTHR) {
@@ -559,14 +561,14 @@ dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
                 __syncthreads();
                 if (fused) {
                     // (the producer does not run ahead out of this pass: it rewrites the tiles)
-                    dtc_stream<NB, YS, 2>(tiles, S, vj, n, NT, PS, (j + 1) >> 3, j, 0, j + 1, -1, P, wp, lane);
+                    dtc_stream<NB, YS, 2, CW>(tiles, S, vj, n, NT, PS, (j + 1) >> 3, j, 0, j + 1, -1, P, wp, lane);
                     __syncthreads();
                     for (int q = tid; q < 2 * NB * PS; q += NTHR) Vs[q] = 0.0;
                     __syncthreads();
                 } else {
                     // the producer may run ahead into the next column's pass (plain or fused: same tiles, unchanged until then)
                     const int nextT0 = j + 1 < n - 1 ? (j + 2) >> 3 : -1;
-                    dtc_stream<NB, YS, 0>(tiles, S, vj, n, NT, PS, (j + 1) >> 3, j, jj, 0, nextT0, P, wp, lane);
+                    dtc_stream<NB, YS, 0, CW>(tiles, S, vj, n, NT, PS, (j + 1) >> 3, j, jj, 0, nextT0, P, wp, lane);
                     __syncthreads();
                 }
                 // ---- corrections, w ----
@@ -582,7 +584,7 @@ dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
                     S.Yd4[YS * r] = pr;
                     dt = fma(pr, vj[r], dt);
                 }
-                dt = dtc_block_sum(dt, red);
+                dt = dtc_block_sum<NTHR / 32>(dt, red);
                 const double hc = -0.5 * tau * dt;
                 for (int r = tid; r < PS; r += NTHR) {
                     Ws[jj * PS + r] = (r > j && r < n) ? fma(hc, vj[r], S.Yd4[YS * r]) : 0.0;

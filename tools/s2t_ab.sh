@@ -1,3 +1,4 @@
-# eigh_batched matrices/s by size (auto path)
+# eigh_batched matrices/s by size: streamed kernel with one / two CTAs per SM, register kernel
 T="timeout -s KILL 120"
-$T python tools/s2_rate.py 256:2072 300:2072 400:1184 500:1184 600:592 800:296 1000:296 1500:148 2000:148 2>&1 | grep -v Warning
+SCQED_DENSE_TILED=2 $T python tools/s2_rate.py 300:2072 400:1184 500:1184 600:592 700:592 800:592 2>&1 | grep -v Warning
+SCQED_DENSE_TILED=2 SCQED_DTC_TWO=0 $T python tools/s2_rate.py 600:592 700:592 800:592 2>&1 | grep -v Warning
