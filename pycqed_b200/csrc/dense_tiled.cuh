@@ -256,11 +256,11 @@ __device__ __forceinline__ void dtc_mbar_wait(unsigned bar, unsigned parity) {
         "{\n"
         ".reg .pred p;\n"
         "DTC_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DTC_DONE_%=;\n"
         "bra DTC_WAIT_%=;\n"
         "DTC_DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680) : "memory");      // suspend-time hint: the warp sleeps in the barrier unit instead of polling
 }
 
 struct DtcSh {
