@@ -184,14 +184,17 @@ static int run_dense_blocked_batch(cplx *A, int n, int B, int k, int want_vec, i
 // ring, every tile read once per column).  *done = false (and nothing written) when the batch is not real symmetric or does
 // not fit: the caller then takes the complex blocked solver.  SCQED_DENSE_TILED = 0 disables the path, 1 forces the
 // register kernel, 2 the streamed one; SCQED_DTC_NB / SCQED_DTC_NST override the panel width / ring depth.
+// measured (reduction ms per 148 matrices, panels in shared memory vs global): n = 1500: 180 vs 186, 2000: 450 vs 421,
+// 3375: 5970 (NB = 2, 32 KB ring) vs 2081 (NB = 8, one-slot row accumulators, 128 KB ring)
+#define DTC_GP_MIN_N 1800
 template <int NB, int YS, int CW>
 static int launch_dtc(scqed_plan *pl, double *tiles, int n, int B, double *dd, double *ee, double *tau, int ringb, int per_sm,
-                      cudaStream_t st) {
-    const size_t sm = DtcGeom::fixed(n, NB, YS) + (size_t)ringb;
+                      double *gpanels, cudaStream_t st) {
+    const size_t sm = DtcGeom::fixed(n, gpanels ? 0 : NB, YS) + (size_t)ringb;
     CK((set_max_dynamic_smem(dtc_tridiag_kernel<NB, YS, CW>, pl->smem_optin)));
     long long grid = (long long)per_sm * pl->sm_count;
     if (grid > B) grid = B;
-    dtc_tridiag_kernel<NB, YS, CW><<<(unsigned)grid, DTC_NTHREADS(CW), sm, st>>>(tiles, n, B, dd, ee, tau, ringb);
+    dtc_tridiag_kernel<NB, YS, CW><<<(unsigned)grid, DTC_NTHREADS(CW), sm, st>>>(tiles, n, B, dd, ee, tau, ringb, gpanels);
     return 0;
 }
 
@@ -208,7 +211,7 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
     bool streamed = mode == 2 || (mode < 0 && n >= 560);        // measured crossover (tools/s2t_ab.sh): n ~ 550
     const size_t cap = pl->smem_optin > 4096 ? pl->smem_optin - 2048 : 0;
     int nb = 0, ys = 0, nst = 0, ringb = 0;
-    bool two = false;
+    bool two = false, gp = false;
     if (streamed) {
         // Panel width NB and ring size (nst units of 16 KB).  Measured at n = 1000 (ms per 296 matrices): NB = 8 with the 48 KB
         // ring that is left: 114-127 (latency bound: 3.7 TB/s); NB = 4 with 96 KB: 108-120 (5.2 TB/s, 33 % more traffic).  So:
@@ -225,11 +228,32 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
                 for (int s = fst ? fst : 6; s >= (fst ? fst : minst); --s)
                     if (DtcGeom::fixed(n, cand[c][0], cand[c][1]) + (size_t)s * 16384 <= cap) { nb = cand[c][0]; ys = cand[c][1]; nst = s; break; }
             }
+        ringb = nst * 16384;
+        // Panels in global memory (L2) and the whole shared memory for vectors + ring: NB = 8 whatever n.
+        {
+            int gmode = -1;
+            if (const char *e = getenv("SCQED_DTC_GP")) gmode = atoi(e);
+            const bool want_gp = gmode == 1 || (gmode < 0 && n >= DTC_GP_MIN_N && !fnb && !fys && !fst);
+            if (want_gp || !nb) {
+                for (int cys : {4, 1}) {
+                    if (fys && cys != fys) continue;
+                    const size_t fx = DtcGeom::fixed(n, 0, cys);
+                    // the four-slot row accumulators only while they leave a ring of >= 96 KB (n = 3375: 38 matrices/s with
+                    // four slots and 48 KB, 66 with one slot and 128 KB)
+                    if (fx + (cys == 4 && !fys ? 98304 : 49152) > cap) continue;
+                    gp = true; nb = fnb ? fnb : 8; ys = cys;
+                    size_t r = ((cap - fx) / 16384) * 16384;
+                    if (r > 131072) r = 131072;
+                    if (fst) r = (size_t)fst * 16384;
+                    ringb = (int)r;
+                    break;
+                }
+            }
+        }
         if (!nb) {
             if (mode == 2) return 0;
             streamed = false;
         }
-        ringb = nst * 16384;
         // Opt-in (SCQED_DTC_TWO=1): two matrices per SM (two CTAs of 8 consumer warps, NB = 4, a ring of >= 32 KB each within
         // half of the SM's shared memory).  Measured SLOWER than one CTA of 16 consumer warps with the whole shared memory
         // (n = 600: 68 vs 58 ms per 592 matrices, 700: 122 vs 84, 300 / 400: equal): a second resident matrix does not
@@ -249,9 +273,11 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
     const size_t sm_bt = DtgGeom::backtr_smem(n);
     if (want_vec && sm_bt + 1024 > cap) return 0;
     const size_t td = DtgGeom::tile_doubles(n);
-    if (pl->dtg.ensure((size_t)B * td * 8 + 256)) return fail(SCQED_ENOMEM, "tile-packed matrices (%zu MB)", ((size_t)B * td * 8) >> 20);
+    const size_t gp_bytes = gp ? (size_t)pl->sm_count * 2 * 8 * DtgGeom::ps(n) * 8 : 0;
+    if (pl->dtg.ensure((size_t)B * td * 8 + 256 + gp_bytes)) return fail(SCQED_ENOMEM, "tile-packed matrices (%zu MB)", ((size_t)B * td * 8) >> 20);
     int *d_flag = (int *)pl->dtg.p;
     double *tiles = (double *)((unsigned char *)pl->dtg.p + 256);
+    double *gpanels = gp ? tiles + (size_t)B * td : nullptr;
     CK(cudaMemsetAsync(d_flag, 0, 4, st));
     const long long warps = (long long)B * (long long)(DtgGeom::nt(n)) * (DtgGeom::nt(n) + 1) / 2;
     if (streamed) dtg_pack_kernel<true><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(A, n, B, tiles, d_flag);
@@ -266,13 +292,13 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
     {
         TimingScope tscope_(st, 8);
         if (streamed) {
-            int rc = two ? launch_dtc<4, 4, 8>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 2, st)
-                   : nb == 8 ? (ys == 4 ? launch_dtc<8, 4, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, st)
-                                        : launch_dtc<8, 1, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, st))
-                   : nb == 4 ? (ys == 4 ? launch_dtc<4, 4, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, st)
-                                        : launch_dtc<4, 1, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, st))
-                             : (ys == 4 ? launch_dtc<2, 4, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, st)
-                                        : launch_dtc<2, 1, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, st));
+            int rc = two ? launch_dtc<4, 4, 8>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 2, gpanels, st)
+                   : nb == 8 ? (ys == 4 ? launch_dtc<8, 4, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, gpanels, st)
+                                        : launch_dtc<8, 1, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, gpanels, st))
+                   : nb == 4 ? (ys == 4 ? launch_dtc<4, 4, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, gpanels, st)
+                                        : launch_dtc<4, 1, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, gpanels, st))
+                             : (ys == 4 ? launch_dtc<2, 4, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, gpanels, st)
+                                        : launch_dtc<2, 1, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, gpanels, st));
             if (rc) return rc;
         } else {
             const size_t sm_tri = DtgGeom::tridiag_smem(n);

@@ -479,7 +479,11 @@ __device__ __forceinline__ double dtc_block_sum(double v, double *red) {
 template <int NB, int YS, int CW>
 static __global__ void __maxnreg__(96)                 // 576 threads, one CTA per SM (__launch_bounds__(576) makes ptxas aim at 56 registers and spill)
 dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *__restrict__ dd_all, double *__restrict__ ee_all,
-                   double *__restrict__ tau_all, int ringb) {
+                   double *__restrict__ tau_all, int ringb, double *__restrict__ gpanels) {
+    // gpanels != NULL: the panels V, W (2 NB PS doubles per CTA) live in GLOBAL memory (L2 resident: <= 0.5 MB per CTA) and
+    // the shared memory they would take goes to the ring instead -- the large sizes, where NB = 8 panels of 2 x 8 x n doubles
+    // would leave no ring at all.  The current reflector then always lives in Vn (shared: the consumers read it per tile)
+    // and is copied into its panel column afterwards; head, tail and the MODE 2 operands read the panels through L2.
     constexpr int NTHR = DTC_NTHREADS(CW);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double red[NTHR / 32];
@@ -492,9 +496,10 @@ dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
     S.ringb = ringb;
     S.ring = (double *)smem;
     S.tpart = S.ring + (size_t)(ringb >> 3);
-    S.Vs = S.tpart + (size_t)2 * DTC_CWMAX * 8;
+    const bool gp = gpanels != nullptr;
+    S.Vs = gp ? gpanels + (size_t)blockIdx.x * 2 * NB * PS : S.tpart + (size_t)2 * DTC_CWMAX * 8;
     S.Ws = S.Vs + NB * PS;
-    S.Yd4 = S.Ws + NB * PS;
+    S.Yd4 = gp ? S.tpart + (size_t)2 * DTC_CWMAX * 8 : S.Ws + NB * PS;
     S.Yt = S.Yd4 + YS * PS;
     S.Vn = S.Yt + PS;
     S.ts = S.Vn + PS;
@@ -515,7 +520,8 @@ dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
     for (long long b = blockIdx.x; b < B; b += gridDim.x) {
         double *tiles = tiles_all + (size_t)b * DtgGeom::tile_doubles(n);
         double *dd = dd_all + (size_t)b * n, *ee = ee_all + (size_t)b * n, *tauo = tau_all + (size_t)b * n;
-        for (int q = tid; q < 2 * NB * PS + (YS + 2) * PS; q += NTHR) Vs[q] = 0.0;
+        for (int q = tid; q < 2 * NB * PS; q += NTHR) Vs[q] = 0.0;
+        for (int q = tid; q < (YS + 2) * PS; q += NTHR) S.Yd4[q] = 0.0;             // Yd4, Yt, Vn
         __syncthreads();
         for (int j0 = 0; j0 < n; j0 += NB) {
             const int pn = min(NB, n - j0);
@@ -526,10 +532,11 @@ dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
                 // update is applied to the rest of the trailing block inside this column's mat-vec pass (MODE 2).
                 const bool fused = jj == 0 && j0 > 0;
                 const int nc = fused ? NB : jj;
-                double *vj = fused ? S.Vn : Vs + jj * PS;
+                const bool in_vn = fused || gp;
+                double *vj = in_vn ? S.Vn : Vs + jj * PS;
                 // ---- column j made current (stale column + the corrections of the panel) ----
                 double xn = 0.0;
-                if (fused) for (int r = tid; r < j; r += NTHR) vj[r] = 0.0;
+                if (in_vn) for (int r = tid; r < j; r += NTHR) vj[r] = 0.0;
                 for (int r = j + tid; r < n; r += NTHR) {
                     double cv = tiles[dtg_off<true>(r >> 3, Cj, NT) + (r & 7) * 8 + cj];
                     for (int k = 0; k < nc; ++k)
@@ -588,7 +595,7 @@ dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
                 const double hc = -0.5 * tau * dt;
                 for (int r = tid; r < PS; r += NTHR) {
                     Ws[jj * PS + r] = (r > j && r < n) ? fma(hc, vj[r], S.Yd4[YS * r]) : 0.0;
-                    if (fused) Vs[r] = vj[r];                                  // the reflector becomes column 0 of the new panel
+                    if (in_vn) Vs[jj * PS + r] = vj[r];                        // the reflector becomes column jj of the panel
                 }
                 __syncthreads();
             }

@@ -247,7 +247,8 @@ def test_eigh_degenerate_and_clustered(engine_mod, solver, n):
                                              ("1", 1000, 10, 2), ("1", 1030, 20, 1),
                                              ("2", 225, 10, 3), ("2", 257, 12, 5), ("2", 400, 8, 2), ("2", 517, 10, 64),
                                              ("2", 1000, 10, 2), ("2", 1030, 20, 1), ("2", 1333, 10, 3), ("2", 2050, 14, 2),
-                                             ("2", 300, 10, 160), ("2two", 300, 10, 160), ("2two", 610, 6, 150)])
+                                             ("2", 300, 10, 160), ("2two", 300, 10, 160), ("2two", 610, 6, 150),
+                                             ("2gp", 400, 10, 3), ("2gp", 1030, 20, 2), ("2gp", 2050, 14, 2), ("2", 3210, 6, 1)])
 def test_eigh_dense_tiled_real_symmetric(engine_mod, monkeypatch, mode, n, k, batch):
     """S2t (dense_tiled.cuh): real symmetric matrices beyond the shared-memory path, one persistent CTA per matrix on the
     tile-packed lower triangle in global memory, against numpy.  SCQED_DENSE_TILED forces the path for the small
@@ -257,6 +258,9 @@ def test_eigh_dense_tiled_real_symmetric(engine_mod, monkeypatch, mode, n, k, ba
     import torch
     if mode == "2two":                       # opt-in variant: two CTAs of 8 consumer warps per SM (needs > 148 matrices)
         monkeypatch.setenv("SCQED_DTC_TWO", "1")
+        mode = "2"
+    if mode == "2gp":                        # panels in global memory (the default for the large sizes), forced
+        monkeypatch.setenv("SCQED_DTC_GP", "1")
         mode = "2"
     monkeypatch.setenv("SCQED_DENSE_TILED", mode)
     rng = np.random.default_rng(4321 + n)
