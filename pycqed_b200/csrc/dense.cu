@@ -187,14 +187,14 @@ static int run_dense_blocked_batch(cplx *A, int n, int B, int k, int want_vec, i
 // measured (reduction ms per 148 matrices, panels in shared memory vs global): n = 1500: 180 vs 186, 2000: 450 vs 421,
 // 3375: 5970 (NB = 2, 32 KB ring) vs 2081 (NB = 8, one-slot row accumulators, 128 KB ring)
 #define DTC_GP_MIN_N 1800
-template <int NB, int YS, int CW>
+template <int NB, int YS, int CW, bool GP = false>
 static int launch_dtc(scqed_plan *pl, double *tiles, int n, int B, double *dd, double *ee, double *tau, int ringb, int per_sm,
                       double *gpanels, cudaStream_t st) {
-    const size_t sm = DtcGeom::fixed(n, gpanels ? 0 : NB, YS) + (size_t)ringb;
-    CK((set_max_dynamic_smem(dtc_tridiag_kernel<NB, YS, CW>, pl->smem_optin)));
+    const size_t sm = DtcGeom::fixed(n, GP ? 0 : NB, YS) + (size_t)ringb;
+    CK((set_max_dynamic_smem(dtc_tridiag_kernel<NB, YS, CW, GP>, pl->smem_optin)));
     long long grid = (long long)per_sm * pl->sm_count;
     if (grid > B) grid = B;
-    dtc_tridiag_kernel<NB, YS, CW><<<(unsigned)grid, DTC_NTHREADS(CW), sm, st>>>(tiles, n, B, dd, ee, tau, ringb, gpanels);
+    dtc_tridiag_kernel<NB, YS, CW, GP><<<(unsigned)grid, DTC_NTHREADS(CW), sm, st>>>(tiles, n, B, dd, ee, tau, ringb, GP ? gpanels : nullptr);
     return 0;
 }
 
@@ -241,7 +241,7 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
                     // the four-slot row accumulators only while they leave a ring of >= 96 KB (n = 3375: 38 matrices/s with
                     // four slots and 48 KB, 66 with one slot and 128 KB)
                     if (fx + (cys == 4 && !fys ? 98304 : 49152) > cap) continue;
-                    gp = true; nb = fnb ? fnb : 8; ys = cys;
+                    gp = true; nb = 8; ys = cys;
                     size_t r = ((cap - fx) / 16384) * 16384;
                     if (r > 131072) r = 131072;
                     if (fst) r = (size_t)fst * 16384;
@@ -259,7 +259,7 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
         // (n = 600: 68 vs 58 ms per 592 matrices, 700: 122 vs 84, 300 / 400: equal): a second resident matrix does not
         // overlap anything the first one waits for -- the passes are bound by bytes in flight per SM, not by their
         // dependent sections.  Kept as a tested variant.
-        if (streamed && B > pl->sm_count && getenv("SCQED_DTC_TWO") && atoi(getenv("SCQED_DTC_TWO")) == 1 && !fnb && !fys && !fst) {
+        if (streamed && !gp && B > pl->sm_count && getenv("SCQED_DTC_TWO") && atoi(getenv("SCQED_DTC_TWO")) == 1 && !fnb && !fys && !fst) {
             const size_t half = (size_t)113 * 1024;
             const size_t fx = DtcGeom::fixed(n, 4, 4);
             if (fx + 32768 <= half) {
@@ -292,7 +292,9 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
     {
         TimingScope tscope_(st, 8);
         if (streamed) {
-            int rc = two ? launch_dtc<4, 4, 8>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 2, gpanels, st)
+            int rc = gp ? (ys == 4 ? launch_dtc<8, 4, 16, true>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, gpanels, st)
+                                   : launch_dtc<8, 1, 16, true>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, gpanels, st))
+                   : two ? launch_dtc<4, 4, 8>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 2, gpanels, st)
                    : nb == 8 ? (ys == 4 ? launch_dtc<8, 4, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, gpanels, st)
                                         : launch_dtc<8, 1, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, gpanels, st))
                    : nb == 4 ? (ys == 4 ? launch_dtc<4, 4, 16>(pl, tiles, n, B, K.dd, K.ee, tau, ringb, 1, gpanels, st)

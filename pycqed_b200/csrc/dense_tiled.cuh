@@ -476,11 +476,11 @@ __device__ __forceinline__ double dtc_block_sum(double v, double *red) {
 }
 
 // One persistent CTA per matrix (column-major tiles).  Outputs d, e, tau [B][n]; reflectors stay in the tiles.
-template <int NB, int YS, int CW>
+template <int NB, int YS, int CW, bool GP>
 static __global__ void __maxnreg__(96)                 // 576 threads, one CTA per SM (__launch_bounds__(576) makes ptxas aim at 56 registers and spill)
 dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *__restrict__ dd_all, double *__restrict__ ee_all,
                    double *__restrict__ tau_all, int ringb, double *__restrict__ gpanels) {
-    // gpanels != NULL: the panels V, W (2 NB PS doubles per CTA) live in GLOBAL memory (L2 resident: <= 0.5 MB per CTA) and
+    // GP: the panels V, W (2 NB PS doubles per CTA) live in GLOBAL memory (L2 resident: <= 0.5 MB per CTA) and
     // the shared memory they would take goes to the ring instead -- the large sizes, where NB = 8 panels of 2 x 8 x n doubles
     // would leave no ring at all.  The current reflector then always lives in Vn (shared: the consumers read it per tile)
     // and is copied into its panel column afterwards; head, tail and the MODE 2 operands read the panels through L2.
@@ -496,7 +496,7 @@ dtc_tridiag_kernel(double *__restrict__ tiles_all, int n, long long B, double *_
     S.ringb = ringb;
     S.ring = (double *)smem;
     S.tpart = S.ring + (size_t)(ringb >> 3);
-    const bool gp = gpanels != nullptr;
+    constexpr bool gp = GP;                   // compile time: with a run-time choice every panel access becomes a generic load (+10 %)
     S.Vs = gp ? gpanels + (size_t)blockIdx.x * 2 * NB * PS : S.tpart + (size_t)2 * DTC_CWMAX * 8;
     S.Ws = S.Vs + NB * PS;
     S.Yd4 = gp ? S.tpart + (size_t)2 * DTC_CWMAX * 8 : S.Ws + NB * PS;
