@@ -404,7 +404,7 @@ def dense_eigh_block(dev, hbm_peak):
         # one-stage tridiagonalisation on the packed lower triangle: stored half read once per column, update written once per
         # panel of NB columns => (4/3)(1 + 1/NB) n^3 B per matrix (the streamed kernel, n >= 560); below that the register
         # kernel reads every tile twice and is latency bound, no HBM roofline quoted
-        nb = 4 if n < 1800 else 8                     # what run_dense_tiled_batch picks at these sizes (panels in shared memory / in L2)
+        nb = 4 if n < 1400 else 8                     # what run_dense_tiled_batch picks at these sizes (panels in shared memory / in L2)
         alg = (4.0 / 3.0) * (1.0 + 1.0 / nb) * n ** 3 * B
         blk = {"workload": "eigh_batched real symmetric n=%d, %d matrices, k=10 + vectors" % (n, B), "n": n, "batch": B,
                "value": B / (t * 1e-3), "unit": "matrices/s", "ms": t, "reduction_ms": rms,

@@ -184,9 +184,9 @@ static int run_dense_blocked_batch(cplx *A, int n, int B, int k, int want_vec, i
 // ring, every tile read once per column).  *done = false (and nothing written) when the batch is not real symmetric or does
 // not fit: the caller then takes the complex blocked solver.  SCQED_DENSE_TILED = 0 disables the path, 1 forces the
 // register kernel, 2 the streamed one; SCQED_DTC_NB / SCQED_DTC_NST override the panel width / ring depth.
-// measured (reduction ms per 148 matrices, panels in shared memory vs global): n = 1500: 180 vs 186, 2000: 450 vs 421,
-// 3375: 5970 (NB = 2, 32 KB ring) vs 2081 (NB = 8, one-slot row accumulators, 128 KB ring)
-#define DTC_GP_MIN_N 1800
+// measured (reduction ms per 148 matrices, panels in shared memory vs global): n = 1000: 52 vs 58, 1200: 83.5 vs 90.9,
+// 1500: 173.8 vs 166.6, 2000: 450 vs 383, 3375: 5970 (NB = 2, 32 KB ring) vs 2000 (NB = 8, one-slot row accumulators, 128 KB ring)
+#define DTC_GP_MIN_N 1400
 template <int NB, int YS, int CW, bool GP = false>
 static int launch_dtc(scqed_plan *pl, double *tiles, int n, int B, double *dd, double *ee, double *tau, int ringb, int per_sm,
                       double *gpanels, cudaStream_t st) {
