@@ -221,8 +221,8 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
         int fnb = 0, fys = 0, fst = 0;
         if (const char *e = getenv("SCQED_DTC_NB")) { int v = atoi(e); if (v == 8 || v == 4 || v == 2) fnb = v; }
         if (const char *e = getenv("SCQED_DTC_YS")) { int v = atoi(e); if (v == 4 || v == 1) fys = v; }
-        if (const char *e = getenv("SCQED_DTC_NST")) { int v = atoi(e); if (v >= 2 && v <= 8) fst = v; }
-        for (int minst = 4; minst >= 2 && !nb; --minst)            // 32 KB: the last resort (n ~ 3100 ... 3400)
+        if (const char *e = getenv("SCQED_DTC_NST")) { int v = atoi(e); if (v >= 4 && v <= 8) fst = v; }    // >= two 32 KB pieces
+        for (int minst = 4; minst >= 4 && !nb; --minst)            // >= 64 KB: two pieces of DTC_PIECE tiles
             for (int c = 0; c < 6 && !nb; ++c) {
                 if ((fnb && cand[c][0] != fnb) || (fys && cand[c][1] != fys)) continue;
                 for (int s = fst ? fst : 6; s >= (fst ? fst : minst); --s)
@@ -240,7 +240,7 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
                     const size_t fx = DtcGeom::fixed(n, 0, cys);
                     // the four-slot row accumulators only while they leave a ring of >= 96 KB (n = 3375: 38 matrices/s with
                     // four slots and 48 KB, 66 with one slot and 128 KB)
-                    if (fx + (cys == 4 && !fys ? 98304 : 49152) > cap) continue;
+                    if (fx + (cys == 4 && !fys ? 98304 : 65536) > cap) continue;
                     gp = true; nb = 8; ys = cys;
                     size_t r = ((cap - fx) / 16384) * 16384;
                     if (r > 131072) r = 131072;
@@ -262,7 +262,7 @@ static int run_dense_tiled_batch(scqed_plan *pl, const cplx *A, int n, int B, in
         if (streamed && !gp && B > pl->sm_count && getenv("SCQED_DTC_TWO") && atoi(getenv("SCQED_DTC_TWO")) == 1 && !fnb && !fys && !fst) {
             const size_t half = (size_t)113 * 1024;
             const size_t fx = DtcGeom::fixed(n, 4, 4);
-            if (fx + 32768 <= half) {
+            if (fx + 65536 <= half) {
                 two = true; nb = 4; ys = 4;
                 ringb = (int)(((half - fx) / 512) * 512);
                 if (ringb > 98304) ringb = 98304;

@@ -215,7 +215,7 @@ dtg_backtr_kernel(const double *__restrict__ tiles_all, int n, int k, long long 
 // register loads of which the compiler keeps two or three in flight per warp: ~10 GB/s per SM.  Here
 //   * the tiles are stored column-major (dtg_off<true>): the trailing block is one contiguous suffix, which a PRODUCER warp
 //     streams through a shared-memory BYTE ring with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx): pieces of at
-//     most DTC_PIECE tiles = 16 KB of one tile column, up to 16 pieces / 48-96 KB in flight per SM;
+//     most DTC_PIECE tiles = 32 KB of one tile column, up to 16 pieces / 64-128 KB in flight per SM;
 //   * every tile is read ONCE per column: the consumer warp R mod 16 takes tile (R, C) out of the ring (one LDS.128 per
 //     lane) and forms both y_R += T v_C (row part: four partial sums per row, one per lane of the quad, accumulated in
 //     place in Yd4[32 R + lane]: no shuffles, rows owned by one warp) and y_C += T^T v_R (column part: two accumulators per
@@ -229,7 +229,8 @@ dtg_backtr_kernel(const double *__restrict__ tiles_all, int n, int k, long long 
 #define DTC_CWMAX 16                                // consumer warps: CW = 16 (one CTA of 18 warps per SM) or CW = 8 (10 warps, two
                                                     // CTAs per SM when two matrices fit the shared memory: the mid sizes)
 #define DTC_NTHREADS(CW) (32 * ((CW) + 2))          // + the producer warp + the folder warp
-#define DTC_PIECE 32                                // tiles per bulk copy (at most; a piece never spans two tile columns)
+#define DTC_PIECE 64                                // tiles per bulk copy (at most; a piece never spans two tile columns); 32 measured
+                                                    // 0 / 2 / 3 / 8 % slower at n = 600 / 1000 / 1500 / 2000
 #define DTC_NBAR 16                                 // pieces in flight (barrier pairs)
 
 struct DtcGeom {
