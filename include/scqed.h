@@ -148,7 +148,11 @@ int scqed_assemble_dense(scqed_plan *plan, const double *params_dev, int64_t n_p
 /* diagonalize / util.diagDenseH replacement (numerical_system.py:809-810, util.py:127-176):
  * lowest k eigenpairs of `batch` Hermitian matrices (row-major, only consistent Hermitian input
  * is supported; H_dev is overwritten).  evals_dev [batch, k] ascending; evecs_dev complex
- * [batch, k, n] unit-norm (NULL = values only); info_dev [batch] (0 = converged). */
+ * [batch, k, n] unit-norm (NULL = values only); info_dev [batch] (0 = converged).
+ * Solver by size and content (solver = 0): H in shared memory (n <= 128, real symmetric <= 224); real symmetric batches of
+ * >= 48 matrices up to n = 3400 on the tile-packed lower triangle, one persistent CTA per matrix (dense_tiled.cuh); the
+ * complex blocked solver otherwise.  The call is synchronous on `stream`; calls on one device are serialised, and a
+ * per-device context keeps the workspaces between calls (released when they exceed 16 GB). */
 int scqed_eigh_batched(int device, double *H_dev, int32_t n, int64_t batch, int32_t k,
                        double *evals_dev, double *evecs_dev, int32_t *info_dev, int32_t solver,
                        void *stream);
